@@ -1,0 +1,305 @@
+// BLS12-381 base field Fp on 12 x 32-bit limbs, Montgomery form (R = 2^384), values kept canonical in [0, p).
+//
+// Replaces arkworks' Fp<MontBackend<FqConfig,6>,6> (the type named at reference src/hasher.rs:1040) for the
+// hot path of src/bls.rs:427-458.  12 x u32 little-endian limbs with R = 2^384 are byte-identical to
+// arkworks' 6 x u64 limbs, so no conversion is needed at the boundary.
+//
+// The multiply is an operand-scanning Montgomery product over two carry-save accumulators ("even" and
+// "odd" columns) so that every 32x32->64 MAC is a single IMAD.WIDE.U32(.X) whose carry rides the predicate
+// chain: 300 IMAD-pipe instructions per product (12*12 product + 12*12 reduction + 12 quotients) and ~70
+// ALU-pipe instructions.  Each carry chain is ONE asm statement, so the compiler cannot interleave chains.
+//
+// The same source builds for the host (g++, tests/hostemu) with plain-C fallbacks of every asm block, which
+// is how the algorithm layer above is debugged without a GPU.  The product library is nvcc-only.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include "consts.cuh"
+
+#if defined(__CUDACC__)
+#define BLS_HD __device__ __forceinline__
+#define BLS_NOINLINE __device__ __noinline__
+#define BLS_CONST static __device__ __constant__
+#else
+#define BLS_HD static inline
+#define BLS_NOINLINE static __attribute__((noinline))
+#define BLS_CONST static const
+#endif
+
+namespace bls {
+
+struct fp { uint32_t l[12]; };
+
+// p, little-endian 32-bit limbs
+#define BLS_P0 0xffffaaabu
+#define BLS_P1 0xb9feffffu
+#define BLS_P2 0xb153ffffu
+#define BLS_P3 0x1eabfffeu
+#define BLS_P4 0xf6b0f624u
+#define BLS_P5 0x6730d2a0u
+#define BLS_P6 0xf38512bfu
+#define BLS_P7 0x64774b84u
+#define BLS_P8 0x434bacd7u
+#define BLS_P9 0x4b1ba7b6u
+#define BLS_P10 0x397fe69au
+#define BLS_P11 0x1a0111eau
+#define BLS_M0 0xfffcfffdu      // -p^-1 mod 2^32
+
+BLS_HD uint32_t fp_p_limb(int i) {
+    const uint32_t P[12] = {BLS_P0, BLS_P1, BLS_P2, BLS_P3, BLS_P4, BLS_P5, BLS_P6, BLS_P7, BLS_P8, BLS_P9, BLS_P10, BLS_P11};
+    return P[i];
+}
+
+// ------------------------------------------------------------------------------------------------ add / sub
+#if defined(__CUDA_ARCH__)
+// r = a + b (384-bit, carry out impossible for a,b < p < 2^381)
+BLS_HD void fp_add_raw(fp& r, const fp& a, const fp& b) {
+    asm("add.cc.u32 %0, %12, %24;\n\taddc.cc.u32 %1, %13, %25;\n\taddc.cc.u32 %2, %14, %26;\n\taddc.cc.u32 %3, %15, %27;\n\t"
+        "addc.cc.u32 %4, %16, %28;\n\taddc.cc.u32 %5, %17, %29;\n\taddc.cc.u32 %6, %18, %30;\n\taddc.cc.u32 %7, %19, %31;\n\t"
+        "addc.cc.u32 %8, %20, %32;\n\taddc.cc.u32 %9, %21, %33;\n\taddc.cc.u32 %10, %22, %34;\n\taddc.u32 %11, %23, %35;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]), "=r"(r.l[8]), "=r"(r.l[9]), "=r"(r.l[10]), "=r"(r.l[11])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]), "r"(a.l[8]), "r"(a.l[9]), "r"(a.l[10]), "r"(a.l[11]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]), "r"(b.l[8]), "r"(b.l[9]), "r"(b.l[10]), "r"(b.l[11]));
+}
+// r = a - b (384-bit), returns the borrow as 0 / 0xffffffff
+BLS_HD uint32_t fp_sub_raw(fp& r, const fp& a, const fp& b) {
+    uint32_t br;
+    asm("sub.cc.u32 %0, %13, %25;\n\tsubc.cc.u32 %1, %14, %26;\n\tsubc.cc.u32 %2, %15, %27;\n\tsubc.cc.u32 %3, %16, %28;\n\t"
+        "subc.cc.u32 %4, %17, %29;\n\tsubc.cc.u32 %5, %18, %30;\n\tsubc.cc.u32 %6, %19, %31;\n\tsubc.cc.u32 %7, %20, %32;\n\t"
+        "subc.cc.u32 %8, %21, %33;\n\tsubc.cc.u32 %9, %22, %34;\n\tsubc.cc.u32 %10, %23, %35;\n\tsubc.cc.u32 %11, %24, %36;\n\t"
+        "subc.u32 %12, 0, 0;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]), "=r"(r.l[8]), "=r"(r.l[9]), "=r"(r.l[10]), "=r"(r.l[11]), "=r"(br)
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]), "r"(a.l[8]), "r"(a.l[9]), "r"(a.l[10]), "r"(a.l[11]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]), "r"(b.l[8]), "r"(b.l[9]), "r"(b.l[10]), "r"(b.l[11]));
+    return br;
+}
+#else
+BLS_HD void fp_add_raw(fp& r, const fp& a, const fp& b) {
+    uint64_t c = 0;
+    for (int i = 0; i < 12; i++) { c += (uint64_t)a.l[i] + b.l[i]; r.l[i] = (uint32_t)c; c >>= 32; }
+}
+BLS_HD uint32_t fp_sub_raw(fp& r, const fp& a, const fp& b) {
+    uint64_t br = 0;
+    for (int i = 0; i < 12; i++) { uint64_t d = (uint64_t)a.l[i] - b.l[i] - br; r.l[i] = (uint32_t)d; br = (d >> 32) & 1; }
+    return br ? 0xffffffffu : 0u;
+}
+#endif
+
+BLS_HD fp fp_modulus() {
+    fp m;
+#pragma unroll
+    for (int i = 0; i < 12; i++) m.l[i] = fp_p_limb(i);
+    return m;
+}
+BLS_HD fp fp_zero() {
+    fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = 0;
+    return r;
+}
+// Montgomery 1 = R mod p
+BLS_HD fp fp_one() {
+    const uint32_t O[12] = BLS_C_ONE;
+    fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = O[i];
+    return r;
+}
+// R^2 mod p (to-Montgomery multiplier)
+BLS_HD fp fp_r2() {
+    const uint32_t O[12] = BLS_C_R2;
+    fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = O[i];
+    return r;
+}
+BLS_HD fp fp_select(uint32_t mask, const fp& a, const fp& b) {   // mask ? a : b, mask in {0, ~0}
+    fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = (a.l[i] & mask) | (b.l[i] & ~mask);
+    return r;
+}
+BLS_HD fp fp_csel(bool c, const fp& a, const fp& b) { return fp_select(c ? 0xffffffffu : 0u, a, b); }
+BLS_HD bool fp_is_zero(const fp& a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) o |= a.l[i];
+    return o == 0;
+}
+BLS_HD bool fp_eq(const fp& a, const fp& b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) o |= a.l[i] ^ b.l[i];
+    return o == 0;
+}
+// reduce a value in [0, 2p) to [0, p)
+BLS_HD fp fp_reduce_once(const fp& a) {
+    fp t; uint32_t br = fp_sub_raw(t, a, fp_modulus());
+    return fp_select(br, a, t);
+}
+BLS_HD fp fp_add(const fp& a, const fp& b) { fp s; fp_add_raw(s, a, b); return fp_reduce_once(s); }
+BLS_HD fp fp_sub(const fp& a, const fp& b) {
+    fp d; uint32_t br = fp_sub_raw(d, a, b);
+    fp m = fp_modulus();
+#pragma unroll
+    for (int i = 0; i < 12; i++) m.l[i] &= br;
+    fp r; fp_add_raw(r, d, m); return r;
+}
+BLS_HD fp fp_neg(const fp& a) {
+    fp d; fp_sub_raw(d, fp_modulus(), a);
+    return fp_select(fp_is_zero(a) ? 0xffffffffu : 0u, a, d);
+}
+BLS_HD fp fp_dbl(const fp& a) { return fp_add(a, a); }
+// canonical (non-Montgomery) integer comparison helpers work on canonical limbs
+BLS_HD bool fp_raw_geq(const fp& a, const fp& b) { fp t; return fp_sub_raw(t, a, b) == 0; }
+
+// ------------------------------------------------------------------------------------------------ Montgomery product
+#if defined(__CUDA_ARCH__)
+// acc[0..11] += a[0,2,..,10] * bi along one carry chain; the carry out is added to top
+#define BLS_CMAD_BODY                                                                                                   \
+    "mad.lo.cc.u32 %0, %13, %19, %0;\n\tmadc.hi.cc.u32 %1, %13, %19, %1;\n\t"                                            \
+    "madc.lo.cc.u32 %2, %14, %19, %2;\n\tmadc.hi.cc.u32 %3, %14, %19, %3;\n\t"                                           \
+    "madc.lo.cc.u32 %4, %15, %19, %4;\n\tmadc.hi.cc.u32 %5, %15, %19, %5;\n\t"                                           \
+    "madc.lo.cc.u32 %6, %16, %19, %6;\n\tmadc.hi.cc.u32 %7, %16, %19, %7;\n\t"                                           \
+    "madc.lo.cc.u32 %8, %17, %19, %8;\n\tmadc.hi.cc.u32 %9, %17, %19, %9;\n\t"                                           \
+    "madc.lo.cc.u32 %10, %18, %19, %10;\n\tmadc.hi.cc.u32 %11, %18, %19, %11;\n\t"                                       \
+    "addc.u32 %12, %12, 0;"
+BLS_HD void cmad_n(uint32_t* acc, uint32_t& top, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t a8, uint32_t a10, uint32_t bi) {
+    asm(BLS_CMAD_BODY
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(top)
+        : "r"(a0), "r"(a2), "r"(a4), "r"(a6), "r"(a8), "r"(a10), "r"(bi));
+}
+// e0 += o[1] (carry into the chain); then o[j],o[j+1] = a_j*bi + o[j+2],o[j+3] for the five low pairs and
+// o[10],o[11] = a_10*bi + carry: "accumulate the odd columns while shifting the accumulator down two limbs"
+BLS_HD void madc_n_rshift(uint32_t& e0, uint32_t* o, uint32_t a1, uint32_t a3, uint32_t a5, uint32_t a7, uint32_t a9, uint32_t a11, uint32_t bi) {
+    asm("add.cc.u32 %12, %12, %1;\n\t"
+        "madc.lo.cc.u32 %0, %13, %19, %2;\n\tmadc.hi.cc.u32 %1, %13, %19, %3;\n\t"
+        "madc.lo.cc.u32 %2, %14, %19, %4;\n\tmadc.hi.cc.u32 %3, %14, %19, %5;\n\t"
+        "madc.lo.cc.u32 %4, %15, %19, %6;\n\tmadc.hi.cc.u32 %5, %15, %19, %7;\n\t"
+        "madc.lo.cc.u32 %6, %16, %19, %8;\n\tmadc.hi.cc.u32 %7, %16, %19, %9;\n\t"
+        "madc.lo.cc.u32 %8, %17, %19, %10;\n\tmadc.hi.cc.u32 %9, %17, %19, %11;\n\t"
+        "madc.lo.cc.u32 %10, %18, %19, 0;\n\tmadc.hi.u32 %11, %18, %19, 0;"
+        : "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(o[8]), "+r"(o[9]), "+r"(o[10]), "+r"(o[11]), "+r"(e0)
+        : "r"(a1), "r"(a3), "r"(a5), "r"(a7), "r"(a9), "r"(a11), "r"(bi));
+}
+#else
+BLS_HD void cmad_n(uint32_t* acc, uint32_t& top, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t a8, uint32_t a10, uint32_t bi) {
+    const uint32_t a[6] = {a0, a2, a4, a6, a8, a10};
+    uint64_t c = 0;
+    for (int j = 0; j < 6; j++) {
+        unsigned __int128 t = (unsigned __int128)a[j] * bi + (((uint64_t)acc[2 * j + 1] << 32) | acc[2 * j]) + c;
+        acc[2 * j] = (uint32_t)t; acc[2 * j + 1] = (uint32_t)(t >> 32); c = (uint64_t)(t >> 64);
+    }
+    top += (uint32_t)c;
+}
+BLS_HD void madc_n_rshift(uint32_t& e0, uint32_t* o, uint32_t a1, uint32_t a3, uint32_t a5, uint32_t a7, uint32_t a9, uint32_t a11, uint32_t bi) {
+    const uint32_t a[6] = {a1, a3, a5, a7, a9, a11};
+    uint64_t s = (uint64_t)e0 + o[1]; e0 = (uint32_t)s; uint64_t c = s >> 32;
+    for (int j = 0; j < 6; j++) {
+        uint64_t addend = j < 5 ? (((uint64_t)o[2 * j + 3] << 32) | o[2 * j + 2]) : 0;
+        unsigned __int128 t = (unsigned __int128)a[j] * bi + addend + c;
+        o[2 * j] = (uint32_t)t; o[2 * j + 1] = (uint32_t)(t >> 32); c = (uint64_t)(t >> 64);
+    }
+}
+#endif
+
+// one row of the interleaved product/reduction: even/odd swap roles every call
+BLS_HD void mad_n_redc(uint32_t* even, uint32_t* odd, const fp& a, uint32_t bi, bool first) {
+    if (first) {
+#pragma unroll
+        for (int j = 0; j < 12; j += 2) {
+            uint64_t te = (uint64_t)a.l[j] * bi, to = (uint64_t)a.l[j + 1] * bi;
+            even[j] = (uint32_t)te; even[j + 1] = (uint32_t)(te >> 32);
+            odd[j] = (uint32_t)to; odd[j + 1] = (uint32_t)(to >> 32);
+        }
+    } else {
+        madc_n_rshift(even[0], odd, a.l[1], a.l[3], a.l[5], a.l[7], a.l[9], a.l[11], bi);
+        cmad_n(even, odd[11], a.l[0], a.l[2], a.l[4], a.l[6], a.l[8], a.l[10], bi);
+    }
+    uint32_t mi = even[0] * BLS_M0;
+    uint32_t drop = 0;
+    cmad_n(odd, drop, BLS_P1, BLS_P3, BLS_P5, BLS_P7, BLS_P9, BLS_P11, mi);
+    cmad_n(even, odd[11], BLS_P0, BLS_P2, BLS_P4, BLS_P6, BLS_P8, BLS_P10, mi);
+}
+
+BLS_HD fp fp_mul_inl(const fp& a, const fp& b) {
+    uint32_t even[12], odd[12];
+#pragma unroll
+    for (int i = 0; i < 12; i += 2) {
+        mad_n_redc(even, odd, a, b.l[i], i == 0);
+        mad_n_redc(odd, even, a, b.l[i + 1], false);
+    }
+    // merge: result = even + (odd >> 32); even[0] absorbs odd[1], ...
+    fp r, s;
+#pragma unroll
+    for (int i = 0; i < 11; i++) { r.l[i] = even[i]; s.l[i] = odd[i + 1]; }
+    r.l[11] = even[11]; s.l[11] = 0;
+    fp t; fp_add_raw(t, r, s);
+    return fp_reduce_once(t);
+}
+
+#if defined(__CUDACC__)
+BLS_NOINLINE fp fp_mul(fp a, fp b) { return fp_mul_inl(a, b); }
+BLS_NOINLINE fp fp_sqr(fp a) { return fp_mul_inl(a, a); }
+#else
+BLS_NOINLINE fp fp_mul(const fp& a, const fp& b) { return fp_mul_inl(a, b); }
+BLS_NOINLINE fp fp_sqr(const fp& a) { return fp_mul_inl(a, a); }
+#endif
+
+BLS_HD fp fp_to_mont(const fp& a) { return fp_mul(a, fp_r2()); }
+BLS_HD fp fp_from_mont(const fp& a) { fp one = fp_zero(); one.l[0] = 1; return fp_mul(a, one); }
+
+// a^e for a fixed public exponent given as 32-bit LE words; 4-bit fixed window
+BLS_HD fp fp_pow(const fp& a, const uint32_t* e, int nwords) {
+    fp tab[16];
+    tab[0] = fp_one(); tab[1] = a;
+    for (int i = 2; i < 16; i++) tab[i] = fp_mul(tab[i - 1], a);
+    fp r = fp_one();
+    bool started = false;
+    for (int w = nwords - 1; w >= 0; w--) {
+        uint32_t word = e[w];
+        for (int s = 28; s >= 0; s -= 4) {
+            uint32_t d = (word >> s) & 15;
+            if (started) { r = fp_sqr(r); r = fp_sqr(r); r = fp_sqr(r); r = fp_sqr(r); }
+            if (d) { r = started ? fp_mul(r, tab[d]) : tab[d]; started = true; }
+        }
+    }
+    return r;
+}
+
+// fixed exponents derived from p (32-bit LE words)
+BLS_CONST uint32_t EXP_P_MINUS_2[12] = BLS_C_EXP_PM2;
+// (p-3)/4 ; note (p+1)/4 = (p-3)/4 + 1
+BLS_CONST uint32_t EXP_P_MINUS_3_DIV_4[12] = BLS_C_EXP_PM3D4;
+
+BLS_HD fp fp_inv(const fp& a) { return fp_pow(a, EXP_P_MINUS_2, 12); }          // 0 -> 0
+// t = a^((p-3)/4).  Then a*t = a^((p+1)/4) is the candidate square root and (a*t)*t = a^((p-1)/2) the Legendre symbol.
+BLS_HD fp fp_pow_pm3d4(const fp& a) { return fp_pow(a, EXP_P_MINUS_3_DIV_4, 12); }
+
+// bytes: 48-byte big-endian canonical <-> Montgomery
+BLS_HD bool fp_from_be48(fp& out, const uint8_t* b, uint32_t top_mask = 0xffu) {
+    fp a;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const uint8_t* q = b + 44 - 4 * i;
+        uint32_t b0 = q[0]; if (i == 11) b0 &= top_mask;
+        a.l[i] = (b0 << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+    }
+    bool ok = !fp_raw_geq(a, fp_modulus());
+    out = fp_to_mont(a);
+    return ok;
+}
+BLS_HD void fp_canon_to_be48(uint8_t* b, const fp& a) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint8_t* q = b + 44 - 4 * i; uint32_t w = a.l[i];
+        q[0] = (uint8_t)(w >> 24); q[1] = (uint8_t)(w >> 16); q[2] = (uint8_t)(w >> 8); q[3] = (uint8_t)w;
+    }
+}
+// canonical "is a > (p-1)/2", i.e. a > -a as integers (a != 0): 2a > p
+BLS_HD bool fp_canon_is_larger_half(const fp& a) {
+    fp d; fp_add_raw(d, a, a);           // 2a < 2^382, no overflow
+    fp t; return fp_sub_raw(t, fp_modulus(), d) != 0;     // p - 2a borrows <=> 2a > p
+}
+
+}  // namespace bls

@@ -1,0 +1,116 @@
+// Optimal-ate pairing check for e(-g1, sig) * e(pk, H(m)) == 1.
+// Replaces Bls12::<P>::multi_pairing + PairingOutput.0.is_one() at reference src/bls.rs:454-457 (arkworks
+// ark-ec models::bls12: G2 line coefficients in homogeneous projective coordinates, M-type twist, sparse
+// mul_by_014, final exponentiation f^(3(p^12-1)/r) with the x-chain of eprint 2020/875).  SURVEY A.8.
+//
+// B200-first: the reference materialises 68 line-coefficient triples per G2 point (19.6 KB) before the loop;
+// here each line is produced and consumed in the same iteration, so a thread's working set is f (576 B) plus
+// two running G2 points (2 x 288 B) and stays L1-resident.  Both pairs share the accumulator f.
+#pragma once
+#include "tower.cuh"
+#include "curve.cuh"
+
+namespace bls {
+
+struct g2_proj { fp2 x, y, z; };          // homogeneous projective running point of the Miller loop
+
+// doubling step: R <- 2R, line coefficients (c0, c1, c2) for mul_by_014(c0, c1*px, c2*py)
+BLS_NOINLINE void miller_dbl(g2_proj& r, fp2& c0, fp2& c1, fp2& c2) {
+    fp two_inv = fp_two_inv();
+    fp2 a = fp2_mul_fp(fp2_mul(r.x, r.y), two_inv);
+    fp2 b = fp2_sqr(r.y), c = fp2_sqr(r.z);
+    fp2 c3 = fp2_add(fp2_dbl(c), c);
+    fp2 e = fp2_mul_xi(fp2_dbl(fp2_dbl(c3)));               // 4(1+u) * 3c
+    fp2 f = fp2_add(fp2_dbl(e), e);
+    fp2 g = fp2_mul_fp(fp2_add(b, f), two_inv);
+    fp2 h = fp2_sub(fp2_sqr(fp2_add(r.y, r.z)), fp2_add(b, c));
+    fp2 i = fp2_sub(e, b);
+    fp2 j = fp2_sqr(r.x);
+    fp2 es = fp2_sqr(e);
+    r.x = fp2_mul(a, fp2_sub(b, f));
+    r.y = fp2_sub(fp2_sqr(g), fp2_add(fp2_dbl(es), es));
+    r.z = fp2_mul(b, h);
+    c0 = i; c1 = fp2_add(fp2_dbl(j), j); c2 = fp2_neg(h);
+}
+// addition step: R <- R + Q (Q affine)
+BLS_NOINLINE void miller_add(g2_proj& r, const g2_aff& q, fp2& c0, fp2& c1, fp2& c2) {
+    fp2 theta = fp2_sub(r.y, fp2_mul(q.y, r.z));
+    fp2 lambda = fp2_sub(r.x, fp2_mul(q.x, r.z));
+    fp2 c = fp2_sqr(theta), d = fp2_sqr(lambda);
+    fp2 e = fp2_mul(lambda, d), f = fp2_mul(r.z, c), g = fp2_mul(r.x, d);
+    fp2 h = fp2_sub(fp2_add(e, f), fp2_dbl(g));
+    r.x = fp2_mul(lambda, h);
+    r.y = fp2_sub(fp2_mul(theta, fp2_sub(g, h)), fp2_mul(e, r.y));
+    r.z = fp2_mul(r.z, e);
+    c0 = fp2_sub(fp2_mul(theta, q.x), fp2_mul(lambda, q.y)); c1 = fp2_neg(theta); c2 = lambda;
+}
+BLS_HD void miller_ell(fp12& f, const fp2& c0, const fp2& c1, const fp2& c2, const g1_aff& p) {
+    fp12_mul_by_014(f, c0, fp2_mul_fp(c1, p.x), fp2_mul_fp(c2, p.y));
+}
+// Shared-accumulator Miller loop over up to two pairs; a pair with use == false is skipped
+// (ark-ec drops pairs that contain the identity).
+BLS_NOINLINE void miller_loop2(fp12& f, const g1_aff& p0, const g2_aff& q0, bool use0, const g1_aff& p1, const g2_aff& q1, bool use1) {
+    g2_proj r0, r1;
+    r0.x = q0.x; r0.y = q0.y; r0.z = fp2_one();
+    r1.x = q1.x; r1.y = q1.y; r1.z = fp2_one();
+    fp12_one(f);
+    fp2 c0, c1, c2;
+    const uint64_t x = BLS_X_ABS;
+    for (int i = 62; i >= 0; i--) {
+        if (i != 62) fp12_sqr(f, f);
+        if (use0) { miller_dbl(r0, c0, c1, c2); miller_ell(f, c0, c1, c2, p0); }
+        if (use1) { miller_dbl(r1, c0, c1, c2); miller_ell(f, c0, c1, c2, p1); }
+        if ((x >> i) & 1) {
+            if (use0) { miller_add(r0, q0, c0, c1, c2); miller_ell(f, c0, c1, c2, p0); }
+            if (use1) { miller_add(r1, q1, c0, c1, c2); miller_ell(f, c0, c1, c2, p1); }
+        }
+    }
+    fp12_conj(f, f);                                        // x < 0
+}
+
+// a^x for a in the cyclotomic subgroup (x negative: conjugate at the end)
+BLS_NOINLINE void fp12_exp_by_x(fp12& r, const fp12& a) {
+    fp12 acc = a;
+    const uint64_t x = BLS_X_ABS;
+    for (int i = 62; i >= 0; i--) {
+        fp12_cyclo_sqr(acc, acc);
+        if ((x >> i) & 1) fp12_mul(acc, acc, a);
+    }
+    fp12_conj(r, acc);
+}
+// f^(3 (p^12 - 1)/r): the exact chain of ark-ec's Bls12::final_exponentiation
+BLS_NOINLINE void final_exponentiation(fp12& r, const fp12& f) {
+    fp12 t, y0, y1, y2;
+    fp12_conj(t, f); fp12_inv(y0, f); fp12_mul(r, t, y0);            // f^(p^6 - 1)
+    fp12_frob2(t, r); fp12_mul(r, t, r);                             // ^(p^2 + 1)
+    fp12_cyclo_sqr(y0, r);
+    fp12_exp_by_x(y1, r);
+    fp12_conj(y2, r);
+    fp12_mul(y1, y1, y2);
+    fp12_exp_by_x(y2, y1);
+    fp12_conj(y1, y1);
+    fp12_mul(y1, y1, y2);
+    fp12_exp_by_x(y2, y1);
+    fp12_frob(y1, y1);
+    fp12_mul(y1, y1, y2);
+    fp12_mul(r, r, y0);
+    fp12_exp_by_x(y0, y1);
+    fp12_exp_by_x(y2, y0);
+    fp12_frob2(y0, y1);
+    fp12_conj(y1, y1);
+    fp12_mul(y1, y1, y2);
+    fp12_mul(y1, y1, y0);
+    fp12_mul(r, r, y1);
+}
+
+// GT wire format: 12 x 48 bytes little-endian canonical, tower order c0.c0.c0 ... c1.c2.c1
+BLS_HD void fp_to_le48(uint8_t* b, const fp& m) {
+    fp a = fp_from_mont(m);
+    for (int i = 0; i < 12; i++) { uint32_t w = a.l[i]; b[4 * i] = (uint8_t)w; b[4 * i + 1] = (uint8_t)(w >> 8); b[4 * i + 2] = (uint8_t)(w >> 16); b[4 * i + 3] = (uint8_t)(w >> 24); }
+}
+BLS_HD void fp12_to_bytes(uint8_t* out, const fp12& a) {
+    const fp2* c[6] = {&a.c0.c0, &a.c0.c1, &a.c0.c2, &a.c1.c0, &a.c1.c1, &a.c1.c2};
+    for (int i = 0; i < 6; i++) { fp_to_le48(out + 96 * i, c[i]->c0); fp_to_le48(out + 96 * i + 48, c[i]->c1); }
+}
+
+}  // namespace bls

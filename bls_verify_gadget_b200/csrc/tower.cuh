@@ -1,0 +1,138 @@
+// Fp6 = Fp2[v]/(v^3 - xi), xi = 1+u;  Fp12 = Fp6[w]/(w^2 - v)   (arkworks Fq6Config / Fq12Config).
+// Fp6/Fp12 values are too large for registers (72 / 144 limbs), so they live in per-thread local memory and
+// every routine here is an out-of-line call on references; only Fp2 operands are staged in registers.
+// Replaces the arkworks tower used by Bls12::multi_pairing (reference src/bls.rs:454-457).
+#pragma once
+#include "fp2.cuh"
+
+namespace bls {
+
+struct fp6 { fp2 c0, c1, c2; };
+struct fp12 { fp6 c0, c1; };
+
+BLS_CONST fp2 FROB1[6] = BLS_C_FROB1;     // xi^(i(p-1)/6)
+BLS_CONST fp FROB2[6] = BLS_C_FROB2;      // xi^(i(p^2-1)/6), in Fp
+
+BLS_HD void fp6_add(fp6& r, const fp6& a, const fp6& b) { r.c0 = fp2_add(a.c0, b.c0); r.c1 = fp2_add(a.c1, b.c1); r.c2 = fp2_add(a.c2, b.c2); }
+BLS_HD void fp6_sub(fp6& r, const fp6& a, const fp6& b) { r.c0 = fp2_sub(a.c0, b.c0); r.c1 = fp2_sub(a.c1, b.c1); r.c2 = fp2_sub(a.c2, b.c2); }
+BLS_HD void fp6_neg(fp6& r, const fp6& a) { r.c0 = fp2_neg(a.c0); r.c1 = fp2_neg(a.c1); r.c2 = fp2_neg(a.c2); }
+BLS_HD void fp6_mul_v(fp6& r, const fp6& a) { fp2 t = fp2_mul_xi(a.c2); r.c2 = a.c1; r.c1 = a.c0; r.c0 = t; }
+
+// 6 Fp2 products (Karatsuba over the cubic extension)
+BLS_NOINLINE void fp6_mul(fp6& r, const fp6& a, const fp6& b) {
+    fp2 v0 = fp2_mul(a.c0, b.c0), v1 = fp2_mul(a.c1, b.c1), v2 = fp2_mul(a.c2, b.c2);
+    fp2 t0 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c1, a.c2), fp2_add(b.c1, b.c2)), v1), v2);
+    fp2 t1 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c0, a.c1), fp2_add(b.c0, b.c1)), v0), v1);
+    fp2 t2 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c0, a.c2), fp2_add(b.c0, b.c2)), v0), v2);
+    r.c0 = fp2_add(v0, fp2_mul_xi(t0));
+    r.c1 = fp2_add(t1, fp2_mul_xi(v2));
+    r.c2 = fp2_add(t2, v1);
+}
+// a * (b0 + b1 v): 5 Fp2 products
+BLS_NOINLINE void fp6_mul_by_01(fp6& r, const fp6& a, const fp2& b0, const fp2& b1) {
+    fp2 v0 = fp2_mul(a.c0, b0), v1 = fp2_mul(a.c1, b1);
+    fp2 t0 = fp2_sub(fp2_mul(fp2_add(a.c1, a.c2), b1), v1);                       // a2 b1
+    fp2 t1 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c0, a.c1), fp2_add(b0, b1)), v0), v1);   // a0 b1 + a1 b0
+    fp2 t2 = fp2_add(fp2_sub(fp2_mul(fp2_add(a.c0, a.c2), b0), v0), v1);           // a2 b0 + a1 b1
+    r.c0 = fp2_add(v0, fp2_mul_xi(t0)); r.c1 = t1; r.c2 = t2;
+}
+// a * (b1 v): 3 Fp2 products
+BLS_NOINLINE void fp6_mul_by_1(fp6& r, const fp6& a, const fp2& b1) {
+    fp2 t0 = fp2_mul_xi(fp2_mul(a.c2, b1)), t1 = fp2_mul(a.c0, b1), t2 = fp2_mul(a.c1, b1);
+    r.c0 = t0; r.c1 = t1; r.c2 = t2;
+}
+BLS_NOINLINE void fp6_inv(fp6& r, const fp6& a) {
+    fp2 t0 = fp2_sub(fp2_sqr(a.c0), fp2_mul_xi(fp2_mul(a.c1, a.c2)));
+    fp2 t1 = fp2_sub(fp2_mul_xi(fp2_sqr(a.c2)), fp2_mul(a.c0, a.c1));
+    fp2 t2 = fp2_sub(fp2_sqr(a.c1), fp2_mul(a.c0, a.c2));
+    fp2 d = fp2_add(fp2_mul(a.c0, t0), fp2_mul_xi(fp2_add(fp2_mul(a.c2, t1), fp2_mul(a.c1, t2))));
+    d = fp2_inv(d);
+    r.c0 = fp2_mul(t0, d); r.c1 = fp2_mul(t1, d); r.c2 = fp2_mul(t2, d);
+}
+
+BLS_HD void fp12_one(fp12& r) {
+    r.c0.c0 = fp2_one(); r.c0.c1 = fp2_zero(); r.c0.c2 = fp2_zero();
+    r.c1.c0 = fp2_zero(); r.c1.c1 = fp2_zero(); r.c1.c2 = fp2_zero();
+}
+BLS_HD bool fp12_is_one(const fp12& a) {
+    return fp2_eq(a.c0.c0, fp2_one()) & fp2_is_zero(a.c0.c1) & fp2_is_zero(a.c0.c2) &
+           fp2_is_zero(a.c1.c0) & fp2_is_zero(a.c1.c1) & fp2_is_zero(a.c1.c2);
+}
+BLS_HD void fp12_conj(fp12& r, const fp12& a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }
+
+// 3 Fp6 products
+BLS_NOINLINE void fp12_mul(fp12& r, const fp12& a, const fp12& b) {
+    fp6 t0, t1, t2, s0, s1;
+    fp6_mul(t0, a.c0, b.c0); fp6_mul(t1, a.c1, b.c1);
+    fp6_add(s0, a.c0, a.c1); fp6_add(s1, b.c0, b.c1);
+    fp6_mul(t2, s0, s1);
+    fp6_sub(t2, t2, t0); fp6_sub(r.c1, t2, t1);
+    fp6_mul_v(t1, t1); fp6_add(r.c0, t0, t1);
+}
+// complex squaring: 2 Fp6 products
+BLS_NOINLINE void fp12_sqr(fp12& r, const fp12& a) {
+    fp6 ab, s0, s1, t;
+    fp6_mul(ab, a.c0, a.c1);
+    fp6_add(s0, a.c0, a.c1);
+    fp6_mul_v(t, a.c1); fp6_add(s1, a.c0, t);
+    fp6_mul(s0, s0, s1);                           // (a0+a1)(a0+v a1) = a0^2 + v a1^2 + (1+v) a0a1
+    fp6_sub(s0, s0, ab); fp6_mul_v(t, ab); fp6_sub(r.c0, s0, t);
+    fp6_add(r.c1, ab, ab);
+}
+// f * (c0 + c1 v + c4 v w): the sparse line element of the M-type twist (arkworks mul_by_014)
+BLS_NOINLINE void fp12_mul_by_014(fp12& f, const fp2& c0, const fp2& c1, const fp2& c4) {
+    fp6 t0, t1, s;
+    fp6_mul_by_01(t0, f.c0, c0, c1);
+    fp6_mul_by_1(t1, f.c1, c4);
+    fp6_add(s, f.c0, f.c1);
+    fp6_mul_by_01(s, s, c0, fp2_add(c1, c4));
+    fp6_sub(s, s, t0); fp6_sub(f.c1, s, t1);
+    fp6_mul_v(t1, t1); fp6_add(f.c0, t0, t1);
+}
+BLS_NOINLINE void fp12_inv(fp12& r, const fp12& a) {
+    fp6 t0, t1;
+    fp6_mul(t0, a.c0, a.c0); fp6_mul(t1, a.c1, a.c1); fp6_mul_v(t1, t1); fp6_sub(t0, t0, t1);
+    fp6_inv(t0, t0);
+    fp6_mul(r.c0, a.c0, t0); fp6_mul(t1, a.c1, t0); fp6_neg(r.c1, t1);
+}
+// a^p
+BLS_NOINLINE void fp12_frob(fp12& r, const fp12& a) {
+    r.c0.c0 = fp2_conj(a.c0.c0);
+    r.c1.c0 = fp2_mul(fp2_conj(a.c1.c0), FROB1[1]);
+    r.c0.c1 = fp2_mul(fp2_conj(a.c0.c1), FROB1[2]);
+    r.c1.c1 = fp2_mul(fp2_conj(a.c1.c1), FROB1[3]);
+    r.c0.c2 = fp2_mul(fp2_conj(a.c0.c2), FROB1[4]);
+    r.c1.c2 = fp2_mul(fp2_conj(a.c1.c2), FROB1[5]);
+}
+// a^(p^2)
+BLS_NOINLINE void fp12_frob2(fp12& r, const fp12& a) {
+    r.c0.c0 = a.c0.c0;
+    r.c1.c0 = fp2_mul_fp(a.c1.c0, FROB2[1]);
+    r.c0.c1 = fp2_mul_fp(a.c0.c1, FROB2[2]);
+    r.c1.c1 = fp2_mul_fp(a.c1.c1, FROB2[3]);
+    r.c0.c2 = fp2_mul_fp(a.c0.c2, FROB2[4]);
+    r.c1.c2 = fp2_mul_fp(a.c1.c2, FROB2[5]);
+}
+// Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part): 3 Fp4 squarings
+BLS_HD void fp4_sqr(fp2& t0, fp2& t1, const fp2& a, const fp2& b) {    // (a + b y)^2, y^2 = xi
+    fp2 ab = fp2_mul(a, b);
+    fp2 s = fp2_mul(fp2_add(a, b), fp2_add(a, fp2_mul_xi(b)));
+    t0 = fp2_sub(fp2_sub(s, ab), fp2_mul_xi(ab));
+    t1 = fp2_dbl(ab);
+}
+BLS_NOINLINE void fp12_cyclo_sqr(fp12& r, const fp12& a) {
+    fp2 t0, t1, t2, t3, t4, t5;
+    fp4_sqr(t0, t1, a.c0.c0, a.c1.c1);
+    fp4_sqr(t2, t3, a.c1.c0, a.c0.c2);
+    fp4_sqr(t4, t5, a.c0.c1, a.c1.c2);
+    fp2 z;
+    z = fp2_sub(t0, a.c0.c0); z = fp2_dbl(z); r.c0.c0 = fp2_add(z, t0);
+    z = fp2_add(t1, a.c1.c1); z = fp2_dbl(z); r.c1.c1 = fp2_add(z, t1);
+    fp2 x5 = fp2_mul_xi(t5);
+    z = fp2_add(x5, a.c1.c0); z = fp2_dbl(z); r.c1.c0 = fp2_add(z, x5);
+    z = fp2_sub(t4, a.c0.c2); z = fp2_dbl(z); r.c0.c2 = fp2_add(z, t4);
+    z = fp2_sub(t2, a.c0.c1); z = fp2_dbl(z); r.c0.c1 = fp2_add(z, t2);
+    z = fp2_add(t3, a.c1.c2); z = fp2_dbl(z); r.c1.c2 = fp2_add(z, t3);
+}
+
+}  // namespace bls
