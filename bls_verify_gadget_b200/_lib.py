@@ -1,0 +1,141 @@
+"""ctypes binding of libblsgpu.so (the C ABI of include/blsgpu.h).  There is NO CPU fallback: loading fails loudly
+when the library is not built, and Context() fails loudly when no sm_100 CUDA device is usable."""
+import ctypes, os, subprocess
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+SO_PATH = os.path.join(_PKG, "libblsgpu.so")
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("blsgpu.cu", "r1cs.cuh", "stages.cuh", "pairing.cuh", "h2c.cuh", "curve.cuh", "tower.cuh",
+                                                    "fp2.cuh", "fp.cuh", "consts.cuh")] + [os.path.join(_ROOT, "include", "blsgpu.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
+
+class BlsGpuError(RuntimeError): pass
+
+def build(force=False, verbose=False):
+    """nvcc cross-compiles for sm_100a without a GPU; the .so is kept in-tree so it travels to the GPU box."""
+    stale = not os.path.exists(SO_PATH) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in _SOURCES)
+    if force or stale:
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, _SOURCES[0]]
+        subprocess.check_call(cmd)
+    return SO_PATH
+
+_lib = None
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise BlsGpuError(f"{SO_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback")
+        L = ctypes.CDLL(SO_PATH)
+        L.blsgpu_last_error.restype = ctypes.c_char_p
+        L.blsgpu_launch_count.restype = ctypes.c_uint64
+        _lib = L
+    return _lib
+
+EXPORTS = ["blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_set_stream", "blsgpu_set_pointer_mode", "blsgpu_synchronize",
+           "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_verify_batch", "blsgpu_fast_aggregate_verify_batch", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
+           "blsgpu_g2_aggregate", "blsgpu_deserialize_g1", "blsgpu_deserialize_g2", "blsgpu_sk_to_pk_batch", "blsgpu_sign_batch", "blsgpu_pairing_gt",
+           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free"]
+
+_sz = ctypes.c_size_t; _vp = ctypes.c_void_p
+def _u8(a):
+    if isinstance(a, np.ndarray): return np.ascontiguousarray(a, dtype=np.uint8).reshape(-1)
+    b = bytes(a); return np.frombuffer(b + b"\0", dtype=np.uint8)[:len(b)].copy()
+def _p(a):
+    if a is None: return None
+    if isinstance(a, int): return _vp(a)                      # raw device pointer
+    if a.size == 0: a = np.zeros(1, dtype=a.dtype)
+    return a.ctypes.data_as(_vp)
+def pack_msgs(msgs):
+    off = np.zeros(len(msgs) + 1, dtype=np.uint32)
+    if len(msgs): off[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
+    return np.frombuffer(b"".join(msgs) + b"\0", dtype=np.uint8).copy(), off
+
+class Context:
+    """One per GPU per process.  Host-pointer mode by default (numpy in, numpy out); `device_mode()` switches the
+    raw-pointer methods (suffix _ptr) to device pointers for callers that keep data resident in HBM (bench.py)."""
+    def __init__(self, device=-1):
+        self._h = _vp()
+        rc = lib().blsgpu_create(ctypes.byref(self._h), int(device))
+        if rc != 0:
+            self._h = None
+            raise BlsGpuError(f"blsgpu_create failed (rc={rc}): no usable sm_100 CUDA device -- this library has no CPU fallback")
+    def close(self):
+        if getattr(self, "_h", None): lib().blsgpu_destroy(self._h); self._h = None
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+    def _ck(self, rc):
+        if rc != 0: raise BlsGpuError(f"rc={rc}: {lib().blsgpu_last_error(self._h).decode()}")
+    def set_stream(self, cuda_stream): self._ck(lib().blsgpu_set_stream(self._h, _vp(cuda_stream) if cuda_stream else None))
+    def set_pointer_mode(self, device): self._ck(lib().blsgpu_set_pointer_mode(self._h, 1 if device else 0))
+    def synchronize(self): self._ck(lib().blsgpu_synchronize(self._h))
+    def launch_count(self): return int(lib().blsgpu_launch_count(self._h))
+    def set_profiling(self, on=True): self._ck(lib().blsgpu_set_profiling(self._h, 1 if on else 0))
+    def stage_times(self):
+        ms = (ctypes.c_float * 6)(); self._ck(lib().blsgpu_stage_times(self._h, ms))
+        return dict(zip(("decode_g1", "decode_g2", "hash_to_g2", "miller", "final_exp", "epilogue"), [float(x) for x in ms]))
+    # ---- raw pointer entry points (host numpy arrays or device pointers as ints, matching the pointer mode)
+    def verify_ptr(self, pk, msg, off, sig, n, status, bitmap=None, gt=None):
+        self._ck(lib().blsgpu_verify_batch(self._h, _p(pk), _p(msg), _p(off), _p(sig), _sz(n), _p(status), _p(bitmap), _p(gt)))
+    def hash_to_g2_ptr(self, msg, off, n, out): self._ck(lib().blsgpu_hash_to_g2_batch(self._h, _p(msg), _p(off), _sz(n), _p(out)))
+    def fast_aggregate_verify_ptr(self, pks, bitmap, k, msg, sig, ncomm, status, agg=None):
+        self._ck(lib().blsgpu_fast_aggregate_verify_batch(self._h, _p(pks), _p(bitmap), _sz(k), _p(msg), _p(sig), _sz(ncomm), _p(status), _p(agg)))
+    # ---- numpy convenience layer (host mode)
+    def verify(self, pk48, msgs, sig96, want_bitmap=False, want_gt=False, fixed32=False):
+        pk = _u8(pk48); sg = _u8(sig96); n = sg.size // 96
+        if fixed32: flat, off = _u8(msgs), None
+        else: flat, off = pack_msgs(msgs)
+        st = np.empty(n, np.uint8); bm = np.zeros((n + 63) // 64, np.uint64) if want_bitmap else None; gt = np.empty(576, np.uint8) if want_gt else None
+        self.verify_ptr(pk, flat, off, sg, n, st, bm, gt)
+        out = (st,) + ((bm,) if want_bitmap else ()) + ((gt,) if want_gt else ())
+        return out[0] if len(out) == 1 else out
+    def fast_aggregate_verify(self, pks48, k, msg32, sig96, bitmap=None, want_agg=False):
+        pk = _u8(pks48); m = _u8(msg32); sg = _u8(sig96); nc = sg.size // 96
+        st = np.empty(nc, np.uint8); agg = np.empty(48 * nc, np.uint8) if want_agg else None
+        bm = np.ascontiguousarray(bitmap, dtype=np.uint64) if bitmap is not None else None
+        self.fast_aggregate_verify_ptr(pk, bm, k, m, sg, nc, st, agg)
+        return (st, agg) if want_agg else st
+    def hash_to_g2(self, msgs):
+        flat, off = pack_msgs(msgs); out = np.empty(96 * len(msgs), np.uint8); self.hash_to_g2_ptr(flat, off, len(msgs), out); return out
+    def g1_aggregate(self, pts48, seg_off):
+        a = _u8(pts48); seg = np.ascontiguousarray(seg_off, dtype=np.uint32); ns = seg.size - 1
+        out = np.empty(48 * ns, np.uint8); st = np.empty(ns, np.uint8)
+        self._ck(lib().blsgpu_g1_aggregate(self._h, _p(a), _p(seg), _sz(ns), _p(out), _p(st))); return out, st
+    def g2_aggregate(self, pts96, seg_off):
+        a = _u8(pts96); seg = np.ascontiguousarray(seg_off, dtype=np.uint32); ns = seg.size - 1
+        out = np.empty(96 * ns, np.uint8); st = np.empty(ns, np.uint8)
+        self._ck(lib().blsgpu_g2_aggregate(self._h, _p(a), _p(seg), _sz(ns), _p(out), _p(st))); return out, st
+    def deserialize_g1(self, in48):
+        a = _u8(in48); n = a.size // 48; st = np.empty(n, np.uint8); self._ck(lib().blsgpu_deserialize_g1(self._h, _p(a), _sz(n), _p(st))); return st
+    def deserialize_g2(self, in96):
+        a = _u8(in96); n = a.size // 96; st = np.empty(n, np.uint8); self._ck(lib().blsgpu_deserialize_g2(self._h, _p(a), _sz(n), _p(st))); return st
+    def sk_to_pk(self, sk_le):
+        sk = _u8(sk_le); n = sk.size // 32; out = np.empty(48 * n, np.uint8); st = np.empty(n, np.uint8)
+        self._ck(lib().blsgpu_sk_to_pk_batch(self._h, _p(sk), _sz(n), _p(out), _p(st))); return out, st
+    def sign(self, sk_le, msgs, fixed32=False):
+        sk = _u8(sk_le); n = sk.size // 32
+        if fixed32: flat, off = _u8(msgs), None
+        else: flat, off = pack_msgs(msgs)
+        out = np.empty(96 * n, np.uint8); st = np.empty(n, np.uint8)
+        self._ck(lib().blsgpu_sign_batch(self._h, _p(sk), _p(flat), _p(off), _sz(n), _p(out), _p(st))); return out, st
+    def pairing_gt(self, g1_48, g2_96, npairs):
+        a = _u8(g1_48); b = _u8(g2_96); nprod = a.size // 48 // npairs; out = np.empty(576 * nprod, np.uint8); st = np.empty(nprod, np.uint8)
+        self._ck(lib().blsgpu_pairing_gt(self._h, _p(a), _p(b), _sz(npairs), _sz(nprod), _p(out), _p(st))); return out.reshape(nprod, 576), st
+    def gt_fold(self, parts):
+        a = _u8(parts); out = np.empty(576, np.uint8); self._ck(lib().blsgpu_gt_fold(self._h, _p(a), _sz(a.size // 576), _p(out))); return out
+    def fp_mul_raw(self, a, b, reps=1):
+        a = _u8(a); b = _u8(b); n = a.size // 48; out = np.empty(48 * n, np.uint8)
+        self._ck(lib().blsgpu_fp_mul_raw(self._h, _p(a), _p(b), _sz(n), _p(out), int(reps))); return out
+    def imad_peak(self, mode=0):
+        v = ctypes.c_double(); ms = ctypes.c_double(); self._ck(lib().blsgpu_imad_peak(self._h, int(mode), ctypes.byref(v), ctypes.byref(ms))); return v.value, ms.value
+    def r1cs_load(self, rowptr, col, coeff48, nrows, ncols):
+        rp = [np.ascontiguousarray(x, dtype=np.uint64) for x in rowptr]; cl = [np.ascontiguousarray(x, dtype=np.uint32) for x in col]
+        cf = [np.ascontiguousarray(x, dtype=np.uint8) for x in coeff48]; P3 = _vp * 3; h = ctypes.c_int(-1)
+        self._ck(lib().blsgpu_r1cs_load(self._h, P3(*[_p(x) for x in rp]), P3(*[_p(x) for x in cl]), P3(*[_p(x) for x in cf]), _sz(nrows), _sz(ncols), ctypes.byref(h)))
+        return h.value
+    def r1cs_check(self, handle, z48, nwit, nrows):
+        z = _u8(z48); words = (nrows + 63) // 64; bits = np.zeros(nwit * words, np.uint64); allsat = np.zeros(nwit, np.uint8)
+        self._ck(lib().blsgpu_r1cs_check(self._h, int(handle), _p(z), _sz(nwit), _p(bits), _p(allsat))); return bits.reshape(nwit, words), allsat
+    def r1cs_check_ptr(self, handle, z, nwit, bits, allsat): self._ck(lib().blsgpu_r1cs_check(self._h, int(handle), _p(z), _sz(nwit), _p(bits), _p(allsat)))
+    def r1cs_free(self, handle): lib().blsgpu_r1cs_free(self._h, int(handle))

@@ -1,0 +1,669 @@
+// libblsgpu: kernels + C ABI (include/blsgpu.h) of the B200-native BLS12-381 verify path.
+// sm_100a only; no CPU fallback -- every entry point needs a CUDA device.
+//
+// Kernel inventory (one item per thread, 128-thread CTAs, grid = ceil(n/128) >> 148 SMs):
+//   k_decode_g1 / k_decode_g2   K1  compressed bytes -> affine Montgomery limb-SoA + decode code
+//   k_hash_to_g2                K2  message -> H(m) affine limb-SoA
+//   k_miller                    K4  (pk, H(m), sig) -> Fp12 Miller value limb-SoA
+//   k_final_exp                 K5  Fp12 -> GT, is_one -> status
+//   k_gt_reduce                 K5' strided product of GT values (per-batch accumulator)
+//   k_status_bitmap                 status -> packed ok bitmap
+//   k_segsum_g1 / k_segsum_g2   K3  warp-per-segment aggregation, tree reduction in shared memory
+//   k_scalar_mul_g1 / _g2       K6  [sk]G1, [sk]H(m)
+//   k_encode_g1 / k_encode_g2   K7  affine limb-SoA -> compressed bytes
+//   k_fp_mul_raw, k_imad_peak   K0  parity hook and integer-multiply roofline microbenchmark
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <new>
+#include "stages.cuh"
+#include "../../include/blsgpu.h"
+
+using namespace bls;
+
+#define TPB 128
+static inline unsigned nblk(size_t n, unsigned tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
+
+// ================================================================================================ kernels
+__global__ void __launch_bounds__(TPB) k_fp_mul_raw(const fp* a, const fp* b, fp* out, size_t n, int reps) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    fp x = a[i], y = b[i];
+    fp r = fp_mul(x, y);
+    for (int k = 1; k < reps; k++) r = fp_mul(r, y);
+    out[i] = r;
+}
+// independent IMAD.WIDE.U32 chains (mode 0) or mad.lo.cc/madc.hi.cc carry chains (mode 1); 16 MACs per inner step
+__global__ void __launch_bounds__(256) k_imad_peak(uint32_t* sink, int iters, int mode) {
+    uint32_t a = threadIdx.x * 2654435761u + 12345u, b = blockIdx.x * 40503u + 977u;
+    if (mode == 0) {
+        unsigned long long acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc[j] = (unsigned long long)j * 0x9e3779b97f4a7c15ull + a;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a + j), "r"(b));
+        }
+        unsigned long long s = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) s ^= acc[j];
+        if (s == 0x1234567ull) sink[0] = (uint32_t)s;
+    } else {
+        uint32_t e[16], o[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) { e[j] = a + j; o[j] = b + j; }
+        for (int it = 0; it < iters; it++) {
+            asm volatile(
+                "mad.lo.cc.u32 %0, %16, %24, %0;\n\tmadc.hi.cc.u32 %1, %16, %24, %1;\n\tmadc.lo.cc.u32 %2, %17, %24, %2;\n\tmadc.hi.cc.u32 %3, %17, %24, %3;\n\t"
+                "madc.lo.cc.u32 %4, %18, %24, %4;\n\tmadc.hi.cc.u32 %5, %18, %24, %5;\n\tmadc.lo.cc.u32 %6, %19, %24, %6;\n\tmadc.hi.cc.u32 %7, %19, %24, %7;\n\t"
+                "madc.lo.cc.u32 %8, %20, %24, %8;\n\tmadc.hi.cc.u32 %9, %20, %24, %9;\n\tmadc.lo.cc.u32 %10, %21, %24, %10;\n\tmadc.hi.cc.u32 %11, %21, %24, %11;\n\t"
+                "madc.lo.cc.u32 %12, %22, %24, %12;\n\tmadc.hi.cc.u32 %13, %22, %24, %13;\n\tmadc.lo.cc.u32 %14, %23, %24, %14;\n\tmadc.hi.u32 %15, %23, %24, %15;"
+                : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "+r"(e[9]), "+r"(e[10]), "+r"(e[11]), "+r"(e[12]), "+r"(e[13]), "+r"(e[14]), "+r"(e[15])
+                : "r"(a), "r"(a + 1), "r"(a + 2), "r"(a + 3), "r"(a + 4), "r"(a + 5), "r"(a + 6), "r"(a + 7), "r"(b));
+            asm volatile(
+                "mad.lo.cc.u32 %0, %16, %24, %0;\n\tmadc.hi.cc.u32 %1, %16, %24, %1;\n\tmadc.lo.cc.u32 %2, %17, %24, %2;\n\tmadc.hi.cc.u32 %3, %17, %24, %3;\n\t"
+                "madc.lo.cc.u32 %4, %18, %24, %4;\n\tmadc.hi.cc.u32 %5, %18, %24, %5;\n\tmadc.lo.cc.u32 %6, %19, %24, %6;\n\tmadc.hi.cc.u32 %7, %19, %24, %7;\n\t"
+                "madc.lo.cc.u32 %8, %20, %24, %8;\n\tmadc.hi.cc.u32 %9, %20, %24, %9;\n\tmadc.lo.cc.u32 %10, %21, %24, %10;\n\tmadc.hi.cc.u32 %11, %21, %24, %11;\n\t"
+                "madc.lo.cc.u32 %12, %22, %24, %12;\n\tmadc.hi.cc.u32 %13, %22, %24, %13;\n\tmadc.lo.cc.u32 %14, %23, %24, %14;\n\tmadc.hi.u32 %15, %23, %24, %15;"
+                : "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(o[8]), "+r"(o[9]), "+r"(o[10]), "+r"(o[11]), "+r"(o[12]), "+r"(o[13]), "+r"(o[14]), "+r"(o[15])
+                : "r"(b), "r"(b + 1), "r"(b + 2), "r"(b + 3), "r"(b + 4), "r"(b + 5), "r"(b + 6), "r"(b + 7), "r"(a));
+        }
+        uint32_t s = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) s ^= e[j] ^ o[j];
+        if (s == 0x12345u) sink[0] = s;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_decode_g1(const uint8_t* in48, size_t n, u32x4* soa, uint8_t* code) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    g1_aff p; int rc = g1_decode(p, in48 + 48 * i);
+    if (soa) soa_store_g1(soa, n, i, p);
+    code[i] = (uint8_t)rc;
+}
+__global__ void __launch_bounds__(TPB) k_decode_g2(const uint8_t* in96, size_t n, u32x4* soa, uint8_t* code) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    g2_aff p; int rc = g2_decode(p, in96 + 96 * i);
+    if (soa) soa_store_g2(soa, n, i, p);
+    code[i] = (uint8_t)rc;
+}
+// status/flags from the two decode codes (bls.rs:434-447), then H(m) for the items still alive
+__global__ void __launch_bounds__(TPB) k_hash_to_g2(const uint8_t* msg, const uint32_t* off, size_t n, const uint8_t* code_pk, const uint8_t* code_sig,
+                                                    u32x4* hm_soa, uint8_t* flags, uint8_t* status) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    uint8_t st = ST_OK, fl = 0;
+    if (code_pk) {
+        if (code_pk[i] != DEC_OK) st = ST_BAD_PK;
+        else if (code_sig[i] != DEC_OK && code_sig[i] != DEC_INF) st = ST_BAD_SIG;
+        else if (code_sig[i] == DEC_INF) fl = FL_SIG_INF;
+    }
+    if (st == ST_OK) {
+        const uint8_t* m; uint32_t len;
+        if (off) { m = msg + off[i]; len = off[i + 1] - off[i]; } else { m = msg + 32 * i; len = 32; }
+        g2_aff hm; uint8_t f2; stage_hash(hm, f2, m, len);
+        soa_store_g2(hm_soa, n, i, hm); fl |= f2;
+    }
+    flags[i] = fl; if (status) status[i] = st;
+}
+__global__ void __launch_bounds__(TPB) k_miller(const u32x4* pk_soa, const u32x4* hm_soa, const u32x4* sig_soa, const uint8_t* flags,
+                                                const uint8_t* status, size_t n, u32x4* f_soa) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    if (status[i] != ST_OK) return;
+    g1_aff pk; g2_aff hm, sig;
+    soa_load_g1(pk, pk_soa, n, i); soa_load_g2(hm, hm_soa, n, i); soa_load_g2(sig, sig_soa, n, i);
+    fp12 f; stage_miller(f, pk, hm, sig, flags[i]);
+    soa_store_fp12(f_soa, n, i, f);
+}
+// generic product of pairings for the GT parity hook: npairs in {1,2}
+__global__ void __launch_bounds__(TPB) k_miller_pairs(const u32x4* g1_soa, const u32x4* g2_soa, const uint8_t* c1, const uint8_t* c2, size_t npairs, size_t nprod,
+                                                      u32x4* f_soa, uint8_t* status) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= nprod) return;
+    size_t tot = npairs * nprod;
+    g1_aff p[2]; g2_aff q[2]; bool use[2] = {false, false}; uint8_t st = ST_OK;
+    for (size_t k = 0; k < npairs; k++) {
+        size_t j = i * npairs + k;
+        soa_load_g1(p[k], g1_soa, tot, j); soa_load_g2(q[k], g2_soa, tot, j);
+        if (c1[j] > DEC_INF) st = ST_BAD_PK; else if (c2[j] > DEC_INF && st == ST_OK) st = ST_BAD_SIG;
+        use[k] = c1[j] == DEC_OK && c2[j] == DEC_OK;
+    }
+    if (npairs < 2) { p[1] = p[0]; q[1] = q[0]; }
+    status[i] = st;
+    if (st != ST_OK) return;
+    fp12 f; miller_loop2(f, p[0], q[0], use[0], p[1], q[1], use[1]);
+    soa_store_fp12(f_soa, nprod, i, f);
+}
+__global__ void __launch_bounds__(TPB) k_final_exp(u32x4* f_soa, const uint8_t* status_in, uint8_t* status_out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    if (status_in[i] != ST_OK) { status_out[i] = status_in[i]; return; }
+    fp12 f, gt; soa_load_fp12(f, f_soa, n, i);
+    status_out[i] = stage_final(gt, f);
+    soa_store_fp12(f_soa, n, i, gt);
+}
+// out[t] = prod_{i = t, t+T, ...} in[i] over items with status <= ST_FALSE (status == NULL: all items)
+__global__ void __launch_bounds__(TPB) k_gt_reduce(const u32x4* in_soa, const uint8_t* status, size_t n, u32x4* out_soa, size_t T) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (t >= T) return;
+    fp12 acc, x; fp12_one(acc);
+    for (size_t i = t; i < n; i += T) {
+        if (status && status[i] > ST_FALSE) continue;
+        soa_load_fp12(x, in_soa, n, i); fp12_mul(acc, acc, x);
+    }
+    soa_store_fp12(out_soa, T, t, acc);
+}
+__global__ void k_gt_mul_into(u32x4* acc_soa, const u32x4* x_soa) {      // single thread: acc *= x
+    if (threadIdx.x || blockIdx.x) return;
+    fp12 a, x; soa_load_fp12(a, acc_soa, 1, 0); soa_load_fp12(x, x_soa, 1, 0); fp12_mul(a, a, x); soa_store_fp12(acc_soa, 1, 0, a);
+}
+__global__ void k_gt_set_one(u32x4* acc_soa) { if (threadIdx.x || blockIdx.x) return; fp12 a; fp12_one(a); soa_store_fp12(acc_soa, 1, 0, a); }
+__global__ void __launch_bounds__(TPB) k_gt_to_bytes(const u32x4* soa, size_t n, uint8_t* out576, const uint8_t* status) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    if (status && status[i] != ST_OK) { for (int k = 0; k < 576; k++) out576[576 * i + k] = 0; return; }
+    fp12 a; soa_load_fp12(a, soa, n, i); fp12_to_bytes(out576 + 576 * i, a);
+}
+__global__ void __launch_bounds__(TPB) k_gt_from_bytes(const uint8_t* in576, size_t n, u32x4* soa) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    fp12 a; fp2* c[6] = {&a.c0.c0, &a.c0.c1, &a.c0.c2, &a.c1.c0, &a.c1.c1, &a.c1.c2};
+    const uint8_t* b = in576 + 576 * i;
+    for (int k = 0; k < 12; k++) {
+        fp v;
+        for (int w = 0; w < 12; w++) { const uint8_t* q = b + 48 * k + 4 * w; v.l[w] = q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24); }
+        v = fp_to_mont(v);
+        if (k & 1) c[k >> 1]->c1 = v; else c[k >> 1]->c0 = v;
+    }
+    soa_store_fp12(soa, n, i, a);
+}
+__global__ void k_status_bitmap(const uint8_t* status, size_t n, uint32_t* bitmap32) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    bool ok = i < n && status[i] == ST_OK;
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && i < ((n + 31) / 32) * 32) bitmap32[i >> 5] = m;
+}
+__global__ void __launch_bounds__(TPB) k_encode_g1(const u32x4* soa, const uint8_t* inf, size_t n, uint8_t* out48) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    g1_aff p; soa_load_g1(p, soa, n, i); g1_encode(out48 + 48 * i, p, inf && inf[i]);
+}
+__global__ void __launch_bounds__(TPB) k_encode_g2(const u32x4* soa, const uint8_t* flags, uint8_t mask, size_t n, uint8_t* out96) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    g2_aff p; soa_load_g2(p, soa, n, i); g2_encode(out96 + 96 * i, p, flags && (flags[i] & mask));
+}
+// canonical Fr check: sk < r, little-endian 32 bytes -> 8 words
+__device__ __forceinline__ bool load_scalar(uint32_t* k, const uint8_t* sk) {
+    const uint32_t R[8] = BLS_C_R_ORDER;
+    for (int w = 0; w < 8; w++) k[w] = sk[4 * w] | ((uint32_t)sk[4 * w + 1] << 8) | ((uint32_t)sk[4 * w + 2] << 16) | ((uint32_t)sk[4 * w + 3] << 24);
+    for (int w = 7; w >= 0; w--) { if (k[w] != R[w]) return k[w] < R[w]; }
+    return false;
+}
+__global__ void __launch_bounds__(TPB) k_scalar_mul_g1(const uint8_t* sk32, size_t n, uint8_t* pk48, uint8_t* status) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    uint32_t k[8]; bool canon = load_scalar(k, sk32 + 32 * i);
+    if (status) status[i] = canon ? ST_OK : ST_BAD_SK;
+    g1_aff g; g.x = fp_const(C_G1X); g.y = fp_const(C_G1Y);
+    g1_jac r; jac_mul_scalar(r, g, k);
+    g1_aff a; bool ok = jac_to_aff(a, r); g1_encode(pk48 + 48 * i, a, !ok || !canon);
+}
+// sig = [sk] H(m): H(m) comes from k_hash_to_g2's limb-SoA output
+__global__ void __launch_bounds__(TPB) k_scalar_mul_g2(const uint8_t* sk32, const u32x4* hm_soa, const uint8_t* flags, size_t n, uint8_t* sig96, uint8_t* status) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    uint32_t k[8]; bool canon = load_scalar(k, sk32 + 32 * i);
+    uint32_t nz = 0; for (int w = 0; w < 8; w++) nz |= k[w];
+    if (!canon || !nz) { status[i] = ST_BAD_SK; for (int b = 0; b < 96; b++) sig96[96 * i + b] = 0; return; }   // bls.rs:417-419
+    status[i] = ST_OK;
+    g2_aff hm; soa_load_g2(hm, hm_soa, n, i);
+    g2_jac r;
+    if (flags[i] & FL_HM_INF) jac_set_identity(r); else jac_mul_scalar(r, hm, k);
+    g2_aff a; bool ok = jac_to_aff(a, r); g2_encode(sig96 + 96 * i, a, !ok);
+}
+
+// K3: one warp per segment.  Each lane folds a strided slice of the segment with mixed additions, then the 32
+// partial sums are combined by a shared-memory tree (5 levels of full Jacobian additions).
+template <class F> struct segsum_traits;
+template <> struct segsum_traits<fp>  { enum { K = 2 }; static __device__ __forceinline__ void load(aff<fp>& p, const u32x4* s, size_t n, size_t i) { soa_load_g1(p, s, n, i); }
+                                        static __device__ __forceinline__ void store(u32x4* s, size_t n, size_t i, const aff<fp>& p) { soa_store_g1(s, n, i, p); } };
+template <> struct segsum_traits<fp2> { enum { K = 4 }; static __device__ __forceinline__ void load(aff<fp2>& p, const u32x4* s, size_t n, size_t i) { soa_load_g2(p, s, n, i); }
+                                        static __device__ __forceinline__ void store(u32x4* s, size_t n, size_t i, const aff<fp2>& p) { soa_store_g2(s, n, i, p); } };
+#define SEG_WARPS 4
+template <class F> __global__ void __launch_bounds__(32 * SEG_WARPS) k_segsum(const u32x4* pts_soa, const uint8_t* code, size_t npts, const uint32_t* seg_off, size_t seg_stride,
+                                                                            const uint64_t* bitmap, size_t nseg, u32x4* out_soa, uint8_t* out_inf, uint8_t* status, uint8_t bad_code) {
+    __shared__ jac<F> sm[SEG_WARPS][32];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    size_t s = blockIdx.x * (size_t)SEG_WARPS + warp;
+    bool active = s < nseg;
+    size_t lo = 0, hi = 0;
+    if (active) { if (seg_off) { lo = seg_off[s]; hi = seg_off[s + 1]; } else { lo = s * seg_stride; hi = lo + seg_stride; } }
+    jac<F> acc; jac_set_identity(acc);
+    bool bad = false; unsigned cnt = 0;
+    for (size_t i = lo + lane; i < hi; i += 32) {
+        if (bitmap && !((bitmap[i >> 6] >> (i & 63)) & 1)) continue;
+        cnt++;
+        uint8_t c = code[i];
+        if (c > DEC_INF) { bad = true; continue; }
+        if (c == DEC_INF) continue;
+        aff<F> p; segsum_traits<F>::load(p, pts_soa, npts, i);
+        jac_add_mixed(acc, acc, p);
+    }
+    sm[warp][lane] = acc;
+    __syncwarp();
+    for (int w = 16; w >= 1; w >>= 1) {
+        if (lane < w) { jac<F> o = sm[warp][lane + w]; jac_add(acc, acc, o); sm[warp][lane] = acc; }
+        __syncwarp();
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    unsigned total = cnt;
+    for (int w = 16; w >= 1; w >>= 1) total += __shfl_xor_sync(0xffffffffu, total, w);
+    if (active && lane == 0) {
+        aff<F> a; bool ok = jac_to_aff(a, acc);
+        segsum_traits<F>::store(out_soa, nseg, s, a);
+        out_inf[s] = ok ? 0 : 1;
+        status[s] = bad ? bad_code : (total == 0 ? ST_EMPTY : ST_OK);
+    }
+}
+// fast_aggregate_verify glue: status/flags from the aggregation outcome and the signature decode code
+__global__ void k_fav_status(const uint8_t* agg_status, const uint8_t* agg_inf, const uint8_t* code_sig, size_t n, uint8_t* code_pk_out) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    // empty committee => None => identity key => InvalidPublicKey (tests.rs:312-316); identity aggregate => bls.rs:434
+    code_pk_out[i] = (agg_status[i] != ST_OK || agg_inf[i]) ? DEC_BAD_FLAGS : DEC_OK;
+}
+
+// ================================================================================================ context
+struct blsgpu_ctx {
+    int device; cudaStream_t own_stream, stream; int ptr_mode; char err[512];
+    uint8_t* ws; size_t ws_bytes, ws_used; unsigned long long launches;
+    struct r1cs_sys* r1cs[16];
+    int prof; cudaEvent_t ev[8];        // stage boundaries of the last verify_batch chunk: g1 | g2 | hash | miller | final | epilogue
+};
+#define STAGE_MARK(k) do { if (ctx->prof) CU(cudaEventRecord(ctx->ev[k], ctx->stream)); } while (0)
+static int fail(blsgpu_ctx* c, int code, const char* fmt, ...) {
+    if (c) { va_list ap; va_start(ap, fmt); vsnprintf(c->err, sizeof c->err, fmt, ap); va_end(ap); }
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, BLSGPU_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define LAUNCH(kern, grid, block, ...) do { kern<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; CU(cudaGetLastError()); } while (0)
+
+static int ws_reserve(blsgpu_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->ws_bytes) { ctx->ws_used = 0; return 0; }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->ws) { cudaFree(ctx->ws); ctx->ws = nullptr; ctx->ws_bytes = 0; }
+    size_t want = bytes + (bytes >> 3);
+    if (cudaMalloc(&ctx->ws, want) != cudaSuccess) { cudaGetLastError(); return fail(ctx, BLSGPU_ERR_ALLOC, "cudaMalloc of %zu workspace bytes failed", want); }
+    ctx->ws_bytes = want; ctx->ws_used = 0; return 0;
+}
+template <class T> static T* ws_take(blsgpu_ctx* ctx, size_t count) {
+    size_t off = (ctx->ws_used + 255) & ~(size_t)255; ctx->ws_used = off + count * sizeof(T);
+    return reinterpret_cast<T*>(ctx->ws + off);
+}
+static inline size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
+// input staging: host mode copies to the workspace, device mode uses the pointer as is
+template <class T> static int stage_in(blsgpu_ctx* ctx, const T*& dev, const T* user, size_t count) {
+    if (!user) { dev = nullptr; return 0; }
+    if (ctx->ptr_mode == BLSGPU_DEVICE) { dev = user; return 0; }
+    T* d = ws_take<T>(ctx, count ? count : 1);
+    if (count) CU(cudaMemcpyAsync(d, user, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    dev = d; return 0;
+}
+template <class T> static T* stage_out(blsgpu_ctx* ctx, T* user, size_t count) {
+    if (!user) return nullptr;
+    return ctx->ptr_mode == BLSGPU_DEVICE ? user : ws_take<T>(ctx, count ? count : 1);
+}
+template <class T> static int finish_out(blsgpu_ctx* ctx, T* user, const T* dev, size_t count) {
+    if (!user || ctx->ptr_mode == BLSGPU_DEVICE || !count) return 0;
+    CU(cudaMemcpyAsync(user, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+static int finish_call(blsgpu_ctx* ctx) {
+    if (ctx->ptr_mode == BLSGPU_HOST) CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+static size_t msg_bytes_total(blsgpu_ctx* ctx, const uint32_t* off, size_t n, int& rc) {
+    rc = 0;
+    if (!off) return 32 * n;
+    if (ctx->ptr_mode == BLSGPU_HOST) return off[n];
+    uint32_t last = 0;
+    if (cudaMemcpyAsync(&last, off + n, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BLSGPU_ERR_CUDA;
+    return last;
+}
+
+// GT product of n values (limb-SoA, filtered by status) into a single value at dst (limb-SoA, n = 1)
+static int gt_product(blsgpu_ctx* ctx, const u32x4* in_soa, const uint8_t* status, size_t n, u32x4* tmp_a, u32x4* tmp_b, u32x4* dst) {
+    const u32x4* cur = in_soa; size_t cnt = n; const uint8_t* st = status; u32x4* bufs[2] = {tmp_a, tmp_b}; int which = 0;
+    while (true) {
+        size_t T = cnt > 4096 ? 4096 : (cnt > 64 ? 64 : 1);
+        u32x4* out = T == 1 ? dst : bufs[which];
+        LAUNCH(k_gt_reduce, nblk(T), TPB, cur, st, cnt, out, T);
+        if (T == 1) break;
+        cur = out; cnt = T; st = nullptr; which ^= 1;
+    }
+    return 0;
+}
+
+extern "C" {
+
+int blsgpu_create(blsgpu_ctx** out, int device) {
+    if (!out) return BLSGPU_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return BLSGPU_ERR_CUDA; }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) return BLSGPU_ERR_CUDA; }
+    if (device >= ndev) return BLSGPU_ERR_ARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BLSGPU_ERR_CUDA;
+    if (prop.major != 10) return BLSGPU_ERR_CUDA;                         // sm_100a cubin only: no other device can run it
+    if (cudaSetDevice(device) != cudaSuccess) return BLSGPU_ERR_CUDA;
+    blsgpu_ctx* c = new (std::nothrow) blsgpu_ctx(); if (!c) return BLSGPU_ERR_ALLOC;
+    memset(c, 0, sizeof *c); c->device = device; c->ptr_mode = BLSGPU_HOST;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return BLSGPU_ERR_CUDA; }
+    c->stream = c->own_stream;
+    *out = c; return 0;
+}
+void blsgpu_destroy(blsgpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 16; i++) if (ctx->r1cs[i]) blsgpu_r1cs_free(ctx, i);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->ev[0]) for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+const char* blsgpu_last_error(blsgpu_ctx* ctx) { return ctx ? ctx->err : "no context (no usable sm_100 CUDA device, or bad device ordinal)"; }
+int blsgpu_set_stream(blsgpu_ctx* ctx, void* s) { if (!ctx) return BLSGPU_ERR_ARG; ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return 0; }
+int blsgpu_set_pointer_mode(blsgpu_ctx* ctx, int mode) { if (!ctx || (mode != BLSGPU_HOST && mode != BLSGPU_DEVICE)) return BLSGPU_ERR_ARG; ctx->ptr_mode = mode; return 0; }
+int blsgpu_synchronize(blsgpu_ctx* ctx) { if (!ctx) return BLSGPU_ERR_ARG; CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); return 0; }
+uint64_t blsgpu_launch_count(blsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int blsgpu_set_profiling(blsgpu_ctx* ctx, int on) {
+    if (!ctx) return BLSGPU_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (on && !ctx->ev[0]) for (int i = 0; i < 8; i++) CU(cudaEventCreate(&ctx->ev[i]));
+    ctx->prof = on ? 1 : 0; return 0;
+}
+int blsgpu_stage_times(blsgpu_ctx* ctx, float* ms6) {
+    if (!ctx || !ms6 || !ctx->ev[0]) return BLSGPU_ERR_ARG;
+    CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 6; i++) CU(cudaEventElapsedTime(&ms6[i], ctx->ev[i], ctx->ev[i + 1]));
+    return 0;
+}
+
+#define ENTER() do { if (!ctx) return BLSGPU_ERR_ARG; CU(cudaSetDevice(ctx->device)); } while (0)
+
+int blsgpu_fp_mul_raw(blsgpu_ctx* ctx, const uint8_t* a48, const uint8_t* b48, size_t n, uint8_t* out48, int reps) {
+    ENTER(); if (!a48 || !b48 || !out48) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (!n) return 0;
+    if (int rc = ws_reserve(ctx, 3 * al(48 * n) + 4096)) return rc;
+    const uint8_t *da, *db; if (int rc = stage_in(ctx, da, a48, 48 * n)) return rc; if (int rc = stage_in(ctx, db, b48, 48 * n)) return rc;
+    uint8_t* dout = stage_out(ctx, out48, 48 * n);
+    LAUNCH(k_fp_mul_raw, nblk(n), TPB, (const fp*)da, (const fp*)db, (fp*)dout, n, reps < 1 ? 1 : reps);
+    if (int rc = finish_out(ctx, out48, dout, 48 * n)) return rc;
+    return finish_call(ctx);
+}
+int blsgpu_imad_peak(blsgpu_ctx* ctx, int mode, double* mac32_per_sec, double* ms_out) {
+    ENTER(); if (!mac32_per_sec) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (int rc = ws_reserve(ctx, 4096)) return rc;
+    uint32_t* sink = ws_take<uint32_t>(ctx, 16);
+    int sms = 0; CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    const int iters = 8192, blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    double best = 1e30;
+    for (int rep = 0; rep < 6; rep++) {
+        CU(cudaEventRecord(e0, ctx->stream));
+        LAUNCH(k_imad_peak, blocks, threads, sink, iters, mode);
+        CU(cudaEventRecord(e1, ctx->stream)); CU(cudaEventSynchronize(e1));
+        float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    double macs = (double)blocks * threads * (double)iters * 16.0;
+    *mac32_per_sec = macs / (best * 1e-3); if (ms_out) *ms_out = best;
+    return 0;
+}
+
+int blsgpu_deserialize_g1(blsgpu_ctx* ctx, const uint8_t* in48, size_t n, uint8_t* status) {
+    ENTER(); if (!in48 || !status) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (!n) return 0;
+    if (int rc = ws_reserve(ctx, al(48 * n) + al(n) + 4096)) return rc;
+    const uint8_t* din; if (int rc = stage_in(ctx, din, in48, 48 * n)) return rc;
+    uint8_t* dst = stage_out(ctx, status, n);
+    LAUNCH(k_decode_g1, nblk(n), TPB, din, n, (u32x4*)nullptr, dst);
+    if (int rc = finish_out(ctx, status, dst, n)) return rc;
+    return finish_call(ctx);
+}
+int blsgpu_deserialize_g2(blsgpu_ctx* ctx, const uint8_t* in96, size_t n, uint8_t* status) {
+    ENTER(); if (!in96 || !status) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (!n) return 0;
+    if (int rc = ws_reserve(ctx, al(96 * n) + al(n) + 4096)) return rc;
+    const uint8_t* din; if (int rc = stage_in(ctx, din, in96, 96 * n)) return rc;
+    uint8_t* dst = stage_out(ctx, status, n);
+    LAUNCH(k_decode_g2, nblk(n), TPB, din, n, (u32x4*)nullptr, dst);
+    if (int rc = finish_out(ctx, status, dst, n)) return rc;
+    return finish_call(ctx);
+}
+
+int blsgpu_hash_to_g2_batch(blsgpu_ctx* ctx, const uint8_t* msg, const uint32_t* msg_off, size_t n, uint8_t* out96) {
+    ENTER(); if (!msg || !out96) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (!n) return 0;
+    int rc; size_t mb = msg_bytes_total(ctx, msg_off, n, rc); if (rc) return fail(ctx, rc, "reading msg_off failed");
+    if ((rc = ws_reserve(ctx, al(mb + 1) + al(4 * (n + 1)) + al(192 * n) + al(96 * n) + al(n) + 8192))) return rc;
+    const uint8_t* dmsg; const uint32_t* doff;
+    if ((rc = stage_in(ctx, dmsg, msg, mb ? mb : 1))) return rc; if ((rc = stage_in(ctx, doff, msg_off, n + 1))) return rc;
+    u32x4* hm = ws_take<u32x4>(ctx, 12 * n); uint8_t* flags = ws_take<uint8_t>(ctx, n);
+    uint8_t* dout = stage_out(ctx, out96, 96 * n);
+    LAUNCH(k_hash_to_g2, nblk(n), TPB, dmsg, doff, n, (const uint8_t*)nullptr, (const uint8_t*)nullptr, hm, flags, (uint8_t*)nullptr);
+    LAUNCH(k_encode_g2, nblk(n), TPB, hm, flags, (uint8_t)FL_HM_INF, n, dout);
+    if ((rc = finish_out(ctx, out96, dout, 96 * n))) return rc;
+    return finish_call(ctx);
+}
+
+// core of verify once pk (limb-SoA + code) is known: decode sig, hash, Miller, final exp, epilogue
+static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code_pk, const uint8_t* dmsg, const uint32_t* doff, const uint8_t* dsig, size_t n,
+                       uint8_t* dstatus, uint32_t* dbitmap, u32x4* gt_acc /* limb-SoA n=1, multiplied into; nullable */) {
+    u32x4* sig_soa = ws_take<u32x4>(ctx, 12 * n); u32x4* hm_soa = ws_take<u32x4>(ctx, 12 * n); u32x4* f_soa = ws_take<u32x4>(ctx, 36 * n);
+    uint8_t* code_sig = ws_take<uint8_t>(ctx, n); uint8_t* flags = ws_take<uint8_t>(ctx, n);
+    STAGE_MARK(1);
+    LAUNCH(k_decode_g2, nblk(n), TPB, dsig, n, sig_soa, code_sig);
+    STAGE_MARK(2);
+    LAUNCH(k_hash_to_g2, nblk(n), TPB, dmsg, doff, n, code_pk, (const uint8_t*)code_sig, hm_soa, flags, dstatus);
+    STAGE_MARK(3);
+    LAUNCH(k_miller, nblk(n), TPB, pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, n, f_soa);
+    STAGE_MARK(4);
+    LAUNCH(k_final_exp, nblk(n), TPB, f_soa, (const uint8_t*)dstatus, dstatus, n);
+    STAGE_MARK(5);
+    if (dbitmap) LAUNCH(k_status_bitmap, nblk(((n + 31) / 32) * 32, 256), 256, (const uint8_t*)dstatus, n, dbitmap);
+    if (gt_acc) {
+        u32x4* ta = ws_take<u32x4>(ctx, 36 * 4096); u32x4* tb = ws_take<u32x4>(ctx, 36 * 64); u32x4* one = ws_take<u32x4>(ctx, 36);
+        if (int rc = gt_product(ctx, f_soa, dstatus, n, ta, tb, one)) return rc;
+        LAUNCH(k_gt_mul_into, 1, 32, gt_acc, (const u32x4*)one);
+    }
+    STAGE_MARK(6);
+    return 0;
+}
+static size_t verify_ws_bytes(size_t n, size_t mb) {
+    return al(48 * n) + al(96 * n) + al(mb + 1) + al(4 * (n + 1)) + al(n) * 6 + al(96 * n) + 2 * al(192 * n) + al(576 * n) + al(8 * ((n + 63) / 64)) +
+           al(576 * 4096) + al(576 * 64) + 3 * al(576) + 65536;
+}
+#define VERIFY_CHUNK ((size_t)1 << 20)
+
+int blsgpu_verify_batch(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg, const uint32_t* msg_off, const uint8_t* sig96, size_t n,
+                        uint8_t* status, uint64_t* ok_bitmap, uint8_t* gt_acc_le576) {
+    ENTER(); if (!pk48 || !msg || !sig96 || !status) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    int rc = 0;
+    // chunks of <= 2^20 items bound the workspace at ~1.2 GB; chunk boundaries are multiples of 64 so bitmaps concatenate
+    uint8_t gt_host[576];
+    for (size_t base = 0; base < n; base += VERIFY_CHUNK) {
+        size_t m = n - base < VERIFY_CHUNK ? n - base : VERIFY_CHUNK;
+        size_t mb0 = 0, mb = 32 * m;
+        const uint32_t* off_chunk = msg_off ? msg_off + base : nullptr;
+        if (msg_off) {
+            if (ctx->ptr_mode == BLSGPU_HOST) { mb0 = msg_off[base]; mb = msg_off[base + m] - mb0; }
+            else { mb = msg_bytes_total(ctx, msg_off, n, rc); if (rc) return fail(ctx, rc, "reading msg_off failed"); }
+        } else mb0 = 32 * base;
+        if ((rc = ws_reserve(ctx, verify_ws_bytes(m, mb)))) return rc;
+        const uint8_t *dpk, *dsig, *dmsg; const uint32_t* doff;
+        if ((rc = stage_in(ctx, dpk, pk48 + 48 * base, 48 * m))) return rc;
+        if ((rc = stage_in(ctx, dsig, sig96 + 96 * base, 96 * m))) return rc;
+        if (ctx->ptr_mode == BLSGPU_HOST) {
+            // offsets in a host chunk are rebased by the kernel through (msg - mb0): stage the chunk's bytes only
+            if ((rc = stage_in(ctx, dmsg, msg + mb0, mb ? mb : 1))) return rc;
+            dmsg -= msg_off ? mb0 : 0;
+        } else dmsg = msg_off ? msg : msg + mb0;
+        if ((rc = stage_in(ctx, doff, off_chunk, m + 1))) return rc;
+        uint8_t* dstatus = stage_out(ctx, status ? status + base : nullptr, m);
+        uint32_t* dbitmap = (uint32_t*)stage_out(ctx, ok_bitmap ? ok_bitmap + base / 64 : nullptr, (m + 63) / 64);
+        u32x4* pk_soa = ws_take<u32x4>(ctx, 6 * m); uint8_t* code_pk = ws_take<uint8_t>(ctx, m);
+        u32x4* gt_acc = nullptr;
+        if (gt_acc_le576) { gt_acc = ws_take<u32x4>(ctx, 36); LAUNCH(k_gt_set_one, 1, 32, gt_acc); }
+        if (dbitmap) CU(cudaMemsetAsync(dbitmap, 0, 8 * ((m + 63) / 64), ctx->stream));
+        STAGE_MARK(0);
+        LAUNCH(k_decode_g1, nblk(m), TPB, dpk, m, pk_soa, code_pk);
+        if ((rc = verify_core(ctx, pk_soa, code_pk, dmsg, doff, dsig, m, dstatus, dbitmap, gt_acc))) return rc;
+        if ((rc = finish_out(ctx, status + base, dstatus, m))) return rc;
+        if (ok_bitmap && (rc = finish_out(ctx, ok_bitmap + base / 64, (uint64_t*)dbitmap, (m + 63) / 64))) return rc;
+        if (gt_acc_le576) {
+            // per-chunk GT partial -> bytes; chunks are folded on the host side of the ABI through blsgpu_gt_fold's kernel path
+            uint8_t* dgt = ws_take<uint8_t>(ctx, 576);
+            LAUNCH(k_gt_to_bytes, 1, TPB, (const u32x4*)gt_acc, (size_t)1, dgt, (const uint8_t*)nullptr);
+            if (n <= VERIFY_CHUNK) {
+                if (ctx->ptr_mode == BLSGPU_DEVICE) CU(cudaMemcpyAsync(gt_acc_le576, dgt, 576, cudaMemcpyDeviceToDevice, ctx->stream));
+                else CU(cudaMemcpyAsync(gt_acc_le576, dgt, 576, cudaMemcpyDeviceToHost, ctx->stream));
+            } else {
+                // multi-chunk: fold sequentially (synchronises; only taken for n > 2^20)
+                uint8_t part[2][576];
+                CU(cudaMemcpyAsync(part[1], dgt, 576, cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream));
+                if (base == 0) memcpy(gt_host, part[1], 576);
+                else {
+                    memcpy(part[0], gt_host, 576);
+                    int saved = ctx->ptr_mode; ctx->ptr_mode = BLSGPU_HOST;
+                    rc = blsgpu_gt_fold(ctx, &part[0][0], 2, gt_host); ctx->ptr_mode = saved; if (rc) return rc;
+                }
+                if (base + m >= n) {
+                    if (ctx->ptr_mode == BLSGPU_DEVICE) { CU(cudaMemcpyAsync(gt_acc_le576, gt_host, 576, cudaMemcpyHostToDevice, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream)); }
+                    else memcpy(gt_acc_le576, gt_host, 576);
+                }
+            }
+        }
+        if (ctx->ptr_mode == BLSGPU_HOST || n > VERIFY_CHUNK) CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+int blsgpu_gt_fold(blsgpu_ctx* ctx, const uint8_t* parts, size_t nparts, uint8_t* out) {
+    ENTER(); if (!parts || !out || !nparts) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
+    if (int rc = ws_reserve(ctx, al(576 * nparts) * 2 + al(576 * 4096) + al(576 * 64) + 2 * al(576) + 8192)) return rc;
+    const uint8_t* din; if (int rc = stage_in(ctx, din, parts, 576 * nparts)) return rc;
+    u32x4* soa = ws_take<u32x4>(ctx, 36 * nparts); u32x4* ta = ws_take<u32x4>(ctx, 36 * 4096); u32x4* tb = ws_take<u32x4>(ctx, 36 * 64); u32x4* one = ws_take<u32x4>(ctx, 36);
+    uint8_t* dout = stage_out(ctx, out, 576);
+    LAUNCH(k_gt_from_bytes, nblk(nparts), TPB, din, nparts, soa);
+    if (int rc = gt_product(ctx, soa, nullptr, nparts, ta, tb, one)) return rc;
+    LAUNCH(k_gt_to_bytes, 1, TPB, (const u32x4*)one, (size_t)1, dout, (const uint8_t*)nullptr);
+    if (int rc = finish_out(ctx, out, dout, 576)) return rc;
+    return finish_call(ctx);
+}
+
+int blsgpu_pairing_gt(blsgpu_ctx* ctx, const uint8_t* g1_48, const uint8_t* g2_96, size_t npairs, size_t nprod, uint8_t* gt, uint8_t* status) {
+    ENTER(); if (!g1_48 || !g2_96 || !gt || npairs < 1 || npairs > 2) return fail(ctx, BLSGPU_ERR_ARG, "bad argument (npairs must be 1 or 2)");
+    if (!nprod) return 0;
+    size_t tot = npairs * nprod;
+    if (int rc = ws_reserve(ctx, al(48 * tot) + al(96 * tot) + al(96 * tot) + al(192 * tot) + 3 * al(tot) + al(576 * nprod) * 2 + 2 * al(nprod) + 8192)) return rc;
+    const uint8_t *d1, *d2; if (int rc = stage_in(ctx, d1, g1_48, 48 * tot)) return rc; if (int rc = stage_in(ctx, d2, g2_96, 96 * tot)) return rc;
+    u32x4* s1 = ws_take<u32x4>(ctx, 6 * tot); u32x4* s2 = ws_take<u32x4>(ctx, 12 * tot); uint8_t* c1 = ws_take<uint8_t>(ctx, tot); uint8_t* c2 = ws_take<uint8_t>(ctx, tot);
+    u32x4* f = ws_take<u32x4>(ctx, 36 * nprod);
+    uint8_t* dst = status && ctx->ptr_mode == BLSGPU_DEVICE ? status : ws_take<uint8_t>(ctx, nprod);
+    uint8_t* dgt = stage_out(ctx, gt, 576 * nprod);
+    LAUNCH(k_decode_g1, nblk(tot), TPB, d1, tot, s1, c1);
+    LAUNCH(k_decode_g2, nblk(tot), TPB, d2, tot, s2, c2);
+    LAUNCH(k_miller_pairs, nblk(nprod), TPB, (const u32x4*)s1, (const u32x4*)s2, (const uint8_t*)c1, (const uint8_t*)c2, npairs, nprod, f, dst);
+    uint8_t* scratch = ws_take<uint8_t>(ctx, nprod);       // is_one outcome, not reported by this hook
+    LAUNCH(k_final_exp, nblk(nprod), TPB, f, (const uint8_t*)dst, scratch, nprod);
+    LAUNCH(k_gt_to_bytes, nblk(nprod), TPB, (const u32x4*)f, nprod, dgt, (const uint8_t*)dst);
+    if (int rc = finish_out(ctx, gt, dgt, 576 * nprod)) return rc;
+    if (status) if (int rc = finish_out(ctx, status, dst, nprod)) return rc;
+    return finish_call(ctx);
+}
+
+int blsgpu_sk_to_pk_batch(blsgpu_ctx* ctx, const uint8_t* sk32, size_t n, uint8_t* pk48, uint8_t* status) {
+    ENTER(); if (!sk32 || !pk48) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (!n) return 0;
+    if (int rc = ws_reserve(ctx, al(32 * n) + al(48 * n) + al(n) + 4096)) return rc;
+    const uint8_t* dsk; if (int rc = stage_in(ctx, dsk, sk32, 32 * n)) return rc;
+    uint8_t* dpk = stage_out(ctx, pk48, 48 * n); uint8_t* dst = stage_out(ctx, status, n);
+    LAUNCH(k_scalar_mul_g1, nblk(n), TPB, dsk, n, dpk, dst);
+    if (int rc = finish_out(ctx, pk48, dpk, 48 * n)) return rc;
+    if (int rc = finish_out(ctx, status, dst, n)) return rc;
+    return finish_call(ctx);
+}
+int blsgpu_sign_batch(blsgpu_ctx* ctx, const uint8_t* sk32, const uint8_t* msg, const uint32_t* msg_off, size_t n, uint8_t* sig96, uint8_t* status) {
+    ENTER(); if (!sk32 || !msg || !sig96 || !status) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (!n) return 0;
+    int rc; size_t mb = msg_bytes_total(ctx, msg_off, n, rc); if (rc) return fail(ctx, rc, "reading msg_off failed");
+    if ((rc = ws_reserve(ctx, al(32 * n) + al(mb + 1) + al(4 * (n + 1)) + al(192 * n) + al(96 * n) + 2 * al(n) + 8192))) return rc;
+    const uint8_t *dsk, *dmsg; const uint32_t* doff;
+    if ((rc = stage_in(ctx, dsk, sk32, 32 * n))) return rc; if ((rc = stage_in(ctx, dmsg, msg, mb ? mb : 1))) return rc; if ((rc = stage_in(ctx, doff, msg_off, n + 1))) return rc;
+    u32x4* hm = ws_take<u32x4>(ctx, 12 * n); uint8_t* flags = ws_take<uint8_t>(ctx, n);
+    uint8_t* dsig = stage_out(ctx, sig96, 96 * n); uint8_t* dst = stage_out(ctx, status, n);
+    LAUNCH(k_hash_to_g2, nblk(n), TPB, dmsg, doff, n, (const uint8_t*)nullptr, (const uint8_t*)nullptr, hm, flags, (uint8_t*)nullptr);
+    LAUNCH(k_scalar_mul_g2, nblk(n), TPB, dsk, (const u32x4*)hm, (const uint8_t*)flags, n, dsig, dst);
+    if ((rc = finish_out(ctx, sig96, dsig, 96 * n))) return rc; if ((rc = finish_out(ctx, status, dst, n))) return rc;
+    return finish_call(ctx);
+}
+
+static int seg_total(blsgpu_ctx* ctx, const uint32_t* seg_off, size_t nseg, size_t& npts) {
+    if (ctx->ptr_mode == BLSGPU_HOST) { npts = seg_off[nseg]; return 0; }
+    uint32_t last = 0; CU(cudaMemcpyAsync(&last, seg_off + nseg, 4, cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream)); npts = last; return 0;
+}
+int blsgpu_g1_aggregate(blsgpu_ctx* ctx, const uint8_t* pts48, const uint32_t* seg_off, size_t nseg, uint8_t* out48, uint8_t* status) {
+    ENTER(); if (!seg_off || !out48 || !status) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (!nseg) return 0;
+    size_t npts; if (int rc = seg_total(ctx, seg_off, nseg, npts)) return rc;
+    if (npts && !pts48) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (int rc = ws_reserve(ctx, al(48 * npts + 16) + al(4 * (nseg + 1)) + al(96 * npts + 16) + al(npts + 1) + al(96 * nseg) + al(48 * nseg) + 3 * al(nseg) + 8192)) return rc;
+    const uint8_t* din; const uint32_t* dseg;
+    if (int rc = stage_in(ctx, din, pts48, 48 * npts)) return rc; if (int rc = stage_in(ctx, dseg, seg_off, nseg + 1)) return rc;
+    u32x4* soa = ws_take<u32x4>(ctx, 6 * npts + 1); uint8_t* code = ws_take<uint8_t>(ctx, npts + 1);
+    u32x4* osoa = ws_take<u32x4>(ctx, 6 * nseg); uint8_t* oinf = ws_take<uint8_t>(ctx, nseg);
+    uint8_t* dout = stage_out(ctx, out48, 48 * nseg); uint8_t* dst = stage_out(ctx, status, nseg);
+    if (npts) LAUNCH(k_decode_g1, nblk(npts), TPB, din, npts, soa, code);
+    LAUNCH(k_segsum<fp>, nblk(nseg, SEG_WARPS), 32 * SEG_WARPS, (const u32x4*)soa, (const uint8_t*)code, npts, dseg, (size_t)0, (const uint64_t*)nullptr, nseg, osoa, oinf, dst, (uint8_t)ST_BAD_PK);
+    LAUNCH(k_encode_g1, nblk(nseg), TPB, (const u32x4*)osoa, (const uint8_t*)oinf, nseg, dout);
+    if (int rc = finish_out(ctx, out48, dout, 48 * nseg)) return rc; if (int rc = finish_out(ctx, status, dst, nseg)) return rc;
+    return finish_call(ctx);
+}
+int blsgpu_g2_aggregate(blsgpu_ctx* ctx, const uint8_t* pts96, const uint32_t* seg_off, size_t nseg, uint8_t* out96, uint8_t* status) {
+    ENTER(); if (!seg_off || !out96 || !status) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (!nseg) return 0;
+    size_t npts; if (int rc = seg_total(ctx, seg_off, nseg, npts)) return rc;
+    if (npts && !pts96) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (int rc = ws_reserve(ctx, al(96 * npts + 16) + al(4 * (nseg + 1)) + al(192 * npts + 16) + al(npts + 1) + al(192 * nseg) + al(96 * nseg) + 3 * al(nseg) + 8192)) return rc;
+    const uint8_t* din; const uint32_t* dseg;
+    if (int rc = stage_in(ctx, din, pts96, 96 * npts)) return rc; if (int rc = stage_in(ctx, dseg, seg_off, nseg + 1)) return rc;
+    u32x4* soa = ws_take<u32x4>(ctx, 12 * npts + 1); uint8_t* code = ws_take<uint8_t>(ctx, npts + 1);
+    u32x4* osoa = ws_take<u32x4>(ctx, 12 * nseg); uint8_t* oinf = ws_take<uint8_t>(ctx, nseg);
+    uint8_t* dout = stage_out(ctx, out96, 96 * nseg); uint8_t* dst = stage_out(ctx, status, nseg);
+    if (npts) LAUNCH(k_decode_g2, nblk(npts), TPB, din, npts, soa, code);
+    LAUNCH(k_segsum<fp2>, nblk(nseg, SEG_WARPS), 32 * SEG_WARPS, (const u32x4*)soa, (const uint8_t*)code, npts, dseg, (size_t)0, (const uint64_t*)nullptr, nseg, osoa, oinf, dst, (uint8_t)ST_BAD_SIG);
+    LAUNCH(k_encode_g2, nblk(nseg), TPB, (const u32x4*)osoa, (const uint8_t*)oinf, (uint8_t)1, nseg, dout);
+    if (int rc = finish_out(ctx, out96, dout, 96 * nseg)) return rc; if (int rc = finish_out(ctx, status, dst, nseg)) return rc;
+    return finish_call(ctx);
+}
+
+int blsgpu_fast_aggregate_verify_batch(blsgpu_ctx* ctx, const uint8_t* pks48, const uint64_t* bitmap, size_t k, const uint8_t* msg32, const uint8_t* sig96, size_t ncomm,
+                                       uint8_t* status, uint8_t* agg_pk48_out) {
+    ENTER(); if (!msg32 || !sig96 || !status || (k && !pks48)) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (!ncomm) return 0;
+    int rc; size_t npts = ncomm * k;
+    size_t need = al(48 * npts + 16) + al(8 * ((npts + 63) / 64 + 1)) + al(96 * npts + 16) + al(npts + 1) + al(96 * ncomm) * 2 + al(48 * ncomm) + 4 * al(ncomm) + verify_ws_bytes(ncomm, 32 * ncomm);
+    if ((rc = ws_reserve(ctx, need))) return rc;
+    const uint8_t *dpks, *dmsg, *dsig; const uint64_t* dbm;
+    if ((rc = stage_in(ctx, dpks, pks48, 48 * npts))) return rc; if ((rc = stage_in(ctx, dbm, bitmap, (npts + 63) / 64))) return rc;
+    if ((rc = stage_in(ctx, dmsg, msg32, 32 * ncomm))) return rc; if ((rc = stage_in(ctx, dsig, sig96, 96 * ncomm))) return rc;
+    u32x4* soa = ws_take<u32x4>(ctx, 6 * npts + 1); uint8_t* code = ws_take<uint8_t>(ctx, npts + 1);
+    u32x4* agg_soa = ws_take<u32x4>(ctx, 6 * ncomm); uint8_t* agg_inf = ws_take<uint8_t>(ctx, ncomm); uint8_t* agg_st = ws_take<uint8_t>(ctx, ncomm); uint8_t* code_pk = ws_take<uint8_t>(ctx, ncomm);
+    uint8_t* dstatus = stage_out(ctx, status, ncomm); uint8_t* dagg = stage_out(ctx, agg_pk48_out, 48 * ncomm);
+    if (npts) LAUNCH(k_decode_g1, nblk(npts), TPB, dpks, npts, soa, code);
+    LAUNCH(k_segsum<fp>, nblk(ncomm, SEG_WARPS), 32 * SEG_WARPS, (const u32x4*)soa, (const uint8_t*)code, npts, (const uint32_t*)nullptr, k, dbm, ncomm, agg_soa, agg_inf, agg_st, (uint8_t)ST_BAD_PK);
+    if (dagg) LAUNCH(k_encode_g1, nblk(ncomm), TPB, (const u32x4*)agg_soa, (const uint8_t*)agg_inf, ncomm, dagg);
+    LAUNCH(k_fav_status, nblk(ncomm), TPB, (const uint8_t*)agg_st, (const uint8_t*)agg_inf, (const uint8_t*)nullptr, ncomm, code_pk);
+    // the aggregate of subgroup points is in the subgroup: the check() of bls.rs:438 on it cannot fail, so it is not re-run
+    if ((rc = verify_core(ctx, agg_soa, code_pk, dmsg, nullptr, dsig, ncomm, dstatus, nullptr, nullptr))) return rc;
+    if ((rc = finish_out(ctx, status, dstatus, ncomm))) return rc; if ((rc = finish_out(ctx, agg_pk48_out, dagg, 48 * ncomm))) return rc;
+    return finish_call(ctx);
+}
+
+}  // extern "C"
+
+#include "r1cs.cuh"

@@ -1,0 +1,128 @@
+/* blsgpu.h -- C ABI of the B200-native BLS12-381 batch-verify / hash-to-G2 / aggregate / R1CS-check engine.
+ *
+ * Drop-in boundary for the hot path of lightec-xyz/bls-verify-gadget.  The reference is a Rust library with no FFI
+ * of its own; each entry point below is what a Rust `extern "C"` block binds to replace the
+ * arkworks call named beside it.  All file:line citations are relative to the reference tree.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Pointers are caller-owned; nothing is retained after return.
+ *  - Pointer mode (blsgpu_set_pointer_mode): BLSGPU_HOST (default) = all data pointers are host memory, the call
+ *    stages H2D/D2H itself and returns when results are in host memory; BLSGPU_DEVICE = all data pointers are
+ *    device memory on the context's GPU (16-byte aligned), work is enqueued on the context's stream and the call
+ *    returns without synchronising.
+ *  - Return value: 0 = call ok, < 0 = call-level error (message via blsgpu_last_error).  Per-item outcomes go to
+ *    status[] and never abort the batch.
+ *  - Byte formats are exactly the reference's serialisations: public key = 48-byte and signature = 96-byte ZCash
+ *    compressed big-endian with flag bits (src/bls.rs:219-260, 316-357), secret key = 32-byte little-endian
+ *    canonical Fr (src/bls.rs:79-121), GT = 12 x 48-byte little-endian canonical in tower order
+ *    c0.c0.c0 ... c1.c2.c1 (ark-serialize of Fp12).
+ *  - One context per GPU per process; a context may be used by one host thread at a time.
+ *  - There is no CPU fallback: every function fails with BLSGPU_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef BLSGPU_H
+#define BLSGPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct blsgpu_ctx blsgpu_ctx;
+
+/* per-item status codes; BLSError of src/bls.rs:359-377 maps to 2 / 3 / 5 */
+#define BLSGPU_ST_TRUE        0  /* Ok(true)                                            (src/bls.rs:457) */
+#define BLSGPU_ST_FALSE       1  /* Ok(false): pairing product != 1                     (src/bls.rs:457) */
+#define BLSGPU_ST_BAD_PUBKEY  2  /* Err(InvalidPublicKey): identity / undecodable / off-curve / wrong subgroup (src/bls.rs:434-442) */
+#define BLSGPU_ST_BAD_SIG     3  /* Err(InvalidSignature): undecodable / off-curve / wrong subgroup          (src/bls.rs:443-447) */
+#define BLSGPU_ST_EMPTY       4  /* aggregate of nothing = None                         (src/bls.rs:184-185, 289-290) */
+#define BLSGPU_ST_BAD_SECKEY  5  /* Err(InvalidSecretKey): zero or non-canonical sk     (src/bls.rs:417-419) */
+/* deserialisation detail codes returned by blsgpu_deserialize_g1/g2 */
+#define BLSGPU_DE_OK 0
+#define BLSGPU_DE_INFINITY 1        /* valid encoding of the identity */
+#define BLSGPU_DE_BAD_FLAGS 2
+#define BLSGPU_DE_OUT_OF_RANGE 3
+#define BLSGPU_DE_NOT_ON_CURVE 4
+#define BLSGPU_DE_NOT_IN_SUBGROUP 5
+
+#define BLSGPU_ERR_ARG   (-1)
+#define BLSGPU_ERR_CUDA  (-2)
+#define BLSGPU_ERR_ALLOC (-3)
+
+#define BLSGPU_HOST 0
+#define BLSGPU_DEVICE 1
+
+/* ---- context ---------------------------------------------------------------------------------------------- */
+int  blsgpu_create(blsgpu_ctx** out, int device /* ordinal, or -1 for the current device */);
+void blsgpu_destroy(blsgpu_ctx* ctx);
+const char* blsgpu_last_error(blsgpu_ctx* ctx);
+int  blsgpu_set_stream(blsgpu_ctx* ctx, void* cuda_stream /* cudaStream_t; NULL = the context's own stream */);
+int  blsgpu_set_pointer_mode(blsgpu_ctx* ctx, int mode);
+int  blsgpu_synchronize(blsgpu_ctx* ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+uint64_t blsgpu_launch_count(blsgpu_ctx* ctx);
+/* measurement hook: record CUDA events at the stage boundaries of blsgpu_verify_batch on the context's stream;
+ * blsgpu_stage_times synchronises and returns the device time in ms of the last call's (last chunk's) stages:
+ * [0] decode+check G1, [1] decode+check G2, [2] hash-to-G2, [3] Miller loop, [4] final exponentiation, [5] epilogue */
+int blsgpu_set_profiling(blsgpu_ctx* ctx, int on);
+int blsgpu_stage_times(blsgpu_ctx* ctx, float ms6[6]);
+
+/* ---- BLS::verify over a batch  (replaces <BLS<P> as SignatureScheme>::verify, src/bls.rs:427-458, incl. the
+ *      TryFrom decoding of tests/tests.rs:244-254) -----------------------------------------------------------
+ * msg_off: n+1 byte offsets into msg, or NULL for fixed 32-byte messages.
+ * status[n]; ok_bitmap (nullable): ceil(n/64) words, bit i set <=> status[i] == 0;
+ * gt_acc_le576 (nullable): product over all items whose pairing was evaluated (status 0 or 1) of the GT value. */
+int blsgpu_verify_batch(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg, const uint32_t* msg_off,
+                        const uint8_t* sig96, size_t n, uint8_t* status, uint64_t* ok_bitmap, uint8_t* gt_acc_le576);
+
+/* ---- PublicKey::aggregate + verify  (src/bls.rs:183-195 then 427-458; tests/tests.rs:297-334) ---------------
+ * ncomm committees of k keys each; bitmap (nullable): bit c*k+j selects key j of committee c (the gadget's
+ * mapped_aggregate semantics, src/constraints.rs:169-191); agg_pk48_out (nullable): the aggregated keys. */
+int blsgpu_fast_aggregate_verify_batch(blsgpu_ctx* ctx, const uint8_t* pks48, const uint64_t* bitmap, size_t k,
+                                       const uint8_t* msg32, const uint8_t* sig96, size_t ncomm,
+                                       uint8_t* status, uint8_t* agg_pk48_out);
+
+/* ---- hash_to_g2  (src/bls.rs:477-493; algorithm spec src/hasher.rs:58-173, 352-502, 294-348, 664-673) ------- */
+int blsgpu_hash_to_g2_batch(blsgpu_ctx* ctx, const uint8_t* msg, const uint32_t* msg_off, size_t n, uint8_t* out96);
+
+/* ---- PublicKey::aggregate / Signature::aggregate  (src/bls.rs:183-195, 288-300) ----------------------------
+ * seg_off: nseg+1 point offsets.  status: 0 ok, 4 = empty segment (None), 2 / 3 = a member failed to decode. */
+int blsgpu_g1_aggregate(blsgpu_ctx* ctx, const uint8_t* pts48, const uint32_t* seg_off, size_t nseg, uint8_t* out48, uint8_t* status);
+int blsgpu_g2_aggregate(blsgpu_ctx* ctx, const uint8_t* pts96, const uint32_t* seg_off, size_t nseg, uint8_t* out96, uint8_t* status);
+
+/* ---- TryFrom<&[u8]> for PublicKey / Signature  (src/bls.rs:219-223, 316-320) -> BLSGPU_DE_* per item -------- */
+int blsgpu_deserialize_g1(blsgpu_ctx* ctx, const uint8_t* in48, size_t n, uint8_t* status);
+int blsgpu_deserialize_g2(blsgpu_ctx* ctx, const uint8_t* in96, size_t n, uint8_t* status);
+
+/* ---- PublicKey::from(&PrivateKey) / keygen's derivation  (src/bls.rs:210-216, 395-409) ---------------------- */
+int blsgpu_sk_to_pk_batch(blsgpu_ctx* ctx, const uint8_t* sk32_le, size_t n, uint8_t* pk48, uint8_t* status /* nullable; 5 = non-canonical */);
+/* ---- BLS::sign  (src/bls.rs:411-425) ------------------------------------------------------------------------ */
+int blsgpu_sign_batch(blsgpu_ctx* ctx, const uint8_t* sk32_le, const uint8_t* msg, const uint32_t* msg_off, size_t n,
+                      uint8_t* sig96, uint8_t* status);
+
+/* ---- Bls12::multi_pairing(...).0  (src/bls.rs:454-455; parity hook for GT bytes) ----------------------------
+ * nprod products of npairs (1 or 2) pairings each: g1_48[nprod*npairs], g2_96[nprod*npairs] -> gt[nprod*576].
+ * Pairs containing the identity are dropped like ark-ec does; status (nullable): 2/3 when a point fails to decode. */
+int blsgpu_pairing_gt(blsgpu_ctx* ctx, const uint8_t* g1_48, const uint8_t* g2_96, size_t npairs, size_t nprod,
+                      uint8_t* gt_le576, uint8_t* status);
+/* fold GT partial products (multi-GPU epilogue): out = prod_i parts[i], parts = nparts x 576 bytes */
+int blsgpu_gt_fold(blsgpu_ctx* ctx, const uint8_t* parts_le576, size_t nparts, uint8_t* out_le576);
+
+/* ---- Fp Montgomery product on raw 48-byte little-endian limb images (kernel K0 parity hook) ----------------- */
+int blsgpu_fp_mul_raw(blsgpu_ctx* ctx, const uint8_t* a48, const uint8_t* b48, size_t n, uint8_t* out48, int reps);
+/* IMAD.WIDE.U32 issue-rate microbenchmark: returns measured 32x32->64 multiply-accumulates per second */
+int blsgpu_imad_peak(blsgpu_ctx* ctx, int mode /* 0 = independent mad.wide.u32, 1 = mad.lo.cc/madc.hi.cc carry chains */,
+                     double* mac32_per_sec, double* ms);
+
+/* ---- R1CS satisfaction check  (ark-relations ConstraintSystem::is_satisfied on the circuit of
+ *      src/constraints.rs:90-128; every row is reported, no early exit) --------------------------------------
+ * Three CSR matrices with canonical 48-byte little-endian coefficients in Fq; z = nwit vectors of ncols canonical
+ * 48-byte little-endian values laid out witness-major ([w][col]); sat_bits: nwit x ceil(nrows/64) words. */
+int blsgpu_r1cs_load(blsgpu_ctx* ctx, const uint64_t* const rowptr[3], const uint32_t* const col[3], const uint8_t* const coeff48[3],
+                     size_t nrows, size_t ncols, int* handle);
+int blsgpu_r1cs_check(blsgpu_ctx* ctx, int handle, const uint8_t* z48, size_t nwit, uint64_t* sat_bits, uint8_t* all_sat);
+int blsgpu_r1cs_free(blsgpu_ctx* ctx, int handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

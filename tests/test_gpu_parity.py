@@ -1,0 +1,297 @@
+"""Parity tests proper: the CUDA path through the C ABI (libblsgpu.so via ctypes) against the CPU oracle on the same
+seeded inputs, against the reference's fixtures (tests/golden/eth_vectors.json = /root/reference/tests/test_cases/**
+and the inline KATs), and through size-independent properties at larger sizes.  Bit-exact everywhere (integer work).
+The harness mirrors /root/reference/tests/tests.rs."""
+import hashlib
+import numpy as np
+import pytest
+from conftest import hx
+
+pytestmark = pytest.mark.gpu
+
+@pytest.fixture(scope="module")
+def ctx():
+    from bls_verify_gadget_b200 import Context
+    c = Context(0); yield c; c.close()
+
+@pytest.fixture(scope="module")
+def C():
+    from oracle import cwrap
+    return cwrap
+
+P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+DE_MAP = {0: 0, 1: 0, 2: 1, 3: 2, 4: 3, 5: 4}      # GPU BLSGPU_DE_* -> oracle DE_* (infinity decodes fine in the oracle)
+
+# ------------------------------------------------------------------------------------------ K0: Fp Montgomery product
+def test_fp_mul_million(ctx, C):
+    rng = np.random.default_rng(1)
+    edge = [0, 1, P - 1, P - 2, (1 << 384) % P, 1 << 380, (1 << 381) - 1 - 0, 2, (P - 1) // 2, 0xffffffff, 1 << 32, (1 << 352) - 1, (1 << 384) % P - 1]
+    edge = [e % P for e in edge]
+    ea = b"".join(x.to_bytes(48, "little") for x in edge for _ in edge); eb = b"".join(y.to_bytes(48, "little") for _ in edge for y in edge)
+    n = 1 << 20
+    a = rng.integers(0, 256, size=(n, 48), dtype=np.uint8); b = rng.integers(0, 256, size=(n, 48), dtype=np.uint8)
+    a[:, 47] &= 0x0f; b[:, 47] &= 0x0f                                    # < 2^380 < p
+    a[::7, 40:47] = 0xff; b[::5, 0:20] = 0xff; a[::11, :] = np.frombuffer((P - 1).to_bytes(48, "little"), dtype=np.uint8)
+    A = np.concatenate([np.frombuffer(ea, dtype=np.uint8), a.reshape(-1)]); B = np.concatenate([np.frombuffer(eb, dtype=np.uint8), b.reshape(-1)])
+    got = ctx.fp_mul_raw(A, B)
+    assert np.array_equal(got, C.fp_mul_raw(A, B))
+    # chained: r = a*b*b*b (reps=3) == oracle applied three times
+    sub = slice(0, 48 * 4096)
+    r = C.fp_mul_raw(C.fp_mul_raw(C.fp_mul_raw(A[sub], B[sub]), B[sub]), B[sub])
+    assert np.array_equal(ctx.fp_mul_raw(A[sub], B[sub], reps=3), r)
+
+# ------------------------------------------------------------------------------------------ K1: decode / validate
+@pytest.mark.parametrize("kind,key,size", [("deserialization_G1", "pubkey", 48), ("deserialization_G2", "signature", 96)])
+def test_deser_fixtures(ctx, eth, kind, key, size):                       # tests.rs:337-364
+    fn = ctx.deserialize_g1 if size == 48 else ctx.deserialize_g2
+    for c in eth[kind]:
+        s = c["input"][key]
+        ok = len(s) % 2 == 0 and len(s) >= 2 * size and fn(bytes.fromhex(s)[:size])[0] <= 1
+        assert ok == c["output"], c["name"]
+
+def _mutated_points(valid, size, rng, n):
+    """valid encodings with random mutations: flag flips, random x, x >= p, sign flips"""
+    out = np.tile(np.frombuffer(valid, dtype=np.uint8).reshape(-1, size), (n // (len(valid) // size) + 1, 1))[:n].copy()
+    for i in range(n):
+        m = i % 8
+        if m == 1: out[i, 0] ^= 0x20                                      # other sign: still valid
+        elif m == 2: out[i, 0] ^= 0x80                                    # compression flag cleared
+        elif m == 3: out[i, 0] |= 0x40                                    # infinity flag with garbage
+        elif m == 4: out[i, 1:] = rng.integers(0, 256, size=size - 1, dtype=np.uint8); out[i, 0] = 0x80 | (out[i, 0] & 0x0f)   # random x
+        elif m == 5: out[i, :48] = 0xff; out[i, 0] = 0x9f                 # x (or x.c1) >= p
+        elif m == 6: out[i, size - 1] ^= 1                                # neighbouring x
+        elif m == 7 and size == 96: out[i, 48:] = np.frombuffer(P.to_bytes(48, "big"), dtype=np.uint8)   # x.c0 == p
+    return out.reshape(-1)
+
+def test_deser_differential(ctx, C, pyv):
+    rng = np.random.default_rng(5)
+    pks = b"".join(hx(v["pk"]) for v in pyv["sign_items"]) + hx(pyv["g1_not_in_subgroup"])
+    sigs = b"".join(hx(v["sig"]) for v in pyv["sign_items"]) + hx(pyv["g2_not_in_subgroup"])
+    a = _mutated_points(pks, 48, rng, 1024); b = _mutated_points(sigs, 96, rng, 512)
+    g1 = ctx.deserialize_g1(a); g2 = ctx.deserialize_g2(b)
+    assert [DE_MAP[x] for x in g1] == list(C.deser_g1(a)) and [DE_MAP[x] for x in g2] == list(C.deser_g2(b))
+    assert len(set(g1)) >= 5 and len(set(g2)) >= 5                        # every outcome class was exercised
+    assert ctx.deserialize_g1(hx(pyv["g1_not_in_subgroup"]))[0] == 5 and ctx.deserialize_g2(hx(pyv["g2_not_in_subgroup"]))[0] == 5
+
+def test_cofactor_torsion_points_rejected(ctx, C):
+    """points of the cofactor subgroups must fail the endomorphism membership tests exactly like [r]P != O"""
+    from oracle import pyref as R
+    rng = np.random.default_rng(9); pts1 = []; pts2 = []
+    h1 = 0x396c8c005555e1568c00aaab0000aaab
+    x = 3
+    while len(pts1) < 24:
+        x += 1
+        try: Pt = R.deser_g1(bytes([0x80]) + x.to_bytes(47, "big"), subgroup=False)
+        except R.DeserErr: continue
+        for k in (R.r, R.r * 3, R.r * (h1 // 3), R.r * (h1 // 11), R.r * (h1 // 10177)):      # kill the r-part, land in cofactor subgroups
+            Q = R.g1mul(k, Pt)
+            if Q is not None: pts1.append(R.ser_g1(Q))
+    x = 1
+    while len(pts2) < 8:
+        x += 1
+        try: Qt = R.deser_g2(bytes([0x80]) + bytes(47) + x.to_bytes(48, "big"), subgroup=False)
+        except R.DeserErr: continue
+        Q = R.smul(R.r, Qt)
+        if Q is not None: pts2.append(R.ser_g2(Q))
+    a = b"".join(pts1); b = b"".join(pts2)
+    assert set(ctx.deserialize_g1(a)) == {5} and set(C.deser_g1(a)) == {4}
+    assert set(ctx.deserialize_g2(b)) == {5} and set(C.deser_g2(b)) == {4}
+
+# ------------------------------------------------------------------------------------------ K2: hash-to-G2
+def test_hash_to_g2_kats(ctx, eth, pyv):                                  # bls.rs:643-652
+    assert ctx.hash_to_g2([bytes(32)]).tobytes().hex() == eth["inline_kats"]["hash_to_g2_zero32"]
+    msgs = [hx(v["msg"]) for v in pyv["hash_to_g2"]]
+    assert ctx.hash_to_g2(msgs).tobytes().hex() == "".join(v["out"] for v in pyv["hash_to_g2"])
+
+def test_hash_to_g2_differential(ctx, C):
+    rng = np.random.default_rng(11)
+    lens = [0, 1, 31, 32, 33, 54, 55, 56, 63, 64, 65, 118, 119, 120, 128, 250, 300] + list(rng.integers(0, 200, size=239))
+    msgs = [rng.bytes(int(l)) for l in lens]                              # ragged, incl. empty and SHA padding boundaries
+    assert np.array_equal(ctx.hash_to_g2(msgs), C.hash_to_g2(msgs, threads=8))
+
+# ------------------------------------------------------------------------------------------ K6/K7: sk -> pk, sign, encode
+def test_sign_fixtures(ctx, eth):                                         # tests.rs:203-237
+    for c in eth["sign"]:
+        sk = hx(c["input"]["privkey"])[::-1]
+        sig, st = ctx.sign(sk, [hx(c["input"]["message"])])
+        if c["output"] is None: assert st[0] == 5, c["name"]
+        else: assert st[0] == 0 and sig.tobytes() == hx(c["output"]), c["name"]
+
+def test_sk_to_pk_and_sign_differential(ctx, C, eth):
+    from bls_verify_gadget_b200 import synth
+    n = 64; sk = synth.secret_keys(n); msg = synth.messages(n)
+    sk[32 * 5:32 * 6] = 0                                                 # zero key -> InvalidSecretKey on sign
+    sk[32 * 6:32 * 7] = 0xff                                              # non-canonical
+    pk, st = ctx.sk_to_pk(sk); opk = C.sk_to_pk(sk)
+    good = np.ones(n, bool); good[6] = False
+    assert st[6] == 5 and np.array_equal(pk.reshape(n, 48)[good], opk.reshape(n, 48)[good])
+    msgs = [msg[32 * i:32 * i + 32].tobytes() for i in range(n)]
+    sig, st = ctx.sign(sk, msgs); osig, ost = C.sign(sk, msgs, threads=8)
+    assert list(st) == list(ost) and np.array_equal(sig, osig)
+    k = eth["inline_kats"]                                                # bls.rs:620-641 aggregate KAT
+    pks, _ = ctx.sk_to_pk(b"".join(hx(s) for s in k["aggregate_sks_le_hex"]))
+    agg, st = ctx.g1_aggregate(pks, [0, 4])
+    assert st[0] == 0 and agg.tobytes().hex() == k["aggregate_pk"]
+
+# ------------------------------------------------------------------------------------------ K3: aggregation
+def test_aggregate_fixtures(ctx, eth):                                    # tests.rs:271-294
+    for c in eth["aggregate"]:
+        out, st = ctx.g2_aggregate(b"".join(hx(s) for s in c["input"]), [0, len(c["input"])])
+        if c["output"] is None: assert st[0] == 4, c["name"]
+        else: assert st[0] == 0 and out.tobytes() == hx(c["output"]), c["name"]
+
+def test_g1_segmented_aggregate_differential(ctx, C):
+    from bls_verify_gadget_b200 import synth
+    n = 700; pk, _ = ctx.sk_to_pk(synth.secret_keys(n)); pk = pk.reshape(n, 48).copy()
+    pk[10] = pk[11]                                                       # equal points: the doubling branch of the addition
+    pk[20, 0] ^= 0x20; pk[21] = pk[20]; pk[21, 0] ^= 0x20                 # P and -P adjacent
+    pk[30] = 0; pk[30, 0] = 0xc0                                          # identity member
+    seg = [0, 1, 1, 3, 12, 22, 40, 41, 553, 700]                          # ragged, an empty segment, one of 512
+    out, st = ctx.g1_aggregate(pk.reshape(-1), seg); oout, ost = C.g1_aggregate(pk.reshape(-1), seg, threads=8)
+    assert list(st) == list(ost) == [0, 4, 0, 0, 0, 0, 0, 0, 0]
+    ok = st == 0
+    assert np.array_equal(out.reshape(-1, 48)[ok], oout.reshape(-1, 48)[ok])
+    pk[600, 5] ^= 0x55                                                    # a member that no longer decodes
+    out, st = ctx.g1_aggregate(pk.reshape(-1), seg); oout, ost = C.g1_aggregate(pk.reshape(-1), seg, threads=8)
+    assert list(st) == list(ost) and st[-1] == 2
+
+def test_fast_aggregate_verify_fixtures(ctx, eth):                        # tests.rs:297-334
+    for c in eth["fast_aggregate_verify"]:
+        i = c["input"]; pks = b"".join(hx(s) for s in i["pubkeys"])
+        st = ctx.fast_aggregate_verify(pks, len(i["pubkeys"]), hx(i["message"]), hx(i["signature"]))[0]
+        assert (st == 0) == c["output"], c["name"]
+
+def test_committees_differential(ctx, C):
+    from bls_verify_gadget_b200 import synth
+    nc, k = 6, 64
+    pks, msg, sig, _, _ = synth.committees(ctx, nc, k=k, pool=256)
+    sig = sig.copy(); msg = msg.copy()
+    msg[32 * 1] ^= 1                                                      # committee 1: wrong message
+    sig[96 * 2 + 95] ^= 1                                                 # committee 2: undecodable / wrong signature
+    st, agg = ctx.fast_aggregate_verify(pks, k, msg, sig, want_agg=True)
+    ost, oagg = C.fast_aggregate_verify(pks, k, msg, sig, want_agg=True, threads=8)
+    assert list(st) == list(ost) and st[0] == 0 and st[1] == 1 and np.array_equal(agg, oagg)
+    # participation bitmap (gadget semantics, constraints.rs:181-182): 2/3 of the bits; signature no longer matches
+    rng = np.random.default_rng(3); bits = rng.random(nc * k) < 0.66
+    bm = np.zeros((nc * k + 63) // 64, dtype=np.uint64)
+    for j in np.nonzero(bits)[0]: bm[j // 64] |= np.uint64(1) << np.uint64(j % 64)
+    st, agg = ctx.fast_aggregate_verify(pks, k, msg, sig, bitmap=bm, want_agg=True)
+    ost, oagg = C.fast_aggregate_verify(pks, k, msg, sig, bitmap=bm, want_agg=True, threads=8)
+    assert list(st) == list(ost) and np.array_equal(agg, oagg)
+
+# ------------------------------------------------------------------------------------------ K4/K5: pairing, verify
+def test_gt_bytes(ctx, C, pyv):                                           # SURVEY A.9 anchor (parity-unpinned vs arkworks)
+    from oracle import pyref as R
+    gt, st = ctx.pairing_gt(R.ser_g1(R.G1), R.ser_g2(R.G2), 1)
+    assert st[0] == 0 and hashlib.sha256(gt[0].tobytes()).hexdigest() == pyv["gt_anchor"]["sha256"]
+    tp = pyv["gt_two_pair"]
+    gt, st = ctx.pairing_gt(b"".join(hx(s) for s in tp["g1"]), b"".join(hx(s) for s in tp["g2"]), 2)
+    assert gt[0].tobytes().hex() == tp["bytes"]
+    # a pair with the identity is dropped: e(O, g2) * e(g1, g2) == e(g1, g2)
+    gt2, _ = ctx.pairing_gt(bytes([0xc0]) + bytes(47) + R.ser_g1(R.G1), R.ser_g2(R.G2) * 2, 2)
+    assert hashlib.sha256(gt2[0].tobytes()).hexdigest() == pyv["gt_anchor"]["sha256"]
+    assert ctx.gt_fold(np.concatenate([gt2[0], gt2[0]])).tobytes() == C.gt_mul(gt2[0], gt2[0]).tobytes()
+
+def test_verify_fixtures(ctx, eth):                                       # tests.rs:240-268
+    pk = b"".join(hx(c["input"]["pubkey"]) for c in eth["verify"]); sig = b"".join(hx(c["input"]["signature"]) for c in eth["verify"])
+    msgs = [hx(c["input"]["message"]) for c in eth["verify"]]
+    st = ctx.verify(pk, msgs, sig)                                        # one batch
+    for c, s in zip(eth["verify"], st): assert (s == 0) == c["output"], c["name"]
+    for c in eth["verify"]:                                               # and one by one (n = 1 calls must work)
+        i = c["input"]; assert (ctx.verify(hx(i["pubkey"]), [hx(i["message"])], hx(i["signature"]))[0] == 0) == c["output"]
+
+def test_verify_differential_with_corruptions(ctx, C):
+    from bls_verify_gadget_b200 import synth
+    n = 320
+    pk, msg, sig, exp = synth.verify_batch_inputs(ctx, n, every=8, fast=False)
+    msgs = [msg[32 * i:32 * i + 32].tobytes() for i in range(n)]
+    st, bm, gt = ctx.verify(pk, msgs, sig, want_bitmap=True, want_gt=True)
+    ost, ogt = C.verify(pk, msgs, sig, want_gt=True, threads=8)
+    assert list(st) == list(ost) == list(exp) and set(st) == {0, 1, 2, 3}
+    assert gt.tobytes() == ogt.tobytes()
+    bits = [(int(bm[i // 64]) >> (i % 64)) & 1 for i in range(n)]
+    assert bits == [int(s == 0) for s in st]
+    # fixed-32 fast path and ragged path agree
+    assert np.array_equal(ctx.verify(pk, msg, sig, fixed32=True), st)
+
+def test_verify_ragged_messages_and_identity_signature(ctx, C):
+    from bls_verify_gadget_b200 import synth
+    rng = np.random.default_rng(21); n = 40
+    sk = synth.secret_keys(n); msgs = [rng.bytes(int(l)) for l in rng.integers(0, 150, size=n)]; msgs[0] = b""
+    pk, _ = ctx.sk_to_pk(sk); sig, _ = ctx.sign(sk, msgs)
+    sig = sig.copy(); sig[96 * 3:96 * 4] = 0; sig[96 * 3] = 0xc0          # identity signature: accepted by check(), verifies false
+    st = ctx.verify(pk, msgs, sig); ost = C.verify(pk, msgs, sig, threads=8)
+    assert list(st) == list(ost) and st[3] == 1 and (np.delete(st, 3) == 0).all()
+
+def test_verify_large_batch_properties(ctx):
+    """2^16 triples (the 2^20 run is bench.py's): statuses equal the by-construction expectation, the bitmap is the
+    status vector, and the GT accumulator is invariant under a permutation of the batch (product is commutative)."""
+    from bls_verify_gadget_b200 import synth
+    n = 1 << 16
+    pk, msg, sig, exp = synth.verify_batch_inputs(ctx, n, every=64)
+    st, bm, gt = ctx.verify(pk, msg, sig, want_bitmap=True, want_gt=True, fixed32=True)
+    assert np.array_equal(st, exp)
+    assert np.array_equal(np.unpackbits(bm.view(np.uint8), bitorder="little")[:n], (st == 0).astype(np.uint8))
+    perm = np.random.default_rng(2).permutation(n)
+    st2, gt2 = ctx.verify(pk.reshape(n, 48)[perm].reshape(-1), msg.reshape(n, 32)[perm].reshape(-1), sig.reshape(n, 96)[perm].reshape(-1), want_gt=True, fixed32=True)
+    assert np.array_equal(st2, exp[perm]) and gt2.tobytes() == gt.tobytes()
+    # two-way split == what two ranks would produce; fold of the partials == whole-batch accumulator
+    h = n // 2
+    parts = [ctx.verify(pk[:48 * h], msg[:32 * h], sig[:96 * h], want_gt=True, fixed32=True)[1], ctx.verify(pk[48 * h:], msg[32 * h:], sig[96 * h:], want_gt=True, fixed32=True)[1]]
+    assert ctx.gt_fold(np.concatenate(parts)).tobytes() == gt.tobytes()
+
+# ------------------------------------------------------------------------------------------ K8: R1CS check
+def _plant(mats, nfree, nrows, ncols, rng, nwit, break_rows):
+    zs = []
+    for w in range(nwit):
+        z = [1] + [int.from_bytes(rng.bytes(47), "little") for _ in range(nfree - 1)] + [0] * nrows
+        for i in range(nrows):
+            d = []
+            for m in range(2):
+                rp, col, cf = mats[m]
+                d.append(sum(int.from_bytes(cf[48 * k:48 * k + 48].tobytes(), "little") * z[col[k]] for k in range(int(rp[i]), int(rp[i + 1]))) % P)
+            z[nfree + i] = d[0] * d[1] % P
+        for r in break_rows.get(w, []): z[nfree + r] = (z[nfree + r] + 1) % P
+        zs.append(b"".join(v.to_bytes(48, "little") for v in z))
+    return b"".join(zs)
+
+def test_r1cs_differential(ctx, C):
+    from bls_verify_gadget_b200 import synth
+    rng = np.random.default_rng(17); nrows, ncols, nwit = 200, 260, 37
+    mats, nfree = synth.r1cs_system(nrows, ncols)
+    broken = {3: [0, 63, 64, 199], 36: [100]}
+    z = _plant(mats, nfree, nrows, ncols, rng, nwit, broken)
+    h = ctx.r1cs_load([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], nrows, ncols)
+    bits, allsat = ctx.r1cs_check(h, z, nwit, nrows)
+    obits, oall = C.r1cs_check([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], nrows, ncols, z, nwit, threads=8)
+    ctx.r1cs_free(h)
+    assert np.array_equal(bits, obits) and list(allsat) == list(oall)
+    assert allsat.sum() == nwit - 2 and allsat[3] == 0 and allsat[36] == 0
+    unsat = lambda w: [i for i in range(nrows) if not (int(bits[w, i // 64]) >> (i % 64)) & 1]
+    assert unsat(3) == [0, 63, 64, 199] and unsat(36) == [100]
+
+# ------------------------------------------------------------------------------------------ the reference-shaped API (src/bls.rs)
+def test_bls_api_like_reference_tests(ctx, eth):
+    from bls_verify_gadget_b200 import BLS, PrivateKey, PublicKey, Signature, BLSError, hash_to_g2
+    from bls_verify_gadget_b200.bls import SerializationError
+    k = eth["inline_kats"]; params = BLS.setup()
+    sk = PrivateKey.try_from(k["sk_le_hex"]); assert sk.to_hex() == k["sk_le_hex"]                       # bls.rs:569-586
+    assert PublicKey.try_from(k["pubkey_roundtrip"], ctx).to_hex() == k["pubkey_roundtrip"]              # bls.rs:588-597
+    pks = [PublicKey.from_private(PrivateKey.try_from(s), ctx) for s in k["aggregate_sks_le_hex"]]
+    assert PublicKey.aggregate(pks, ctx).to_hex() == k["aggregate_pk"] and PublicKey.aggregate([], ctx) is None   # bls.rs:620-641
+    assert hash_to_g2(bytes(32), ctx).to_hex() == k["hash_to_g2_zero32"]                                 # bls.rs:643-652
+    with pytest.raises(BLSError): BLS.sign(params, PrivateKey(), b"x", ctx=ctx)                          # zero key, bls.rs:417-419
+    for c in eth["verify"]:                                                                              # tests.rs:240-268
+        i = c["input"]
+        try: pk = PublicKey.try_from(i["pubkey"], ctx)
+        except SerializationError: pk = PublicKey()
+        try: sig = Signature.try_from(i["signature"], ctx)
+        except SerializationError: sig = Signature()
+        try: res = BLS.verify(params, pk, hx(i["message"]), sig, ctx=ctx)
+        except BLSError: res = False
+        assert res == c["output"], c["name"]
+    rng = np.random.default_rng(4)
+    pk, sk = BLS.keygen(params, rng, ctx=ctx); sig = BLS.sign(params, sk, b"hello", ctx=ctx)
+    assert BLS.verify(params, pk, b"hello", sig, ctx=ctx) and not BLS.verify(params, pk, b"hellp", sig, ctx=ctx)
+    with pytest.raises(BLSError) as e: BLS.verify(params, PublicKey(), b"hello", sig, ctx=ctx)
+    assert e.value.kind == "InvalidPublicKey"
