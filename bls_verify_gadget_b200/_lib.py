@@ -5,20 +5,20 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-SO_PATH = os.path.join(_PKG, "libblsgpu.so")
+SO_PATH = os.environ.get("BLSGPU_SO") or os.path.join(_PKG, "libblsgpu.so")      # BLSGPU_SO: tuning builds (profiles/), never a fallback
 _SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("blsgpu.cu", "r1cs.cuh", "stages.cuh", "pairing.cuh", "h2c.cuh", "curve.cuh", "tower.cuh",
                                                     "fp2.cuh", "fp.cuh", "consts.cuh")] + [os.path.join(_ROOT, "include", "blsgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
 class BlsGpuError(RuntimeError): pass
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), out=None):
     """nvcc cross-compiles for sm_100a without a GPU; the .so is kept in-tree so it travels to the GPU box."""
     stale = not os.path.exists(SO_PATH) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in _SOURCES)
     if force or stale:
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, _SOURCES[0]]
+        cmd = ["nvcc"] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or SO_PATH, _SOURCES[0]]
         subprocess.check_call(cmd)
-    return SO_PATH
+    return out or SO_PATH
 
 _lib = None
 def lib():
@@ -67,7 +67,7 @@ class Context:
         except Exception: pass
     def _ck(self, rc):
         if rc != 0: raise BlsGpuError(f"rc={rc}: {lib().blsgpu_last_error(self._h).decode()}")
-    def set_stream(self, cuda_stream): self._ck(lib().blsgpu_set_stream(self._h, _vp(cuda_stream) if cuda_stream else None))
+    def set_stream(self, cuda_stream, use_own=False): self._ck(lib().blsgpu_set_stream(self._h, _vp(cuda_stream) if cuda_stream else None, 1 if use_own else 0))
     def set_pointer_mode(self, device): self._ck(lib().blsgpu_set_pointer_mode(self._h, 1 if device else 0))
     def synchronize(self): self._ck(lib().blsgpu_synchronize(self._h))
     def launch_count(self): return int(lib().blsgpu_launch_count(self._h))

@@ -23,10 +23,13 @@
 using namespace bls;
 
 #define TPB 128
+#ifndef BLS_MINB
+#define BLS_MINB 2      // resident 128-thread CTAs per SM the heavy kernels are compiled for (register cap = 65536 / (128 * BLS_MINB))
+#endif
 static inline unsigned nblk(size_t n, unsigned tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
 
 // ================================================================================================ kernels
-__global__ void __launch_bounds__(TPB) k_fp_mul_raw(const fp* a, const fp* b, fp* out, size_t n, int reps) {
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_fp_mul_raw(const fp* a, const fp* b, fp* out, size_t n, int reps) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     fp x = a[i], y = b[i];
     fp r = fp_mul(x, y);
@@ -75,20 +78,20 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* sink, int iters, in
     }
 }
 
-__global__ void __launch_bounds__(TPB) k_decode_g1(const uint8_t* in48, size_t n, u32x4* soa, uint8_t* code) {
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_decode_g1(const uint8_t* in48, size_t n, u32x4* soa, uint8_t* code) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     g1_aff p; int rc = g1_decode(p, in48 + 48 * i);
     if (soa) soa_store_g1(soa, n, i, p);
     code[i] = (uint8_t)rc;
 }
-__global__ void __launch_bounds__(TPB) k_decode_g2(const uint8_t* in96, size_t n, u32x4* soa, uint8_t* code) {
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_decode_g2(const uint8_t* in96, size_t n, u32x4* soa, uint8_t* code) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     g2_aff p; int rc = g2_decode(p, in96 + 96 * i);
     if (soa) soa_store_g2(soa, n, i, p);
     code[i] = (uint8_t)rc;
 }
 // status/flags from the two decode codes (bls.rs:434-447), then H(m) for the items still alive
-__global__ void __launch_bounds__(TPB) k_hash_to_g2(const uint8_t* msg, const uint32_t* off, size_t n, const uint8_t* code_pk, const uint8_t* code_sig,
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_hash_to_g2(const uint8_t* msg, const uint32_t* off, size_t n, const uint8_t* code_pk, const uint8_t* code_sig,
                                                     u32x4* hm_soa, uint8_t* flags, uint8_t* status) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     uint8_t st = ST_OK, fl = 0;
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(TPB) k_hash_to_g2(const uint8_t* msg, const ui
     }
     flags[i] = fl; if (status) status[i] = st;
 }
-__global__ void __launch_bounds__(TPB) k_miller(const u32x4* pk_soa, const u32x4* hm_soa, const u32x4* sig_soa, const uint8_t* flags,
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_miller(const u32x4* pk_soa, const u32x4* hm_soa, const u32x4* sig_soa, const uint8_t* flags,
                                                 const uint8_t* status, size_t n, u32x4* f_soa) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     if (status[i] != ST_OK) return;
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(TPB) k_miller(const u32x4* pk_soa, const u32x4
     soa_store_fp12(f_soa, n, i, f);
 }
 // generic product of pairings for the GT parity hook: npairs in {1,2}
-__global__ void __launch_bounds__(TPB) k_miller_pairs(const u32x4* g1_soa, const u32x4* g2_soa, const uint8_t* c1, const uint8_t* c2, size_t npairs, size_t nprod,
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_miller_pairs(const u32x4* g1_soa, const u32x4* g2_soa, const uint8_t* c1, const uint8_t* c2, size_t npairs, size_t nprod,
                                                       u32x4* f_soa, uint8_t* status) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= nprod) return;
     size_t tot = npairs * nprod;
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(TPB) k_miller_pairs(const u32x4* g1_soa, const
     fp12 f; miller_loop2(f, p[0], q[0], use[0], p[1], q[1], use[1]);
     soa_store_fp12(f_soa, nprod, i, f);
 }
-__global__ void __launch_bounds__(TPB) k_final_exp(u32x4* f_soa, const uint8_t* status_in, uint8_t* status_out, size_t n) {
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_final_exp(u32x4* f_soa, const uint8_t* status_in, uint8_t* status_out, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     if (status_in[i] != ST_OK) { status_out[i] = status_in[i]; return; }
     fp12 f, gt; soa_load_fp12(f, f_soa, n, i);
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(TPB) k_final_exp(u32x4* f_soa, const uint8_t* 
     soa_store_fp12(f_soa, n, i, gt);
 }
 // out[t] = prod_{i = t, t+T, ...} in[i] over items with status <= ST_FALSE (status == NULL: all items)
-__global__ void __launch_bounds__(TPB) k_gt_reduce(const u32x4* in_soa, const uint8_t* status, size_t n, u32x4* out_soa, size_t T) {
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_gt_reduce(const u32x4* in_soa, const uint8_t* status, size_t n, u32x4* out_soa, size_t T) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (t >= T) return;
     fp12 acc, x; fp12_one(acc);
     for (size_t i = t; i < n; i += T) {
@@ -154,12 +157,12 @@ __global__ void k_gt_mul_into(u32x4* acc_soa, const u32x4* x_soa) {      // sing
     fp12 a, x; soa_load_fp12(a, acc_soa, 1, 0); soa_load_fp12(x, x_soa, 1, 0); fp12_mul(a, a, x); soa_store_fp12(acc_soa, 1, 0, a);
 }
 __global__ void k_gt_set_one(u32x4* acc_soa) { if (threadIdx.x || blockIdx.x) return; fp12 a; fp12_one(a); soa_store_fp12(acc_soa, 1, 0, a); }
-__global__ void __launch_bounds__(TPB) k_gt_to_bytes(const u32x4* soa, size_t n, uint8_t* out576, const uint8_t* status) {
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_gt_to_bytes(const u32x4* soa, size_t n, uint8_t* out576, const uint8_t* status) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     if (status && status[i] != ST_OK) { for (int k = 0; k < 576; k++) out576[576 * i + k] = 0; return; }
     fp12 a; soa_load_fp12(a, soa, n, i); fp12_to_bytes(out576 + 576 * i, a);
 }
-__global__ void __launch_bounds__(TPB) k_gt_from_bytes(const uint8_t* in576, size_t n, u32x4* soa) {
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_gt_from_bytes(const uint8_t* in576, size_t n, u32x4* soa) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     fp12 a; fp2* c[6] = {&a.c0.c0, &a.c0.c1, &a.c0.c2, &a.c1.c0, &a.c1.c1, &a.c1.c2};
     const uint8_t* b = in576 + 576 * i;
@@ -177,11 +180,11 @@ __global__ void k_status_bitmap(const uint8_t* status, size_t n, uint32_t* bitma
     unsigned m = __ballot_sync(0xffffffffu, ok);
     if ((threadIdx.x & 31) == 0 && i < ((n + 31) / 32) * 32) bitmap32[i >> 5] = m;
 }
-__global__ void __launch_bounds__(TPB) k_encode_g1(const u32x4* soa, const uint8_t* inf, size_t n, uint8_t* out48) {
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_encode_g1(const u32x4* soa, const uint8_t* inf, size_t n, uint8_t* out48) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     g1_aff p; soa_load_g1(p, soa, n, i); g1_encode(out48 + 48 * i, p, inf && inf[i]);
 }
-__global__ void __launch_bounds__(TPB) k_encode_g2(const u32x4* soa, const uint8_t* flags, uint8_t mask, size_t n, uint8_t* out96) {
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_encode_g2(const u32x4* soa, const uint8_t* flags, uint8_t mask, size_t n, uint8_t* out96) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     g2_aff p; soa_load_g2(p, soa, n, i); g2_encode(out96 + 96 * i, p, flags && (flags[i] & mask));
 }
@@ -192,7 +195,7 @@ __device__ __forceinline__ bool load_scalar(uint32_t* k, const uint8_t* sk) {
     for (int w = 7; w >= 0; w--) { if (k[w] != R[w]) return k[w] < R[w]; }
     return false;
 }
-__global__ void __launch_bounds__(TPB) k_scalar_mul_g1(const uint8_t* sk32, size_t n, uint8_t* pk48, uint8_t* status) {
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_scalar_mul_g1(const uint8_t* sk32, size_t n, uint8_t* pk48, uint8_t* status) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     uint32_t k[8]; bool canon = load_scalar(k, sk32 + 32 * i);
     if (status) status[i] = canon ? ST_OK : ST_BAD_SK;
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(TPB) k_scalar_mul_g1(const uint8_t* sk32, size
     g1_aff a; bool ok = jac_to_aff(a, r); g1_encode(pk48 + 48 * i, a, !ok || !canon);
 }
 // sig = [sk] H(m): H(m) comes from k_hash_to_g2's limb-SoA output
-__global__ void __launch_bounds__(TPB) k_scalar_mul_g2(const uint8_t* sk32, const u32x4* hm_soa, const uint8_t* flags, size_t n, uint8_t* sig96, uint8_t* status) {
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_scalar_mul_g2(const uint8_t* sk32, const u32x4* hm_soa, const uint8_t* flags, size_t n, uint8_t* sig96, uint8_t* status) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     uint32_t k[8]; bool canon = load_scalar(k, sk32 + 32 * i);
     uint32_t nz = 0; for (int w = 0; w < 8; w++) nz |= k[w];
@@ -364,7 +367,7 @@ void blsgpu_destroy(blsgpu_ctx* ctx) {
     delete ctx;
 }
 const char* blsgpu_last_error(blsgpu_ctx* ctx) { return ctx ? ctx->err : "no context (no usable sm_100 CUDA device, or bad device ordinal)"; }
-int blsgpu_set_stream(blsgpu_ctx* ctx, void* s) { if (!ctx) return BLSGPU_ERR_ARG; ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return 0; }
+int blsgpu_set_stream(blsgpu_ctx* ctx, void* s, int use_own) { if (!ctx) return BLSGPU_ERR_ARG; ctx->stream = use_own ? ctx->own_stream : (cudaStream_t)s; return 0; }
 int blsgpu_set_pointer_mode(blsgpu_ctx* ctx, int mode) { if (!ctx || (mode != BLSGPU_HOST && mode != BLSGPU_DEVICE)) return BLSGPU_ERR_ARG; ctx->ptr_mode = mode; return 0; }
 int blsgpu_synchronize(blsgpu_ctx* ctx) { if (!ctx) return BLSGPU_ERR_ARG; CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); return 0; }
 uint64_t blsgpu_launch_count(blsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }

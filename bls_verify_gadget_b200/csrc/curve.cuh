@@ -52,23 +52,25 @@ template <class F> BLS_NOINLINE void jac_dbl(jac<F>& r, const jac<F>& p) {
     r.Y = f_sub(f_mul(E, f_sub(D, X3)), C8); r.X = X3; r.Z = Z3;
 }
 // r = p + q, q affine (never the identity).  madd-2007-bl: 7M + 4S, plus the exceptional cases.
+// The exceptional-case test is taken only after all arithmetic (no arithmetic follows the branch): ptxas 12.9 was seen
+// to miscompile the carry chains it sank across an `if (H == 0) return` placed in the middle (tests/devcheck op 6).
 template <class F> BLS_NOINLINE void jac_add_mixed(jac<F>& r, const jac<F>& p, const aff<F>& q) {
     if (f_is_zero(p.Z)) { jac_from_aff(r, q); return; }
     F Z1Z1 = f_sqr(p.Z), U2 = f_mul(q.x, Z1Z1), S2 = f_mul(f_mul(q.y, p.Z), Z1Z1);
     F H = f_sub(U2, p.X), rr = f_sub(S2, p.Y);
-    if (f_is_zero(H)) {
-        if (f_is_zero(rr)) { jac<F> t = p; jac_dbl(r, t); } else jac_set_identity(r);
-        return;
-    }
+    bool h_zero = f_is_zero(H), r_zero = f_is_zero(rr);
     rr = f_add(rr, rr);
     F HH = f_sqr(H), I = f_add(HH, HH); I = f_add(I, I);
     F J = f_mul(H, I), V = f_mul(p.X, I);
     F X3 = f_sub(f_sub(f_sqr(rr), J), f_add(V, V));
     F YJ = f_mul(p.Y, J);
     F Z3 = f_sub(f_sub(f_sqr(f_add(p.Z, H)), Z1Z1), HH);
-    r.Y = f_sub(f_mul(rr, f_sub(V, X3)), f_add(YJ, YJ)); r.X = X3; r.Z = Z3;
+    F Y3 = f_sub(f_mul(rr, f_sub(V, X3)), f_add(YJ, YJ));
+    if (h_zero) {                                          // p == +-q
+        if (r_zero) { jac<F> t; jac_from_aff(t, q); jac_dbl(r, t); } else jac_set_identity(r);
+    } else { r.X = X3; r.Y = Y3; r.Z = Z3; }
 }
-// r = p + q, both Jacobian.  add-2007-bl: 11M + 5S, plus the exceptional cases.
+// r = p + q, both Jacobian.  add-2007-bl: 11M + 5S, plus the exceptional cases (tested after the arithmetic, as above).
 template <class F> BLS_NOINLINE void jac_add(jac<F>& r, const jac<F>& p, const jac<F>& q) {
     if (f_is_zero(p.Z)) { r = q; return; }
     if (f_is_zero(q.Z)) { r = p; return; }
@@ -76,17 +78,17 @@ template <class F> BLS_NOINLINE void jac_add(jac<F>& r, const jac<F>& p, const j
     F U1 = f_mul(p.X, Z2Z2), U2 = f_mul(q.X, Z1Z1);
     F S1 = f_mul(f_mul(p.Y, q.Z), Z2Z2), S2 = f_mul(f_mul(q.Y, p.Z), Z1Z1);
     F H = f_sub(U2, U1), rr = f_sub(S2, S1);
-    if (f_is_zero(H)) {
-        if (f_is_zero(rr)) { jac<F> t = p; jac_dbl(r, t); } else jac_set_identity(r);
-        return;
-    }
+    bool h_zero = f_is_zero(H), r_zero = f_is_zero(rr);
     rr = f_add(rr, rr);
     F I = f_add(H, H); I = f_sqr(I);
     F J = f_mul(H, I), V = f_mul(U1, I);
     F X3 = f_sub(f_sub(f_sqr(rr), J), f_add(V, V));
     F SJ = f_mul(S1, J);
     F Z3 = f_mul(f_sub(f_sub(f_sqr(f_add(p.Z, q.Z)), Z1Z1), Z2Z2), H);
-    r.Y = f_sub(f_mul(rr, f_sub(V, X3)), f_add(SJ, SJ)); r.X = X3; r.Z = Z3;
+    F Y3 = f_sub(f_mul(rr, f_sub(V, X3)), f_add(SJ, SJ));
+    if (h_zero) {
+        if (r_zero) { jac<F> t = p; jac_dbl(r, t); } else jac_set_identity(r);
+    } else { r.X = X3; r.Y = Y3; r.Z = Z3; }
 }
 // Jacobian -> affine; returns false for the identity
 template <class F> BLS_HD bool jac_to_aff(aff<F>& a, const jac<F>& p) {

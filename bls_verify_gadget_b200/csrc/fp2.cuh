@@ -11,8 +11,18 @@ struct fp2 { fp c0, c1; };
 
 BLS_HD fp2 fp2_zero() { fp2 r; r.c0 = fp_zero(); r.c1 = fp_zero(); return r; }
 BLS_HD fp2 fp2_one() { fp2 r; r.c0 = fp_one(); r.c1 = fp_zero(); return r; }
+#ifndef BLS_FP2_ADDSUB_OUTOFLINE
+#define BLS_FP2_ADDSUB_OUTOFLINE 0
+#endif
+#if BLS_FP2_ADDSUB_OUTOFLINE
+BLS_NOINLINE void fp2_add_p(fp2& r, const fp2& a, const fp2& b);
+BLS_NOINLINE void fp2_sub_p(fp2& r, const fp2& a, const fp2& b);
+BLS_HD fp2 fp2_add(const fp2& a, const fp2& b) { fp2 r; fp2_add_p(r, a, b); return r; }
+BLS_HD fp2 fp2_sub(const fp2& a, const fp2& b) { fp2 r; fp2_sub_p(r, a, b); return r; }
+#else
 BLS_HD fp2 fp2_add(const fp2& a, const fp2& b) { fp2 r; r.c0 = fp_add(a.c0, b.c0); r.c1 = fp_add(a.c1, b.c1); return r; }
 BLS_HD fp2 fp2_sub(const fp2& a, const fp2& b) { fp2 r; r.c0 = fp_sub(a.c0, b.c0); r.c1 = fp_sub(a.c1, b.c1); return r; }
+#endif
 BLS_HD fp2 fp2_dbl(const fp2& a) { return fp2_add(a, a); }
 BLS_HD fp2 fp2_neg(const fp2& a) { fp2 r; r.c0 = fp_neg(a.c0); r.c1 = fp_neg(a.c1); return r; }
 BLS_HD fp2 fp2_conj(const fp2& a) { fp2 r; r.c0 = a.c0; r.c1 = fp_neg(a.c1); return r; }
@@ -21,23 +31,39 @@ BLS_HD fp2 fp2_mul_u(const fp2& a) { fp2 r; r.c0 = fp_neg(a.c1); r.c1 = a.c0; re
 BLS_HD bool fp2_is_zero(const fp2& a) { return fp_is_zero(a.c0) & fp_is_zero(a.c1); }
 BLS_HD bool fp2_eq(const fp2& a, const fp2& b) { return fp_eq(a.c0, b.c0) & fp_eq(a.c1, b.c1); }
 BLS_HD fp2 fp2_csel(bool c, const fp2& a, const fp2& b) { fp2 r; r.c0 = fp_csel(c, a.c0, b.c0); r.c1 = fp_csel(c, a.c1, b.c1); return r; }
-BLS_HD fp2 fp2_mul_fp(const fp2& a, const fp& s) { fp2 r; r.c0 = fp_mul(a.c0, s); r.c1 = fp_mul(a.c1, s); return r; }
-
-BLS_HD fp2 fp2_mul_inl(const fp2& a, const fp2& b) {          // Karatsuba: 3 products
-    fp t0 = fp_mul(a.c0, b.c0), t1 = fp_mul(a.c1, b.c1);
-    fp t2 = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
-    fp2 r; r.c0 = fp_sub(t0, t1); r.c1 = fp_sub(fp_sub(t2, t0), t1); return r;
-}
-BLS_HD fp2 fp2_sqr_inl(const fp2& a) {                        // 2 products
-    fp t = fp_mul(a.c0, a.c1);
-    fp2 r; r.c0 = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1)); r.c1 = fp_add(t, t); return r;
-}
-#if defined(__CUDACC__)
-BLS_NOINLINE fp2 fp2_mul(fp2 a, fp2 b) { return fp2_mul_inl(a, b); }
-BLS_NOINLINE fp2 fp2_sqr(fp2 a) { return fp2_sqr_inl(a); }
+// Out-of-line arithmetic works memory-to-memory (operands by reference in the thread's local memory, staged with
+// 128-bit loads/stores): nothing is live in registers across a call, so the 300-IMAD cores exist once in the
+// instruction cache and the callers stay small.  BLS_FP2_MODE selects what is inlined inside fp2_mul/fp2_sqr:
+//   0 = calls to the out-of-line fp_mul/fp_sqr, 1 = the three (two) Montgomery products inlined (18 / 12 KB bodies)
+#ifndef BLS_FP2_MODE
+#define BLS_FP2_MODE 1
+#endif
+#if BLS_FP2_MODE == 1
+#define BLS_FPM fp_mul_inl
 #else
-BLS_NOINLINE fp2 fp2_mul(const fp2& a, const fp2& b) { return fp2_mul_inl(a, b); }
-BLS_NOINLINE fp2 fp2_sqr(const fp2& a) { return fp2_sqr_inl(a); }
+#define BLS_FPM fp_mul
+#endif
+BLS_NOINLINE void fp2_mul_p(fp2& r, const fp2& a, const fp2& b) {   // Karatsuba: 3 products
+    fp a0 = a.c0, a1 = a.c1, b0 = b.c0, b1 = b.c1;
+    fp t0 = BLS_FPM(a0, b0), t1 = BLS_FPM(a1, b1);
+    fp t2 = BLS_FPM(fp_add(a0, a1), fp_add(b0, b1));
+    r.c0 = fp_sub(t0, t1); r.c1 = fp_sub(fp_sub(t2, t0), t1);
+}
+BLS_NOINLINE void fp2_sqr_p(fp2& r, const fp2& a) {                 // 2 products
+    fp a0 = a.c0, a1 = a.c1;
+    fp t = BLS_FPM(a0, a1);
+    r.c0 = BLS_FPM(fp_add(a0, a1), fp_sub(a0, a1)); r.c1 = fp_add(t, t);
+}
+BLS_NOINLINE void fp2_mul_fp_p(fp2& r, const fp2& a, const fp& s) {
+    fp a0 = a.c0, a1 = a.c1, ss = s;
+    r.c0 = BLS_FPM(a0, ss); r.c1 = BLS_FPM(a1, ss);
+}
+BLS_HD fp2 fp2_mul(const fp2& a, const fp2& b) { fp2 r; fp2_mul_p(r, a, b); return r; }
+BLS_HD fp2 fp2_sqr(const fp2& a) { fp2 r; fp2_sqr_p(r, a); return r; }
+BLS_HD fp2 fp2_mul_fp(const fp2& a, const fp& s) { fp2 r; fp2_mul_fp_p(r, a, s); return r; }
+#if BLS_FP2_ADDSUB_OUTOFLINE
+BLS_NOINLINE void fp2_add_p(fp2& r, const fp2& a, const fp2& b) { fp x0 = a.c0, x1 = a.c1, y0 = b.c0, y1 = b.c1; r.c0 = fp_add(x0, y0); r.c1 = fp_add(x1, y1); }
+BLS_NOINLINE void fp2_sub_p(fp2& r, const fp2& a, const fp2& b) { fp x0 = a.c0, x1 = a.c1, y0 = b.c0, y1 = b.c1; r.c0 = fp_sub(x0, y0); r.c1 = fp_sub(x1, y1); }
 #endif
 
 BLS_HD fp fp2_norm(const fp2& a) { return fp_add(fp_sqr(a.c0), fp_sqr(a.c1)); }

@@ -18,7 +18,7 @@ struct r1cs_sys {
 enum { R1_GENERAL = 0, R1_PLUS_ONE = 1, R1_MINUS_ONE = 2 };
 #define R1_GROUP 32
 
-__global__ void __launch_bounds__(TPB) k_r1cs_prepare(const uint8_t* coeff48, size_t nnz, fp* out, uint8_t* cls) {
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_r1cs_prepare(const uint8_t* coeff48, size_t nnz, fp* out, uint8_t* cls) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= nnz) return;
     fp v; const uint8_t* b = coeff48 + 48 * i;
     for (int w = 0; w < 12; w++) v.l[w] = b[4 * w] | ((uint32_t)b[4 * w + 1] << 8) | ((uint32_t)b[4 * w + 2] << 16) | ((uint32_t)b[4 * w + 3] << 24);
@@ -53,7 +53,7 @@ __device__ __forceinline__ fp r1cs_row_dot(const uint64_t* rowptr, const uint32_
     return acc;
 }
 // one warp per block of 64 rows; lane = witness in the group.  sat word for (witness, row block) written by its lane.
-__global__ void __launch_bounds__(TPB) k_r1cs_rows(r1cs_sys s, const u32x4* zt, size_t w0, size_t g, size_t words, uint64_t* sat_bits) {
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_r1cs_rows(r1cs_sys s, const u32x4* zt, size_t w0, size_t g, size_t words, uint64_t* sat_bits) {
     size_t rb = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
     if (rb >= words) return;
     uint64_t bits = 0;

@@ -55,7 +55,9 @@ typedef struct blsgpu_ctx blsgpu_ctx;
 int  blsgpu_create(blsgpu_ctx** out, int device /* ordinal, or -1 for the current device */);
 void blsgpu_destroy(blsgpu_ctx* ctx);
 const char* blsgpu_last_error(blsgpu_ctx* ctx);
-int  blsgpu_set_stream(blsgpu_ctx* ctx, void* cuda_stream /* cudaStream_t; NULL = the context's own stream */);
+/* work is enqueued on the context's own non-blocking stream until a caller stream is set; cuda_stream is a cudaStream_t
+ * (NULL = the legacy default stream); use_own != 0 switches back to the context's own stream */
+int  blsgpu_set_stream(blsgpu_ctx* ctx, void* cuda_stream, int use_own);
 int  blsgpu_set_pointer_mode(blsgpu_ctx* ctx, int mode);
 int  blsgpu_synchronize(blsgpu_ctx* ctx);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */

@@ -1,0 +1,113 @@
+// Single-operation harness shared by the host-emulation build (tests/hostemu) and the device unit-test library
+// (tests/devcheck): run_op applies ONE device-library primitive to raw Montgomery limb images, so every layer of the
+// CUDA path can be compared host-vs-device (and against big-int arithmetic) in isolation.  TEST TOOL ONLY.
+#pragma once
+#include "stages.cuh"
+namespace bls {
+#define AM_BODY \
+    fp2 Z1Z1 = f_sqr(p.Z), U2 = f_mul(q.x, Z1Z1), S2 = f_mul(f_mul(q.y, p.Z), Z1Z1); \
+    fp2 H = f_sub(U2, p.X), rr = f_sub(S2, p.Y);
+#define AM_TAIL \
+    rr = f_add(rr, rr); \
+    fp2 HH = f_sqr(H), I = f_add(HH, HH); I = f_add(I, I); \
+    fp2 J = f_mul(H, I), V = f_mul(p.X, I); \
+    fp2 X3 = f_sub(f_sub(f_sqr(rr), J), f_add(V, V)); \
+    fp2 YJ = f_mul(p.Y, J); \
+    fp2 Z3 = f_sub(f_sub(f_sqr(f_add(p.Z, H)), Z1Z1), HH); \
+    r.Y = f_sub(f_mul(rr, f_sub(V, X3)), f_add(YJ, YJ)); r.X = X3; r.Z = Z3;
+BLS_NOINLINE void am_nobranch(g2_jac& r, const g2_jac& p, const g2_aff& q) { AM_BODY AM_TAIL }
+BLS_NOINLINE void am_if1(g2_jac& r, const g2_jac& p, const g2_aff& q) { if (f_is_zero(p.Z)) { jac_from_aff(r, q); return; } AM_BODY AM_TAIL }
+BLS_NOINLINE void am_if2(g2_jac& r, const g2_jac& p, const g2_aff& q) { AM_BODY if (f_is_zero(H)) { if (f_is_zero(rr)) { g2_jac t = p; jac_dbl(r, t); } else jac_set_identity(r); return; } AM_TAIL }
+BLS_NOINLINE void am_if2b(g2_jac& r, const g2_jac& p, const g2_aff& q) { AM_BODY if (f_is_zero(H)) { jac_set_identity(r); return; } AM_TAIL }
+struct op_desc { int n_in, n_out; };
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline op_desc op_shape(int op) {
+    switch (op) {
+        case 1: return {4, 2};    // fp2_mul
+        case 2: return {2, 2};    // fp2_sqr
+        case 3: return {4, 2};    // fp2_add
+        case 4: return {4, 2};    // fp2_sub
+        case 5: return {6, 6};    // jac_dbl<fp2>
+        case 6: return {10, 6};   // jac_add_mixed<fp2>(jac, aff)
+        case 7: return {12, 6};   // jac_add<fp2>
+        case 8: return {12, 6};   // fp6_mul
+        case 9: return {24, 12};  // fp12_mul
+        case 10: return {12, 12}; // fp12_sqr
+        case 11: return {18, 12}; // fp12_mul_by_014(f, c0, c1, c4)
+        case 12: return {12, 12}; // fp12_cyclo_sqr
+        case 13: return {12, 12}; // fp12_inv
+        case 14: return {12, 12}; // fp12_frob
+        case 15: return {12, 12}; // fp12_frob2
+        case 16: return {2, 3};   // fp2_sqrt -> root, ok flag in out[2].l[0]
+        case 17: return {2, 2};   // fp2_inv
+        case 18: return {3, 3};   // jac_dbl<fp>
+        case 19: return {5, 3};   // jac_add_mixed<fp>
+        case 20: return {6, 3};   // jac_add<fp>
+        case 21: return {2, 1};   // fp_mul
+        case 22: return {1, 1};   // fp_inv
+        case 23: return {4, 6};   // jac_mul_x_abs<fp2>(aff)
+        case 24: return {12, 12}; // final_exponentiation
+        case 25: return {4, 3};   // fp2_sqrt_ratio(u, v) -> y, is_sq
+        case 26: return {2, 2};   // fp2_mul_xi
+        case 27: return {3, 2};   // fp2_mul_fp
+        case 28: return {10, 6};  // jac_add_mixed<fp2>, separate output
+        case 29: return {10, 12}; // add_mixed intermediates
+        case 30: return {10, 12}; // add_mixed intermediates, second half
+        case 31: case 32: case 33: case 34: return {10, 6};
+        default: return {0, 0};
+    }
+}
+BLS_HD void ld2(fp2& r, const fp* in) { r.c0 = in[0]; r.c1 = in[1]; }
+BLS_HD void st2(fp* out, const fp2& a) { out[0] = a.c0; out[1] = a.c1; }
+BLS_HD void ld12(fp12& f, const fp* in) { ld2(f.c0.c0, in); ld2(f.c0.c1, in + 2); ld2(f.c0.c2, in + 4); ld2(f.c1.c0, in + 6); ld2(f.c1.c1, in + 8); ld2(f.c1.c2, in + 10); }
+BLS_HD void st12(fp* out, const fp12& f) { st2(out, f.c0.c0); st2(out + 2, f.c0.c1); st2(out + 4, f.c0.c2); st2(out + 6, f.c1.c0); st2(out + 8, f.c1.c1); st2(out + 10, f.c1.c2); }
+BLS_HD void run_op(int op, const fp* in, fp* out) {
+    fp2 a, b, c, d; fp12 f, g, h; g2_jac P, Q, R; g2_aff A; g1_jac p1, q1, r1; g1_aff a1;
+    switch (op) {
+        case 1: ld2(a, in); ld2(b, in + 2); st2(out, fp2_mul(a, b)); break;
+        case 2: ld2(a, in); st2(out, fp2_sqr(a)); break;
+        case 3: ld2(a, in); ld2(b, in + 2); st2(out, fp2_add(a, b)); break;
+        case 4: ld2(a, in); ld2(b, in + 2); st2(out, fp2_sub(a, b)); break;
+        case 5: ld2(P.X, in); ld2(P.Y, in + 2); ld2(P.Z, in + 4); jac_dbl(P, P); st2(out, P.X); st2(out + 2, P.Y); st2(out + 4, P.Z); break;
+        case 6: ld2(P.X, in); ld2(P.Y, in + 2); ld2(P.Z, in + 4); ld2(A.x, in + 6); ld2(A.y, in + 8); jac_add_mixed(P, P, A); st2(out, P.X); st2(out + 2, P.Y); st2(out + 4, P.Z); break;
+        case 7: ld2(P.X, in); ld2(P.Y, in + 2); ld2(P.Z, in + 4); ld2(Q.X, in + 6); ld2(Q.Y, in + 8); ld2(Q.Z, in + 10); jac_add(R, P, Q); st2(out, R.X); st2(out + 2, R.Y); st2(out + 4, R.Z); break;
+        case 8: { fp6 x, y, z; ld2(x.c0, in); ld2(x.c1, in + 2); ld2(x.c2, in + 4); ld2(y.c0, in + 6); ld2(y.c1, in + 8); ld2(y.c2, in + 10); fp6_mul(z, x, y); st2(out, z.c0); st2(out + 2, z.c1); st2(out + 4, z.c2); break; }
+        case 9: ld12(f, in); ld12(g, in + 12); fp12_mul(h, f, g); st12(out, h); break;
+        case 10: ld12(f, in); fp12_sqr(f, f); st12(out, f); break;
+        case 11: ld12(f, in); ld2(a, in + 12); ld2(b, in + 14); ld2(c, in + 16); fp12_mul_by_014(f, a, b, c); st12(out, f); break;
+        case 12: ld12(f, in); fp12_cyclo_sqr(f, f); st12(out, f); break;
+        case 13: ld12(f, in); fp12_inv(g, f); st12(out, g); break;
+        case 14: ld12(f, in); fp12_frob(g, f); st12(out, g); break;
+        case 15: ld12(f, in); fp12_frob2(g, f); st12(out, g); break;
+        case 16: { ld2(a, in); bool ok = fp2_sqrt(b, a); st2(out, b); out[2] = fp_zero(); out[2].l[0] = ok ? 1u : 0u; break; }
+        case 17: ld2(a, in); st2(out, fp2_inv(a)); break;
+        case 18: p1.X = in[0]; p1.Y = in[1]; p1.Z = in[2]; jac_dbl(p1, p1); out[0] = p1.X; out[1] = p1.Y; out[2] = p1.Z; break;
+        case 19: p1.X = in[0]; p1.Y = in[1]; p1.Z = in[2]; a1.x = in[3]; a1.y = in[4]; jac_add_mixed(p1, p1, a1); out[0] = p1.X; out[1] = p1.Y; out[2] = p1.Z; break;
+        case 20: p1.X = in[0]; p1.Y = in[1]; p1.Z = in[2]; q1.X = in[3]; q1.Y = in[4]; q1.Z = in[5]; jac_add(r1, p1, q1); out[0] = r1.X; out[1] = r1.Y; out[2] = r1.Z; break;
+        case 21: out[0] = fp_mul(in[0], in[1]); break;
+        case 22: out[0] = fp_inv(in[0]); break;
+        case 23: ld2(A.x, in); ld2(A.y, in + 2); jac_mul_x_abs(P, A); st2(out, P.X); st2(out + 2, P.Y); st2(out + 4, P.Z); break;
+        case 24: ld12(f, in); final_exponentiation(g, f); st12(out, g); break;
+        case 25: { ld2(a, in); ld2(b, in + 2); bool sq = fp2_sqrt_ratio(c, a, b); st2(out, c); out[2] = fp_zero(); out[2].l[0] = sq ? 1u : 0u; break; }
+        case 26: ld2(a, in); st2(out, fp2_mul_xi(a)); break;
+        case 27: ld2(a, in); st2(out, fp2_mul_fp(a, in[2])); break;
+        case 28: ld2(P.X, in); ld2(P.Y, in + 2); ld2(P.Z, in + 4); ld2(A.x, in + 6); ld2(A.y, in + 8); jac_add_mixed(R, P, A); st2(out, R.X); st2(out + 2, R.Y); st2(out + 4, R.Z); break;
+        case 29: { ld2(P.X, in); ld2(P.Y, in + 2); ld2(P.Z, in + 4); ld2(A.x, in + 6); ld2(A.y, in + 8);
+                   fp2 Z1Z1 = f_sqr(P.Z), U2 = f_mul(A.x, Z1Z1), S2 = f_mul(f_mul(A.y, P.Z), Z1Z1); fp2 H = f_sub(U2, P.X), rr = f_sub(S2, P.Y);
+                   st2(out, Z1Z1); st2(out + 2, U2); st2(out + 4, S2); st2(out + 6, H); st2(out + 8, rr); fp2 HH = f_sqr(H), I = f_add(HH, HH); I = f_add(I, I); st2(out + 10, I); break; }
+        case 30: { ld2(P.X, in); ld2(P.Y, in + 2); ld2(P.Z, in + 4); ld2(A.x, in + 6); ld2(A.y, in + 8);
+                   fp2 Z1Z1 = f_sqr(P.Z), U2 = f_mul(A.x, Z1Z1), S2 = f_mul(f_mul(A.y, P.Z), Z1Z1); fp2 H = f_sub(U2, P.X), rr = f_sub(S2, P.Y);
+                   rr = f_add(rr, rr); fp2 HH = f_sqr(H), I = f_add(HH, HH); I = f_add(I, I);
+                   fp2 J = f_mul(H, I), V = f_mul(P.X, I); fp2 X3 = f_sub(f_sub(f_sqr(rr), J), f_add(V, V)); fp2 YJ = f_mul(P.Y, J);
+                   fp2 Y3 = f_sub(f_mul(rr, f_sub(V, X3)), f_add(YJ, YJ));
+                   st2(out, rr); st2(out + 2, J); st2(out + 4, V); st2(out + 6, X3); st2(out + 8, YJ); st2(out + 10, Y3); break; }
+        case 31: case 32: case 33: case 34: ld2(P.X, in); ld2(P.Y, in + 2); ld2(P.Z, in + 4); ld2(A.x, in + 6); ld2(A.y, in + 8);
+            if (op == 31) am_nobranch(R, P, A); else if (op == 32) am_if1(R, P, A); else if (op == 33) am_if2(R, P, A); else am_if2b(R, P, A);
+            st2(out, R.X); st2(out + 2, R.Y); st2(out + 4, R.Z); break;
+        default: break;
+    }
+    (void)d;
+}
+}  // namespace bls

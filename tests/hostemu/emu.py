@@ -3,7 +3,7 @@ import ctypes, os, subprocess
 import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__)); ROOT = os.path.dirname(os.path.dirname(HERE))
 SO = os.path.join(ROOT, "tests", "_hostemu", "libhostemu.so")
-SRC = [os.path.join(HERE, "hostemu.cpp")] + [os.path.join(ROOT, "bls_verify_gadget_b200", "csrc", f) for f in
+SRC = [os.path.join(HERE, "hostemu.cpp"), os.path.join(ROOT, "tests", "devcheck", "ops.h")] + [os.path.join(ROOT, "bls_verify_gadget_b200", "csrc", f) for f in
       ("fp.cuh", "fp2.cuh", "tower.cuh", "curve.cuh", "h2c.cuh", "pairing.cuh", "stages.cuh", "consts.cuh")]
 def build():
     if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in SRC):
@@ -40,3 +40,10 @@ def sign(sk, msgs):
 def g1_sum(pts): x = _u8(pts); o = np.empty(48, np.uint8); lib().emu_g1_sum(_p(x), _sz(x.size // 48), _p(o)); return o
 def g2_sum(pts): x = _u8(pts); o = np.empty(96, np.uint8); lib().emu_g2_sum(_p(x), _sz(x.size // 96), _p(o)); return o
 def pairing_gt(g1, g2): a = _u8(g1); b = _u8(g2); o = np.empty(576, np.uint8); lib().emu_pairing_gt(_p(a), _p(b), _sz(a.size // 48), _p(o)); return o
+
+def op_shape(op):
+    import ctypes as c
+    a = c.c_int(); b = c.c_int(); lib().emu_op_shape(int(op), c.byref(a), c.byref(b)); return a.value, b.value
+def run_op(op, inp):
+    n_in, n_out = op_shape(op); x = _u8(inp); n = x.size // (48 * n_in); o = np.zeros(48 * n_out * n, np.uint8)
+    assert lib().emu_run_op(int(op), _p(x), _p(o), _sz(n)) == 0; return o

@@ -2,7 +2,7 @@
 // The headers under bls_verify_gadget_b200/csrc compile for the host with plain-C fallbacks of the PTX carry
 // chains; this file loops the very same stage functions the kernels call, so the algorithm layer can be checked
 // against the oracle in the GPU-less authoring container.  The `-m gpu` tests exercise the real kernels.
-#include "stages.cuh"
+#include "../devcheck/ops.h"
 #include <cstring>
 #include <vector>
 using namespace bls;
@@ -11,6 +11,12 @@ static inline const uint8_t* msg_at(const uint8_t* msg, const uint32_t* off, siz
     if (off) { len = off[i + 1] - off[i]; return msg + off[i]; } len = 32; return msg + 32 * i;
 }
 extern "C" {
+int emu_run_op(int op, const uint8_t* in, uint8_t* out, size_t n) {
+    op_desc d = op_shape(op); if (!d.n_in) return -1;
+    for (size_t i = 0; i < n; i++) { fp a[24], r[12]; memcpy(a, in + i * d.n_in * 48, d.n_in * 48); for (int k = 0; k < d.n_out; k++) r[k] = fp_zero(); run_op(op, a, r); memcpy(out + i * d.n_out * 48, r, d.n_out * 48); }
+    return 0;
+}
+void emu_op_shape(int op, int* n_in, int* n_out) { op_desc d = op_shape(op); *n_in = d.n_in; *n_out = d.n_out; }
 void emu_fp_mul_raw(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
     for (size_t i = 0; i < n; i++) { fp x, y; memcpy(&x, a + 48 * i, 48); memcpy(&y, b + 48 * i, 48); fp z = fp_mul(x, y); memcpy(out + 48 * i, &z, 48); }
 }
