@@ -22,12 +22,27 @@
 
 using namespace bls;
 
-#define TPB 128
+#ifndef BLS_TPB
+#define BLS_TPB 128
+#endif
+#define TPB BLS_TPB
 #ifndef BLS_MINB
 #define BLS_MINB 2      // resident 128-thread CTAs per SM the heavy kernels are compiled for (register cap = 65536 / (128 * BLS_MINB))
 #endif
 static inline unsigned nblk(size_t n, unsigned tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
 
+// Phase skew: the IMAD.WIDE pipe issues one warp instruction per 4 cycles per SM sub-partition and a single warp inside
+// fp_mul saturates it; two warps that start together stay in lockstep (both in their IMAD phase, then both in their ALU
+// phase), leaving each pipe idle half of the time.  Delaying every second warp of a sub-partition by about one phase at
+// kernel entry moves the pair to the stable anti-phase schedule.  BLS_SKEW = delay in cycles (0 = off).
+#ifndef BLS_SKEW
+#define BLS_SKEW 0
+#endif
+__device__ __forceinline__ void phase_skew() {
+#if BLS_SKEW > 0
+    if ((threadIdx.x >> 5) & 4) { long long t0 = clock64(); while (clock64() - t0 < BLS_SKEW) { } }
+#endif
+}
 // ================================================================================================ kernels
 __global__ void __launch_bounds__(TPB, BLS_MINB) k_fp_mul_raw(const fp* a, const fp* b, fp* out, size_t n, int reps) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
@@ -45,7 +60,8 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* sink, int iters, in
         for (int j = 0; j < 16; j++) acc[j] = (unsigned long long)j * 0x9e3779b97f4a7c15ull + a;
         for (int it = 0; it < iters; it++) {
 #pragma unroll
-            for (int j = 0; j < 16; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a + j), "r"(b));
+            for (int j = 0; j < 16; j++)      // the multiplicand changes every iteration (low half of another accumulator): nothing to strength-reduce
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"((uint32_t)acc[(j + 5) & 15]), "r"(b));
         }
         unsigned long long s = 0;
 #pragma unroll
@@ -62,14 +78,14 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* sink, int iters, in
                 "madc.lo.cc.u32 %8, %20, %24, %8;\n\tmadc.hi.cc.u32 %9, %20, %24, %9;\n\tmadc.lo.cc.u32 %10, %21, %24, %10;\n\tmadc.hi.cc.u32 %11, %21, %24, %11;\n\t"
                 "madc.lo.cc.u32 %12, %22, %24, %12;\n\tmadc.hi.cc.u32 %13, %22, %24, %13;\n\tmadc.lo.cc.u32 %14, %23, %24, %14;\n\tmadc.hi.u32 %15, %23, %24, %15;"
                 : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "+r"(e[9]), "+r"(e[10]), "+r"(e[11]), "+r"(e[12]), "+r"(e[13]), "+r"(e[14]), "+r"(e[15])
-                : "r"(a), "r"(a + 1), "r"(a + 2), "r"(a + 3), "r"(a + 4), "r"(a + 5), "r"(a + 6), "r"(a + 7), "r"(b));
+                : "r"(a), "r"(a + 1), "r"(a + 2), "r"(a + 3), "r"(a + 4), "r"(a + 5), "r"(a + 6), "r"(a + 7), "r"(o[3]));
             asm volatile(
                 "mad.lo.cc.u32 %0, %16, %24, %0;\n\tmadc.hi.cc.u32 %1, %16, %24, %1;\n\tmadc.lo.cc.u32 %2, %17, %24, %2;\n\tmadc.hi.cc.u32 %3, %17, %24, %3;\n\t"
                 "madc.lo.cc.u32 %4, %18, %24, %4;\n\tmadc.hi.cc.u32 %5, %18, %24, %5;\n\tmadc.lo.cc.u32 %6, %19, %24, %6;\n\tmadc.hi.cc.u32 %7, %19, %24, %7;\n\t"
                 "madc.lo.cc.u32 %8, %20, %24, %8;\n\tmadc.hi.cc.u32 %9, %20, %24, %9;\n\tmadc.lo.cc.u32 %10, %21, %24, %10;\n\tmadc.hi.cc.u32 %11, %21, %24, %11;\n\t"
                 "madc.lo.cc.u32 %12, %22, %24, %12;\n\tmadc.hi.cc.u32 %13, %22, %24, %13;\n\tmadc.lo.cc.u32 %14, %23, %24, %14;\n\tmadc.hi.u32 %15, %23, %24, %15;"
                 : "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(o[8]), "+r"(o[9]), "+r"(o[10]), "+r"(o[11]), "+r"(o[12]), "+r"(o[13]), "+r"(o[14]), "+r"(o[15])
-                : "r"(b), "r"(b + 1), "r"(b + 2), "r"(b + 3), "r"(b + 4), "r"(b + 5), "r"(b + 6), "r"(b + 7), "r"(a));
+                : "r"(b), "r"(b + 1), "r"(b + 2), "r"(b + 3), "r"(b + 4), "r"(b + 5), "r"(b + 6), "r"(b + 7), "r"(e[5]));
         }
         uint32_t s = 0;
 #pragma unroll
@@ -79,12 +95,14 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* sink, int iters, in
 }
 
 __global__ void __launch_bounds__(TPB, BLS_MINB) k_decode_g1(const uint8_t* in48, size_t n, u32x4* soa, uint8_t* code) {
+    phase_skew();
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     g1_aff p; int rc = g1_decode(p, in48 + 48 * i);
     if (soa) soa_store_g1(soa, n, i, p);
     code[i] = (uint8_t)rc;
 }
 __global__ void __launch_bounds__(TPB, BLS_MINB) k_decode_g2(const uint8_t* in96, size_t n, u32x4* soa, uint8_t* code) {
+    phase_skew();
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     g2_aff p; int rc = g2_decode(p, in96 + 96 * i);
     if (soa) soa_store_g2(soa, n, i, p);
@@ -93,6 +111,7 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_decode_g2(const uint8_t* in96
 // status/flags from the two decode codes (bls.rs:434-447), then H(m) for the items still alive
 __global__ void __launch_bounds__(TPB, BLS_MINB) k_hash_to_g2(const uint8_t* msg, const uint32_t* off, size_t n, const uint8_t* code_pk, const uint8_t* code_sig,
                                                     u32x4* hm_soa, uint8_t* flags, uint8_t* status) {
+    phase_skew();
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     uint8_t st = ST_OK, fl = 0;
     if (code_pk) {
@@ -110,6 +129,7 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_hash_to_g2(const uint8_t* msg
 }
 __global__ void __launch_bounds__(TPB, BLS_MINB) k_miller(const u32x4* pk_soa, const u32x4* hm_soa, const u32x4* sig_soa, const uint8_t* flags,
                                                 const uint8_t* status, size_t n, u32x4* f_soa) {
+    phase_skew();
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     if (status[i] != ST_OK) return;
     g1_aff pk; g2_aff hm, sig;
@@ -136,6 +156,7 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_miller_pairs(const u32x4* g1_
     soa_store_fp12(f_soa, nprod, i, f);
 }
 __global__ void __launch_bounds__(TPB, BLS_MINB) k_final_exp(u32x4* f_soa, const uint8_t* status_in, uint8_t* status_out, size_t n) {
+    phase_skew();
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     if (status_in[i] != ST_OK) { status_out[i] = status_in[i]; return; }
     fp12 f, gt; soa_load_fp12(f, f_soa, n, i);

@@ -26,6 +26,12 @@
 #define BLS_CONST static const
 #endif
 
+#ifdef BLS_ASM_VOLATILE
+#define BLS_ASM asm volatile
+#else
+#define BLS_ASM asm
+#endif
+
 namespace bls {
 
 struct alignas(16) fp { uint32_t l[12]; };
@@ -55,7 +61,7 @@ BLS_HD uint32_t fp_p_limb(int i) {
 // r = a + b (384-bit, carry out impossible for a,b < p < 2^381).  Outputs are early-clobber: limb i is written before
 // the inputs of limbs > i are read, so an output must never share a register with an input.
 BLS_HD void fp_add_raw(fp& r, const fp& a, const fp& b) {
-    asm("add.cc.u32 %0, %12, %24;\n\taddc.cc.u32 %1, %13, %25;\n\taddc.cc.u32 %2, %14, %26;\n\taddc.cc.u32 %3, %15, %27;\n\t"
+    BLS_ASM("add.cc.u32 %0, %12, %24;\n\taddc.cc.u32 %1, %13, %25;\n\taddc.cc.u32 %2, %14, %26;\n\taddc.cc.u32 %3, %15, %27;\n\t"
         "addc.cc.u32 %4, %16, %28;\n\taddc.cc.u32 %5, %17, %29;\n\taddc.cc.u32 %6, %18, %30;\n\taddc.cc.u32 %7, %19, %31;\n\t"
         "addc.cc.u32 %8, %20, %32;\n\taddc.cc.u32 %9, %21, %33;\n\taddc.cc.u32 %10, %22, %34;\n\taddc.u32 %11, %23, %35;"
         : "=&r"(r.l[0]), "=&r"(r.l[1]), "=&r"(r.l[2]), "=&r"(r.l[3]), "=&r"(r.l[4]), "=&r"(r.l[5]), "=&r"(r.l[6]), "=&r"(r.l[7]), "=&r"(r.l[8]), "=&r"(r.l[9]), "=&r"(r.l[10]), "=&r"(r.l[11])
@@ -65,7 +71,7 @@ BLS_HD void fp_add_raw(fp& r, const fp& a, const fp& b) {
 // r = a - b (384-bit), returns the borrow as 0 / 0xffffffff
 BLS_HD uint32_t fp_sub_raw(fp& r, const fp& a, const fp& b) {
     uint32_t br;
-    asm("sub.cc.u32 %0, %13, %25;\n\tsubc.cc.u32 %1, %14, %26;\n\tsubc.cc.u32 %2, %15, %27;\n\tsubc.cc.u32 %3, %16, %28;\n\t"
+    BLS_ASM("sub.cc.u32 %0, %13, %25;\n\tsubc.cc.u32 %1, %14, %26;\n\tsubc.cc.u32 %2, %15, %27;\n\tsubc.cc.u32 %3, %16, %28;\n\t"
         "subc.cc.u32 %4, %17, %29;\n\tsubc.cc.u32 %5, %18, %30;\n\tsubc.cc.u32 %6, %19, %31;\n\tsubc.cc.u32 %7, %20, %32;\n\t"
         "subc.cc.u32 %8, %21, %33;\n\tsubc.cc.u32 %9, %22, %34;\n\tsubc.cc.u32 %10, %23, %35;\n\tsubc.cc.u32 %11, %24, %36;\n\t"
         "subc.u32 %12, 0, 0;"
@@ -166,14 +172,14 @@ BLS_HD bool fp_raw_geq(const fp& a, const fp& b) { fp t; return fp_sub_raw(t, a,
     "madc.lo.cc.u32 %10, %18, %19, %10;\n\tmadc.hi.cc.u32 %11, %18, %19, %11;\n\t"                                       \
     "addc.u32 %12, %12, 0;"
 BLS_HD void cmad_n(uint32_t* acc, uint32_t& top, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t a8, uint32_t a10, uint32_t bi) {
-    asm(BLS_CMAD_BODY
+    BLS_ASM(BLS_CMAD_BODY
         : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(top)
         : "r"(a0), "r"(a2), "r"(a4), "r"(a6), "r"(a8), "r"(a10), "r"(bi));
 }
 // e0 += o[1] (carry into the chain); then o[j],o[j+1] = a_j*bi + o[j+2],o[j+3] for the five low pairs and
 // o[10],o[11] = a_10*bi + carry: "accumulate the odd columns while shifting the accumulator down two limbs"
 BLS_HD void madc_n_rshift(uint32_t& e0, uint32_t* o, uint32_t a1, uint32_t a3, uint32_t a5, uint32_t a7, uint32_t a9, uint32_t a11, uint32_t bi) {
-    asm("add.cc.u32 %12, %12, %1;\n\t"
+    BLS_ASM("add.cc.u32 %12, %12, %1;\n\t"
         "madc.lo.cc.u32 %0, %13, %19, %2;\n\tmadc.hi.cc.u32 %1, %13, %19, %3;\n\t"
         "madc.lo.cc.u32 %2, %14, %19, %4;\n\tmadc.hi.cc.u32 %3, %14, %19, %5;\n\t"
         "madc.lo.cc.u32 %4, %15, %19, %6;\n\tmadc.hi.cc.u32 %5, %15, %19, %7;\n\t"

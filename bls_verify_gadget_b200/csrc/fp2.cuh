@@ -34,9 +34,10 @@ BLS_HD fp2 fp2_csel(bool c, const fp2& a, const fp2& b) { fp2 r; r.c0 = fp_csel(
 // Out-of-line arithmetic works memory-to-memory (operands by reference in the thread's local memory, staged with
 // 128-bit loads/stores): nothing is live in registers across a call, so the 300-IMAD cores exist once in the
 // instruction cache and the callers stay small.  BLS_FP2_MODE selects what is inlined inside fp2_mul/fp2_sqr:
-//   0 = calls to the out-of-line fp_mul/fp_sqr, 1 = the three (two) Montgomery products inlined (18 / 12 KB bodies)
+//   0 = calls to the out-of-line fp_mul/fp_sqr, 1 = the three (two) Montgomery products inlined (18 / 12 KB bodies),
+//   2 = by-value register ABI (no memory staging); measured fastest on B200 (profiles/r01_tuning.md)
 #ifndef BLS_FP2_MODE
-#define BLS_FP2_MODE 1
+#define BLS_FP2_MODE 2
 #endif
 #if BLS_FP2_MODE == 1
 #define BLS_FPM fp_mul_inl
@@ -58,9 +59,23 @@ BLS_NOINLINE void fp2_mul_fp_p(fp2& r, const fp2& a, const fp& s) {
     fp a0 = a.c0, a1 = a.c1, ss = s;
     r.c0 = BLS_FPM(a0, ss); r.c1 = BLS_FPM(a1, ss);
 }
+#if BLS_FP2_MODE == 2 && defined(__CUDACC__)
+// mode 2: operands and results by value in registers, three (two) calls to the out-of-line fp_mul
+BLS_NOINLINE fp2 fp2_mul(fp2 a, fp2 b) {
+    fp t0 = fp_mul(a.c0, b.c0), t1 = fp_mul(a.c1, b.c1);
+    fp t2 = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+    fp2 r; r.c0 = fp_sub(t0, t1); r.c1 = fp_sub(fp_sub(t2, t0), t1); return r;
+}
+BLS_NOINLINE fp2 fp2_sqr(fp2 a) {
+    fp t = fp_mul(a.c0, a.c1);
+    fp2 r; r.c0 = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1)); r.c1 = fp_add(t, t); return r;
+}
+BLS_HD fp2 fp2_mul_fp(const fp2& a, const fp& s) { fp2 r; r.c0 = fp_mul(a.c0, s); r.c1 = fp_mul(a.c1, s); return r; }
+#else
 BLS_HD fp2 fp2_mul(const fp2& a, const fp2& b) { fp2 r; fp2_mul_p(r, a, b); return r; }
 BLS_HD fp2 fp2_sqr(const fp2& a) { fp2 r; fp2_sqr_p(r, a); return r; }
 BLS_HD fp2 fp2_mul_fp(const fp2& a, const fp& s) { fp2 r; fp2_mul_fp_p(r, a, s); return r; }
+#endif
 #if BLS_FP2_ADDSUB_OUTOFLINE
 BLS_NOINLINE void fp2_add_p(fp2& r, const fp2& a, const fp2& b) { fp x0 = a.c0, x1 = a.c1, y0 = b.c0, y1 = b.c1; r.c0 = fp_add(x0, y0); r.c1 = fp_add(x1, y1); }
 BLS_NOINLINE void fp2_sub_p(fp2& r, const fp2& a, const fp2& b) { fp x0 = a.c0, x1 = a.c1, y0 = b.c0, y1 = b.c1; r.c0 = fp_sub(x0, y0); r.c1 = fp_sub(x1, y1); }

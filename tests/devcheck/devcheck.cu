@@ -1,21 +1,30 @@
 // Device unit-test library (TEST TOOL ONLY): applies one primitive of the CUDA device library per thread.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "ops.h"
 using namespace bls;
-__global__ void __launch_bounds__(128, 2) k_run_op(int op, const fp* in, fp* out, size_t n, int n_in, int n_out) {
+// one kernel per primitive (template instantiation): keeps each kernel small -- a single kernel holding all cases behind a
+// run-time switch (10 KB frame, ~1 MB of code) was itself miscompiled by nvcc 12.9 (inputs of some cases read back as garbage).
+template <int OP> __global__ void __launch_bounds__(128, 2) k_run_op(const fp* in, fp* out, size_t n, int n_in, int n_out) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     fp a[24], r[12];
     for (int k = 0; k < n_in; k++) a[k] = in[i * n_in + k];
     for (int k = 0; k < n_out; k++) r[k] = fp_zero();
-    run_op(op, a, r);
+    run_op(OP, a, r);
     for (int k = 0; k < n_out; k++) out[i * n_out + k] = r[k];
 }
+template <int OP> static void launch(const fp* din, fp* dout, size_t n, op_desc d) { k_run_op<OP><<<(unsigned)((n + 127) / 128), 128>>>(din, dout, n, d.n_in, d.n_out); }
 extern "C" int dev_run_op(int op, const uint8_t* in, uint8_t* out, size_t n) {
     op_desc d = op_shape(op); if (!d.n_in) return -1;
     fp *din, *dout; size_t bi = n * d.n_in * 48, bo = n * d.n_out * 48;
     if (cudaMalloc(&din, bi) != cudaSuccess || cudaMalloc(&dout, bo) != cudaSuccess) return -2;
     cudaMemcpy(din, in, bi, cudaMemcpyHostToDevice);
-    k_run_op<<<(unsigned)((n + 127) / 128), 128>>>(op, din, dout, n, d.n_in, d.n_out);
+    switch (op) {
+#define L(K) case K: launch<K>(din, dout, n, d); break;
+        L(1) L(2) L(3) L(4) L(5) L(6) L(7) L(8) L(9) L(10) L(11) L(12) L(13) L(14) L(15) L(16) L(17) L(18) L(19) L(20) L(21) L(22) L(23) L(24) L(25) L(26) L(27) L(28)
+#undef L
+        default: cudaFree(din); cudaFree(dout); return -1;
+    }
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(out, dout, bo, cudaMemcpyDeviceToHost); cudaFree(din); cudaFree(dout);
     return e == cudaSuccess ? 0 : -3;

@@ -4,21 +4,6 @@
 #pragma once
 #include "stages.cuh"
 namespace bls {
-#define AM_BODY \
-    fp2 Z1Z1 = f_sqr(p.Z), U2 = f_mul(q.x, Z1Z1), S2 = f_mul(f_mul(q.y, p.Z), Z1Z1); \
-    fp2 H = f_sub(U2, p.X), rr = f_sub(S2, p.Y);
-#define AM_TAIL \
-    rr = f_add(rr, rr); \
-    fp2 HH = f_sqr(H), I = f_add(HH, HH); I = f_add(I, I); \
-    fp2 J = f_mul(H, I), V = f_mul(p.X, I); \
-    fp2 X3 = f_sub(f_sub(f_sqr(rr), J), f_add(V, V)); \
-    fp2 YJ = f_mul(p.Y, J); \
-    fp2 Z3 = f_sub(f_sub(f_sqr(f_add(p.Z, H)), Z1Z1), HH); \
-    r.Y = f_sub(f_mul(rr, f_sub(V, X3)), f_add(YJ, YJ)); r.X = X3; r.Z = Z3;
-BLS_NOINLINE void am_nobranch(g2_jac& r, const g2_jac& p, const g2_aff& q) { AM_BODY AM_TAIL }
-BLS_NOINLINE void am_if1(g2_jac& r, const g2_jac& p, const g2_aff& q) { if (f_is_zero(p.Z)) { jac_from_aff(r, q); return; } AM_BODY AM_TAIL }
-BLS_NOINLINE void am_if2(g2_jac& r, const g2_jac& p, const g2_aff& q) { AM_BODY if (f_is_zero(H)) { if (f_is_zero(rr)) { g2_jac t = p; jac_dbl(r, t); } else jac_set_identity(r); return; } AM_TAIL }
-BLS_NOINLINE void am_if2b(g2_jac& r, const g2_jac& p, const g2_aff& q) { AM_BODY if (f_is_zero(H)) { jac_set_identity(r); return; } AM_TAIL }
 struct op_desc { int n_in, n_out; };
 #if defined(__CUDACC__)
 __host__ __device__
@@ -53,9 +38,6 @@ static inline op_desc op_shape(int op) {
         case 26: return {2, 2};   // fp2_mul_xi
         case 27: return {3, 2};   // fp2_mul_fp
         case 28: return {10, 6};  // jac_add_mixed<fp2>, separate output
-        case 29: return {10, 12}; // add_mixed intermediates
-        case 30: return {10, 12}; // add_mixed intermediates, second half
-        case 31: case 32: case 33: case 34: return {10, 6};
         default: return {0, 0};
     }
 }
@@ -94,18 +76,6 @@ BLS_HD void run_op(int op, const fp* in, fp* out) {
         case 26: ld2(a, in); st2(out, fp2_mul_xi(a)); break;
         case 27: ld2(a, in); st2(out, fp2_mul_fp(a, in[2])); break;
         case 28: ld2(P.X, in); ld2(P.Y, in + 2); ld2(P.Z, in + 4); ld2(A.x, in + 6); ld2(A.y, in + 8); jac_add_mixed(R, P, A); st2(out, R.X); st2(out + 2, R.Y); st2(out + 4, R.Z); break;
-        case 29: { ld2(P.X, in); ld2(P.Y, in + 2); ld2(P.Z, in + 4); ld2(A.x, in + 6); ld2(A.y, in + 8);
-                   fp2 Z1Z1 = f_sqr(P.Z), U2 = f_mul(A.x, Z1Z1), S2 = f_mul(f_mul(A.y, P.Z), Z1Z1); fp2 H = f_sub(U2, P.X), rr = f_sub(S2, P.Y);
-                   st2(out, Z1Z1); st2(out + 2, U2); st2(out + 4, S2); st2(out + 6, H); st2(out + 8, rr); fp2 HH = f_sqr(H), I = f_add(HH, HH); I = f_add(I, I); st2(out + 10, I); break; }
-        case 30: { ld2(P.X, in); ld2(P.Y, in + 2); ld2(P.Z, in + 4); ld2(A.x, in + 6); ld2(A.y, in + 8);
-                   fp2 Z1Z1 = f_sqr(P.Z), U2 = f_mul(A.x, Z1Z1), S2 = f_mul(f_mul(A.y, P.Z), Z1Z1); fp2 H = f_sub(U2, P.X), rr = f_sub(S2, P.Y);
-                   rr = f_add(rr, rr); fp2 HH = f_sqr(H), I = f_add(HH, HH); I = f_add(I, I);
-                   fp2 J = f_mul(H, I), V = f_mul(P.X, I); fp2 X3 = f_sub(f_sub(f_sqr(rr), J), f_add(V, V)); fp2 YJ = f_mul(P.Y, J);
-                   fp2 Y3 = f_sub(f_mul(rr, f_sub(V, X3)), f_add(YJ, YJ));
-                   st2(out, rr); st2(out + 2, J); st2(out + 4, V); st2(out + 6, X3); st2(out + 8, YJ); st2(out + 10, Y3); break; }
-        case 31: case 32: case 33: case 34: ld2(P.X, in); ld2(P.Y, in + 2); ld2(P.Z, in + 4); ld2(A.x, in + 6); ld2(A.y, in + 8);
-            if (op == 31) am_nobranch(R, P, A); else if (op == 32) am_if1(R, P, A); else if (op == 33) am_if2(R, P, A); else am_if2b(R, P, A);
-            st2(out, R.X); st2(out + 2, R.Y); st2(out + 4, R.Z); break;
         default: break;
     }
     (void)d;

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from hostemu import emu
 P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
 def dev_lib():
-    so = os.path.join(ROOT, "tests", "_hostemu", "libdevcheck.so")
+    so = os.environ.get("DEVCHECK_SO") or os.path.join(ROOT, "tests", "_hostemu", "libdevcheck.so")
     return ctypes.CDLL(so)
 def rand_fp(rng, n):
     a = rng.integers(0, 256, size=(n, 48), dtype=np.uint8); a[:, 47] &= 0x0f      # < 2^380 < p: a valid Montgomery image
