@@ -112,7 +112,7 @@ int blsgpu_gt_fold(blsgpu_ctx* ctx, const uint8_t* parts_le576, size_t nparts, u
 /* ---- Fp Montgomery product on raw 48-byte little-endian limb images (kernel K0 parity hook) ----------------- */
 int blsgpu_fp_mul_raw(blsgpu_ctx* ctx, const uint8_t* a48, const uint8_t* b48, size_t n, uint8_t* out48, int reps);
 /* IMAD.WIDE.U32 issue-rate microbenchmark: returns measured 32x32->64 multiply-accumulates per second */
-int blsgpu_imad_peak(blsgpu_ctx* ctx, int mode /* 0 = independent mad.wide.u32, 1 = mad.lo.cc/madc.hi.cc carry chains */,
+int blsgpu_imad_peak(blsgpu_ctx* ctx, int mode /* 0 = independent mad.wide.u32, 1 = mad.lo.cc/madc.hi.cc carry chains, 2 = chained Montgomery products */,
                      double* mac32_per_sec, double* ms);
 
 /* ---- R1CS satisfaction check  (ark-relations ConstraintSystem::is_satisfied on the circuit of

@@ -1,0 +1,58 @@
+"""world_size-2 gloo test (CPU) of the N>1 host logic: contiguous sharding, the all-gather exchange of bitmap shards and
+GT partials, and the rank-order fold.  Kernels are replaced by the CPU oracle here (no GPU in this container); the
+exchange code is the one bench.py runs over NCCL."""
+import os, socket, sys
+import numpy as np
+import torch, torch.distributed as dist, torch.multiprocessing as mp
+from conftest import ROOT
+
+N = 200                      # not a multiple of 64 * world: ragged last shard
+
+def _inputs():
+    from oracle import cwrap as C
+    rng = np.random.default_rng(12)
+    sk = rng.integers(0, 256, size=(N, 32), dtype=np.uint8); sk[:, 31] &= 0x3f; sk[:, 0] |= 1
+    msgs = [rng.bytes(32) for _ in range(N)]
+    pk = C.sk_to_pk(sk, threads=8).reshape(N, 48); sig = C.sign(sk, msgs, threads=8)[0].reshape(N, 96).copy()
+    for i in (5, 70, 130, 199): sig[i] = sig[(i + 1) % N]                  # valid points, wrong signatures
+    return pk, msgs, sig
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import cwrap as C
+    from bls_verify_gadget_b200.dist import shard_range, shard_words, exchange
+    pk, msgs, sig = _inputs()
+    lo, hi = shard_range(N, world, rank); words = shard_words(N, world)
+    st, gt = C.verify(pk[lo:hi].reshape(-1), msgs[lo:hi], sig[lo:hi].reshape(-1), want_gt=True, threads=2) if hi > lo else (np.zeros(0, np.uint8), C.pairing_gt(b"", b""))
+    bits = np.zeros(words * 64, dtype=np.uint8); bits[:hi - lo] = st == 0
+    bm = torch.from_numpy(np.packbits(bits, bitorder="little").view(np.int64).copy())
+    def fold(parts):
+        acc = parts[:576].numpy()
+        for r in range(1, world): acc = C.gt_mul(acc, parts[576 * r:576 * (r + 1)].numpy())
+        return torch.from_numpy(np.asarray(acc).copy())
+    full_bm, gt_all = exchange(bm, torch.from_numpy(gt.copy()), fold)
+    q.put((rank, lo, hi, full_bm.numpy().tobytes(), gt_all.numpy().tobytes()))
+    dist.destroy_process_group()
+
+def test_two_rank_exchange_matches_single_process():
+    from oracle import cwrap as C
+    from bls_verify_gadget_b200.dist import shard_range, shard_words
+    world = 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn"); q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps: p.start()
+    res = sorted(q.get(timeout=600) for _ in range(world))
+    for p in ps: p.join(60)
+    pk, msgs, sig = _inputs()
+    st, gt = C.verify(pk.reshape(-1), msgs, sig.reshape(-1), want_gt=True, threads=8)
+    assert (st != 0).sum() == 4
+    words = shard_words(N, world)
+    assert [r[1:3] for r in res] == [shard_range(N, world, r) for r in range(world)] == [(0, 128), (128, 200)]
+    for rank, lo, hi, bm, gt_all in res:
+        bits = np.unpackbits(np.frombuffer(bm, dtype=np.uint8), bitorder="little")
+        got = np.concatenate([bits[r * words * 64: r * words * 64 + (shard_range(N, world, r)[1] - shard_range(N, world, r)[0])] for r in range(world)])
+        assert np.array_equal(got, (st == 0).astype(np.uint8))             # every rank holds the whole bitmap
+        assert gt_all == gt.tobytes()                                      # and the same folded GT accumulator
