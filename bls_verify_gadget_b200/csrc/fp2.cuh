@@ -14,7 +14,10 @@ BLS_HD fp2 fp2_one() { fp2 r; r.c0 = fp_one(); r.c1 = fp_zero(); return r; }
 #ifndef BLS_FP2_ADDSUB_OUTOFLINE
 #define BLS_FP2_ADDSUB_OUTOFLINE 0
 #endif
-#if BLS_FP2_ADDSUB_OUTOFLINE
+#if BLS_FP2_ADDSUB_OUTOFLINE == 2 && defined(__CUDACC__)
+BLS_NOINLINE fp2 fp2_add(fp2 a, fp2 b) { fp2 r; r.c0 = fp_add(a.c0, b.c0); r.c1 = fp_add(a.c1, b.c1); return r; }
+BLS_NOINLINE fp2 fp2_sub(fp2 a, fp2 b) { fp2 r; r.c0 = fp_sub(a.c0, b.c0); r.c1 = fp_sub(a.c1, b.c1); return r; }
+#elif BLS_FP2_ADDSUB_OUTOFLINE == 1
 BLS_NOINLINE void fp2_add_p(fp2& r, const fp2& a, const fp2& b);
 BLS_NOINLINE void fp2_sub_p(fp2& r, const fp2& a, const fp2& b);
 BLS_HD fp2 fp2_add(const fp2& a, const fp2& b) { fp2 r; fp2_add_p(r, a, b); return r; }
@@ -59,16 +62,22 @@ BLS_NOINLINE void fp2_mul_fp_p(fp2& r, const fp2& a, const fp& s) {
     fp a0 = a.c0, a1 = a.c1, ss = s;
     r.c0 = BLS_FPM(a0, ss); r.c1 = BLS_FPM(a1, ss);
 }
-#if BLS_FP2_MODE == 2 && defined(__CUDACC__)
+#if BLS_FP2_MODE >= 2 && defined(__CUDACC__)
 // mode 2: operands and results by value in registers, three (two) calls to the out-of-line fp_mul
+// mode 3: the same with the Montgomery products inlined, so the additions can be scheduled into the IMAD stream
+#if BLS_FP2_MODE == 3
+#define BLS_FPM2 fp_mul_inl
+#else
+#define BLS_FPM2 fp_mul
+#endif
 BLS_NOINLINE fp2 fp2_mul(fp2 a, fp2 b) {
-    fp t0 = fp_mul(a.c0, b.c0), t1 = fp_mul(a.c1, b.c1);
-    fp t2 = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
-    fp2 r; r.c0 = fp_sub(t0, t1); r.c1 = fp_sub(fp_sub(t2, t0), t1); return r;
+    fp t0 = BLS_FPM2(a.c0, b.c0), t1 = BLS_FPM2(a.c1, b.c1);
+    fp t2 = BLS_FPM2(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+    fp2 r; r.c0 = fp_sub(t0, t1); r.c1 = fp_sub(t2, fp_add(t0, t1)); return r;
 }
 BLS_NOINLINE fp2 fp2_sqr(fp2 a) {
-    fp t = fp_mul(a.c0, a.c1);
-    fp2 r; r.c0 = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1)); r.c1 = fp_add(t, t); return r;
+    fp t = BLS_FPM2(a.c0, a.c1);
+    fp2 r; r.c0 = BLS_FPM2(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1)); r.c1 = fp_add(t, t); return r;
 }
 BLS_HD fp2 fp2_mul_fp(const fp2& a, const fp& s) { fp2 r; r.c0 = fp_mul(a.c0, s); r.c1 = fp_mul(a.c1, s); return r; }
 #else
@@ -76,7 +85,7 @@ BLS_HD fp2 fp2_mul(const fp2& a, const fp2& b) { fp2 r; fp2_mul_p(r, a, b); retu
 BLS_HD fp2 fp2_sqr(const fp2& a) { fp2 r; fp2_sqr_p(r, a); return r; }
 BLS_HD fp2 fp2_mul_fp(const fp2& a, const fp& s) { fp2 r; fp2_mul_fp_p(r, a, s); return r; }
 #endif
-#if BLS_FP2_ADDSUB_OUTOFLINE
+#if BLS_FP2_ADDSUB_OUTOFLINE == 1
 BLS_NOINLINE void fp2_add_p(fp2& r, const fp2& a, const fp2& b) { fp x0 = a.c0, x1 = a.c1, y0 = b.c0, y1 = b.c1; r.c0 = fp_add(x0, y0); r.c1 = fp_add(x1, y1); }
 BLS_NOINLINE void fp2_sub_p(fp2& r, const fp2& a, const fp2& b) { fp x0 = a.c0, x1 = a.c1, y0 = b.c0, y1 = b.c1; r.c0 = fp_sub(x0, y0); r.c1 = fp_sub(x1, y1); }
 #endif

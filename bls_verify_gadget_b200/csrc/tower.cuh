@@ -13,10 +13,32 @@ struct fp12 { fp6 c0, c1; };
 BLS_CONST fp2 FROB1[6] = BLS_C_FROB1;     // xi^(i(p-1)/6)
 BLS_CONST fp FROB2[6] = BLS_C_FROB2;      // xi^(i(p^2-1)/6), in Fp
 
-BLS_HD void fp6_add(fp6& r, const fp6& a, const fp6& b) { r.c0 = fp2_add(a.c0, b.c0); r.c1 = fp2_add(a.c1, b.c1); r.c2 = fp2_add(a.c2, b.c2); }
-BLS_HD void fp6_sub(fp6& r, const fp6& a, const fp6& b) { r.c0 = fp2_sub(a.c0, b.c0); r.c1 = fp2_sub(a.c1, b.c1); r.c2 = fp2_sub(a.c2, b.c2); }
-BLS_HD void fp6_neg(fp6& r, const fp6& a) { r.c0 = fp2_neg(a.c0); r.c1 = fp2_neg(a.c1); r.c2 = fp2_neg(a.c2); }
-BLS_HD void fp6_mul_v(fp6& r, const fp6& a) { fp2 t = fp2_mul_xi(a.c2); r.c2 = a.c1; r.c1 = a.c0; r.c0 = t; }
+// Fp6 values live in local memory, so the linear operations on them are out-of-line memory-to-memory routines
+// (BLS_FP6_OUTOFLINE, default on): inlined they are 3.5 KB each and made the Fp12 routines 20 KB+ apiece.
+#ifndef BLS_FP6_OUTOFLINE
+#define BLS_FP6_OUTOFLINE 1
+#endif
+#if BLS_FP6_OUTOFLINE
+#define BLS_FP6_LIN BLS_NOINLINE
+#else
+#define BLS_FP6_LIN BLS_HD
+#endif
+BLS_FP6_LIN void fp6_add(fp6& r, const fp6& a, const fp6& b) {
+    const fp* x = &a.c0.c0; const fp* y = &b.c0.c0; fp* z = &r.c0.c0;
+#pragma unroll 1
+    for (int i = 0; i < 6; i++) z[i] = fp_add(x[i], y[i]);
+}
+BLS_FP6_LIN void fp6_sub(fp6& r, const fp6& a, const fp6& b) {
+    const fp* x = &a.c0.c0; const fp* y = &b.c0.c0; fp* z = &r.c0.c0;
+#pragma unroll 1
+    for (int i = 0; i < 6; i++) z[i] = fp_sub(x[i], y[i]);
+}
+BLS_FP6_LIN void fp6_neg(fp6& r, const fp6& a) {
+    const fp* x = &a.c0.c0; fp* z = &r.c0.c0;
+#pragma unroll 1
+    for (int i = 0; i < 6; i++) z[i] = fp_neg(x[i]);
+}
+BLS_FP6_LIN void fp6_mul_v(fp6& r, const fp6& a) { fp2 t = fp2_mul_xi(a.c2); fp2 u = a.c1, w = a.c0; r.c2 = u; r.c1 = w; r.c0 = t; }
 
 // 6 Fp2 products (Karatsuba over the cubic extension)
 BLS_NOINLINE void fp6_mul(fp6& r, const fp6& a, const fp6& b) {
