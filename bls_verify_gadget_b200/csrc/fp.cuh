@@ -245,6 +245,95 @@ BLS_HD fp fp_mul_inl(const fp& a, const fp& b) {
     return fp_reduce_once(t);
 }
 
+// ------------------------------------------------------------------------------------------------ double-width arithmetic
+// Unreduced 768-bit products and a separate Montgomery reduction, for lazy reduction in Fp2 (one reduction per output
+// coefficient instead of one per product).  Rows are added into a resolved 24-limb accumulator T with two carry chains
+// (even / odd columns of the multiplicand); the carry out of a chain that ends at limb k is *counted* in C[k] instead of
+// rippling (limbs >= 12 are never read before the final resolve, so deferring the carries is exact).
+struct fpw { uint32_t l[24]; };
+#if defined(__CUDA_ARCH__)
+BLS_HD uint32_t add12c(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t cin) {      // r = a + b + cin, returns carry (0/1)
+    uint32_t cout, tmp = 0; (void)tmp;
+    BLS_ASM("add.cc.u32 %13, %38, 0xffffffff;\n\taddc.cc.u32 %0, %14, %26;\n\taddc.cc.u32 %1, %15, %27;\n\taddc.cc.u32 %2, %16, %28;\n\taddc.cc.u32 %3, %17, %29;\n\t"
+        "addc.cc.u32 %4, %18, %30;\n\taddc.cc.u32 %5, %19, %31;\n\taddc.cc.u32 %6, %20, %32;\n\taddc.cc.u32 %7, %21, %33;\n\t"
+        "addc.cc.u32 %8, %22, %34;\n\taddc.cc.u32 %9, %23, %35;\n\taddc.cc.u32 %10, %24, %36;\n\taddc.cc.u32 %11, %25, %37;\n\taddc.u32 %12, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(r[8]), "=&r"(r[9]), "=&r"(r[10]), "=&r"(r[11]), "=&r"(cout), "=&r"(tmp)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]), "r"(b[10]), "r"(b[11]), "r"(cin));
+    return cout;
+}
+BLS_HD uint32_t sub12b(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t bin) {      // r = a - b - bin, returns borrow (0/1)
+    uint32_t bout, tmp = 0; (void)tmp;
+    BLS_ASM("sub.cc.u32 %13, 0, %38;\n\tsubc.cc.u32 %0, %14, %26;\n\tsubc.cc.u32 %1, %15, %27;\n\tsubc.cc.u32 %2, %16, %28;\n\tsubc.cc.u32 %3, %17, %29;\n\t"
+        "subc.cc.u32 %4, %18, %30;\n\tsubc.cc.u32 %5, %19, %31;\n\tsubc.cc.u32 %6, %20, %32;\n\tsubc.cc.u32 %7, %21, %33;\n\t"
+        "subc.cc.u32 %8, %22, %34;\n\tsubc.cc.u32 %9, %23, %35;\n\tsubc.cc.u32 %10, %24, %36;\n\tsubc.cc.u32 %11, %25, %37;\n\tsubc.u32 %12, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(r[8]), "=&r"(r[9]), "=&r"(r[10]), "=&r"(r[11]), "=&r"(bout), "=&r"(tmp)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]), "r"(b[10]), "r"(b[11]), "r"(bin));
+    return bout & 1u;
+}
+#else
+BLS_HD uint32_t add12c(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t cin) {
+    uint64_t c = cin; uint32_t t[12];
+    for (int i = 0; i < 12; i++) { c += (uint64_t)a[i] + b[i]; t[i] = (uint32_t)c; c >>= 32; }
+    for (int i = 0; i < 12; i++) r[i] = t[i];
+    return (uint32_t)c;
+}
+BLS_HD uint32_t sub12b(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t bin) {
+    uint64_t br = bin; uint32_t t[12];
+    for (int i = 0; i < 12; i++) { uint64_t d = (uint64_t)a[i] - b[i] - br; t[i] = (uint32_t)d; br = (d >> 32) & 1; }
+    for (int i = 0; i < 12; i++) r[i] = t[i];
+    return (uint32_t)br;
+}
+#endif
+BLS_HD void fpw_add(fpw& r, const fpw& a, const fpw& b) { uint32_t c = add12c(r.l, a.l, b.l, 0); add12c(r.l + 12, a.l + 12, b.l + 12, c); }
+BLS_HD void fpw_sub(fpw& r, const fpw& a, const fpw& b) { uint32_t c = sub12b(r.l, a.l, b.l, 0); sub12b(r.l + 12, a.l + 12, b.l + 12, c); }   // mod 2^768
+
+// T = a * b, 768 bits, resolved.  a, b < 2^384 (not necessarily reduced).
+BLS_HD void fp_mul_wide(fpw& T, const fp& a, const fp& b) {
+    uint32_t C[14];
+#pragma unroll
+    for (int i = 0; i < 24; i++) T.l[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 14; i++) C[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        cmad_n(&T.l[i], C[i], a.l[0], a.l[2], a.l[4], a.l[6], a.l[8], a.l[10], b.l[i]);              // carry belongs to limb i+12
+        if (i < 11) cmad_n(&T.l[i + 1], C[i + 1], a.l[1], a.l[3], a.l[5], a.l[7], a.l[9], a.l[11], b.l[i]);   // limb i+13
+        else {      // last odd row: the top pair lands on limbs 22,23 and the product cannot carry out of limb 23
+            uint32_t drop = 0; cmad_n(&T.l[12], drop, a.l[1], a.l[3], a.l[5], a.l[7], a.l[9], a.l[11], b.l[11]);
+        }
+    }
+    // resolve: limb 12+k += C[k] (C[k] counts carries out of the chains that ended at limb 11+k)
+    uint32_t hi[12], cc[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) { hi[k] = T.l[12 + k]; cc[k] = C[k]; }
+    add12c(&T.l[12], hi, cc, 0);
+}
+// Montgomery reduction of X < p * 2^384 to [0, p)
+BLS_HD fp fp_redc_wide(const fpw& Xin) {
+    fpw X = Xin; uint32_t C[14];
+#pragma unroll
+    for (int i = 0; i < 14; i++) C[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint32_t m = X.l[i] * BLS_M0;
+        cmad_n(&X.l[i], C[i], BLS_P0, BLS_P2, BLS_P4, BLS_P6, BLS_P8, BLS_P10, m);
+        if (i < 11) cmad_n(&X.l[i + 1], C[i + 1], BLS_P1, BLS_P3, BLS_P5, BLS_P7, BLS_P9, BLS_P11, m);
+        else { uint32_t drop = 0; cmad_n(&X.l[12], drop, BLS_P1, BLS_P3, BLS_P5, BLS_P7, BLS_P9, BLS_P11, m); }   // result < 2p: no carry out of limb 23
+    }
+    fp hi, cc, t;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { hi.l[k] = X.l[12 + k]; cc.l[k] = C[k]; }
+    fp_add_raw(t, hi, cc);
+    return fp_reduce_once(t);
+}
+// p^2 (768 bits): added to a difference of two products to keep it non-negative (it is 0 mod p)
+BLS_HD fpw fpw_p_squared() { const uint32_t Q[24] = BLS_C_P_SQUARED; fpw r;
+#pragma unroll
+    for (int i = 0; i < 24; i++) r.l[i] = Q[i];
+    return r; }
+
 #if defined(__CUDACC__)
 BLS_NOINLINE fp fp_mul(fp a, fp b) { return fp_mul_inl(a, b); }
 BLS_NOINLINE fp fp_sqr(fp a) { return fp_mul_inl(a, a); }

@@ -49,6 +49,12 @@ BLS_HD fp2 fp2_csel(bool c, const fp2& a, const fp2& b) { fp2 r; r.c0 = fp_csel(
 #endif
 BLS_NOINLINE void fp2_mul_p(fp2& r, const fp2& a, const fp2& b) {   // Karatsuba: 3 products
     fp a0 = a.c0, a1 = a.c1, b0 = b.c0, b1 = b.c1;
+#if BLS_FP2_LAZY
+    { fpw T0, T1, T2; fp_mul_wide(T0, a0, b0); fp_mul_wide(T1, a1, b1);
+      fp sa, sb; fp_add_raw(sa, a0, a1); fp_add_raw(sb, b0, b1); fp_mul_wide(T2, sa, sb);
+      fpw_sub(T2, T2, T0); fpw_sub(T2, T2, T1); fpw_sub(T0, T0, T1); fpw_add(T0, T0, fpw_p_squared());
+      r.c0 = fp_redc_wide(T0); r.c1 = fp_redc_wide(T2); return; }
+#endif
     fp t0 = BLS_FPM(a0, b0), t1 = BLS_FPM(a1, b1);
     fp t2 = BLS_FPM(fp_add(a0, a1), fp_add(b0, b1));
     r.c0 = fp_sub(t0, t1); r.c1 = fp_sub(fp_sub(t2, t0), t1);
@@ -62,6 +68,9 @@ BLS_NOINLINE void fp2_mul_fp_p(fp2& r, const fp2& a, const fp& s) {
     fp a0 = a.c0, a1 = a.c1, ss = s;
     r.c0 = BLS_FPM(a0, ss); r.c1 = BLS_FPM(a1, ss);
 }
+#ifndef BLS_FP2_LAZY
+#define BLS_FP2_LAZY 0
+#endif
 #if BLS_FP2_MODE >= 2 && defined(__CUDACC__)
 // mode 2: operands and results by value in registers, three (two) calls to the out-of-line fp_mul
 // mode 3: the same with the Montgomery products inlined, so the additions can be scheduled into the IMAD stream
@@ -70,11 +79,25 @@ BLS_NOINLINE void fp2_mul_fp_p(fp2& r, const fp2& a, const fp& s) {
 #else
 #define BLS_FPM2 fp_mul
 #endif
+#if BLS_FP2_LAZY
+// Lazy reduction: three unreduced 768-bit products, double-width Karatsuba recombination, two Montgomery reductions
+// (744 IMAD.WIDE instead of 900).  c1 = T2 - T0 - T1 >= 0; c0 = T0 - T1 + p^2 in (0, 2p^2) < p 2^384.
+BLS_NOINLINE fp2 fp2_mul(fp2 a, fp2 b) {
+    fpw T0, T1, T2;
+    fp_mul_wide(T0, a.c0, b.c0); fp_mul_wide(T1, a.c1, b.c1);
+    fp sa, sb; fp_add_raw(sa, a.c0, a.c1); fp_add_raw(sb, b.c0, b.c1);          // < 2p < 2^382: no reduction needed
+    fp_mul_wide(T2, sa, sb);
+    fpw_sub(T2, T2, T0); fpw_sub(T2, T2, T1);
+    fpw_sub(T0, T0, T1); fpw_add(T0, T0, fpw_p_squared());
+    fp2 r; r.c0 = fp_redc_wide(T0); r.c1 = fp_redc_wide(T2); return r;
+}
+#else
 BLS_NOINLINE fp2 fp2_mul(fp2 a, fp2 b) {
     fp t0 = BLS_FPM2(a.c0, b.c0), t1 = BLS_FPM2(a.c1, b.c1);
     fp t2 = BLS_FPM2(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
     fp2 r; r.c0 = fp_sub(t0, t1); r.c1 = fp_sub(t2, fp_add(t0, t1)); return r;
 }
+#endif
 BLS_NOINLINE fp2 fp2_sqr(fp2 a) {
     fp t = BLS_FPM2(a.c0, a.c1);
     fp2 r; r.c0 = BLS_FPM2(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1)); r.c1 = fp_add(t, t); return r;

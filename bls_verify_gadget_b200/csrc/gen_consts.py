@@ -41,6 +41,7 @@ emit_words("BLS_C_EXP_PM3D4", (p - 3) // 4, 12)
 emit_fp("BLS_C_TWO_INV", pow(2, p - 2, p))
 emit_fp("BLS_C_FOUR", 4)
 emit_fp("BLS_C_2_256", 1 << 256)
+emit_words("BLS_C_P_SQUARED", p * p, 24)
 
 # --- G1 generator and its negation
 G1X = 0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb
