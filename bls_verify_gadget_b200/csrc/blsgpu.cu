@@ -349,7 +349,7 @@ static size_t msg_bytes_total(blsgpu_ctx* ctx, const uint32_t* off, size_t n, in
 static int gt_product(blsgpu_ctx* ctx, const u32x4* in_soa, const uint8_t* status, size_t n, u32x4* tmp_a, u32x4* tmp_b, u32x4* dst) {
     const u32x4* cur = in_soa; size_t cnt = n; const uint8_t* st = status; u32x4* bufs[2] = {tmp_a, tmp_b}; int which = 0;
     while (true) {
-        size_t T = cnt > 4096 ? 4096 : (cnt > 64 ? 64 : 1);
+        size_t T = (cnt + 7) / 8;                       // radix-8 tree: every pass multiplies 8 values per thread
         u32x4* out = T == 1 ? dst : bufs[which];
         LAUNCH(k_gt_reduce, nblk(T), TPB, cur, st, cnt, out, T);
         if (T == 1) break;
@@ -508,7 +508,7 @@ static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code
     STAGE_MARK(5);
     if (dbitmap) LAUNCH(k_status_bitmap, nblk(((n + 31) / 32) * 32, 256), 256, (const uint8_t*)dstatus, n, dbitmap);
     if (gt_acc) {
-        u32x4* ta = ws_take<u32x4>(ctx, 36 * 4096); u32x4* tb = ws_take<u32x4>(ctx, 36 * 64); u32x4* one = ws_take<u32x4>(ctx, 36);
+        u32x4* ta = ws_take<u32x4>(ctx, 36 * ((n + 7) / 8)); u32x4* tb = ws_take<u32x4>(ctx, 36 * ((n + 63) / 64)); u32x4* one = ws_take<u32x4>(ctx, 36);
         if (int rc = gt_product(ctx, f_soa, dstatus, n, ta, tb, one)) return rc;
         LAUNCH(k_gt_mul_into, 1, 32, gt_acc, (const u32x4*)one);
     }
@@ -517,7 +517,7 @@ static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code
 }
 static size_t verify_ws_bytes(size_t n, size_t mb) {
     return al(48 * n) + al(96 * n) + al(mb + 1) + al(4 * (n + 1)) + al(n) * 6 + al(96 * n) + 2 * al(192 * n) + al(576 * n) + al(8 * ((n + 63) / 64)) +
-           al(576 * 4096) + al(576 * 64) + 3 * al(576) + 65536;
+           al(576 * ((n + 7) / 8)) + al(576 * ((n + 63) / 64)) + 3 * al(576) + 65536;
 }
 #define VERIFY_CHUNK ((size_t)1 << 20)
 
@@ -586,9 +586,9 @@ int blsgpu_verify_batch(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg
 
 int blsgpu_gt_fold(blsgpu_ctx* ctx, const uint8_t* parts, size_t nparts, uint8_t* out) {
     ENTER(); if (!parts || !out || !nparts) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
-    if (int rc = ws_reserve(ctx, al(576 * nparts) * 2 + al(576 * 4096) + al(576 * 64) + 2 * al(576) + 8192)) return rc;
+    if (int rc = ws_reserve(ctx, al(576 * nparts) * 2 + al(576 * ((nparts + 7) / 8)) + al(576 * ((nparts + 63) / 64)) + 2 * al(576) + 8192)) return rc;
     const uint8_t* din; if (int rc = stage_in(ctx, din, parts, 576 * nparts)) return rc;
-    u32x4* soa = ws_take<u32x4>(ctx, 36 * nparts); u32x4* ta = ws_take<u32x4>(ctx, 36 * 4096); u32x4* tb = ws_take<u32x4>(ctx, 36 * 64); u32x4* one = ws_take<u32x4>(ctx, 36);
+    u32x4* soa = ws_take<u32x4>(ctx, 36 * nparts); u32x4* ta = ws_take<u32x4>(ctx, 36 * ((nparts + 7) / 8)); u32x4* tb = ws_take<u32x4>(ctx, 36 * ((nparts + 63) / 64)); u32x4* one = ws_take<u32x4>(ctx, 36);
     uint8_t* dout = stage_out(ctx, out, 576);
     LAUNCH(k_gt_from_bytes, nblk(nparts), TPB, din, nparts, soa);
     if (int rc = gt_product(ctx, soa, nullptr, nparts, ta, tb, one)) return rc;
