@@ -26,6 +26,7 @@ using namespace bls;
 #define BLS_TPB 128
 #endif
 #define TPB BLS_TPB
+#define VERIFY_CHUNK_DEFAULT ((size_t)1 << 20)
 #ifndef BLS_MINB
 #define BLS_MINB 2      // resident 128-thread CTAs per SM the heavy kernels are compiled for (register cap = 65536 / (128 * BLS_MINB))
 #endif
@@ -292,6 +293,7 @@ struct blsgpu_ctx {
     int device; cudaStream_t own_stream, stream; int ptr_mode; char err[512];
     uint8_t* ws; size_t ws_bytes, ws_used; unsigned long long launches;
     struct r1cs_sys* r1cs[16];
+    size_t chunk;                       // items per internal pass of verify_batch (bounds the workspace); multiple of 64
     int prof; cudaEvent_t ev[8];        // stage boundaries of the last verify_batch chunk: g1 | g2 | hash | miller | final | epilogue
 };
 #define STAGE_MARK(k) do { if (ctx->prof) CU(cudaEventRecord(ctx->ev[k], ctx->stream)); } while (0)
@@ -372,7 +374,7 @@ int blsgpu_create(blsgpu_ctx** out, int device) {
     if (prop.major != 10) return BLSGPU_ERR_CUDA;                         // sm_100a cubin only: no other device can run it
     if (cudaSetDevice(device) != cudaSuccess) return BLSGPU_ERR_CUDA;
     blsgpu_ctx* c = new (std::nothrow) blsgpu_ctx(); if (!c) return BLSGPU_ERR_ALLOC;
-    memset(c, 0, sizeof *c); c->device = device; c->ptr_mode = BLSGPU_HOST;
+    memset(c, 0, sizeof *c); c->device = device; c->ptr_mode = BLSGPU_HOST; c->chunk = VERIFY_CHUNK_DEFAULT;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return BLSGPU_ERR_CUDA; }
     c->stream = c->own_stream;
     *out = c; return 0;
@@ -392,6 +394,7 @@ int blsgpu_set_stream(blsgpu_ctx* ctx, void* s, int use_own) { if (!ctx) return 
 int blsgpu_set_pointer_mode(blsgpu_ctx* ctx, int mode) { if (!ctx || (mode != BLSGPU_HOST && mode != BLSGPU_DEVICE)) return BLSGPU_ERR_ARG; ctx->ptr_mode = mode; return 0; }
 int blsgpu_synchronize(blsgpu_ctx* ctx) { if (!ctx) return BLSGPU_ERR_ARG; CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); return 0; }
 uint64_t blsgpu_launch_count(blsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int blsgpu_set_chunk(blsgpu_ctx* ctx, size_t items) { if (!ctx || items < 64 || (items & 63)) return BLSGPU_ERR_ARG; ctx->chunk = items; return 0; }
 int blsgpu_set_profiling(blsgpu_ctx* ctx, int on) {
     if (!ctx) return BLSGPU_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
@@ -519,16 +522,14 @@ static size_t verify_ws_bytes(size_t n, size_t mb) {
     return al(48 * n) + al(96 * n) + al(mb + 1) + al(4 * (n + 1)) + al(n) * 6 + al(96 * n) + 2 * al(192 * n) + al(576 * n) + al(8 * ((n + 63) / 64)) +
            al(576 * ((n + 7) / 8)) + al(576 * ((n + 63) / 64)) + 3 * al(576) + 65536;
 }
-#define VERIFY_CHUNK ((size_t)1 << 20)
-
 int blsgpu_verify_batch(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg, const uint32_t* msg_off, const uint8_t* sig96, size_t n,
                         uint8_t* status, uint64_t* ok_bitmap, uint8_t* gt_acc_le576) {
     ENTER(); if (!pk48 || !msg || !sig96 || !status) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
     int rc = 0;
     // chunks of <= 2^20 items bound the workspace at ~1.2 GB; chunk boundaries are multiples of 64 so bitmaps concatenate
     uint8_t gt_host[576];
-    for (size_t base = 0; base < n; base += VERIFY_CHUNK) {
-        size_t m = n - base < VERIFY_CHUNK ? n - base : VERIFY_CHUNK;
+    for (size_t base = 0; base < n; base += ctx->chunk) {
+        size_t m = n - base < ctx->chunk ? n - base : ctx->chunk;
         size_t mb0 = 0, mb = 32 * m;
         const uint32_t* off_chunk = msg_off ? msg_off + base : nullptr;
         if (msg_off) {
@@ -560,7 +561,7 @@ int blsgpu_verify_batch(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg
             // per-chunk GT partial -> bytes; chunks are folded on the host side of the ABI through blsgpu_gt_fold's kernel path
             uint8_t* dgt = ws_take<uint8_t>(ctx, 576);
             LAUNCH(k_gt_to_bytes, 1, TPB, (const u32x4*)gt_acc, (size_t)1, dgt, (const uint8_t*)nullptr);
-            if (n <= VERIFY_CHUNK) {
+            if (n <= ctx->chunk) {
                 if (ctx->ptr_mode == BLSGPU_DEVICE) CU(cudaMemcpyAsync(gt_acc_le576, dgt, 576, cudaMemcpyDeviceToDevice, ctx->stream));
                 else CU(cudaMemcpyAsync(gt_acc_le576, dgt, 576, cudaMemcpyDeviceToHost, ctx->stream));
             } else {
@@ -579,7 +580,7 @@ int blsgpu_verify_batch(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg
                 }
             }
         }
-        if (ctx->ptr_mode == BLSGPU_HOST || n > VERIFY_CHUNK) CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->ptr_mode == BLSGPU_HOST || n > ctx->chunk) CU(cudaStreamSynchronize(ctx->stream));
     }
     return 0;
 }

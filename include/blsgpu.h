@@ -66,6 +66,8 @@ uint64_t blsgpu_launch_count(blsgpu_ctx* ctx);
  * blsgpu_stage_times synchronises and returns the device time in ms of the last call's (last chunk's) stages:
  * [0] decode+check G1, [1] decode+check G2, [2] hash-to-G2, [3] Miller loop, [4] final exponentiation, [5] epilogue */
 int blsgpu_set_profiling(blsgpu_ctx* ctx, int on);
+/* blsgpu_verify_batch works in internal passes of at most `items` triples (default 2^20, ~1.2 GB of workspace); a multiple of 64 */
+int blsgpu_set_chunk(blsgpu_ctx* ctx, size_t items);
 int blsgpu_stage_times(blsgpu_ctx* ctx, float ms6[6]);
 
 /* ---- BLS::verify over a batch  (replaces <BLS<P> as SignatureScheme>::verify, src/bls.rs:427-458, incl. the

@@ -29,4 +29,35 @@ extern "C" int dev_run_op(int op, const uint8_t* in, uint8_t* out, size_t n) {
     cudaMemcpy(out, dout, bo, cudaMemcpyDeviceToHost); cudaFree(din); cudaFree(dout);
     return e == cudaSuccess ? 0 : -3;
 }
+
+// ---- throughput ladder (profiles/r01_tuning.md): `reps` dependent applications of one primitive per thread, output fed back
+template <int OP> __global__ void __launch_bounds__(128, 2) k_bench_op(const fp* in, fp* out, size_t n, int n_in, int n_out, int reps) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    fp a[24], r[12];
+    for (int k = 0; k < n_in; k++) a[k] = in[i * n_in + k];
+    for (int k = 0; k < n_out; k++) r[k] = fp_zero();
+    for (int it = 0; it < reps; it++) { run_op(OP, a, r); for (int k = 0; k < n_out && k < n_in; k++) a[k] = r[k]; }
+    for (int k = 0; k < n_out; k++) out[i * n_out + k] = r[k];
+}
+template <int OP> static void launch_bench(const fp* din, fp* dout, size_t n, op_desc d, int reps) { k_bench_op<OP><<<(unsigned)((n + 127) / 128), 128>>>(din, dout, n, d.n_in, d.n_out, reps); }
+extern "C" float dev_bench_op(int op, size_t n, int reps) {
+    op_desc d = op_shape(op); if (!d.n_in) return -1.f;
+    fp *din, *dout; size_t bi = n * d.n_in * 48, bo = n * d.n_out * 48;
+    if (cudaMalloc(&din, bi) != cudaSuccess || cudaMalloc(&dout, bo) != cudaSuccess) return -2.f;
+    cudaMemset(din, 0x11, bi);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+        cudaEventRecord(e0);
+        switch (op) {
+#define L(K) case K: launch_bench<K>(din, dout, n, d, reps); break;
+            L(21) L(1) L(2) L(3) L(8) L(9) L(10) L(11) L(12) L(5) L(6)
+#undef L
+            default: return -1.f;
+        }
+        cudaEventRecord(e1); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); if (r && ms < best) best = ms;
+    }
+    cudaFree(din); cudaFree(dout);
+    return best;
+}
+
 extern "C" void dev_op_shape(int op, int* n_in, int* n_out) { op_desc d = op_shape(op); *n_in = d.n_in; *n_out = d.n_out; }

@@ -311,3 +311,34 @@ def test_device_primitives_match_host_emulation():
     sys.path.insert(0, os.path.join(ROOT, "tests", "devcheck"))
     import run_devcheck
     for seed in (1, 2): assert run_devcheck.check(n=512, seed=seed) == []
+
+# ------------------------------------------------------------------------------------------ boundary behaviour of the ABI
+def test_empty_batch_and_multi_chunk_paths(ctx, C):
+    """n = 0 is a no-op; a batch larger than the internal chunk (set to 64 here) takes the multi-pass path: statuses, bitmap
+    words and the folded GT accumulator must equal the single-pass results, with ragged messages and in both pointer modes."""
+    import torch
+    from bls_verify_gadget_b200 import synth
+    assert ctx.verify(b"", [], b"").size == 0 and ctx.hash_to_g2([]).size == 0
+    rng = np.random.default_rng(33); n = 200
+    sk = synth.secret_keys(n); msgs = [rng.bytes(int(l)) for l in rng.integers(0, 90, size=n)]
+    pk, _ = ctx.sk_to_pk(sk); sig, _ = ctx.sign(sk, msgs)
+    sig = sig.reshape(n, 96).copy(); sig[[3, 64, 130, 199]] = sig[[4, 65, 131, 0]]; sig = sig.reshape(-1)
+    st0, bm0, gt0 = ctx.verify(pk, msgs, sig, want_bitmap=True, want_gt=True)
+    ctx.set_chunk(64)
+    try:
+        st1, bm1, gt1 = ctx.verify(pk, msgs, sig, want_bitmap=True, want_gt=True)
+        assert np.array_equal(st0, st1) and np.array_equal(bm0, bm1) and gt0.tobytes() == gt1.tobytes() and (st0 != 0).sum() == 4
+        # device-pointer mode, fixed 32-byte messages, multi-chunk
+        m32 = synth.messages(n); sig32, _ = ctx.sign(sk, m32, fixed32=True)
+        ref = ctx.verify(pk, m32, sig32, fixed32=True)
+        dev = torch.device("cuda", 0)
+        d = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (pk, m32, sig32)]
+        dst = torch.zeros(n, dtype=torch.uint8, device=dev); dbm = torch.zeros((n + 63) // 64, dtype=torch.int64, device=dev); dgt = torch.zeros(576, dtype=torch.uint8, device=dev)
+        ctx.set_pointer_mode(True)
+        ctx.verify_ptr(d[0].data_ptr(), d[1].data_ptr(), None, d[2].data_ptr(), n, dst.data_ptr(), dbm.data_ptr(), dgt.data_ptr()); ctx.synchronize()
+        ctx.set_pointer_mode(False)
+        assert np.array_equal(dst.cpu().numpy(), ref) and not ref.any()
+        assert dgt.cpu().numpy().tobytes() == C.pairing_gt(b"", b"").tobytes()          # all valid: accumulator is one
+        assert int(np.unpackbits(dbm.cpu().numpy().view(np.uint8), bitorder="little").sum()) == n
+    finally:
+        ctx.set_pointer_mode(False); ctx.set_chunk(1 << 20)
