@@ -33,7 +33,7 @@ def lib():
     return _lib
 
 EXPORTS = ["blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_set_stream", "blsgpu_set_pointer_mode", "blsgpu_synchronize",
-           "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_verify_batch", "blsgpu_fast_aggregate_verify_batch", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
+           "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_verify_batch", "blsgpu_fast_aggregate_verify_batch", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
            "blsgpu_g2_aggregate", "blsgpu_deserialize_g1", "blsgpu_deserialize_g2", "blsgpu_sk_to_pk_batch", "blsgpu_sign_batch", "blsgpu_pairing_gt",
            "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free"]
 
@@ -71,6 +71,7 @@ class Context:
     def set_pointer_mode(self, device): self._ck(lib().blsgpu_set_pointer_mode(self._h, 1 if device else 0))
     def synchronize(self): self._ck(lib().blsgpu_synchronize(self._h))
     def launch_count(self): return int(lib().blsgpu_launch_count(self._h))
+    def set_lanes(self, lanes): self._ck(lib().blsgpu_set_lanes(self._h, int(lanes)))
     def set_chunk(self, items): self._ck(lib().blsgpu_set_chunk(self._h, _sz(items)))
     def set_profiling(self, on=True): self._ck(lib().blsgpu_set_profiling(self._h, 1 if on else 0))
     def stage_times(self):

@@ -293,6 +293,7 @@ struct blsgpu_ctx {
     int device; cudaStream_t own_stream, stream; int ptr_mode; char err[512];
     uint8_t* ws; size_t ws_bytes, ws_used; unsigned long long launches;
     struct r1cs_sys* r1cs[16];
+    int lanes; cudaStream_t lane_stream[4]; cudaEvent_t lane_done[4], fork;   // concurrent sub-ranges of a verify pass
     size_t chunk;                       // items per internal pass of verify_batch (bounds the workspace); multiple of 64
     int prof; cudaEvent_t ev[8];        // stage boundaries of the last verify_batch chunk: g1 | g2 | hash | miller | final | epilogue
 };
@@ -374,7 +375,7 @@ int blsgpu_create(blsgpu_ctx** out, int device) {
     if (prop.major != 10) return BLSGPU_ERR_CUDA;                         // sm_100a cubin only: no other device can run it
     if (cudaSetDevice(device) != cudaSuccess) return BLSGPU_ERR_CUDA;
     blsgpu_ctx* c = new (std::nothrow) blsgpu_ctx(); if (!c) return BLSGPU_ERR_ALLOC;
-    memset(c, 0, sizeof *c); c->device = device; c->ptr_mode = BLSGPU_HOST; c->chunk = VERIFY_CHUNK_DEFAULT;
+    memset(c, 0, sizeof *c); c->device = device; c->ptr_mode = BLSGPU_HOST; c->chunk = VERIFY_CHUNK_DEFAULT; c->lanes = 2;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return BLSGPU_ERR_CUDA; }
     c->stream = c->own_stream;
     *out = c; return 0;
@@ -386,6 +387,7 @@ void blsgpu_destroy(blsgpu_ctx* ctx) {
     for (int i = 0; i < 16; i++) if (ctx->r1cs[i]) blsgpu_r1cs_free(ctx, i);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ev[0]) for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->lane_stream[0]) { for (int l = 0; l < 4; l++) { cudaStreamDestroy(ctx->lane_stream[l]); cudaEventDestroy(ctx->lane_done[l]); } cudaEventDestroy(ctx->fork); }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -394,6 +396,7 @@ int blsgpu_set_stream(blsgpu_ctx* ctx, void* s, int use_own) { if (!ctx) return 
 int blsgpu_set_pointer_mode(blsgpu_ctx* ctx, int mode) { if (!ctx || (mode != BLSGPU_HOST && mode != BLSGPU_DEVICE)) return BLSGPU_ERR_ARG; ctx->ptr_mode = mode; return 0; }
 int blsgpu_synchronize(blsgpu_ctx* ctx) { if (!ctx) return BLSGPU_ERR_ARG; CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); return 0; }
 uint64_t blsgpu_launch_count(blsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int blsgpu_set_lanes(blsgpu_ctx* ctx, int lanes) { if (!ctx || lanes < 1 || lanes > 4) return BLSGPU_ERR_ARG; ctx->lanes = lanes; return 0; }
 int blsgpu_set_chunk(blsgpu_ctx* ctx, size_t items) { if (!ctx || items < 64 || (items & 63)) return BLSGPU_ERR_ARG; ctx->chunk = items; return 0; }
 int blsgpu_set_profiling(blsgpu_ctx* ctx, int on) {
     if (!ctx) return BLSGPU_ERR_ARG;
@@ -522,50 +525,88 @@ static size_t verify_ws_bytes(size_t n, size_t mb) {
     return al(48 * n) + al(96 * n) + al(mb + 1) + al(4 * (n + 1)) + al(n) * 6 + al(96 * n) + 2 * al(192 * n) + al(576 * n) + al(8 * ((n + 63) / 64)) +
            al(576 * ((n + 7) / 8)) + al(576 * ((n + 63) / 64)) + 3 * al(576) + 65536;
 }
+// One contiguous sub-range [base, base+m) of a verify batch, enqueued entirely on ctx->stream (the caller may have pointed
+// it at a lane stream): staging, the five stage kernels, epilogue, outputs, and the range's GT partial (limb-SoA, n = 1).
+static int verify_range(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg, const uint32_t* msg_off, const uint8_t* sig96, size_t base, size_t m,
+                        uint8_t* status, uint64_t* ok_bitmap, u32x4* gt_acc, size_t mb0, size_t mb) {
+    int rc = 0;
+    const uint8_t *dpk, *dsig, *dmsg; const uint32_t* doff;
+    if ((rc = stage_in(ctx, dpk, pk48 + 48 * base, 48 * m))) return rc;
+    if ((rc = stage_in(ctx, dsig, sig96 + 96 * base, 96 * m))) return rc;
+    if (ctx->ptr_mode == BLSGPU_HOST) {
+        // offsets in a host range are rebased by the kernel through (msg - mb0): stage the range's bytes only
+        if ((rc = stage_in(ctx, dmsg, msg + mb0, mb ? mb : 1))) return rc;
+        dmsg -= msg_off ? mb0 : 0;
+    } else dmsg = msg_off ? msg : msg + mb0;
+    if ((rc = stage_in(ctx, doff, msg_off ? msg_off + base : nullptr, m + 1))) return rc;
+    uint8_t* dstatus = stage_out(ctx, status + base, m);
+    uint32_t* dbitmap = (uint32_t*)stage_out(ctx, ok_bitmap ? ok_bitmap + base / 64 : nullptr, (m + 63) / 64);
+    u32x4* pk_soa = ws_take<u32x4>(ctx, 6 * m); uint8_t* code_pk = ws_take<uint8_t>(ctx, m);
+    if (gt_acc) LAUNCH(k_gt_set_one, 1, 32, gt_acc);
+    if (dbitmap) CU(cudaMemsetAsync(dbitmap, 0, 8 * ((m + 63) / 64), ctx->stream));
+    STAGE_MARK(0);
+    LAUNCH(k_decode_g1, nblk(m), TPB, dpk, m, pk_soa, code_pk);
+    if ((rc = verify_core(ctx, pk_soa, code_pk, dmsg, doff, dsig, m, dstatus, dbitmap, gt_acc))) return rc;
+    if ((rc = finish_out(ctx, status + base, dstatus, m))) return rc;
+    if (ok_bitmap && (rc = finish_out(ctx, ok_bitmap + base / 64, (uint64_t*)dbitmap, (m + 63) / 64))) return rc;
+    return 0;
+}
+#define MAX_LANES 4
+static int ensure_lanes(blsgpu_ctx* ctx) {
+    if (ctx->lane_stream[0]) return 0;
+    for (int l = 0; l < MAX_LANES; l++) { CU(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&ctx->lane_done[l], cudaEventDisableTiming)); }
+    CU(cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
+    return 0;
+}
+
 int blsgpu_verify_batch(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg, const uint32_t* msg_off, const uint8_t* sig96, size_t n,
                         uint8_t* status, uint64_t* ok_bitmap, uint8_t* gt_acc_le576) {
     ENTER(); if (!pk48 || !msg || !sig96 || !status) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
     int rc = 0;
-    // chunks of <= 2^20 items bound the workspace at ~1.2 GB; chunk boundaries are multiples of 64 so bitmaps concatenate
+    // Passes of <= ctx->chunk items bound the workspace (~1.2 GB at 2^20).  Inside a pass the items are split into `lanes`
+    // contiguous sub-ranges enqueued on separate streams: the stage kernels of different sub-ranges are independent, so the
+    // tail wave of one kernel overlaps the next sub-range's kernels (and, in host mode, its H2D copies) instead of idling SMs.
+    // All range boundaries are multiples of 64 so bitmap words never straddle ranges.
     uint8_t gt_host[576];
+    const uint32_t* off_host = ctx->ptr_mode == BLSGPU_HOST ? msg_off : nullptr;
+    size_t total_mb = 0;
+    if (msg_off && !off_host) { total_mb = msg_bytes_total(ctx, msg_off, n, rc); if (rc) return fail(ctx, rc, "reading msg_off failed"); }
     for (size_t base = 0; base < n; base += ctx->chunk) {
         size_t m = n - base < ctx->chunk ? n - base : ctx->chunk;
-        size_t mb0 = 0, mb = 32 * m;
-        const uint32_t* off_chunk = msg_off ? msg_off + base : nullptr;
-        if (msg_off) {
-            if (ctx->ptr_mode == BLSGPU_HOST) { mb0 = msg_off[base]; mb = msg_off[base + m] - mb0; }
-            else { mb = msg_bytes_total(ctx, msg_off, n, rc); if (rc) return fail(ctx, rc, "reading msg_off failed"); }
-        } else mb0 = 32 * base;
-        if ((rc = ws_reserve(ctx, verify_ws_bytes(m, mb)))) return rc;
-        const uint8_t *dpk, *dsig, *dmsg; const uint32_t* doff;
-        if ((rc = stage_in(ctx, dpk, pk48 + 48 * base, 48 * m))) return rc;
-        if ((rc = stage_in(ctx, dsig, sig96 + 96 * base, 96 * m))) return rc;
-        if (ctx->ptr_mode == BLSGPU_HOST) {
-            // offsets in a host chunk are rebased by the kernel through (msg - mb0): stage the chunk's bytes only
-            if ((rc = stage_in(ctx, dmsg, msg + mb0, mb ? mb : 1))) return rc;
-            dmsg -= msg_off ? mb0 : 0;
-        } else dmsg = msg_off ? msg : msg + mb0;
-        if ((rc = stage_in(ctx, doff, off_chunk, m + 1))) return rc;
-        uint8_t* dstatus = stage_out(ctx, status ? status + base : nullptr, m);
-        uint32_t* dbitmap = (uint32_t*)stage_out(ctx, ok_bitmap ? ok_bitmap + base / 64 : nullptr, (m + 63) / 64);
-        u32x4* pk_soa = ws_take<u32x4>(ctx, 6 * m); uint8_t* code_pk = ws_take<uint8_t>(ctx, m);
-        u32x4* gt_acc = nullptr;
-        if (gt_acc_le576) { gt_acc = ws_take<u32x4>(ctx, 36); LAUNCH(k_gt_set_one, 1, 32, gt_acc); }
-        if (dbitmap) CU(cudaMemsetAsync(dbitmap, 0, 8 * ((m + 63) / 64), ctx->stream));
-        STAGE_MARK(0);
-        LAUNCH(k_decode_g1, nblk(m), TPB, dpk, m, pk_soa, code_pk);
-        if ((rc = verify_core(ctx, pk_soa, code_pk, dmsg, doff, dsig, m, dstatus, dbitmap, gt_acc))) return rc;
-        if ((rc = finish_out(ctx, status + base, dstatus, m))) return rc;
-        if (ok_bitmap && (rc = finish_out(ctx, ok_bitmap + base / 64, (uint64_t*)dbitmap, (m + 63) / 64))) return rc;
+        int lanes = ctx->lanes; if (lanes > MAX_LANES) lanes = MAX_LANES;
+        while (lanes > 1 && m / lanes < 8192) lanes--;                     // keep every lane above ~0.2 waves of CTAs
+        size_t per = ((m + lanes - 1) / lanes + 63) & ~(size_t)63;
+        size_t ws = 65536;
+        for (int l = 0; l < lanes; l++) {
+            size_t lo = base + l * per, hi = lo + per < base + m ? lo + per : base + m; if (lo >= hi) break;
+            size_t mb = msg_off ? (off_host ? off_host[hi] - off_host[lo] : total_mb) : 32 * (hi - lo);
+            ws += verify_ws_bytes(hi - lo, ctx->ptr_mode == BLSGPU_HOST ? mb : 0) + 4096;
+        }
+        if ((rc = ws_reserve(ctx, ws))) return rc;
+        u32x4* gt_lane[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+        cudaStream_t main_stream = ctx->stream;
+        if (lanes > 1) { if ((rc = ensure_lanes(ctx))) return rc; CU(cudaEventRecord(ctx->fork, main_stream)); }
+        int used = 0;
+        for (int l = 0; l < lanes; l++) {
+            size_t lo = base + l * per, hi = lo + per < base + m ? lo + per : base + m; if (lo >= hi) break;
+            size_t mb0 = msg_off ? (off_host ? off_host[lo] : 0) : 32 * lo;
+            size_t mb = msg_off ? (off_host ? off_host[hi] - off_host[lo] : 0) : 32 * (hi - lo);
+            if (gt_acc_le576) gt_lane[l] = ws_take<u32x4>(ctx, 36);
+            if (lanes > 1) { ctx->stream = ctx->lane_stream[l]; cudaStreamWaitEvent(ctx->stream, ctx->fork, 0); }
+            rc = verify_range(ctx, pk48, msg, msg_off, sig96, lo, hi - lo, status, ok_bitmap, gt_lane[l], mb0, mb);
+            if (lanes > 1) { if (!rc) cudaEventRecord(ctx->lane_done[l], ctx->stream); ctx->stream = main_stream; }
+            if (rc) return rc;
+            used = l + 1;
+        }
+        if (lanes > 1) for (int l = 0; l < used; l++) CU(cudaStreamWaitEvent(main_stream, ctx->lane_done[l], 0));
         if (gt_acc_le576) {
-            // per-chunk GT partial -> bytes; chunks are folded on the host side of the ABI through blsgpu_gt_fold's kernel path
+            for (int l = 1; l < used; l++) LAUNCH(k_gt_mul_into, 1, 32, gt_lane[0], (const u32x4*)gt_lane[l]);
             uint8_t* dgt = ws_take<uint8_t>(ctx, 576);
-            LAUNCH(k_gt_to_bytes, 1, TPB, (const u32x4*)gt_acc, (size_t)1, dgt, (const uint8_t*)nullptr);
+            LAUNCH(k_gt_to_bytes, 1, TPB, (const u32x4*)gt_lane[0], (size_t)1, dgt, (const uint8_t*)nullptr);
             if (n <= ctx->chunk) {
-                if (ctx->ptr_mode == BLSGPU_DEVICE) CU(cudaMemcpyAsync(gt_acc_le576, dgt, 576, cudaMemcpyDeviceToDevice, ctx->stream));
-                else CU(cudaMemcpyAsync(gt_acc_le576, dgt, 576, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaMemcpyAsync(gt_acc_le576, dgt, 576, ctx->ptr_mode == BLSGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
             } else {
-                // multi-chunk: fold sequentially (synchronises; only taken for n > 2^20)
+                // several passes: fold the pass partials one by one (synchronises; only taken for n > chunk)
                 uint8_t part[2][576];
                 CU(cudaMemcpyAsync(part[1], dgt, 576, cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream));
                 if (base == 0) memcpy(gt_host, part[1], 576);

@@ -68,6 +68,10 @@ uint64_t blsgpu_launch_count(blsgpu_ctx* ctx);
 int blsgpu_set_profiling(blsgpu_ctx* ctx, int on);
 /* blsgpu_verify_batch works in internal passes of at most `items` triples (default 2^20, ~1.2 GB of workspace); a multiple of 64 */
 int blsgpu_set_chunk(blsgpu_ctx* ctx, size_t items);
+/* inside a pass the items are split into `lanes` (1..4, default 2) sub-ranges enqueued on separate internal streams that fork from and
+ * join the context's stream, so that the tail wave of a stage kernel overlaps the other sub-range's work; 1 = strictly serial kernels
+ * (use it with blsgpu_set_profiling: stage events of concurrent lanes would overlap) */
+int blsgpu_set_lanes(blsgpu_ctx* ctx, int lanes);
 int blsgpu_stage_times(blsgpu_ctx* ctx, float ms6[6]);
 
 /* ---- BLS::verify over a batch  (replaces <BLS<P> as SignatureScheme>::verify, src/bls.rs:427-458, incl. the

@@ -232,6 +232,11 @@ def test_verify_large_batch_properties(ctx):
     st, bm, gt = ctx.verify(pk, msg, sig, want_bitmap=True, want_gt=True, fixed32=True)
     assert np.array_equal(st, exp)
     assert np.array_equal(np.unpackbits(bm.view(np.uint8), bitorder="little")[:n], (st == 0).astype(np.uint8))
+    for lanes in (1, 4):                                                  # serial kernels vs four concurrent sub-range streams
+        ctx.set_lanes(lanes)
+        st_l, bm_l, gt_l = ctx.verify(pk, msg, sig, want_bitmap=True, want_gt=True, fixed32=True)
+        assert np.array_equal(st_l, st) and np.array_equal(bm_l, bm) and gt_l.tobytes() == gt.tobytes()
+    ctx.set_lanes(2)
     perm = np.random.default_rng(2).permutation(n)
     st2, gt2 = ctx.verify(pk.reshape(n, 48)[perm].reshape(-1), msg.reshape(n, 32)[perm].reshape(-1), sig.reshape(n, 96)[perm].reshape(-1), want_gt=True, fixed32=True)
     assert np.array_equal(st2, exp[perm]) and gt2.tobytes() == gt.tobytes()
