@@ -174,7 +174,16 @@ struct Fp12 { Fp6 c0, c1; };
 static inline Fp6 operator+(const Fp6& a, const Fp6& b) { return {a.c0 + b.c0, a.c1 + b.c1, a.c2 + b.c2}; }
 static inline Fp6 operator-(const Fp6& a, const Fp6& b) { return {a.c0 - b.c0, a.c1 - b.c1, a.c2 - b.c2}; }
 static inline Fp6 operator-(const Fp6& a) { return {-a.c0, -a.c1, -a.c2}; }
+// ORA_FAST selects the algorithm set: 0 (default, used by every parity test) = the simple forms described in the header;
+// 1 = the forms arkworks itself uses (Karatsuba Fp6, cyclotomic squaring, endomorphism subgroup tests, psi cofactor clearing),
+// used only by the timed CPU-baseline legs so that the reported CPU figure is not handicapped.  tests/test_oracle_golden.py
+// checks that both sets produce identical bytes.
+static int ORA_FAST = 0;
 static Fp6 operator*(const Fp6& a, const Fp6& b) {
+    if (ORA_FAST) {
+        Fp2 v0 = a.c0 * b.c0, v1 = a.c1 * b.c1, v2 = a.c2 * b.c2;
+        return {v0 + mul_xi((a.c1 + a.c2) * (b.c1 + b.c2) - v1 - v2), (a.c0 + a.c1) * (b.c0 + b.c1) - v0 - v1 + mul_xi(v2), (a.c0 + a.c2) * (b.c0 + b.c2) - v0 - v2 + v1};
+    }
     return {a.c0 * b.c0 + mul_xi(a.c1 * b.c2 + a.c2 * b.c1),
             a.c0 * b.c1 + a.c1 * b.c0 + mul_xi(a.c2 * b.c2),
             a.c0 * b.c2 + a.c1 * b.c1 + a.c2 * b.c0};
@@ -285,7 +294,27 @@ static u8 R_BE[32], HEFF_BE[80];
 static G1A G1_GEN, G1_GEN_NEG;
 static bool on_curve(const G1A& a) { return a.inf || feq(fsqr(a.y), fadd(fmul(fsqr(a.x), a.x), B1)); }
 static bool on_curve(const G2A& a) { return a.inf || sqr(a.y) == sqr(a.x) * a.x + B2C; }
-template <class F> static bool in_subgroup(const Aff<F>& a) { return f_zero(smul(to_jac(a), R_BE, 32).Z); }   // [r]P == O
+static Fp BETA; static Fp2 PSI_CX, PSI_CY; static u8 X_BE[8];
+template <class F> static bool jac_eq_aff(const Jac<F>& p, const Aff<F>& q) {
+    if (f_zero(p.Z)) return q.inf;
+    if (q.inf) return false;
+    F zz = f_sqr(p.Z); return f_eq(p.X, f_mul(q.x, zz)) && f_eq(p.Y, f_mul(q.y, f_mul(zz, p.Z)));
+}
+static G2J psi(const G2J& p) { return {conj(p.X) * PSI_CX, conj(p.Y) * PSI_CY, conj(p.Z)}; }
+static bool in_subgroup_slow(const G1A& a) { return f_zero(smul(to_jac(a), R_BE, 32).Z); }   // [r]P == O
+static bool in_subgroup_slow(const G2A& a) { return f_zero(smul(to_jac(a), R_BE, 32).Z); }
+static bool in_subgroup(const G1A& a) {
+    if (!ORA_FAST || a.inf) return in_subgroup_slow(a);
+    G1J t = smul(smul(to_jac(a), X_BE, 8), X_BE, 8);                     // [x^2]P
+    G1A s = {fmul(a.x, BETA), fneg(a.y), false};                         // -sigma(P)
+    return jac_eq_aff(t, s);
+}
+static bool in_subgroup(const G2A& a) {
+    if (!ORA_FAST || a.inf) return in_subgroup_slow(a);
+    G2J t = smul(to_jac(a), X_BE, 8);                                    // [|x|]P = -[x]P
+    G2J ps = psi(to_jac(a)); G2A s = {ps.X, -ps.Y, false};               // -psi(P)   (Z = 1)
+    return jac_eq_aff(t, s);
+}
 
 // ---------------------------------------------------------------------------------------- ZCash compressed codec
 enum { DE_OK = 0, DE_FLAGS = 1, DE_RANGE = 2, DE_CURVE = 3, DE_SUBGROUP = 4 };
@@ -408,7 +437,15 @@ static G2J map_uncleared(const u8* msg, size_t mlen) {
     Fp2 x0, y0, x1, y1; sswu(x0, y0, u[0]); sswu(x1, y1, u[1]);
     return add(to_jac(iso3(x0, y0)), to_jac(iso3(x1, y1)));
 }
-static G2A hash_to_g2(const u8* msg, size_t mlen) { return to_aff(smul(map_uncleared(msg, mlen), HEFF_BE, 80)); }
+static G2J clear_cofactor_psi(const G2J& P) {              // Budroni-Pintore: [x^2-x-1]P + [x-1]psi(P) + psi^2(2P)
+    G2J t1 = neg(smul(P, X_BE, 8)), t2 = psi(P), t3 = psi(psi(dbl(P)));
+    t3 = add(t3, neg(t2)); t2 = add(t1, t2); t2 = neg(smul(t2, X_BE, 8)); t3 = add(t3, t2); t3 = add(t3, neg(t1));
+    return add(t3, neg(P));
+}
+static G2A hash_to_g2(const u8* msg, size_t mlen) {
+    G2J m = map_uncleared(msg, mlen);
+    return to_aff(ORA_FAST ? clear_cofactor_psi(m) : smul(m, HEFF_BE, 80));
+}
 
 // ---------------------------------------------------------------------------------------- pairing (ark-ec bls12 style)
 static const u64 X_ABS = 0xd201000000010000ULL;
@@ -445,9 +482,18 @@ static Fp12 miller(const G1A* ps, const G2A* qs, int n) {
     }
     return conj(f);
 }
+static void fp4_sqr(Fp2& t0, Fp2& t1, const Fp2& a, const Fp2& b) { Fp2 ab = a * b; t0 = (a + b) * (a + mul_xi(b)) - ab - mul_xi(ab); t1 = ab + ab; }
+static Fp12 cyclo_sqr(const Fp12& a) {                     // Granger-Scott, valid in the cyclotomic subgroup
+    Fp2 t0, t1, t2, t3, t4, t5; fp4_sqr(t0, t1, a.c0.c0, a.c1.c1); fp4_sqr(t2, t3, a.c1.c0, a.c0.c2); fp4_sqr(t4, t5, a.c0.c1, a.c1.c2);
+    auto f = [](const Fp2& t, const Fp2& z, bool plus) { Fp2 d = plus ? t + z : t - z; return d + d + t; };
+    Fp12 r; Fp2 x5 = mul_xi(t5);
+    r.c0.c0 = f(t0, a.c0.c0, false); r.c1.c1 = f(t1, a.c1.c1, true); r.c1.c0 = f(x5, a.c1.c0, true);
+    r.c0.c2 = f(t4, a.c0.c2, false); r.c0.c1 = f(t2, a.c0.c1, false); r.c1.c2 = f(t3, a.c1.c2, true);
+    return r;
+}
 static Fp12 exp_by_x(const Fp12& a) {                      // a^x, x negative; a in the cyclotomic subgroup
     Fp12 r = F12_ONE;
-    for (int i = 63; i >= 0; i--) { r = sqr(r); if ((X_ABS >> i) & 1) r = r * a; }
+    for (int i = 63; i >= 0; i--) { r = ORA_FAST ? cyclo_sqr(r) : sqr(r); if ((X_ABS >> i) & 1) r = r * a; }
     return conj(r);
 }
 static Fp12 final_exp(const Fp12& f) {                     // ark-ec bls12 final_exponentiation: f^(3(p^12-1)/r)
@@ -487,12 +533,21 @@ static void init() {
     B1 = fp_from_u64(4); B2C = {B1, B1};
     Fp2 xi = {FP_ONE, FP_ONE}, g = pow2(xi, E_PM1D6.l, 6);
     FROB_G[0] = F2_ONE; for (int i = 1; i < 6; i++) FROB_G[i] = FROB_G[i - 1] * g;
+    hex_to_be(X_BE, 8, "d201000000010000");
+    { Big e3 = big_p(); big_add_small(e3, -1); big_div_small(e3, 3); Big e2 = E_PM1D2;
+      PSI_CX = inv(pow2(xi, e3.l, 6)); PSI_CY = inv(pow2(xi, e2.l, 6)); }
     hex_to_be(R_BE, 32, "73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001");
     hex_to_be(HEFF_BE, 80, "0bc69f08f2ee75b3584c6a0ea91b352888e2a8e9145ad7689986ff031508ffe1329c2f178731db956d82bf015d1212b02ec0ec69d7477c1ae954cbc06689f6a359894c0adebbf6b4e8020005aaa95551");   // hasher.rs:666
     G1_GEN.inf = false;
     G1_GEN.x = fp_from_hex("17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb");
     G1_GEN.y = fp_from_hex("08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1");
     G1_GEN_NEG = G1_GEN; G1_GEN_NEG.y = fneg(G1_GEN.y);
+    { // beta: the primitive cube root of unity with sigma(P) = (beta x, y) = -[x^2]P on G1 (found by testing both on the generator)
+      Big e3 = big_p(); big_add_small(e3, -1); big_div_small(e3, 3);
+      Fp b = fpow(fp_from_u64(2), e3.l, 6); if (feq(b, FP_ONE)) b = fpow(fp_from_u64(3), e3.l, 6);
+      G1J t = smul(smul(to_jac(G1_GEN), X_BE, 8), X_BE, 8);
+      G1A c1 = {fmul(G1_GEN.x, b), fneg(G1_GEN.y), false};
+      BETA = jac_eq_aff(t, c1) ? b : fsqr(b); }
     ISO_A = {FP_ZERO, fp_from_u64(240)}; ISO_B = {fp_from_u64(1012), fp_from_u64(1012)};          // hasher.rs:229-236
     SSWU_Z = {fneg(fp_from_u64(2)), fneg(FP_ONE)};                                                // hasher.rs:237-240
     // 3-isogeny coefficients, RFC 9380 E.3 (ascending degree)
@@ -555,6 +610,7 @@ static inline const u8* msg_ptr(const u8* msg, const uint32_t* off, size_t i, si
 
 extern "C" {
 int ora_init() { init(); return 0; }
+int ora_set_fast(int on) { init(); ORA_FAST = on ? 1 : 0; return 0; }
 // Fp Montgomery product on raw 48-byte LE limb images (for the K0 parity test)
 void ora_fp_mul_raw(const u8* a, const u8* b, u8* out, size_t n) {
     init(); for (size_t i = 0; i < n; i++) { Fp x, y; memcpy(&x, a + 48 * i, 48); memcpy(&y, b + 48 * i, 48); Fp z = fmul(x, y); memcpy(out + 48 * i, &z, 48); }

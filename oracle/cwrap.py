@@ -29,6 +29,10 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 _sz = ctypes.c_size_t
 def hw_threads(): return lib().ora_hw_threads()
+def set_fast(on):
+    """algorithm set of the oracle: False (default) = the simple forms every parity test uses; True = arkworks-style fast forms,
+    for the timed CPU-baseline legs only (both produce identical bytes: tests/test_oracle_golden.py::test_fast_set_matches_simple_set)"""
+    lib().ora_set_fast(1 if on else 0)
 
 def msgs_pack(msgs):
     """list of bytes -> (flat uint8 array, uint32 offsets[n+1])"""

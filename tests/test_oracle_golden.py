@@ -122,3 +122,21 @@ def test_r1cs_oracles_agree():
     want = R.r1cs_check(A, B, Cm, z)
     got = [bool((int(bits[0, i // 64]) >> (i % 64)) & 1) for i in range(nrows)]
     assert got == want and want.count(False) == 3 and allsat[0] == 0
+
+def test_fast_set_matches_simple_set(eth, pyv):
+    """the arkworks-style algorithm set used for the timed CPU baseline gives the same bytes as the simple set used by the parity tests"""
+    from conftest import hx
+    rng = np.random.default_rng(44)
+    pk = b"".join(hx(c["input"]["pubkey"]) for c in eth["verify"]); sig = b"".join(hx(c["input"]["signature"]) for c in eth["verify"])
+    msgs = [hx(c["input"]["message"]) for c in eth["verify"]]
+    mm = [rng.bytes(int(l)) for l in rng.integers(0, 120, size=12)]
+    pts1 = b"".join(hx(c["input"]["pubkey"])[:48].ljust(48, b"\0") for c in eth["deserialization_G1"]) + hx(pyv["g1_not_in_subgroup"])
+    pts2 = b"".join(hx(c["input"]["signature"])[:96].ljust(96, b"\0") for c in eth["deserialization_G2"] if len(c["input"]["signature"]) % 2 == 0) + hx(pyv["g2_not_in_subgroup"])
+    def run():
+        st, gt = C.verify(pk, msgs, sig, want_gt=True, threads=8)
+        return st.tobytes(), gt.tobytes(), C.hash_to_g2(mm, threads=8).tobytes(), C.deser_g1(pts1).tobytes(), C.deser_g2(pts2).tobytes()
+    slow = run()
+    C.set_fast(True)
+    try: fast = run()
+    finally: C.set_fast(False)
+    assert slow == fast
