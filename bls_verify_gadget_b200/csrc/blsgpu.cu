@@ -36,6 +36,9 @@ static inline unsigned nblk(size_t n, unsigned tpb = TPB) { return (unsigned)((n
 // fp_mul saturates it; two warps that start together stay in lockstep (both in their IMAD phase, then both in their ALU
 // phase), leaving each pipe idle half of the time.  Delaying every second warp of a sub-partition by about one phase at
 // kernel entry moves the pair to the stable anti-phase schedule.  BLS_SKEW = delay in cycles (0 = off).
+#ifndef BLS_F_IN_SMEM
+#define BLS_F_IN_SMEM 0
+#endif
 #ifndef BLS_SKEW
 #define BLS_SKEW 0
 #endif
@@ -135,7 +138,13 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_miller(const u32x4* pk_soa, c
     if (status[i] != ST_OK) return;
     g1_aff pk; g2_aff hm, sig;
     soa_load_g1(pk, pk_soa, n, i); soa_load_g2(hm, hm_soa, n, i); soa_load_g2(sig, sig_soa, n, i);
-    fp12 f; stage_miller(f, pk, hm, sig, flags[i]);
+#if BLS_F_IN_SMEM
+    extern __shared__ uint4 f_smem[];                       // accumulator f in shared memory, 592-byte stride (conflict-free 128-bit accesses)
+    fp12& f = *reinterpret_cast<fp12*>(f_smem + threadIdx.x * 37);
+#else
+    fp12 f;
+#endif
+    stage_miller(f, pk, hm, sig, flags[i]);
     soa_store_fp12(f_soa, n, i, f);
 }
 // generic product of pairings for the GT parity hook: npairs in {1,2}
@@ -508,7 +517,12 @@ static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code
     STAGE_MARK(2);
     LAUNCH(k_hash_to_g2, nblk(n), TPB, dmsg, doff, n, code_pk, (const uint8_t*)code_sig, hm_soa, flags, dstatus);
     STAGE_MARK(3);
+#if BLS_F_IN_SMEM
+    { static bool attr_set = false; if (!attr_set) { cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, TPB * 592); attr_set = true; }
+      k_miller<<<nblk(n), TPB, TPB * 592, ctx->stream>>>(pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, n, f_soa); ctx->launches++; CU(cudaGetLastError()); }
+#else
     LAUNCH(k_miller, nblk(n), TPB, pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, n, f_soa);
+#endif
     STAGE_MARK(4);
     LAUNCH(k_final_exp, nblk(n), TPB, f_soa, (const uint8_t*)dstatus, dstatus, n);
     STAGE_MARK(5);

@@ -251,9 +251,12 @@ BLS_HD fp fp_mul_inl(const fp& a, const fp& b) {
 // (even / odd columns of the multiplicand); the carry out of a chain that ends at limb k is *counted* in C[k] instead of
 // rippling (limbs >= 12 are never read before the final resolve, so deferring the carries is exact).
 struct fpw { uint32_t l[24]; };
+#if defined(__CUDACC__)
+#pragma nv_diag_suppress 550
+#endif
 #if defined(__CUDA_ARCH__)
 BLS_HD uint32_t add12c(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t cin) {      // r = a + b + cin, returns carry (0/1)
-    uint32_t cout, tmp = 0; (void)tmp;
+    uint32_t cout, tmp;
     BLS_ASM("add.cc.u32 %13, %38, 0xffffffff;\n\taddc.cc.u32 %0, %14, %26;\n\taddc.cc.u32 %1, %15, %27;\n\taddc.cc.u32 %2, %16, %28;\n\taddc.cc.u32 %3, %17, %29;\n\t"
         "addc.cc.u32 %4, %18, %30;\n\taddc.cc.u32 %5, %19, %31;\n\taddc.cc.u32 %6, %20, %32;\n\taddc.cc.u32 %7, %21, %33;\n\t"
         "addc.cc.u32 %8, %22, %34;\n\taddc.cc.u32 %9, %23, %35;\n\taddc.cc.u32 %10, %24, %36;\n\taddc.cc.u32 %11, %25, %37;\n\taddc.u32 %12, 0, 0;"
@@ -263,7 +266,7 @@ BLS_HD uint32_t add12c(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32
     return cout;
 }
 BLS_HD uint32_t sub12b(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t bin) {      // r = a - b - bin, returns borrow (0/1)
-    uint32_t bout, tmp = 0; (void)tmp;
+    uint32_t bout, tmp;
     BLS_ASM("sub.cc.u32 %13, 0, %38;\n\tsubc.cc.u32 %0, %14, %26;\n\tsubc.cc.u32 %1, %15, %27;\n\tsubc.cc.u32 %2, %16, %28;\n\tsubc.cc.u32 %3, %17, %29;\n\t"
         "subc.cc.u32 %4, %18, %30;\n\tsubc.cc.u32 %5, %19, %31;\n\tsubc.cc.u32 %6, %20, %32;\n\tsubc.cc.u32 %7, %21, %33;\n\t"
         "subc.cc.u32 %8, %22, %34;\n\tsubc.cc.u32 %9, %23, %35;\n\tsubc.cc.u32 %10, %24, %36;\n\tsubc.cc.u32 %11, %25, %37;\n\tsubc.u32 %12, 0, 0;"
