@@ -7,7 +7,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("BLSGPU_SO") or os.path.join(_PKG, "libblsgpu.so")      # BLSGPU_SO: tuning builds (profiles/), never a fallback
 _SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("blsgpu.cu", "r1cs.cuh", "stages.cuh", "pairing.cuh", "h2c.cuh", "curve.cuh", "tower.cuh",
-                                                    "fp2.cuh", "fp.cuh", "consts.cuh")] + [os.path.join(_ROOT, "include", "blsgpu.h")]
+                                                    "fp2.cuh", "fp.cuh", "consts.cuh", "coop.cuh")] + [os.path.join(_ROOT, "include", "blsgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
 class BlsGpuError(RuntimeError): pass
@@ -33,7 +33,7 @@ def lib():
     return _lib
 
 EXPORTS = ["blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_set_stream", "blsgpu_set_pointer_mode", "blsgpu_synchronize",
-           "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_verify_batch", "blsgpu_fast_aggregate_verify_batch", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
+           "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_set_coop", "blsgpu_verify_batch", "blsgpu_fast_aggregate_verify_batch", "blsgpu_pool_create", "blsgpu_pool_free", "blsgpu_pool_fast_aggregate_verify", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
            "blsgpu_g2_aggregate", "blsgpu_deserialize_g1", "blsgpu_deserialize_g2", "blsgpu_sk_to_pk_batch", "blsgpu_sign_batch", "blsgpu_pairing_gt",
            "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free"]
 
@@ -71,6 +71,7 @@ class Context:
     def set_pointer_mode(self, device): self._ck(lib().blsgpu_set_pointer_mode(self._h, 1 if device else 0))
     def synchronize(self): self._ck(lib().blsgpu_synchronize(self._h))
     def launch_count(self): return int(lib().blsgpu_launch_count(self._h))
+    def set_coop(self, on): self._ck(lib().blsgpu_set_coop(self._h, 1 if on else 0))
     def set_lanes(self, lanes): self._ck(lib().blsgpu_set_lanes(self._h, int(lanes)))
     def set_chunk(self, items): self._ck(lib().blsgpu_set_chunk(self._h, _sz(items)))
     def set_profiling(self, on=True): self._ck(lib().blsgpu_set_profiling(self._h, 1 if on else 0))
@@ -97,6 +98,18 @@ class Context:
         st = np.empty(nc, np.uint8); agg = np.empty(48 * nc, np.uint8) if want_agg else None
         bm = np.ascontiguousarray(bitmap, dtype=np.uint64) if bitmap is not None else None
         self.fast_aggregate_verify_ptr(pk, bm, k, m, sg, nc, st, agg)
+        return (st, agg) if want_agg else st
+    def pool_create(self, pks48):
+        a = _u8(pks48); n = a.size // 48; st = np.empty(n, np.uint8); h = ctypes.c_int(-1)
+        self._ck(lib().blsgpu_pool_create(self._h, _p(a), _sz(n), ctypes.byref(h), _p(st))); return h.value, st
+    def pool_free(self, handle): lib().blsgpu_pool_free(self._h, int(handle))
+    def pool_fast_aggregate_verify_ptr(self, handle, idx, bitmap, k, msg, sig, ncomm, status, agg=None):
+        self._ck(lib().blsgpu_pool_fast_aggregate_verify(self._h, int(handle), _p(idx), _p(bitmap), _sz(k), _p(msg), _p(sig), _sz(ncomm), _p(status), _p(agg)))
+    def pool_fast_aggregate_verify(self, handle, idx, k, msg32, sig96, bitmap=None, want_agg=False):
+        ix = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1); m = _u8(msg32); sg = _u8(sig96); nc = sg.size // 96
+        st = np.empty(nc, np.uint8); agg = np.empty(48 * nc, np.uint8) if want_agg else None
+        bm = np.ascontiguousarray(bitmap, dtype=np.uint64) if bitmap is not None else None
+        self.pool_fast_aggregate_verify_ptr(handle, ix, bm, k, m, sg, nc, st, agg)
         return (st, agg) if want_agg else st
     def hash_to_g2(self, msgs):
         flat, off = pack_msgs(msgs); out = np.empty(96 * len(msgs), np.uint8); self.hash_to_g2_ptr(flat, off, len(msgs), out); return out

@@ -18,6 +18,7 @@
 #include <cstdarg>
 #include <new>
 #include "stages.cuh"
+#include "coop.cuh"
 #include "../../include/blsgpu.h"
 
 using namespace bls;
@@ -173,6 +174,31 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_final_exp(u32x4* f_soa, const
     status_out[i] = stage_final(gt, f);
     soa_store_fp12(f_soa, n, i, gt);
 }
+// K5 split for the cooperative path: easy part f^((p^6-1)(p^2+1)) per thread (one inversion), hard part six lanes per item
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_final_easy(u32x4* f_soa, const uint8_t* status, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    if (status[i] != ST_OK) return;
+    fp12 f, t, r; soa_load_fp12(f, f_soa, n, i);
+    fp12_conj(t, f); fp12_inv(r, f); fp12_mul(r, t, r);
+    fp12_frob2(t, r); fp12_mul(r, t, r);
+    soa_store_fp12(f_soa, n, i, r);
+}
+__global__ void __launch_bounds__(128, 2) k_final_hard_coop(u32x4* f_soa, const uint8_t* status_in, uint8_t* status_out, size_t n) {
+    __shared__ coop_smem sm[4];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane / 6;
+    coop_lane c = coop_init(&sm[warp]);
+    size_t item = (blockIdx.x * (size_t)4 + warp) * 5 + g;
+    bool in_range = g < 5 && item < n;
+    uint8_t st = in_range ? status_in[item] : (uint8_t)ST_BAD_PK;
+    bool active = in_range && st == ST_OK;
+    fp2 r = c.k == 0 ? fp2_one() : fp2_zero();
+    if (active) r = soa_load_fp2(f_soa, n, item, COOP_TOWER_POS[c.k]);
+    r = coop_final_exp_hard(c, r);
+    bool mine = c.k == 0 ? fp2_eq(r, fp2_one()) : fp2_is_zero(r);
+    unsigned ball = __ballot_sync(0xffffffffu, mine);
+    if (active) soa_store_fp2(f_soa, n, item, COOP_TOWER_POS[c.k], r);
+    if (in_range && c.k == 0) status_out[item] = active ? ((((ball >> (6 * g)) & 63u) == 63u) ? (uint8_t)ST_OK : (uint8_t)ST_FALSE) : st;
+}
 // out[t] = prod_{i = t, t+T, ...} in[i] over items with status <= ST_FALSE (status == NULL: all items)
 __global__ void __launch_bounds__(TPB, BLS_MINB) k_gt_reduce(const u32x4* in_soa, const uint8_t* status, size_t n, u32x4* out_soa, size_t T) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (t >= T) return;
@@ -247,49 +273,62 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_scalar_mul_g2(const uint8_t* 
     g2_aff a; bool ok = jac_to_aff(a, r); g2_encode(sig96 + 96 * i, a, !ok);
 }
 
-// K3: one warp per segment.  Each lane folds a strided slice of the segment with mixed additions, then the 32
-// partial sums are combined by a shared-memory tree (5 levels of full Jacobian additions).
+// K3: segmented aggregation.  L lanes cooperate on one segment (32/L segments per warp; L is picked so that a lane folds
+// >= ~64 points): each lane folds a strided slice with mixed additions, the L partial sums are combined by a shared-memory
+// tree of full Jacobian additions, and the Jacobian result goes to HBM.  The to-affine inversion (one 380-bit
+// exponentiation per segment) runs in a second, thread-per-segment kernel so that it is not serialised on one lane per warp.
 template <class F> struct segsum_traits;
 template <> struct segsum_traits<fp>  { enum { K = 2 }; static __device__ __forceinline__ void load(aff<fp>& p, const u32x4* s, size_t n, size_t i) { soa_load_g1(p, s, n, i); }
-                                        static __device__ __forceinline__ void store(u32x4* s, size_t n, size_t i, const aff<fp>& p) { soa_store_g1(s, n, i, p); } };
+                                        static __device__ __forceinline__ void store(u32x4* s, size_t n, size_t i, const aff<fp>& p) { soa_store_g1(s, n, i, p); }
+                                        static __device__ __forceinline__ void storej(u32x4* s, size_t n, size_t i, const jac<fp>& p) { soa_store_fp(s, n, i, 0, p.X); soa_store_fp(s, n, i, 1, p.Y); soa_store_fp(s, n, i, 2, p.Z); }
+                                        static __device__ __forceinline__ void loadj(jac<fp>& p, const u32x4* s, size_t n, size_t i) { p.X = soa_load_fp(s, n, i, 0); p.Y = soa_load_fp(s, n, i, 1); p.Z = soa_load_fp(s, n, i, 2); } };
 template <> struct segsum_traits<fp2> { enum { K = 4 }; static __device__ __forceinline__ void load(aff<fp2>& p, const u32x4* s, size_t n, size_t i) { soa_load_g2(p, s, n, i); }
-                                        static __device__ __forceinline__ void store(u32x4* s, size_t n, size_t i, const aff<fp2>& p) { soa_store_g2(s, n, i, p); } };
+                                        static __device__ __forceinline__ void store(u32x4* s, size_t n, size_t i, const aff<fp2>& p) { soa_store_g2(s, n, i, p); }
+                                        static __device__ __forceinline__ void storej(u32x4* s, size_t n, size_t i, const jac<fp2>& p) { soa_store_fp2(s, n, i, 0, p.X); soa_store_fp2(s, n, i, 1, p.Y); soa_store_fp2(s, n, i, 2, p.Z); }
+                                        static __device__ __forceinline__ void loadj(jac<fp2>& p, const u32x4* s, size_t n, size_t i) { p.X = soa_load_fp2(s, n, i, 0); p.Y = soa_load_fp2(s, n, i, 1); p.Z = soa_load_fp2(s, n, i, 2); } };
 #define SEG_WARPS 4
 template <class F> __global__ void __launch_bounds__(32 * SEG_WARPS) k_segsum(const u32x4* pts_soa, const uint8_t* code, size_t npts, const uint32_t* seg_off, size_t seg_stride,
-                                                                            const uint64_t* bitmap, size_t nseg, u32x4* out_soa, uint8_t* out_inf, uint8_t* status, uint8_t bad_code) {
+                                                                            const uint64_t* bitmap, size_t nseg, u32x4* out_jac, uint8_t* status, uint8_t bad_code,
+                                                                            const uint32_t* idx /* nullable: member i of the flat list is point idx[i] of the resident pool */, int L) {
     __shared__ jac<F> sm[SEG_WARPS][32];
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    size_t s = blockIdx.x * (size_t)SEG_WARPS + warp;
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / L, sl = lane % L, per_warp = 32 / L;
+    size_t s = (blockIdx.x * (size_t)SEG_WARPS + warp) * per_warp + sub;
     bool active = s < nseg;
     size_t lo = 0, hi = 0;
     if (active) { if (seg_off) { lo = seg_off[s]; hi = seg_off[s + 1]; } else { lo = s * seg_stride; hi = lo + seg_stride; } }
     jac<F> acc; jac_set_identity(acc);
-    bool bad = false; unsigned cnt = 0;
-    for (size_t i = lo + lane; i < hi; i += 32) {
+    unsigned bad = 0, cnt = 0;
+    for (size_t i = lo + sl; i < hi; i += L) {
         if (bitmap && !((bitmap[i >> 6] >> (i & 63)) & 1)) continue;
         cnt++;
-        uint8_t c = code[i];
-        if (c > DEC_INF) { bad = true; continue; }
+        size_t pi = idx ? (size_t)idx[i] : i;
+        if (pi >= npts) { bad = 1; continue; }
+        uint8_t c = code[pi];
+        if (c > DEC_INF) { bad = 1; continue; }
         if (c == DEC_INF) continue;
-        aff<F> p; segsum_traits<F>::load(p, pts_soa, npts, i);
+        aff<F> p; segsum_traits<F>::load(p, pts_soa, npts, pi);
         jac_add_mixed(acc, acc, p);
     }
     sm[warp][lane] = acc;
     __syncwarp();
-    for (int w = 16; w >= 1; w >>= 1) {
-        if (lane < w) { jac<F> o = sm[warp][lane + w]; jac_add(acc, acc, o); sm[warp][lane] = acc; }
+    for (int w = L >> 1; w >= 1; w >>= 1) {
+        if (sl < w) { jac<F> o = sm[warp][lane + w]; jac_add(acc, acc, o); sm[warp][lane] = acc; }
         __syncwarp();
+        bad |= __shfl_down_sync(0xffffffffu, bad, w); cnt += __shfl_down_sync(0xffffffffu, cnt, w);     // stays inside the L-lane group for sl < w
     }
-    bad = __any_sync(0xffffffffu, bad);
-    unsigned total = cnt;
-    for (int w = 16; w >= 1; w >>= 1) total += __shfl_xor_sync(0xffffffffu, total, w);
-    if (active && lane == 0) {
-        aff<F> a; bool ok = jac_to_aff(a, acc);
-        segsum_traits<F>::store(out_soa, nseg, s, a);
-        out_inf[s] = ok ? 0 : 1;
-        status[s] = bad ? bad_code : (total == 0 ? ST_EMPTY : ST_OK);
+    if (active && sl == 0) {
+        segsum_traits<F>::storej(out_jac, nseg, s, acc);
+        status[s] = bad ? bad_code : (cnt == 0 ? ST_EMPTY : ST_OK);
     }
 }
+template <class F> __global__ void __launch_bounds__(TPB, BLS_MINB) k_jac_to_aff(const u32x4* jac_soa, size_t n, u32x4* aff_soa, uint8_t* inf) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    jac<F> p; segsum_traits<F>::loadj(p, jac_soa, n, i);
+    aff<F> a; bool ok = jac_to_aff(a, p);
+    segsum_traits<F>::store(aff_soa, n, i, a); inf[i] = ok ? 0 : 1;
+}
+// lanes per segment: the largest power of two <= 32 that still leaves ~64 points per lane (at least 1)
+static int seg_lanes(size_t avg_len) { int L = 32; while (L > 1 && avg_len / L < 64) L >>= 1; return L; }
 // fast_aggregate_verify glue: status/flags from the aggregation outcome and the signature decode code
 __global__ void k_fav_status(const uint8_t* agg_status, const uint8_t* agg_inf, const uint8_t* code_sig, size_t n, uint8_t* code_pk_out) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
@@ -302,6 +341,8 @@ struct blsgpu_ctx {
     int device; cudaStream_t own_stream, stream; int ptr_mode; char err[512];
     uint8_t* ws; size_t ws_bytes, ws_used; unsigned long long launches;
     struct r1cs_sys* r1cs[16];
+    struct { u32x4* soa; uint8_t* code; size_t n; } pool[16];   // resident decoded validator pools
+    int coop;                           // 1 = warp-cooperative hard part of the final exponentiation (coop.cuh)
     int lanes; cudaStream_t lane_stream[4]; cudaEvent_t lane_done[4], fork;   // concurrent sub-ranges of a verify pass
     size_t chunk;                       // items per internal pass of verify_batch (bounds the workspace); multiple of 64
     int prof; cudaEvent_t ev[8];        // stage boundaries of the last verify_batch chunk: g1 | g2 | hash | miller | final | epilogue
@@ -394,6 +435,7 @@ void blsgpu_destroy(blsgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 16; i++) if (ctx->r1cs[i]) blsgpu_r1cs_free(ctx, i);
+    for (int i = 0; i < 16; i++) if (ctx->pool[i].soa) { cudaFree(ctx->pool[i].soa); cudaFree(ctx->pool[i].code); }
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ev[0]) for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
     if (ctx->lane_stream[0]) { for (int l = 0; l < 4; l++) { cudaStreamDestroy(ctx->lane_stream[l]); cudaEventDestroy(ctx->lane_done[l]); } cudaEventDestroy(ctx->fork); }
@@ -405,6 +447,7 @@ int blsgpu_set_stream(blsgpu_ctx* ctx, void* s, int use_own) { if (!ctx) return 
 int blsgpu_set_pointer_mode(blsgpu_ctx* ctx, int mode) { if (!ctx || (mode != BLSGPU_HOST && mode != BLSGPU_DEVICE)) return BLSGPU_ERR_ARG; ctx->ptr_mode = mode; return 0; }
 int blsgpu_synchronize(blsgpu_ctx* ctx) { if (!ctx) return BLSGPU_ERR_ARG; CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); return 0; }
 uint64_t blsgpu_launch_count(blsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int blsgpu_set_coop(blsgpu_ctx* ctx, int on) { if (!ctx) return BLSGPU_ERR_ARG; ctx->coop = on ? 1 : 0; return 0; }
 int blsgpu_set_lanes(blsgpu_ctx* ctx, int lanes) { if (!ctx || lanes < 1 || lanes > 4) return BLSGPU_ERR_ARG; ctx->lanes = lanes; return 0; }
 int blsgpu_set_chunk(blsgpu_ctx* ctx, size_t items) { if (!ctx || items < 64 || (items & 63)) return BLSGPU_ERR_ARG; ctx->chunk = items; return 0; }
 int blsgpu_set_profiling(blsgpu_ctx* ctx, int on) {
@@ -524,7 +567,10 @@ static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code
     LAUNCH(k_miller, nblk(n), TPB, pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, n, f_soa);
 #endif
     STAGE_MARK(4);
-    LAUNCH(k_final_exp, nblk(n), TPB, f_soa, (const uint8_t*)dstatus, dstatus, n);
+    if (ctx->coop) {
+        LAUNCH(k_final_easy, nblk(n), TPB, f_soa, (const uint8_t*)dstatus, n);
+        LAUNCH(k_final_hard_coop, nblk(n, 20), 128, f_soa, (const uint8_t*)dstatus, dstatus, n);
+    } else LAUNCH(k_final_exp, nblk(n), TPB, f_soa, (const uint8_t*)dstatus, dstatus, n);
     STAGE_MARK(5);
     if (dbitmap) LAUNCH(k_status_bitmap, nblk(((n + 31) / 32) * 32, 256), 256, (const uint8_t*)dstatus, n, dbitmap);
     if (gt_acc) {
@@ -709,14 +755,16 @@ int blsgpu_g1_aggregate(blsgpu_ctx* ctx, const uint8_t* pts48, const uint32_t* s
     if (!nseg) return 0;
     size_t npts; if (int rc = seg_total(ctx, seg_off, nseg, npts)) return rc;
     if (npts && !pts48) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
-    if (int rc = ws_reserve(ctx, al(48 * npts + 16) + al(4 * (nseg + 1)) + al(96 * npts + 16) + al(npts + 1) + al(96 * nseg) + al(48 * nseg) + 3 * al(nseg) + 8192)) return rc;
+    if (int rc = ws_reserve(ctx, al(48 * npts + 16) + al(4 * (nseg + 1)) + al(96 * npts + 16) + al(npts + 1) + al(96 * nseg) + al(144 * nseg) + al(48 * nseg) + 3 * al(nseg) + 8192)) return rc;
     const uint8_t* din; const uint32_t* dseg;
     if (int rc = stage_in(ctx, din, pts48, 48 * npts)) return rc; if (int rc = stage_in(ctx, dseg, seg_off, nseg + 1)) return rc;
     u32x4* soa = ws_take<u32x4>(ctx, 6 * npts + 1); uint8_t* code = ws_take<uint8_t>(ctx, npts + 1);
     u32x4* osoa = ws_take<u32x4>(ctx, 6 * nseg); uint8_t* oinf = ws_take<uint8_t>(ctx, nseg);
     uint8_t* dout = stage_out(ctx, out48, 48 * nseg); uint8_t* dst = stage_out(ctx, status, nseg);
     if (npts) LAUNCH(k_decode_g1, nblk(npts), TPB, din, npts, soa, code);
-    LAUNCH(k_segsum<fp>, nblk(nseg, SEG_WARPS), 32 * SEG_WARPS, (const u32x4*)soa, (const uint8_t*)code, npts, dseg, (size_t)0, (const uint64_t*)nullptr, nseg, osoa, oinf, dst, (uint8_t)ST_BAD_PK);
+    { int L = seg_lanes(npts / nseg); u32x4* ojac = ws_take<u32x4>(ctx, 9 * nseg);
+      LAUNCH(k_segsum<fp>, nblk(nseg, SEG_WARPS * (32 / L)), 32 * SEG_WARPS, (const u32x4*)soa, (const uint8_t*)code, npts, dseg, (size_t)0, (const uint64_t*)nullptr, nseg, ojac, dst, (uint8_t)ST_BAD_PK, (const uint32_t*)nullptr, L);
+      LAUNCH(k_jac_to_aff<fp>, nblk(nseg), TPB, (const u32x4*)ojac, nseg, osoa, oinf); }
     LAUNCH(k_encode_g1, nblk(nseg), TPB, (const u32x4*)osoa, (const uint8_t*)oinf, nseg, dout);
     if (int rc = finish_out(ctx, out48, dout, 48 * nseg)) return rc; if (int rc = finish_out(ctx, status, dst, nseg)) return rc;
     return finish_call(ctx);
@@ -726,14 +774,16 @@ int blsgpu_g2_aggregate(blsgpu_ctx* ctx, const uint8_t* pts96, const uint32_t* s
     if (!nseg) return 0;
     size_t npts; if (int rc = seg_total(ctx, seg_off, nseg, npts)) return rc;
     if (npts && !pts96) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
-    if (int rc = ws_reserve(ctx, al(96 * npts + 16) + al(4 * (nseg + 1)) + al(192 * npts + 16) + al(npts + 1) + al(192 * nseg) + al(96 * nseg) + 3 * al(nseg) + 8192)) return rc;
+    if (int rc = ws_reserve(ctx, al(96 * npts + 16) + al(4 * (nseg + 1)) + al(192 * npts + 16) + al(npts + 1) + al(192 * nseg) + al(288 * nseg) + al(96 * nseg) + 3 * al(nseg) + 8192)) return rc;
     const uint8_t* din; const uint32_t* dseg;
     if (int rc = stage_in(ctx, din, pts96, 96 * npts)) return rc; if (int rc = stage_in(ctx, dseg, seg_off, nseg + 1)) return rc;
     u32x4* soa = ws_take<u32x4>(ctx, 12 * npts + 1); uint8_t* code = ws_take<uint8_t>(ctx, npts + 1);
     u32x4* osoa = ws_take<u32x4>(ctx, 12 * nseg); uint8_t* oinf = ws_take<uint8_t>(ctx, nseg);
     uint8_t* dout = stage_out(ctx, out96, 96 * nseg); uint8_t* dst = stage_out(ctx, status, nseg);
     if (npts) LAUNCH(k_decode_g2, nblk(npts), TPB, din, npts, soa, code);
-    LAUNCH(k_segsum<fp2>, nblk(nseg, SEG_WARPS), 32 * SEG_WARPS, (const u32x4*)soa, (const uint8_t*)code, npts, dseg, (size_t)0, (const uint64_t*)nullptr, nseg, osoa, oinf, dst, (uint8_t)ST_BAD_SIG);
+    { int L = seg_lanes(npts / nseg); u32x4* ojac = ws_take<u32x4>(ctx, 18 * nseg);
+      LAUNCH(k_segsum<fp2>, nblk(nseg, SEG_WARPS * (32 / L)), 32 * SEG_WARPS, (const u32x4*)soa, (const uint8_t*)code, npts, dseg, (size_t)0, (const uint64_t*)nullptr, nseg, ojac, dst, (uint8_t)ST_BAD_SIG, (const uint32_t*)nullptr, L);
+      LAUNCH(k_jac_to_aff<fp2>, nblk(nseg), TPB, (const u32x4*)ojac, nseg, osoa, oinf); }
     LAUNCH(k_encode_g2, nblk(nseg), TPB, (const u32x4*)osoa, (const uint8_t*)oinf, (uint8_t)1, nseg, dout);
     if (int rc = finish_out(ctx, out96, dout, 96 * nseg)) return rc; if (int rc = finish_out(ctx, status, dst, nseg)) return rc;
     return finish_call(ctx);
@@ -744,7 +794,7 @@ int blsgpu_fast_aggregate_verify_batch(blsgpu_ctx* ctx, const uint8_t* pks48, co
     ENTER(); if (!msg32 || !sig96 || !status || (k && !pks48)) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
     if (!ncomm) return 0;
     int rc; size_t npts = ncomm * k;
-    size_t need = al(48 * npts + 16) + al(8 * ((npts + 63) / 64 + 1)) + al(96 * npts + 16) + al(npts + 1) + al(96 * ncomm) * 2 + al(48 * ncomm) + 4 * al(ncomm) + verify_ws_bytes(ncomm, 32 * ncomm);
+    size_t need = al(48 * npts + 16) + al(8 * ((npts + 63) / 64 + 1)) + al(96 * npts + 16) + al(npts + 1) + al(96 * ncomm) * 2 + al(144 * ncomm) + al(48 * ncomm) + 4 * al(ncomm) + verify_ws_bytes(ncomm, 32 * ncomm);
     if ((rc = ws_reserve(ctx, need))) return rc;
     const uint8_t *dpks, *dmsg, *dsig; const uint64_t* dbm;
     if ((rc = stage_in(ctx, dpks, pks48, 48 * npts))) return rc; if ((rc = stage_in(ctx, dbm, bitmap, (npts + 63) / 64))) return rc;
@@ -753,10 +803,53 @@ int blsgpu_fast_aggregate_verify_batch(blsgpu_ctx* ctx, const uint8_t* pks48, co
     u32x4* agg_soa = ws_take<u32x4>(ctx, 6 * ncomm); uint8_t* agg_inf = ws_take<uint8_t>(ctx, ncomm); uint8_t* agg_st = ws_take<uint8_t>(ctx, ncomm); uint8_t* code_pk = ws_take<uint8_t>(ctx, ncomm);
     uint8_t* dstatus = stage_out(ctx, status, ncomm); uint8_t* dagg = stage_out(ctx, agg_pk48_out, 48 * ncomm);
     if (npts) LAUNCH(k_decode_g1, nblk(npts), TPB, dpks, npts, soa, code);
-    LAUNCH(k_segsum<fp>, nblk(ncomm, SEG_WARPS), 32 * SEG_WARPS, (const u32x4*)soa, (const uint8_t*)code, npts, (const uint32_t*)nullptr, k, dbm, ncomm, agg_soa, agg_inf, agg_st, (uint8_t)ST_BAD_PK);
+    { int L = seg_lanes(k); u32x4* ojac = ws_take<u32x4>(ctx, 9 * ncomm);
+      LAUNCH(k_segsum<fp>, nblk(ncomm, SEG_WARPS * (32 / L)), 32 * SEG_WARPS, (const u32x4*)soa, (const uint8_t*)code, npts, (const uint32_t*)nullptr, k, dbm, ncomm, ojac, agg_st, (uint8_t)ST_BAD_PK, (const uint32_t*)nullptr, L);
+      LAUNCH(k_jac_to_aff<fp>, nblk(ncomm), TPB, (const u32x4*)ojac, ncomm, agg_soa, agg_inf); }
     if (dagg) LAUNCH(k_encode_g1, nblk(ncomm), TPB, (const u32x4*)agg_soa, (const uint8_t*)agg_inf, ncomm, dagg);
     LAUNCH(k_fav_status, nblk(ncomm), TPB, (const uint8_t*)agg_st, (const uint8_t*)agg_inf, (const uint8_t*)nullptr, ncomm, code_pk);
     // the aggregate of subgroup points is in the subgroup: the check() of bls.rs:438 on it cannot fail, so it is not re-run
+    if ((rc = verify_core(ctx, agg_soa, code_pk, dmsg, nullptr, dsig, ncomm, dstatus, nullptr, nullptr))) return rc;
+    if ((rc = finish_out(ctx, status, dstatus, ncomm))) return rc; if ((rc = finish_out(ctx, agg_pk48_out, dagg, 48 * ncomm))) return rc;
+    return finish_call(ctx);
+}
+
+// ---- resident validator pool (cfg 3a): keys are decoded and subgroup-checked once and stay in HBM as affine limb-SoA
+int blsgpu_pool_create(blsgpu_ctx* ctx, const uint8_t* pks48, size_t n, int* handle, uint8_t* status) {
+    ENTER(); if (!pks48 || !handle || !n) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
+    int h = -1; for (int i = 0; i < 16; i++) if (!ctx->pool[i].soa) { h = i; break; }
+    if (h < 0) return fail(ctx, BLSGPU_ERR_ARG, "too many pools");
+    if (int rc = ws_reserve(ctx, al(48 * n) + al(n) + 8192)) return rc;
+    const uint8_t* din; if (int rc = stage_in(ctx, din, pks48, 48 * n)) return rc;
+    u32x4* soa; uint8_t* code;
+    if (cudaMalloc(&soa, 96 * n) != cudaSuccess || cudaMalloc(&code, n) != cudaSuccess) { cudaGetLastError(); return fail(ctx, BLSGPU_ERR_ALLOC, "pool allocation failed"); }
+    LAUNCH(k_decode_g1, nblk(n), TPB, din, n, soa, code);
+    if (status) { if (ctx->ptr_mode == BLSGPU_DEVICE) CU(cudaMemcpyAsync(status, code, n, cudaMemcpyDeviceToDevice, ctx->stream)); else CU(cudaMemcpyAsync(status, code, n, cudaMemcpyDeviceToHost, ctx->stream)); }
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->pool[h].soa = soa; ctx->pool[h].code = code; ctx->pool[h].n = n; *handle = h; return 0;
+}
+int blsgpu_pool_free(blsgpu_ctx* ctx, int handle) {
+    if (!ctx || handle < 0 || handle >= 16 || !ctx->pool[handle].soa) return BLSGPU_ERR_ARG;
+    cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->pool[handle].soa); cudaFree(ctx->pool[handle].code); ctx->pool[handle].soa = nullptr; ctx->pool[handle].code = nullptr; ctx->pool[handle].n = 0; return 0;
+}
+int blsgpu_pool_fast_aggregate_verify(blsgpu_ctx* ctx, int handle, const uint32_t* idx, const uint64_t* bitmap, size_t k, const uint8_t* msg32, const uint8_t* sig96, size_t ncomm,
+                                      uint8_t* status, uint8_t* agg_pk48_out) {
+    ENTER(); if (handle < 0 || handle >= 16 || !ctx->pool[handle].soa || !idx || !msg32 || !sig96 || !status) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
+    if (!ncomm) return 0;
+    int rc; size_t nm = ncomm * k;
+    if ((rc = ws_reserve(ctx, al(4 * nm + 16) + al(8 * ((nm + 63) / 64 + 1)) + al(96 * ncomm) * 2 + al(144 * ncomm) + al(48 * ncomm) + 4 * al(ncomm) + verify_ws_bytes(ncomm, 32 * ncomm)))) return rc;
+    const uint32_t* didx; const uint8_t *dmsg, *dsig; const uint64_t* dbm;
+    if ((rc = stage_in(ctx, didx, idx, nm))) return rc; if ((rc = stage_in(ctx, dbm, bitmap, (nm + 63) / 64))) return rc;
+    if ((rc = stage_in(ctx, dmsg, msg32, 32 * ncomm))) return rc; if ((rc = stage_in(ctx, dsig, sig96, 96 * ncomm))) return rc;
+    u32x4* agg_soa = ws_take<u32x4>(ctx, 6 * ncomm); uint8_t* agg_inf = ws_take<uint8_t>(ctx, ncomm); uint8_t* agg_st = ws_take<uint8_t>(ctx, ncomm); uint8_t* code_pk = ws_take<uint8_t>(ctx, ncomm);
+    uint8_t* dstatus = stage_out(ctx, status, ncomm); uint8_t* dagg = stage_out(ctx, agg_pk48_out, 48 * ncomm);
+    { int L = seg_lanes(k); u32x4* ojac = ws_take<u32x4>(ctx, 9 * ncomm);
+      LAUNCH(k_segsum<fp>, nblk(ncomm, SEG_WARPS * (32 / L)), 32 * SEG_WARPS, (const u32x4*)ctx->pool[handle].soa, (const uint8_t*)ctx->pool[handle].code, ctx->pool[handle].n, (const uint32_t*)nullptr, k, dbm, ncomm,
+             ojac, agg_st, (uint8_t)ST_BAD_PK, didx, L);
+      LAUNCH(k_jac_to_aff<fp>, nblk(ncomm), TPB, (const u32x4*)ojac, ncomm, agg_soa, agg_inf); }
+    if (dagg) LAUNCH(k_encode_g1, nblk(ncomm), TPB, (const u32x4*)agg_soa, (const uint8_t*)agg_inf, ncomm, dagg);
+    LAUNCH(k_fav_status, nblk(ncomm), TPB, (const uint8_t*)agg_st, (const uint8_t*)agg_inf, (const uint8_t*)nullptr, ncomm, code_pk);
     if ((rc = verify_core(ctx, agg_soa, code_pk, dmsg, nullptr, dsig, ncomm, dstatus, nullptr, nullptr))) return rc;
     if ((rc = finish_out(ctx, status, dstatus, ncomm))) return rc; if ((rc = finish_out(ctx, agg_pk48_out, dagg, 48 * ncomm))) return rc;
     return finish_call(ctx);

@@ -42,6 +42,9 @@ emit_fp("BLS_C_TWO_INV", pow(2, p - 2, p))
 emit_fp("BLS_C_FOUR", 4)
 emit_fp("BLS_C_2_256", 1 << 256)
 emit_words("BLS_C_P_SQUARED", p * p, 24)
+# offsets of the lazily reduced cooperative Fp12 product (coop.cuh): (16 - 2k) p^2 on the real and (5 - k) p^2 on the imaginary accumulator of lane k
+out.append("#define BLS_C_COOP_OFF_RE {" + ", ".join(fmt(limbs((16 - 2 * k) * p * p, 24)) for k in range(6)) + "}")
+out.append("#define BLS_C_COOP_OFF_IM {" + ", ".join(fmt(limbs((5 - k) * p * p, 24)) for k in range(6)) + "}")
 
 # --- G1 generator and its negation
 G1X = 0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb

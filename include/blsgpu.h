@@ -72,6 +72,9 @@ int blsgpu_set_chunk(blsgpu_ctx* ctx, size_t items);
  * join the context's stream, so that the tail wave of a stage kernel overlaps the other sub-range's work; 1 = strictly serial kernels
  * (use it with blsgpu_set_profiling: stage events of concurrent lanes would overlap) */
 int blsgpu_set_lanes(blsgpu_ctx* ctx, int lanes);
+/* final exponentiation: 0 = one thread per item throughout; 1 = hard part with six lanes per item (warp-cooperative Fp12, coop.cuh).
+ * Both produce identical GT bytes. */
+int blsgpu_set_coop(blsgpu_ctx* ctx, int on);
 int blsgpu_stage_times(blsgpu_ctx* ctx, float ms6[6]);
 
 /* ---- BLS::verify over a batch  (replaces <BLS<P> as SignatureScheme>::verify, src/bls.rs:427-458, incl. the
@@ -88,6 +91,15 @@ int blsgpu_verify_batch(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg
 int blsgpu_fast_aggregate_verify_batch(blsgpu_ctx* ctx, const uint8_t* pks48, const uint64_t* bitmap, size_t k,
                                        const uint8_t* msg32, const uint8_t* sig96, size_t ncomm,
                                        uint8_t* status, uint8_t* agg_pk48_out);
+
+/* ---- the same with a RESIDENT validator pool (BASELINE configs[2], variant "keys pre-decoded in HBM"): the pool's keys are
+ *      decoded and subgroup-checked once (PublicKey::try_from, src/bls.rs:219-223) and kept in HBM as affine Montgomery limb-SoA;
+ *      committees are lists of pool indices.  status (nullable) of pool_create: BLSGPU_DE_* per key; an index that is out of range or
+ *      names an undecodable key makes its committee BLSGPU_ST_BAD_PUBKEY. */
+int blsgpu_pool_create(blsgpu_ctx* ctx, const uint8_t* pks48, size_t n, int* handle, uint8_t* status);
+int blsgpu_pool_free(blsgpu_ctx* ctx, int handle);
+int blsgpu_pool_fast_aggregate_verify(blsgpu_ctx* ctx, int handle, const uint32_t* idx /* ncomm*k */, const uint64_t* bitmap, size_t k,
+                                      const uint8_t* msg32, const uint8_t* sig96, size_t ncomm, uint8_t* status, uint8_t* agg_pk48_out);
 
 /* ---- hash_to_g2  (src/bls.rs:477-493; algorithm spec src/hasher.rs:58-173, 352-502, 294-348, 664-673) ------- */
 int blsgpu_hash_to_g2_batch(blsgpu_ctx* ctx, const uint8_t* msg, const uint32_t* msg_off, size_t n, uint8_t* out96);

@@ -38,6 +38,8 @@ static inline op_desc op_shape(int op) {
         case 26: return {2, 2};   // fp2_mul_xi
         case 27: return {3, 2};   // fp2_mul_fp
         case 28: return {10, 6};  // jac_add_mixed<fp2>, separate output
+        case 29: return {2, 1};   // fp_redc_wide(fp_mul_wide(a, b)) == fp_mul
+        case 30: return {4, 2};   // lazy-reduction fp2 product (3 wide products, 2 reductions)
         default: return {0, 0};
     }
 }
@@ -76,6 +78,10 @@ BLS_HD void run_op(int op, const fp* in, fp* out) {
         case 26: ld2(a, in); st2(out, fp2_mul_xi(a)); break;
         case 27: ld2(a, in); st2(out, fp2_mul_fp(a, in[2])); break;
         case 28: ld2(P.X, in); ld2(P.Y, in + 2); ld2(P.Z, in + 4); ld2(A.x, in + 6); ld2(A.y, in + 8); jac_add_mixed(R, P, A); st2(out, R.X); st2(out + 2, R.Y); st2(out + 4, R.Z); break;
+        case 29: { fpw T; fp_mul_wide(T, in[0], in[1]); out[0] = fp_redc_wide(T); break; }
+        case 30: { fpw T0, T1, T2; fp_mul_wide(T0, in[0], in[2]); fp_mul_wide(T1, in[1], in[3]); fp sa, sb; fp_add_raw(sa, in[0], in[1]); fp_add_raw(sb, in[2], in[3]);
+                   fp_mul_wide(T2, sa, sb); fpw_sub(T2, T2, T0); fpw_sub(T2, T2, T1); fpw_sub(T0, T0, T1); fpw_add(T0, T0, fpw_p_squared());
+                   out[0] = fp_redc_wide(T0); out[1] = fp_redc_wide(T2); break; }
         default: break;
     }
     (void)d;

@@ -347,3 +347,39 @@ def test_empty_batch_and_multi_chunk_paths(ctx, C):
         assert int(np.unpackbits(dbm.cpu().numpy().view(np.uint8), bitorder="little").sum()) == n
     finally:
         ctx.set_pointer_mode(False); ctx.set_chunk(1 << 20)
+
+def test_resident_pool_committees(ctx, C):
+    """cfg 3a: committees as indices into a pool decoded once == the same committees given as compressed keys == the oracle"""
+    from bls_verify_gadget_b200 import synth
+    nc, k, pool = 8, 96, 512
+    pks, msg, sig, pool_pk, idx = synth.committees(ctx, nc, k=k, pool=pool)
+    pool_pk = pool_pk.copy(); pool_pk[7, 20] ^= 0x40                            # one undecodable key in the pool
+    pks = pool_pk[idx.reshape(-1)].reshape(-1).copy()
+    h, codes = ctx.pool_create(pool_pk.reshape(-1)); assert codes[7] > 1 and (np.delete(codes, 7) == 0).all()
+    rng = np.random.default_rng(8); bits = rng.random(nc * k) < 0.7
+    bm = np.zeros((nc * k + 63) // 64, dtype=np.uint64)
+    for j in np.nonzero(bits)[0]: bm[j // 64] |= np.uint64(1) << np.uint64(j % 64)
+    for bitmap in (None, bm):
+        st, agg = ctx.pool_fast_aggregate_verify(h, idx, k, msg, sig, bitmap=bitmap, want_agg=True)
+        st2, agg2 = ctx.fast_aggregate_verify(pks, k, msg, sig, bitmap=bitmap, want_agg=True)
+        ost, oagg = C.fast_aggregate_verify(pks, k, msg, sig, bitmap=bitmap, want_agg=True, threads=8)
+        assert list(st) == list(st2) == list(ost)
+        ok = st <= 1
+        assert np.array_equal(agg.reshape(nc, 48)[ok], oagg.reshape(nc, 48)[ok]) and np.array_equal(agg2.reshape(nc, 48)[ok], oagg.reshape(nc, 48)[ok])
+    uses7 = [(idx[c] == 7).any() for c in range(nc)]
+    st = ctx.pool_fast_aggregate_verify(h, idx, k, msg, sig)
+    assert all((s == 2) == u for s, u in zip(st, uses7)) and (st[~np.array(uses7)] == 0).all()
+    ctx.pool_free(h)
+
+def test_cooperative_final_exponentiation_matches(ctx, C):
+    """six-lanes-per-item hard part (csrc/coop.cuh) == one-thread-per-item final exponentiation == oracle: statuses and GT bytes"""
+    from bls_verify_gadget_b200 import synth
+    n = 333                                                               # not a multiple of 5 (items per warp) nor 20 (items per CTA)
+    pk, msg, sig, exp = synth.verify_batch_inputs(ctx, n, every=6, fast=False)
+    msgs = [msg[32 * i:32 * i + 32].tobytes() for i in range(n)]
+    st0, gt0 = ctx.verify(pk, msgs, sig, want_gt=True)
+    ctx.set_coop(True)
+    try: st1, gt1 = ctx.verify(pk, msgs, sig, want_gt=True)
+    finally: ctx.set_coop(False)
+    ost, ogt = C.verify(pk, msgs, sig, want_gt=True, threads=8)
+    assert list(st0) == list(st1) == list(ost) == list(exp) and gt0.tobytes() == gt1.tobytes() == ogt.tobytes()
