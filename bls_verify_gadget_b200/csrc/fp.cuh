@@ -157,6 +157,19 @@ BLS_HD fp fp_neg(const fp& a) {
     return fp_select(fp_is_zero(a) ? 0xffffffffu : 0u, a, d);
 }
 BLS_HD fp fp_dbl(const fp& a) { return fp_add(a, a); }
+// a / 2 mod p: (a + (a odd ? p : 0)) >> 1 -- ALU only (the Montgomery image of a/2 is half the image of a)
+BLS_HD fp fp_half(const fp& a) {
+    uint32_t mask = 0u - (a.l[0] & 1u);
+    fp m = fp_modulus();
+#pragma unroll
+    for (int i = 0; i < 12; i++) m.l[i] &= mask;
+    fp t; fp_add_raw(t, a, m);                       // < 2p < 2^382: no carry out
+    fp r;
+#pragma unroll
+    for (int i = 0; i < 11; i++) r.l[i] = (t.l[i] >> 1) | (t.l[i + 1] << 31);
+    r.l[11] = t.l[11] >> 1;
+    return r;
+}
 // canonical (non-Montgomery) integer comparison helpers work on canonical limbs
 BLS_HD bool fp_raw_geq(const fp& a, const fp& b) { fp t; return fp_sub_raw(t, a, b) == 0; }
 

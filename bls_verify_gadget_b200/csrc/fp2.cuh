@@ -27,6 +27,7 @@ BLS_HD fp2 fp2_add(const fp2& a, const fp2& b) { fp2 r; r.c0 = fp_add(a.c0, b.c0
 BLS_HD fp2 fp2_sub(const fp2& a, const fp2& b) { fp2 r; r.c0 = fp_sub(a.c0, b.c0); r.c1 = fp_sub(a.c1, b.c1); return r; }
 #endif
 BLS_HD fp2 fp2_dbl(const fp2& a) { return fp2_add(a, a); }
+BLS_HD fp2 fp2_half(const fp2& a) { fp2 r; r.c0 = fp_half(a.c0); r.c1 = fp_half(a.c1); return r; }
 BLS_HD fp2 fp2_neg(const fp2& a) { fp2 r; r.c0 = fp_neg(a.c0); r.c1 = fp_neg(a.c1); return r; }
 BLS_HD fp2 fp2_conj(const fp2& a) { fp2 r; r.c0 = a.c0; r.c1 = fp_neg(a.c1); return r; }
 BLS_HD fp2 fp2_mul_xi(const fp2& a) { fp2 r; r.c0 = fp_sub(a.c0, a.c1); r.c1 = fp_add(a.c0, a.c1); return r; }   // * (1+u)

@@ -42,6 +42,7 @@ emit_fp("BLS_C_TWO_INV", pow(2, p - 2, p))
 emit_fp("BLS_C_FOUR", 4)
 emit_fp("BLS_C_2_256", 1 << 256)
 emit_words("BLS_C_P_SQUARED", p * p, 24)
+emit_words("BLS_C_3P_SQUARED", 3 * p * p, 24)      # offset of the lazily reduced Fp2 dot products (wide.cuh)
 # offsets of the lazily reduced cooperative Fp12 product (coop.cuh): (16 - 2k) p^2 on the real and (5 - k) p^2 on the imaginary accumulator of lane k
 out.append("#define BLS_C_COOP_OFF_RE {" + ", ".join(fmt(limbs((16 - 2 * k) * p * p, 24)) for k in range(6)) + "}")
 out.append("#define BLS_C_COOP_OFF_IM {" + ", ".join(fmt(limbs((5 - k) * p * p, 24)) for k in range(6)) + "}")

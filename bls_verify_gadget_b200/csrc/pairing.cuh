@@ -16,13 +16,12 @@ struct g2_proj { fp2 x, y, z; };          // homogeneous projective running poin
 
 // doubling step: R <- 2R, line coefficients (c0, c1, c2) for mul_by_014(c0, c1*px, c2*py)
 BLS_NOINLINE void miller_dbl(g2_proj& r, fp2& c0, fp2& c1, fp2& c2) {
-    fp two_inv = fp_two_inv();
-    fp2 a = fp2_mul_fp(fp2_mul(r.x, r.y), two_inv);
+    fp2 a = fp2_half(fp2_mul(r.x, r.y));                    // ark-ec multiplies by 1/2; halving is ALU-only and gives the same element
     fp2 b = fp2_sqr(r.y), c = fp2_sqr(r.z);
     fp2 c3 = fp2_add(fp2_dbl(c), c);
     fp2 e = fp2_mul_xi(fp2_dbl(fp2_dbl(c3)));               // 4(1+u) * 3c
     fp2 f = fp2_add(fp2_dbl(e), e);
-    fp2 g = fp2_mul_fp(fp2_add(b, f), two_inv);
+    fp2 g = fp2_half(fp2_add(b, f));
     fp2 h = fp2_sub(fp2_sqr(fp2_add(r.y, r.z)), fp2_add(b, c));
     fp2 i = fp2_sub(e, b);
     fp2 j = fp2_sqr(r.x);

@@ -4,6 +4,7 @@
 // Replaces the arkworks tower used by Bls12::multi_pairing (reference src/bls.rs:454-457).
 #pragma once
 #include "fp2.cuh"
+#include "wide.cuh"
 
 namespace bls {
 
@@ -40,6 +41,12 @@ BLS_FP6_LIN void fp6_neg(fp6& r, const fp6& a) {
 }
 BLS_FP6_LIN void fp6_mul_v(fp6& r, const fp6& a) { fp2 t = fp2_mul_xi(a.c2); fp2 u = a.c1, w = a.c0; r.c2 = u; r.c1 = w; r.c0 = t; }
 
+// BLS_LAZY (default): in the Miller loop the Fp6/Fp12 products are sums of Fp2 products accumulated UNREDUCED (wide.cuh) --
+// one Montgomery reduction per output coefficient, no conditional subtractions between the products, fewer Fp6 temporaries.
+// The final exponentiation keeps the separately reduced Karatsuba forms: measured faster there (profiles/r01_tuning.md).
+#ifndef BLS_LAZY
+#define BLS_LAZY 1
+#endif
 // 6 Fp2 products (Karatsuba over the cubic extension)
 BLS_NOINLINE void fp6_mul(fp6& r, const fp6& a, const fp6& b) {
     fp2 v0 = fp2_mul(a.c0, b.c0), v1 = fp2_mul(a.c1, b.c1), v2 = fp2_mul(a.c2, b.c2);
@@ -49,6 +56,16 @@ BLS_NOINLINE void fp6_mul(fp6& r, const fp6& a, const fp6& b) {
     r.c0 = fp2_add(v0, fp2_mul_xi(t0));
     r.c1 = fp2_add(t1, fp2_mul_xi(v2));
     r.c2 = fp2_add(t2, v1);
+}
+// schoolbook over the cubic extension, each output coefficient one 3-term dot product (27 wide products + 6 reductions =
+// 4,824 IMAD.WIDE against 5,400 for six separately reduced Karatsuba products)
+BLS_NOINLINE void fp6_mul_lz(fp6& r, const fp6& a, const fp6& b) {
+    fp2 xb1 = fp2_mul_xi(b.c1), xb2 = fp2_mul_xi(b.c2);
+    fp2 t0, t1, t2;
+    fp2_dot3(t0, a.c0, b.c0, a.c1, xb2, a.c2, xb1);
+    fp2_dot3(t1, a.c0, b.c1, a.c1, b.c0, a.c2, xb2);
+    fp2_dot3(t2, a.c0, b.c2, a.c1, b.c1, a.c2, b.c0);
+    r.c0 = t0; r.c1 = t1; r.c2 = t2;
 }
 // a * (b0 + b1 v): 5 Fp2 products
 BLS_NOINLINE void fp6_mul_by_01(fp6& r, const fp6& a, const fp2& b0, const fp2& b1) {
@@ -94,14 +111,35 @@ BLS_NOINLINE void fp12_mul(fp12& r, const fp12& a, const fp12& b) {
 // complex squaring: 2 Fp6 products
 BLS_NOINLINE void fp12_sqr(fp12& r, const fp12& a) {
     fp6 ab, s0, s1, t;
-    fp6_mul(ab, a.c0, a.c1);
+#if BLS_LAZY
+#define BLS_FP6_MUL_SQR fp6_mul_lz
+#else
+#define BLS_FP6_MUL_SQR fp6_mul
+#endif
+    BLS_FP6_MUL_SQR(ab, a.c0, a.c1);
     fp6_add(s0, a.c0, a.c1);
     fp6_mul_v(t, a.c1); fp6_add(s1, a.c0, t);
-    fp6_mul(s0, s0, s1);                           // (a0+a1)(a0+v a1) = a0^2 + v a1^2 + (1+v) a0a1
+    BLS_FP6_MUL_SQR(s0, s0, s1);                   // (a0+a1)(a0+v a1) = a0^2 + v a1^2 + (1+v) a0a1
     fp6_sub(s0, s0, ab); fp6_mul_v(t, ab); fp6_sub(r.c0, s0, t);
     fp6_add(r.c1, ab, ab);
 }
 // f * (c0 + c1 v + c4 v w): the sparse line element of the M-type twist (arkworks mul_by_014)
+#if BLS_LAZY
+// In the basis 1, w, .., w^5 (w^2 = v, w^6 = xi) f = sum g_k w^k with g = (c0.c0, c1.c0, c0.c1, c1.c1, c0.c2, c1.c2) and the
+// line is l0 + l2 w^2 + l3 w^3: out_k = g_k l0 + g_{k-2} l2 + g_{k-3} l3, indices mod 6, wrapped terms times xi (folded
+// into the line coefficient).  Six 3-term dot products: 9,648 IMAD.WIDE against 11,700, and no Fp6 temporaries.
+BLS_NOINLINE void fp12_mul_by_014(fp12& f, const fp2& c0, const fp2& c1, const fp2& c4) {
+    fp2 l0 = c0, l2 = c1, l3 = c4, xl2 = fp2_mul_xi(c1), xl3 = fp2_mul_xi(c4);
+    fp2 o0, o1, o2, o3, o4, o5;
+    fp2_dot3(o0, f.c0.c0, l0, f.c0.c2, xl2, f.c1.c1, xl3);
+    fp2_dot3(o1, f.c1.c0, l0, f.c1.c2, xl2, f.c0.c2, xl3);
+    fp2_dot3(o2, f.c0.c1, l0, f.c0.c0, l2, f.c1.c2, xl3);
+    fp2_dot3(o3, f.c1.c1, l0, f.c1.c0, l2, f.c0.c0, l3);
+    fp2_dot3(o4, f.c0.c2, l0, f.c0.c1, l2, f.c1.c0, l3);
+    fp2_dot3(o5, f.c1.c2, l0, f.c1.c1, l2, f.c0.c1, l3);
+    f.c0.c0 = o0; f.c1.c0 = o1; f.c0.c1 = o2; f.c1.c1 = o3; f.c0.c2 = o4; f.c1.c2 = o5;
+}
+#else
 BLS_NOINLINE void fp12_mul_by_014(fp12& f, const fp2& c0, const fp2& c1, const fp2& c4) {
     fp6 t0, t1, s;
     fp6_mul_by_01(t0, f.c0, c0, c1);
@@ -111,6 +149,7 @@ BLS_NOINLINE void fp12_mul_by_014(fp12& f, const fp2& c0, const fp2& c1, const f
     fp6_sub(s, s, t0); fp6_sub(f.c1, s, t1);
     fp6_mul_v(t1, t1); fp6_add(f.c0, t0, t1);
 }
+#endif
 BLS_NOINLINE void fp12_inv(fp12& r, const fp12& a) {
     fp6 t0, t1;
     fp6_mul(t0, a.c0, a.c0); fp6_mul(t1, a.c1, a.c1); fp6_mul_v(t1, t1); fp6_sub(t0, t0, t1);

@@ -1,7 +1,8 @@
 import ctypes, sys
-D = ctypes.CDLL("tests/_hostemu/libdevcheck.so"); D.dev_bench_op.restype = ctypes.c_float
+import os
+D = ctypes.CDLL(os.environ.get("DEVCHECK_SO", "tests/_hostemu/libdevcheck.so")); D.dev_bench_op.restype = ctypes.c_float
 # (op, name, Fp products per application)
-ops = [(21, "fp_mul", 1), (29, "wide+redc", 1), (30, "fp2_mul lazy inline", 3), (1, "fp2_mul", 3), (2, "fp2_sqr", 2), (3, "fp2_add", 0), (8, "fp6_mul", 18), (9, "fp12_mul", 54), (10, "fp12_sqr", 36), (11, "fp12_mul_by_014", 39), (12, "fp12_cyclo_sqr", 18), (5, "jac_dbl<fp2>", 16), (6, "jac_add_mixed<fp2>", 29)]
+ops = [(21, "fp_mul", 1), (29, "wide+redc", 1), (30, "fp2_mul lazy inline", 3), (31, "fp_mul_lz (split wide)", 1), (32, "fp2_dot n=1", 3), (33, "fp2_dot n=3", 9), (1, "fp2_mul", 3), (2, "fp2_sqr", 2), (3, "fp2_add", 0), (8, "fp6_mul", 18), (9, "fp12_mul", 54), (10, "fp12_sqr", 36), (11, "fp12_mul_by_014", 39), (12, "fp12_cyclo_sqr", 18), (5, "jac_dbl<fp2>", 16), (6, "jac_add_mixed<fp2>", 29)]
 for wps in (2,):
     n = 148 * 128 * wps
     for op, name, m in ops:

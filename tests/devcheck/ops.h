@@ -3,6 +3,7 @@
 // CUDA path can be compared host-vs-device (and against big-int arithmetic) in isolation.  TEST TOOL ONLY.
 #pragma once
 #include "stages.cuh"
+#include "wide.cuh"
 namespace bls {
 struct op_desc { int n_in, n_out; };
 #if defined(__CUDACC__)
@@ -40,6 +41,9 @@ static inline op_desc op_shape(int op) {
         case 28: return {10, 6};  // jac_add_mixed<fp2>, separate output
         case 29: return {2, 1};   // fp_redc_wide(fp_mul_wide(a, b)) == fp_mul
         case 30: return {4, 2};   // lazy-reduction fp2 product (3 wide products, 2 reductions)
+        case 31: return {2, 1};   // fp_mul_lz (split wide accumulator + reduction) == fp_mul
+        case 32: return {4, 2};   // fp2_dot, n = 1 == fp2_mul
+        case 33: return {12, 2};  // fp2_dot, n = 3 == x0 y0 + x1 y1 + x2 y2
         default: return {0, 0};
     }
 }
@@ -82,6 +86,9 @@ BLS_HD void run_op(int op, const fp* in, fp* out) {
         case 30: { fpw T0, T1, T2; fp_mul_wide(T0, in[0], in[2]); fp_mul_wide(T1, in[1], in[3]); fp sa, sb; fp_add_raw(sa, in[0], in[1]); fp_add_raw(sb, in[2], in[3]);
                    fp_mul_wide(T2, sa, sb); fpw_sub(T2, T2, T0); fpw_sub(T2, T2, T1); fpw_sub(T0, T0, T1); fpw_add(T0, T0, fpw_p_squared());
                    out[0] = fp_redc_wide(T0); out[1] = fp_redc_wide(T2); break; }
+        case 31: out[0] = fp_mul_lz(in[0], in[1]); break;
+        case 32: ld2(a, in); ld2(b, in + 2); fp2_dot1(c, a, b); st2(out, c); break;
+        case 33: { fp2 x0, y0, x1, y1, x2, y2; ld2(x0, in); ld2(y0, in + 2); ld2(x1, in + 4); ld2(y1, in + 6); ld2(x2, in + 8); ld2(y2, in + 10); fp2_dot3(c, x0, y0, x1, y1, x2, y2); st2(out, c); break; }
         default: break;
     }
     (void)d;

@@ -11,7 +11,7 @@ def dev_lib():
 def rand_fp(rng, n):
     a = rng.integers(0, 256, size=(n, 48), dtype=np.uint8); a[:, 47] &= 0x0f      # < 2^380 < p: a valid Montgomery image
     return a
-def check(ops=range(1, 31), n=256, seed=1):
+def check(ops=range(1, 34), n=256, seed=1):
     D = dev_lib(); rng = np.random.default_rng(seed); bad = []
     for op in ops:
         n_in, n_out = emu.op_shape(op)

@@ -4,7 +4,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__)); ROOT = os.path.dirname(os.path.dirname(HERE))
 SO = os.path.join(ROOT, "tests", "_hostemu", "libhostemu.so")
 SRC = [os.path.join(HERE, "hostemu.cpp"), os.path.join(ROOT, "tests", "devcheck", "ops.h")] + [os.path.join(ROOT, "bls_verify_gadget_b200", "csrc", f) for f in
-      ("fp.cuh", "fp2.cuh", "tower.cuh", "curve.cuh", "h2c.cuh", "pairing.cuh", "stages.cuh", "consts.cuh")]
+      ("fp.cuh", "fp2.cuh", "tower.cuh", "curve.cuh", "h2c.cuh", "pairing.cuh", "stages.cuh", "consts.cuh", "wide.cuh")]
 def build():
     if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in SRC):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
