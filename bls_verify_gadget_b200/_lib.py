@@ -7,7 +7,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("BLSGPU_SO") or os.path.join(_PKG, "libblsgpu.so")      # BLSGPU_SO: tuning builds (profiles/), never a fallback
 _SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("blsgpu.cu", "r1cs.cuh", "stages.cuh", "pairing.cuh", "h2c.cuh", "curve.cuh", "tower.cuh",
-                                                    "fp2.cuh", "fp.cuh", "consts.cuh", "coop.cuh")] + [os.path.join(_ROOT, "include", "blsgpu.h")]
+                                                    "fp2.cuh", "fp.cuh", "consts.cuh", "coop.cuh", "wide.cuh")] + [os.path.join(_ROOT, "include", "blsgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
 class BlsGpuError(RuntimeError): pass

@@ -1,0 +1,78 @@
+"""Host-side circuit builder: ctypes binding of libblsgadget.so (gadget/*.hpp), the C++ mirror of the reference's gadget
+code -- hash_to_g2_with_cons (src/hasher.rs:727-740) and BlsSignatureVerifyGadget::verify (src/constraints.rs:90-128).
+
+It produces what the K8 kernel consumes: the R1CS matrices (A, B, C) as CSR with canonical 48-byte little-endian
+coefficients and the assignment z = [1, instance.., witness..], in exactly the layout of `Context.r1cs_load` /
+`Context.r1cs_check`.  The satisfaction check itself runs on the GPU (csrc/r1cs.cuh); nothing here computes it for the
+product path.
+"""
+import ctypes, os, subprocess
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_PKG, "libblsgadget.so")
+_SRC = [os.path.join(_PKG, "gadget", f) for f in ("gadget_api.cpp", "r1cs_core.hpp", "r1cs_hasher.hpp", "r1cs_verify.hpp")] + \
+       [os.path.join(_PKG, "csrc", f) for f in ("fp.cuh", "fp2.cuh", "wide.cuh", "tower.cuh", "curve.cuh", "h2c.cuh", "pairing.cuh", "stages.cuh", "consts.cuh")]
+
+def build(force=False):
+    stale = not os.path.exists(SO_PATH) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in _SRC)
+    if force or stale:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(_PKG, "csrc"), "-o", SO_PATH, _SRC[0]])
+    return SO_PATH
+
+_lib = None
+def lib():
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(build())
+        L.blsgadget_first_unsatisfied.restype = ctypes.c_long
+        _lib = L
+    return _lib
+
+def _u8(b): return np.frombuffer(bytes(b) + b"\0", dtype=np.uint8)[:len(b)].copy()
+def _p(a): return a.ctypes.data_as(ctypes.c_void_p)
+
+class Circuit:
+    """A synthesised constraint system with its assignment.  `result` is the value of the Boolean the verify gadget returns
+    (None for the hash circuit), `output` the compressed H(m) of the hash circuit, `gt` the 576-byte GT element of the verify
+    circuit."""
+    def __init__(self, handle, result=None, output=None, gt=None):
+        if handle < 0: raise RuntimeError({-1: "synthesis failed", -2: "public key or signature does not decode"}.get(handle, f"error {handle}"))
+        self.h = handle; self.result = result; self.output = output; self.gt = gt
+        nr = ctypes.c_uint64(); nc = ctypes.c_uint64(); ni = ctypes.c_uint64(); nnz = (ctypes.c_uint64 * 3)()
+        lib().blsgadget_shape(handle, ctypes.byref(nr), ctypes.byref(nc), ctypes.byref(ni), nnz)
+        self.nrows, self.ncols, self.ninstance, self.nnz = nr.value, nc.value, ni.value, list(nnz)
+    def matrices(self):
+        """[(rowptr u64[nrows+1], col u32[nnz], coeff48 u8[nnz*48])] for A, B, C"""
+        rp = [np.empty(self.nrows + 1, np.uint64) for _ in range(3)]; cl = [np.empty(max(n, 1), np.uint32) for n in self.nnz]; cf = [np.empty(max(n, 1) * 48, np.uint8) for n in self.nnz]
+        P3 = ctypes.c_void_p * 3
+        lib().blsgadget_export(self.h, P3(*[_p(x) for x in rp]), P3(*[_p(x) for x in cl]), P3(*[_p(x) for x in cf]), None)
+        return [(rp[m], cl[m][:self.nnz[m]], cf[m][:48 * self.nnz[m]]) for m in range(3)]
+    def assignment(self):
+        """z as ncols * 48 bytes, canonical little-endian"""
+        z = np.empty(self.ncols * 48, np.uint8); lib().blsgadget_export(self.h, None, None, None, _p(z)); return z
+    def first_unsatisfied(self): return int(lib().blsgadget_first_unsatisfied(self.h))
+    def free(self):
+        if self.h >= 0: lib().blsgadget_free(self.h); self.h = -1
+    def __del__(self):
+        try: self.free()
+        except Exception: pass
+
+def hash_to_g2_circuit(message, message_is_instance=False):
+    m = _u8(message); out = np.zeros(96, np.uint8)
+    h = lib().blsgadget_hash_to_g2(_p(m), ctypes.c_size_t(len(message)), int(message_is_instance), _p(out))
+    return Circuit(h, output=out.tobytes())
+
+def verify_circuit(pk48, message, sig96):
+    pk = _u8(pk48); m = _u8(message); sg = _u8(sig96); res = ctypes.c_int(-1); gt = np.zeros(576, np.uint8)
+    h = lib().blsgadget_verify(_p(pk), _p(m), ctypes.c_size_t(len(message)), _p(sg), ctypes.byref(res), _p(gt))
+    return Circuit(h, result=bool(res.value) if h >= 0 else None, gt=gt.tobytes())
+
+def verify_witnesses(triples, threads=None):
+    """assignments of the verify circuit for a list of (pk48, msg, sig96) (all with the same message length), synthesised on
+    `threads` host threads; returns (z [n, ncols*48] u8, results [n] bool).  The matrices do not depend on the inputs."""
+    from concurrent.futures import ThreadPoolExecutor
+    def one(t):
+        c = verify_circuit(*t); z = c.assignment(); r = c.result; c.free(); return z, r
+    with ThreadPoolExecutor(max_workers=threads or os.cpu_count() or 1) as ex: out = list(ex.map(one, triples))
+    return np.stack([o[0] for o in out]), np.array([o[1] for o in out])

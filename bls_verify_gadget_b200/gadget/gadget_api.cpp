@@ -1,0 +1,64 @@
+// C ABI of the host-side circuit builder (libblsgadget.so): synthesises the reference's circuits and exports
+// (A, B, C) as CSR with canonical 48-byte little-endian coefficients plus the assignment z, exactly the layout
+// blsgpu_r1cs_load / blsgpu_r1cs_check (include/blsgpu.h) consume.  Host code only: no CUDA, no oracle.
+#include "r1cs_verify.hpp"
+#include <memory>
+#include <mutex>
+using namespace gadget;
+
+namespace {
+struct Circuit { ConstraintSystem cs; uint8_t out[96]; int out_len = 0; int result = -1; };
+std::mutex g_mu; std::vector<std::unique_ptr<Circuit>> g_tab;
+int put(std::unique_ptr<Circuit> c) { std::lock_guard<std::mutex> l(g_mu); for (size_t i = 0; i < g_tab.size(); i++) if (!g_tab[i]) { g_tab[i] = std::move(c); return (int)i; } g_tab.push_back(std::move(c)); return (int)g_tab.size() - 1; }
+Circuit* get(int h) { std::lock_guard<std::mutex> l(g_mu); return h >= 0 && (size_t)h < g_tab.size() ? g_tab[h].get() : nullptr; }
+void le48(uint8_t* o, const fp& m) { fp a = fp_from_mont(m); memcpy(o, a.l, 48); }
+}
+
+extern "C" {
+// hash_to_g2_with_cons(cs, message) of src/hasher.rs:727-740; the message bytes are witnesses (as in the reference's tests,
+// UInt8::new_witness_vec) or instance variables.  out96 = compressed H(m) as computed by the circuit.
+int blsgadget_hash_to_g2(const uint8_t* msg, size_t len, int msg_is_instance, uint8_t out96[96]) {
+    try {
+        auto c = std::make_unique<Circuit>();
+        std::vector<UInt8> m(len); for (size_t i = 0; i < len; i++) m[i] = msg_is_instance ? u8_input(c->cs, msg[i]) : u8_witness(c->cs, msg[i]);
+        G2Var h = hash_to_g2_with_cons(c->cs, m);
+        g2_aff a; bool ok = h.value_affine(a); g2_encode(c->out, a, !ok); c->out_len = 96;
+        if (out96) memcpy(out96, c->out, 96);
+        return put(std::move(c));
+    } catch (...) { return -1; }
+}
+// BlsSignatureVerifyGadget::verify of src/constraints.rs:90-128 on (pk, msg, sig) given as the reference's byte formats;
+// *result = the Boolean the gadget outputs.  Returns -2 when a point does not decode (the native path rejects it first).
+int blsgadget_verify(const uint8_t pk48[48], const uint8_t* msg, size_t len, const uint8_t sig96[96], int* result, uint8_t* gt576 /*nullable: GT computed by the circuit*/) {
+    try {
+        g1_aff pk; g2_aff sig;
+        int rp = g1_decode(pk, pk48), rs = g2_decode(sig, sig96);
+        if (rp != DEC_OK || rs != DEC_OK) return -2;
+        auto c = std::make_unique<Circuit>();
+        fp12 gt; c->result = synthesize_verify(c->cs, pk, msg, len, sig, &gt) ? 1 : 0;
+        if (gt576) fp12_to_bytes(gt576, gt);
+        if (result) *result = c->result;
+        return put(std::move(c));
+    } catch (...) { return -1; }
+}
+int blsgadget_shape(int h, uint64_t* nrows, uint64_t* ncols, uint64_t* ninstance, uint64_t nnz[3]) {
+    Circuit* c = get(h); if (!c) return -1;
+    *nrows = c->cs.num_constraints(); *ncols = c->cs.num_variables(); *ninstance = c->cs.num_instance;
+    for (int m = 0; m < 3; m++) nnz[m] = c->cs.col[m].size();
+    return 0;
+}
+// any pointer may be NULL; rowptr[m] has nrows + 1 entries, col[m] / coeff48[m] nnz[m], z48 ncols * 48 bytes
+int blsgadget_export(int h, uint64_t* const rowptr[3], uint32_t* const col[3], uint8_t* const coeff48[3], uint8_t* z48) {
+    Circuit* c = get(h); if (!c) return -1;
+    for (int m = 0; m < 3; m++) {
+        if (rowptr && rowptr[m]) memcpy(rowptr[m], c->cs.rowptr[m].data(), 8 * c->cs.rowptr[m].size());
+        if (col && col[m]) memcpy(col[m], c->cs.col[m].data(), 4 * c->cs.col[m].size());
+        if (coeff48 && coeff48[m]) for (size_t k = 0; k < c->cs.val[m].size(); k++) le48(coeff48[m] + 48 * k, c->cs.val[m][k]);
+    }
+    if (z48) for (size_t i = 0; i < c->cs.z.size(); i++) le48(z48 + 48 * i, c->cs.z[i]);
+    return 0;
+}
+// builder self-check on the host: index of the first unsatisfied row of the stored assignment, -1 if none
+long blsgadget_first_unsatisfied(int h) { Circuit* c = get(h); return c ? c->cs.first_unsatisfied() : -2; }
+int blsgadget_free(int h) { std::lock_guard<std::mutex> l(g_mu); if (h < 0 || (size_t)h >= g_tab.size() || !g_tab[h]) return -1; g_tab[h].reset(); return 0; }
+}

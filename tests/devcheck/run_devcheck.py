@@ -11,12 +11,23 @@ def dev_lib():
 def rand_fp(rng, n):
     a = rng.integers(0, 256, size=(n, 48), dtype=np.uint8); a[:, 47] &= 0x0f      # < 2^380 < p: a valid Montgomery image
     return a
-def check(ops=range(1, 34), n=256, seed=1):
+def edge_fp(rng, n):
+    """canonical field elements biased to the extremes the lazy-reduction bounds depend on: 0, 1, p-1, p-2, 2^380.., random"""
+    specials = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, (1 << 380) - 1, 1 << 380, P - (1 << 32), 0xffffffff, (1 << 352) - 1]
+    out = np.zeros((n, 48), np.uint8)
+    pick = rng.integers(0, 2 * len(specials), size=n)
+    for i in range(n):
+        v = specials[pick[i]] if pick[i] < len(specials) else int.from_bytes(rng.bytes(48), "little") % P
+        out[i] = np.frombuffer(v.to_bytes(48, "little"), np.uint8)
+    return out
+EDGE_OPS = (1, 2, 3, 4, 8, 9, 10, 11, 12, 21, 26, 27, 29, 30, 31, 32, 33)      # pure field arithmetic: any canonical input is valid
+def check(ops=range(1, 34), n=256, seed=1, edge=False):
     D = dev_lib(); rng = np.random.default_rng(seed); bad = []
     for op in ops:
         n_in, n_out = emu.op_shape(op)
         if not n_in: continue
-        x = rand_fp(rng, n * n_in).reshape(-1)
+        if edge and op not in EDGE_OPS: continue
+        x = (edge_fp(rng, n * n_in) if edge else rand_fp(rng, n * n_in)).reshape(-1)
         if op in (16,):          # make half of the inputs squares
             pass
         want = emu.run_op(op, x)
@@ -30,4 +41,4 @@ def check(ops=range(1, 34), n=256, seed=1):
             print('   mismatching output fps (item 0):', [k for k in range(n_out) if not np.array_equal(g[0, k], w[0, k])], ' items:', np.nonzero((g != w).any(axis=(1, 2)))[0][:8])
     return bad
 if __name__ == "__main__":
-    bad = check(); print("bad ops:", bad); sys.exit(1 if bad else 0)
+    bad = check() + check(edge=True, seed=7); print("bad ops:", bad); sys.exit(1 if bad else 0)

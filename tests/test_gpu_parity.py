@@ -275,6 +275,26 @@ def test_r1cs_differential(ctx, C):
     unsat = lambda w: [i for i in range(nrows) if not (int(bits[w, i // 64]) >> (i % 64)) & 1]
     assert unsat(3) == [0, 63, 64, 199] and unsat(36) == [100]
 
+def test_r1cs_verify_circuit_on_gpu(ctx, C):
+    """K8 on the REAL system: the matrices and assignments of BlsSignatureVerifyGadget::verify (constraints.rs:90-128) built
+    by the host-side builder (714 k rows).  Assignments of a valid and an invalid signature are both satisfying (the gadget
+    returns a Boolean), a perturbed one is not; every per-constraint bit must equal the oracle's."""
+    from bls_verify_gadget_b200 import gadget as G
+    pk = bytes.fromhex("a491d1b0ecd9bb917989f0e74f0dea0422eac4a873e5e2644f368dffb9a6e20fd6e10c1b77654d067c0618f6e5a7f79a")
+    sig = bytes.fromhex("882730e5d03f6b42c3abc26d3372625034e1d871b65a8a6b900a56dae22da98abbe1b68f85e49fe7652a55ec3d0591c2"
+                        "0767677e33e5cbb1207315c41a9ac03be39c2e7668edc043d6cb1d9fd93033caa8a1c5b0e84bedaeb6c64972503a43eb")
+    c = G.verify_circuit(pk, bytes.fromhex("56" * 32), sig); assert c.result is True         # constraints.rs:326-332
+    z, res = G.verify_witnesses([(pk, bytes.fromhex("56" * 32), sig), (pk, bytes.fromhex("78" * 32), sig)], threads=2)
+    assert list(res) == [True, False]
+    bad = z[0].reshape(c.ncols, 48).copy(); bad[c.ncols // 2, 0] ^= 1; bad[c.ncols - 5, 3] ^= 0x40
+    zz = np.concatenate([z[0], z[1], bad.reshape(-1)])
+    mats = c.matrices()
+    h = ctx.r1cs_load([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], c.nrows, c.ncols)
+    bits, allsat = ctx.r1cs_check(h, zz, 3, c.nrows)
+    ctx.r1cs_free(h)
+    obits, oall = C.r1cs_check([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], c.nrows, c.ncols, zz, 3, threads=C.hw_threads())
+    assert np.array_equal(bits, obits) and list(allsat) == list(oall) == [1, 1, 0]
+
 # ------------------------------------------------------------------------------------------ the reference-shaped API (src/bls.rs)
 def test_bls_api_like_reference_tests(ctx, eth):
     from bls_verify_gadget_b200 import BLS, PrivateKey, PublicKey, Signature, BLSError, hash_to_g2
@@ -308,7 +328,7 @@ def test_device_primitives_match_host_emulation():
     import subprocess, sys, os
     from conftest import ROOT
     so = os.path.join(ROOT, "tests", "_hostemu", "libdevcheck.so")
-    src = [os.path.join(ROOT, "tests", "devcheck", f) for f in ("devcheck.cu", "ops.h")]
+    src = [os.path.join(ROOT, "tests", "devcheck", f) for f in ("devcheck.cu", "ops.h")] + [os.path.join(ROOT, "bls_verify_gadget_b200", "csrc", f) for f in ("fp.cuh", "fp2.cuh", "wide.cuh", "tower.cuh", "pairing.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         os.makedirs(os.path.dirname(so), exist_ok=True)
         subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
@@ -316,6 +336,7 @@ def test_device_primitives_match_host_emulation():
     sys.path.insert(0, os.path.join(ROOT, "tests", "devcheck"))
     import run_devcheck
     for seed in (1, 2): assert run_devcheck.check(n=512, seed=seed) == []
+    assert run_devcheck.check(n=512, seed=3, edge=True) == []       # 0, 1, p-1, (p+-1)/2 ...: the bounds of the lazy-reduction accumulators
 
 # ------------------------------------------------------------------------------------------ boundary behaviour of the ABI
 def test_empty_batch_and_multi_chunk_paths(ctx, C):
