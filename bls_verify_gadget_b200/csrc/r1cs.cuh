@@ -7,65 +7,138 @@
 // Mapping: lane <-> witness, warp <-> 64 consecutive rows.  All lanes of a warp walk the same CSR row, so column
 // indices and coefficients are warp-uniform broadcast loads and the only divergent traffic is the gather of z,
 // which is coalesced by transposing each group of 32 witnesses to  uint4 [col][3][32]  first.
-// Coefficients +1 / -1 (the bulk of boolean/uint gadget rows) skip the Montgomery multiply; the branch is
-// warp-uniform.  z stays canonical: coeff(Montgomery) x z(canonical) -> canonical, no conversion of z needed.
+//
+// What the real verify circuit (714 k rows, built by bls_verify_gadget_b200/gadget) needed beyond the synthetic one:
+//  * 93 % of its columns are boolean variables (SHA-256 bits) and 40 % of its "general" coefficients (powers of two of the
+//    bit-packing rows) multiply such a column: the transpose marks columns that are 0/1 in all 32 witnesses and the
+//    product becomes a masked addition of the canonical coefficient (warp-uniform branch);
+//  * a few hundred rows carry 300-760 general coefficients (linear combinations that grow through runs of cyclotomic
+//    squarings): rows longer than R1_LONG are cut into R1_SEG-entry segments, one warp each, and combined afterwards --
+//    otherwise one warp serialises ~10^7 instructions while the rest of the GPU idles (measured: 34 ms per group -> see
+//    profiles/r01_summary.md).
+// Coefficients +1 / -1 (the bulk of boolean/uint gadget rows) skip the multiply; z stays canonical:
+// coeff(Montgomery) x z(canonical) -> canonical, no conversion of z needed.
 #pragma once
+#include <vector>
 
 struct r1cs_sys {
     size_t nrows, ncols, nnz[3];
-    uint64_t* rowptr[3]; uint32_t* col[3]; fp* coeff[3]; uint8_t* cls[3];
+    uint64_t* rowptr[3]; uint32_t* col[3]; fp* coeff[3]; fp* coeffc[3]; uint8_t* cls[3];
+    uint8_t* is_long; size_t n_long, n_seg;
+    uint32_t* long_row;            // [n_long] row index
+    uint32_t* seg_ptr;             // [n_long * 3 + 1] first segment of (long row, matrix)
+    uint64_t* seg_lo; uint64_t* seg_hi; uint8_t* seg_mat;     // [n_seg] non-zero range and matrix of a segment
 };
 enum { R1_GENERAL = 0, R1_PLUS_ONE = 1, R1_MINUS_ONE = 2 };
 #define R1_GROUP 32
+#ifndef R1_LONG
+#define R1_LONG 32
+#endif
+#define R1_SEG 64
+// The row kernels are bound by the latency of the z gather (1.5 KB per non-zero and 32 witnesses, from HBM: a group's
+// transposed z is 1 GB), not by registers: more resident warps than the pairing kernels' 8 per SM
+#ifndef R1_MINB
+#define R1_MINB 4
+#endif
 
-__global__ void __launch_bounds__(TPB, BLS_MINB) k_r1cs_prepare(const uint8_t* coeff48, size_t nnz, fp* out, uint8_t* cls) {
+// coefficient -> Montgomery image (for general z), canonical copy (for 0/1-valued z) and class byte
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_r1cs_prepare(const uint8_t* coeff48, size_t nnz, fp* out, fp* outc, uint8_t* cls) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= nnz) return;
     fp v; const uint8_t* b = coeff48 + 48 * i;
     for (int w = 0; w < 12; w++) v.l[w] = b[4 * w] | ((uint32_t)b[4 * w + 1] << 8) | ((uint32_t)b[4 * w + 2] << 16) | ((uint32_t)b[4 * w + 3] << 24);
     fp one = fp_zero(); one.l[0] = 1;
     fp m1; fp_sub_raw(m1, fp_modulus(), one);
     cls[i] = fp_eq(v, one) ? R1_PLUS_ONE : (fp_eq(v, m1) ? R1_MINUS_ONE : R1_GENERAL);
-    out[i] = fp_to_mont(v);
+    out[i] = fp_to_mont(v); outc[i] = v;
 }
-// z[w][col] (48-byte LE canonical) for witnesses w0 .. w0+g-1  ->  zt[(col*3 + c)*32 + lane]
-__global__ void __launch_bounds__(256) k_r1cs_transpose(const u32x4* z, size_t ncols, size_t w0, size_t g, u32x4* zt) {
+// z[w][col] (48-byte LE canonical) for witnesses w0 .. w0+g-1  ->  zt[(col*3 + c)*32 + lane];
+// zbool[col] = 1 when the column is 0/1-valued in every witness of the group
+__global__ void __launch_bounds__(256) k_r1cs_transpose(const u32x4* z, size_t ncols, size_t w0, size_t g, u32x4* zt, uint8_t* zbool) {
     size_t col = blockIdx.x * (size_t)8 + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
     if (col >= ncols) return;
     u32x4 zero; zero.x = zero.y = zero.z = zero.w = 0;
     const u32x4* src = z + ((w0 + lane) * ncols + col) * 3;
     bool live = (size_t)lane < g;
-    for (int c = 0; c < 3; c++) zt[(col * 3 + c) * 32 + lane] = live ? src[c] : zero;
+    u32x4 a = live ? src[0] : zero, b = live ? src[1] : zero, c = live ? src[2] : zero;
+    zt[(col * 3) * 32 + lane] = a; zt[(col * 3 + 1) * 32 + lane] = b; zt[(col * 3 + 2) * 32 + lane] = c;
+    bool small = a.x < 2 && !(a.y | a.z | a.w | b.x | b.y | b.z | b.w | c.x | c.y | c.z | c.w);
+    bool all = __all_sync(0xffffffffu, small);
+    if (lane == 0) zbool[col] = all ? 1 : 0;
 }
 __device__ __forceinline__ fp r1cs_load_z(const u32x4* zt, uint32_t col, int lane) {
     u32x4 a = zt[((size_t)col * 3) * 32 + lane], b = zt[((size_t)col * 3 + 1) * 32 + lane], c = zt[((size_t)col * 3 + 2) * 32 + lane];
     fp v; v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w; v.l[8] = c.x; v.l[9] = c.y; v.l[10] = c.z; v.l[11] = c.w;
     return v;
 }
-__device__ __forceinline__ fp r1cs_row_dot(const uint64_t* rowptr, const uint32_t* col, const fp* coeff, const uint8_t* cls, size_t row, const u32x4* zt, int lane) {
+// sum over the non-zeros [lo, hi) of one matrix row; every branch is warp-uniform (class per non-zero, zbool per column)
+__device__ __forceinline__ fp r1cs_range_dot(const r1cs_sys& s, int m, uint64_t lo, uint64_t hi, const u32x4* zt, const uint8_t* zbool, int lane) {
+    const uint32_t* col = s.col[m]; const uint8_t* cls = s.cls[m];
     fp acc = fp_zero();
-    for (uint64_t k = rowptr[row], e = rowptr[row + 1]; k < e; k++) {
-        fp zv = r1cs_load_z(zt, col[k], lane);
-        uint8_t c = cls[k];
+    for (uint64_t k = lo; k < hi; k++) {
+        uint32_t cj = col[k]; uint8_t c = cls[k];
+        if (c == R1_GENERAL && zbool[cj]) {                       // coefficient times a 0/1 column: masked addition
+            uint32_t bit = zt[((size_t)cj * 3) * 32 + lane].x;
+            acc = fp_add(acc, fp_select(0u - bit, s.coeffc[m][k], fp_zero()));
+            continue;
+        }
+        fp zv = r1cs_load_z(zt, cj, lane);
         if (c == R1_PLUS_ONE) acc = fp_add(acc, zv);
         else if (c == R1_MINUS_ONE) acc = fp_sub(acc, zv);
-        else acc = fp_add(acc, fp_mul(coeff[k], zv));
+        else acc = fp_add(acc, fp_mul(s.coeff[m][k], zv));
     }
     return acc;
 }
-// one warp per block of 64 rows; lane = witness in the group.  sat word for (witness, row block) written by its lane.
-__global__ void __launch_bounds__(TPB, BLS_MINB) k_r1cs_rows(r1cs_sys s, const u32x4* zt, size_t w0, size_t g, size_t words, uint64_t* sat_bits) {
+// a b == c (all canonical).  In the boolean / uint32 gadget rows (95 % of the verify circuit) a and b are small integers
+// (bits, 35-bit word sums): when one fits 64 bits and the other 32 bits in every lane the product is a 96-bit integer
+// below p and is compared directly -- two Montgomery products per row saved.  The test is warp-uniform.
+__device__ __forceinline__ bool r1cs_product_ok(const fp& a, const fp& b, const fp& c) {
+    uint32_t ah = a.l[2] | a.l[3] | a.l[4] | a.l[5] | a.l[6] | a.l[7] | a.l[8] | a.l[9] | a.l[10] | a.l[11];
+    uint32_t bh = b.l[2] | b.l[3] | b.l[4] | b.l[5] | b.l[6] | b.l[7] | b.l[8] | b.l[9] | b.l[10] | b.l[11];
+    bool small = (ah | bh) == 0 && (a.l[1] == 0 || b.l[1] == 0);
+    if (__all_sync(0xffffffffu, small)) {
+        uint64_t x = ((uint64_t)a.l[1] << 32) | a.l[0], y = ((uint64_t)b.l[1] << 32) | b.l[0];
+        uint64_t lo = x * y, hi = __umul64hi(x, y);               // < 2^96
+        uint32_t ch = c.l[3] | c.l[4] | c.l[5] | c.l[6] | c.l[7] | c.l[8] | c.l[9] | c.l[10] | c.l[11];
+        return ch == 0 && c.l[0] == (uint32_t)lo && c.l[1] == (uint32_t)(lo >> 32) && c.l[2] == (uint32_t)hi && (hi >> 32) == 0;
+    }
+    fp ab = fp_mul(fp_to_mont(a), b);                             // (aR)(b)/R = ab, canonical
+    return fp_eq(ab, c);
+}
+// one warp per block of 64 rows; lane = witness in the group.  Long rows are left to the segment kernels (bit 0 here).
+__global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_rows(r1cs_sys s, const u32x4* zt, const uint8_t* zbool, size_t w0, size_t g, size_t words, uint64_t* sat_bits) {
     size_t rb = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
     if (rb >= words) return;
     uint64_t bits = 0;
     size_t r_end = rb * 64 + 64 < s.nrows ? rb * 64 + 64 : s.nrows;
     for (size_t row = rb * 64; row < r_end; row++) {
-        fp a = r1cs_row_dot(s.rowptr[0], s.col[0], s.coeff[0], s.cls[0], row, zt, lane);
-        fp b = r1cs_row_dot(s.rowptr[1], s.col[1], s.coeff[1], s.cls[1], row, zt, lane);
-        fp c = r1cs_row_dot(s.rowptr[2], s.col[2], s.coeff[2], s.cls[2], row, zt, lane);
-        fp ab = fp_mul(fp_to_mont(a), b);                       // (aR)(b)/R = ab, canonical
-        if (fp_eq(ab, c)) bits |= 1ull << (row & 63);
+        if (s.is_long[row]) continue;
+        fp a = r1cs_range_dot(s, 0, s.rowptr[0][row], s.rowptr[0][row + 1], zt, zbool, lane);
+        fp b = r1cs_range_dot(s, 1, s.rowptr[1][row], s.rowptr[1][row + 1], zt, zbool, lane);
+        fp c = r1cs_range_dot(s, 2, s.rowptr[2][row], s.rowptr[2][row + 1], zt, zbool, lane);
+        if (r1cs_product_ok(a, b, c)) bits |= 1ull << (row & 63);
     }
     if ((size_t)lane < g) sat_bits[(w0 + lane) * words + rb] = bits;
+}
+// one warp per segment of a long row: partial dot product of 32 witnesses -> part (limb-SoA over n_seg * 32 slots)
+__global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_segments(r1cs_sys s, const u32x4* zt, const uint8_t* zbool, u32x4* part) {
+    size_t sg = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
+    if (sg >= s.n_seg) return;
+    fp v = r1cs_range_dot(s, s.seg_mat[sg], s.seg_lo[sg], s.seg_hi[sg], zt, zbool, lane);
+    soa_store_fp(part, s.n_seg * 32, sg * 32 + lane, 0, v);
+}
+// one warp per long row: add the partial sums of each matrix, test the product, OR the bit into the row's word
+__global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_combine(r1cs_sys s, const u32x4* part, size_t w0, size_t g, size_t words, uint64_t* sat_bits) {
+    size_t li = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
+    if (li >= s.n_long) return;
+    fp v[3];
+    for (int m = 0; m < 3; m++) {
+        fp acc = fp_zero();
+        for (uint32_t sg = s.seg_ptr[li * 3 + m]; sg < s.seg_ptr[li * 3 + m + 1]; sg++) acc = fp_add(acc, soa_load_fp(part, s.n_seg * 32, (size_t)sg * 32 + lane, 0));
+        v[m] = acc;
+    }
+    size_t row = s.long_row[li];
+    if ((size_t)lane < g && r1cs_product_ok(v[0], v[1], v[2]))
+        atomicOr((unsigned long long*)&sat_bits[(w0 + lane) * words + (row >> 6)], 1ull << (row & 63));
 }
 __global__ void k_r1cs_all(const uint64_t* sat_bits, size_t nwit, size_t words, size_t nrows, uint8_t* all_sat) {
     size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (w >= nwit) return;
@@ -77,6 +150,13 @@ __global__ void k_r1cs_all(const uint64_t* sat_bits, size_t nwit, size_t words, 
     all_sat[w] = all ? 1 : 0;
 }
 
+template <class T> static int r1cs_upload(blsgpu_ctx* ctx, T** dst, const std::vector<T>& v) {
+    size_t n = v.size() ? v.size() : 1;
+    CU(cudaMalloc(dst, n * sizeof(T)));
+    if (v.size()) CU(cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
 extern "C" {
 int blsgpu_r1cs_load(blsgpu_ctx* ctx, const uint64_t* const rowptr[3], const uint32_t* const col[3], const uint8_t* const coeff48[3], size_t nrows, size_t ncols, int* handle) {
     ENTER(); if (!rowptr || !col || !coeff48 || !handle || !nrows || !ncols) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
@@ -86,21 +166,41 @@ int blsgpu_r1cs_load(blsgpu_ctx* ctx, const uint64_t* const rowptr[3], const uin
     memset(s, 0, sizeof *s); s->nrows = nrows; s->ncols = ncols;
     cudaMemcpyKind kind = ctx->ptr_mode == BLSGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     ctx->r1cs[h] = s;
+    std::vector<uint64_t> hrp[3];                                 // host copy of the row pointers: the long-row tables are built here
     for (int m = 0; m < 3; m++) {
-        uint64_t last = 0;
-        if (ctx->ptr_mode == BLSGPU_DEVICE) { CU(cudaMemcpyAsync(&last, rowptr[m] + nrows, 8, cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream)); }
-        else last = rowptr[m][nrows];
-        size_t nnz = s->nnz[m] = last, na = nnz ? nnz : 1;
-        CU(cudaMalloc(&s->rowptr[m], 8 * (nrows + 1))); CU(cudaMalloc(&s->col[m], 4 * na)); CU(cudaMalloc(&s->coeff[m], 48 * na)); CU(cudaMalloc(&s->cls[m], na));
+        hrp[m].resize(nrows + 1);
+        if (ctx->ptr_mode == BLSGPU_DEVICE) { CU(cudaMemcpyAsync(hrp[m].data(), rowptr[m], 8 * (nrows + 1), cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream)); }
+        else memcpy(hrp[m].data(), rowptr[m], 8 * (nrows + 1));
+        size_t nnz = s->nnz[m] = hrp[m][nrows], na = nnz ? nnz : 1;
+        CU(cudaMalloc(&s->rowptr[m], 8 * (nrows + 1))); CU(cudaMalloc(&s->col[m], 4 * na)); CU(cudaMalloc(&s->coeff[m], 48 * na)); CU(cudaMalloc(&s->coeffc[m], 48 * na)); CU(cudaMalloc(&s->cls[m], na));
         CU(cudaMemcpyAsync(s->rowptr[m], rowptr[m], 8 * (nrows + 1), kind, ctx->stream));
         if (nnz) {
             CU(cudaMemcpyAsync(s->col[m], col[m], 4 * nnz, kind, ctx->stream));
             uint8_t* raw; CU(cudaMalloc(&raw, 48 * nnz));
             CU(cudaMemcpyAsync(raw, coeff48[m], 48 * nnz, kind, ctx->stream));
-            LAUNCH(k_r1cs_prepare, nblk(nnz), TPB, (const uint8_t*)raw, nnz, s->coeff[m], s->cls[m]);
+            LAUNCH(k_r1cs_prepare, nblk(nnz), TPB, (const uint8_t*)raw, nnz, s->coeff[m], s->coeffc[m], s->cls[m]);
             CU(cudaStreamSynchronize(ctx->stream)); cudaFree(raw);
         }
     }
+    // long rows and their segments
+    std::vector<uint8_t> is_long(nrows, 0), seg_mat; std::vector<uint32_t> long_row, seg_ptr; std::vector<uint64_t> seg_lo, seg_hi;
+    for (size_t r = 0; r < nrows; r++) {
+        size_t len = 0; for (int m = 0; m < 3; m++) len += hrp[m][r + 1] - hrp[m][r];
+        if (len <= R1_LONG) continue;
+        is_long[r] = 1; long_row.push_back((uint32_t)r);
+        for (int m = 0; m < 3; m++) {
+            seg_ptr.push_back((uint32_t)seg_lo.size());
+            for (uint64_t k = hrp[m][r]; k < hrp[m][r + 1]; k += R1_SEG) { seg_lo.push_back(k); seg_hi.push_back(k + R1_SEG < hrp[m][r + 1] ? k + R1_SEG : hrp[m][r + 1]); seg_mat.push_back((uint8_t)m); }
+        }
+    }
+    seg_ptr.push_back((uint32_t)seg_lo.size());
+    s->n_long = long_row.size(); s->n_seg = seg_lo.size();
+    if (int rc = r1cs_upload(ctx, &s->is_long, is_long)) return rc;
+    if (int rc = r1cs_upload(ctx, &s->long_row, long_row)) return rc;
+    if (int rc = r1cs_upload(ctx, &s->seg_ptr, seg_ptr)) return rc;
+    if (int rc = r1cs_upload(ctx, &s->seg_lo, seg_lo)) return rc;
+    if (int rc = r1cs_upload(ctx, &s->seg_hi, seg_hi)) return rc;
+    if (int rc = r1cs_upload(ctx, &s->seg_mat, seg_mat)) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     *handle = h; return 0;
 }
@@ -108,7 +208,8 @@ int blsgpu_r1cs_free(blsgpu_ctx* ctx, int handle) {
     if (!ctx || handle < 0 || handle >= 16 || !ctx->r1cs[handle]) return BLSGPU_ERR_ARG;
     cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
     r1cs_sys* s = ctx->r1cs[handle];
-    for (int m = 0; m < 3; m++) { cudaFree(s->rowptr[m]); cudaFree(s->col[m]); cudaFree(s->coeff[m]); cudaFree(s->cls[m]); }
+    for (int m = 0; m < 3; m++) { cudaFree(s->rowptr[m]); cudaFree(s->col[m]); cudaFree(s->coeff[m]); cudaFree(s->coeffc[m]); cudaFree(s->cls[m]); }
+    cudaFree(s->is_long); cudaFree(s->long_row); cudaFree(s->seg_ptr); cudaFree(s->seg_lo); cudaFree(s->seg_hi); cudaFree(s->seg_mat);
     delete s; ctx->r1cs[handle] = nullptr; return 0;
 }
 int blsgpu_r1cs_check(blsgpu_ctx* ctx, int handle, const uint8_t* z48, size_t nwit, uint64_t* sat_bits, uint8_t* all_sat) {
@@ -118,10 +219,12 @@ int blsgpu_r1cs_check(blsgpu_ctx* ctx, int handle, const uint8_t* z48, size_t nw
     size_t words = (s.nrows + 63) / 64;
     bool host = ctx->ptr_mode == BLSGPU_HOST;
     // host mode stages one group of 32 witnesses at a time (32 * ncols * 48 bytes) so the workspace stays bounded
-    size_t zgroup = (size_t)R1_GROUP * s.ncols * 48;
-    if (int rc = ws_reserve(ctx, (host ? al(zgroup) : 0) + al(zgroup) + (host ? al(8 * words * nwit) + al(nwit) : 0) + 8192)) return rc;
+    size_t zgroup = (size_t)R1_GROUP * s.ncols * 48, part_bytes = (s.n_seg ? s.n_seg : 1) * 32 * 48;
+    if (int rc = ws_reserve(ctx, (host ? al(zgroup) : 0) + al(zgroup) + al(s.ncols) + al(part_bytes) + (host ? al(8 * words * nwit) + al(nwit) : 0) + 8192)) return rc;
     u32x4* zstage = host ? ws_take<u32x4>(ctx, zgroup / 16) : nullptr;
     u32x4* zt = ws_take<u32x4>(ctx, zgroup / 16);
+    uint8_t* zbool = ws_take<uint8_t>(ctx, s.ncols);
+    u32x4* part = ws_take<u32x4>(ctx, part_bytes / 16);
     uint64_t* dbits = host ? ws_take<uint64_t>(ctx, words * nwit) : sat_bits;
     uint8_t* dall = all_sat ? (host ? ws_take<uint8_t>(ctx, nwit) : all_sat) : nullptr;
     for (size_t w0 = 0; w0 < nwit; w0 += R1_GROUP) {
@@ -129,8 +232,12 @@ int blsgpu_r1cs_check(blsgpu_ctx* ctx, int handle, const uint8_t* z48, size_t nw
         const u32x4* zsrc; size_t wbase;
         if (host) { CU(cudaMemcpyAsync(zstage, z48 + w0 * s.ncols * 48, g * s.ncols * 48, cudaMemcpyHostToDevice, ctx->stream)); zsrc = zstage; wbase = 0; }
         else { zsrc = (const u32x4*)z48; wbase = w0; }
-        LAUNCH(k_r1cs_transpose, nblk(s.ncols, 8), 256, zsrc, s.ncols, wbase, g, zt);
-        LAUNCH(k_r1cs_rows, nblk(words, TPB / 32), TPB, s, (const u32x4*)zt, w0, g, words, dbits);
+        LAUNCH(k_r1cs_transpose, nblk(s.ncols, 8), 256, zsrc, s.ncols, wbase, g, zt, zbool);
+        LAUNCH(k_r1cs_rows, nblk(words, TPB / 32), TPB, s, (const u32x4*)zt, (const uint8_t*)zbool, w0, g, words, dbits);
+        if (s.n_long) {
+            LAUNCH(k_r1cs_segments, nblk(s.n_seg, TPB / 32), TPB, s, (const u32x4*)zt, (const uint8_t*)zbool, part);
+            LAUNCH(k_r1cs_combine, nblk(s.n_long, TPB / 32), TPB, s, (const u32x4*)part, w0, g, words, dbits);
+        }
     }
     if (dall) LAUNCH(k_r1cs_all, nblk(nwit), TPB, (const uint64_t*)dbits, nwit, words, s.nrows, dall);
     if (host) {

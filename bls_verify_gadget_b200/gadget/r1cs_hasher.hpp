@@ -183,11 +183,29 @@ struct DefaultFieldHasherWithCons {                                  // hasher.r
         ret.resize(len_in_bytes);
         return ret;
     }
-    // big-endian bytes -> field element modulo p: a linear combination of the bits (hasher.rs:71-104: head * 256^tail + tail)
+    // UInt8 slice (little-endian bytes, at most 47) -> one field variable: ToConstraintFieldGadget packs the bits into a fresh
+    // variable tied to the bit combination by one row (Boolean::le_bits_to_fp_var), so later rows read ONE column per element
+    FpVar to_constraint_field(const UInt8* bytes_le, size_t n) {
+        LC sum; fp val = fp_zero(), pw = fp_one(); bool all_const = true;
+        for (size_t i = 0; i < n; i++) for (int k = 0; k < 8; k++) {
+            const Boolean& b = bytes_le[i].b[k]; all_const &= b.cst;
+            if (!b.lc.t.empty()) sum += b.lc.scaled(pw);
+            if (b.val) val = fp_add(val, pw);
+            pw = fp_add(pw, pw);
+        }
+        if (all_const) return FpVar::constant(val);
+        FpVar v = FpVar::witness(cs, val);
+        cs.enforce(sum, LC::constant(fp_one()), v.lc);
+        return v;
+    }
+    // 64 big-endian bytes -> field element modulo p (hasher.rs:71-104): reverse, split into the 47 high bytes ("head") and the
+    // 17 low bytes ("tail"), pack each, f = head * 256^17 + tail
     FpVar bytes_be_to_fp(const UInt8* bytes, size_t n) {
-        FpVar f = FpVar::zero(); fp pw = fp_one();
-        for (size_t i = n; i-- > 0;) for (int k = 0; k < 8; k++) { f = f + bytes[i].b[k].to_fp().scaled(pw); pw = fp_add(pw, pw); }
-        return f;
+        std::vector<UInt8> le(bytes, bytes + n); std::reverse(le.begin(), le.end());
+        size_t pos = (381 - 1) / 8, ntail = n - pos;
+        FpVar f_tail = to_constraint_field(le.data(), ntail), f_head = to_constraint_field(le.data() + ntail, pos);
+        fp sh = fp_one(); for (size_t i = 0; i < 8 * ntail; i++) sh = fp_add(sh, sh);
+        return f_head.scaled(sh) + f_tail;
     }
     std::vector<Fp2Var> hash_to_field(const std::vector<UInt8>& message, size_t count) {                // hasher.rs:58-107
         if (count != 2) throw std::invalid_argument("count must be 2");
