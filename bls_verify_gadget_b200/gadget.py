@@ -68,6 +68,15 @@ def verify_circuit(pk48, message, sig96):
     h = lib().blsgadget_verify(_p(pk), _p(m), ctypes.c_size_t(len(message)), _p(sg), ctypes.byref(res), _p(gt))
     return Circuit(h, result=bool(res.value) if h >= 0 else None, gt=gt.tobytes())
 
+def aggregate_verify_circuit(pks48, bitmap, message, sig96):
+    """BlsSignatureVerifyGadget::aggregate_verify (constraints.rs:153-167): `pks48` n*48 bytes, `bitmap` n truthy/falsy values.
+    The returned circuit carries `result` and `count` (the UInt32 participant count the gadget outputs)."""
+    pk = _u8(pks48); n = len(pk) // 48; bm = np.array([1 if b else 0 for b in bitmap], dtype=np.uint8); assert len(bm) == n
+    m = _u8(message); sg = _u8(sig96); res = ctypes.c_int(-1); cnt = ctypes.c_uint32(0)
+    h = lib().blsgadget_aggregate_verify(_p(pk), ctypes.c_size_t(n), _p(bm), _p(m), ctypes.c_size_t(len(message)), _p(sg), ctypes.byref(res), ctypes.byref(cnt))
+    c = Circuit(h, result=bool(res.value) if h >= 0 else None); c.count = cnt.value
+    return c
+
 def verify_witnesses(triples, threads=None):
     """assignments of the verify circuit for a list of (pk48, msg, sig96) (all with the same message length), synthesised on
     `threads` host threads; returns (z [n, ncols*48] u8, results [n] bool).  The matrices do not depend on the inputs."""

@@ -41,6 +41,23 @@ int blsgadget_verify(const uint8_t pk48[48], const uint8_t* msg, size_t len, con
         return put(std::move(c));
     } catch (...) { return -1; }
 }
+// aggregate_verify of src/constraints.rs:153-167: n compressed keys, one bitmap byte per key (0 / non-zero)
+int blsgadget_aggregate_verify(const uint8_t* pks48, size_t n, const uint8_t* bitmap, const uint8_t* msg, size_t len, const uint8_t sig96[96], int* result, uint32_t* count) {
+    try {
+        std::vector<g1_aff> pks(n); g2_aff sig;
+        for (size_t i = 0; i < n; i++) {
+            if (i && !memcmp(pks48 + 48 * i, pks48 + 48 * (i - 1), 48)) { pks[i] = pks[i - 1]; continue; }                // repeated keys (the reference's test uses 511 copies) decode once
+            if (g1_decode(pks[i], pks48 + 48 * i) != DEC_OK) return -2;
+        }
+        if (g2_decode(sig, sig96) != DEC_OK) return -2;
+        auto c = std::make_unique<Circuit>();
+        uint32_t cnt = 0;
+        c->result = synthesize_aggregate_verify(c->cs, pks, std::vector<uint8_t>(bitmap, bitmap + n), msg, len, sig, &cnt) ? 1 : 0;
+        if (result) *result = c->result;
+        if (count) *count = cnt;
+        return put(std::move(c));
+    } catch (...) { return -1; }
+}
 int blsgadget_shape(int h, uint64_t* nrows, uint64_t* ncols, uint64_t* ninstance, uint64_t nnz[3]) {
     Circuit* c = get(h); if (!c) return -1;
     *nrows = c->cs.num_constraints(); *ncols = c->cs.num_variables(); *ninstance = c->cs.num_instance;

@@ -176,17 +176,33 @@ struct PairingVar {
     }
 };
 
-// BlsSignatureVerifyGadget::verify with the allocation modes of the reference's own test (constraints.rs:335-366):
-// parameters constant, public key / message / signature witnesses.  Returns the value of the output Boolean; *gt (nullable)
-// receives the GT element the circuit computed.
-inline bool synthesize_verify(ConstraintSystem& cs, const g1_aff& pk, const uint8_t* msg, size_t len, const g2_aff& sig, fp12* gt = nullptr) {
-    // PublicKeyVar / SignatureVar: projective witnesses (x, y, z = 1); like the reference, no on-curve / subgroup rows (constraints.rs:101-106)
-    FpVar pkx = FpVar::witness(cs, pk.x), pky = FpVar::witness(cs, pk.y), pkz = FpVar::witness(cs, fp_one());
-    std::vector<UInt8> m(len); for (size_t i = 0; i < len; i++) m[i] = u8_witness(cs, msg[i]);
+// G1Var: homogeneous projective point on y^2 = x^3 + 4 over Fp, complete addition (Renes-Costello-Batina, a = 0), as
+// ark-r1cs-std's short_weierstrass::ProjectiveVar.  (0 : 1 : 0) is the identity.
+struct G1Var {
+    FpVar x, y, z;
+    static G1Var make(const FpVar& x, const FpVar& y, const FpVar& z) { G1Var r; r.x = x; r.y = y; r.z = z; return r; }
+    static G1Var zero() { return make(FpVar::zero(), FpVar::one(), FpVar::zero()); }
+    static G1Var witness(ConstraintSystem& cs, const g1_aff& p) { return make(FpVar::witness(cs, p.x), FpVar::witness(cs, p.y), FpVar::witness(cs, fp_one())); }
+    G1Var add(ConstraintSystem& cs, const G1Var& q) const {
+        fp b3 = fp_from_u64(12);
+        FpVar t0 = x.mul(cs, q.x), t1 = y.mul(cs, q.y), t2 = z.mul(cs, q.z);
+        FpVar t3 = (x + y).mul(cs, q.x + q.y) - t0 - t1;
+        FpVar t4 = (y + z).mul(cs, q.y + q.z) - t1 - t2;
+        FpVar y3 = (x + z).mul(cs, q.x + q.z) - t0 - t2;
+        FpVar x3 = t0.dbl() + t0;
+        FpVar bt2 = t2.scaled(b3), z3 = t1 + bt2, t1m = t1 - bt2, by3 = y3.scaled(b3);
+        return make(t3.mul(cs, t1m) - t4.mul(cs, by3), t1m.mul(cs, z3) + by3.mul(cs, x3), z3.mul(cs, t4) + x3.mul(cs, t3));
+    }
+};
+inline G1Var select_g1(ConstraintSystem& cs, const Boolean& c, const G1Var& t, const G1Var& f) { return G1Var::make(c.select(cs, t.x, f.x), c.select(cs, t.y, f.y), c.select(cs, t.z, f.z)); }
+
+// BlsSignatureVerifyGadget::verify (constraints.rs:90-128) on an already allocated public key; message bytes and the
+// signature are allocated as witnesses (the modes of the reference's tests, constraints.rs:335-366), parameters constant.
+inline bool verify_gadget(ConstraintSystem& cs, const G1Var& pk, const std::vector<UInt8>& m, const g2_aff& sig, fp12* gt) {
     G2Var sg = G2Var::make(Fp2Var::witness(cs, sig.x), Fp2Var::witness(cs, sig.y), Fp2Var::witness(cs, fp2_one()));
     // public_key.enforce_not_equal(zero) and prepare_g1: z has an inverse, affine coordinates by two products
-    FpVar zi = pkz.inverse(cs);
-    G1AffineVar P1; P1.x = pkx.mul(cs, zi); P1.y = pky.mul(cs, zi);
+    FpVar zi = pk.z.inverse(cs);
+    G1AffineVar P1; P1.x = pk.x.mul(cs, zi); P1.y = pk.y.mul(cs, zi);
     G1AffineVar G; G.x = FpVar::constant(fp_const(C_G1X)); G.y = FpVar::constant(fp_const(C_G1Y_NEG));               // -g1, a constant (bls.rs:449-450)
     G2Var h = hash_to_g2_with_cons(cs, m);
     G2PreparedVar hp = PairingVar::prepare_g2(cs, h), sp = PairingVar::prepare_g2(cs, sg);
@@ -194,6 +210,32 @@ inline bool synthesize_verify(ConstraintSystem& cs, const g1_aff& pk, const uint
     Fp12Var e = PairingVar::final_exponentiation(cs, f);
     if (gt) *gt = e.value();
     return e.is_one(cs).val;
+}
+// PublicKeyVar / SignatureVar are projective witnesses (x, y, z = 1); like the reference, no on-curve / subgroup rows
+// (constraints.rs:101-106).  Returns the value of the output Boolean; *gt (nullable) receives the GT element.
+inline bool synthesize_verify(ConstraintSystem& cs, const g1_aff& pk, const uint8_t* msg, size_t len, const g2_aff& sig, fp12* gt = nullptr) {
+    G1Var pkv = G1Var::witness(cs, pk);
+    std::vector<UInt8> m(len); for (size_t i = 0; i < len; i++) m[i] = u8_witness(cs, msg[i]);
+    return verify_gadget(cs, pkv, m, sig, gt);
+}
+// aggregate_verify / mapped_aggregate (constraints.rs:153-191): keys masked by a witness bitmap (select key or zero), summed
+// with the complete addition, the participant count accumulated with UInt32::addmany; then verify on the aggregate.
+// Allocation order follows the reference's test (constraints.rs:393-440): keys, bitmap, message, signature.
+inline bool synthesize_aggregate_verify(ConstraintSystem& cs, const std::vector<g1_aff>& pks, const std::vector<uint8_t>& bitmap, const uint8_t* msg, size_t len,
+                                        const g2_aff& sig, uint32_t* count_out, fp12* gt = nullptr) {
+    if (pks.size() != bitmap.size() || pks.empty()) throw std::invalid_argument("public_keys.len() != bitmap.len()");
+    std::vector<G1Var> keys; for (auto& p : pks) keys.push_back(G1Var::witness(cs, p));
+    std::vector<Boolean> bits; for (uint8_t b : bitmap) bits.push_back(Boolean::witness(cs, b != 0));
+    std::vector<UInt8> m(len); for (size_t i = 0; i < len; i++) m[i] = u8_witness(cs, msg[i]);
+    G1Var zero = G1Var::zero(), ret = zero;
+    UInt32 count; for (int i = 0; i < 32; i++) count.b[i] = Boolean::witness(cs, false);                              // UInt32::new_variable(|| Ok(0), Witness)
+    for (size_t i = 0; i < keys.size(); i++) {
+        ret = ret.add(cs, select_g1(cs, bits[i], keys[i], zero));
+        UInt32 inc = UInt32::constant(0); inc.b[0] = bits[i];                                                         // bit.select(&count_one, &count_zero)
+        count = u32_addmany(cs, {count, inc});
+    }
+    if (count_out) *count_out = count.value();
+    return verify_gadget(cs, ret, m, sig, gt);
 }
 
 }  // namespace gadget

@@ -60,3 +60,19 @@ def test_verify_circuit_oracle_check_and_perturbation():
     nun = c.nrows - int(np.unpackbits(bits[1].view(np.uint8), bitorder="little")[:c.nrows].sum())
     assert 1 <= nun <= 64                                                               # a flipped variable breaks only the rows that read it
     with pytest.raises(RuntimeError): G.verify_circuit(b"\xc0" + bytes(47), CASES[0][0], SIG)    # identity public key: rejected before synthesis (bls.rs:434)
+
+def test_aggregate_verify_circuit_reference_cases():
+    """constraints.rs:378-520: 512 keys (pk1, then 511 copies of pk2); bitmap {0, 1} set -> true with count 2; all set -> false"""
+    pk1 = PK
+    pk2 = bytes.fromhex("b301803f8b5ac4a1133581fc676dfedc60d891dd5fa99028805e5ea5b08d3491af75d0707adab3b70c6a6a580217bf81")
+    sig = bytes.fromhex("912c3615f69575407db9392eb21fee18fff797eeb2fbe1816366ca2a08ae574d8824dbfafb4c9eaa1cf61b63c6f9b69911f269b664c42947dd1b53ef1081926c"
+                        "1e82bb2a465f927124b08391a5249036146d6f3f1e17ff5f162f779746d830d1")
+    msg = bytes.fromhex("56" * 32); shapes = set()
+    for bitmap, expect, count in (([1, 1] + [0] * 510, True, 2), ([1] * 512, False, 512)):
+        c = G.aggregate_verify_circuit(pk1 + pk2 * 511, bitmap, msg, sig)
+        assert c.result == expect and c.count == count and c.first_unsatisfied() == -1
+        shapes.add((c.nrows, c.ncols, tuple(c.nnz))); c.free()
+    assert len(shapes) == 1
+    # native cross-check of the first case: fast_aggregate_verify over the two selected keys (tests/test_cases/fast_aggregate_verify)
+    st = C.fast_aggregate_verify(np.frombuffer(pk1 + pk2, np.uint8), 2, np.frombuffer(msg, np.uint8), np.frombuffer(sig, np.uint8), threads=1)
+    assert st[0] == 0
