@@ -174,7 +174,30 @@ BLS_NOINLINE void fp12_frob2(fp12& r, const fp12& a) {
     r.c0.c2 = fp2_mul_fp(a.c0.c2, FROB2[4]);
     r.c1.c2 = fp2_mul_fp(a.c1.c2, FROB2[5]);
 }
-// Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part): 3 Fp4 squarings
+// Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part): 3 Fp4 squarings.
+// BLS_CYCLO_COMPACT: the Fp4 squaring and the 3t +- 2a combination are out-of-line functions with operands and results BY
+// VALUE in registers -- inlined three / six times the routine was 52 KB, and with a 32 KB instruction cache behind L0
+// nearly half of its stall samples were `no_instruction`.  (A first compact form that passed the operands by reference
+// was slower: the round trip through local memory cost more than the instruction fetches.)
+#ifndef BLS_CYCLO_COMPACT
+#define BLS_CYCLO_COMPACT 1
+#endif
+#if BLS_CYCLO_COMPACT && defined(__CUDACC__)
+struct fp4_pair { fp2 t0, t1; };
+BLS_NOINLINE fp4_pair fp4_sqr_v(fp2 a, fp2 b) {                       // (a + b y)^2, y^2 = xi
+    fp2 ab = fp2_mul(a, b);
+    fp2 s = fp2_mul(fp2_add(a, b), fp2_add(a, fp2_mul_xi(b)));
+    fp4_pair r; r.t0 = fp2_sub(fp2_sub(s, ab), fp2_mul_xi(ab)); r.t1 = fp2_dbl(ab); return r;
+}
+BLS_NOINLINE fp2 cyclo_comb_v(fp2 t, fp2 a) { fp2 z = fp2_add(t, a); z = fp2_dbl(z); return fp2_add(z, t); }      // 3 t + 2 a
+BLS_NOINLINE void fp12_cyclo_sqr(fp12& r, const fp12& a) {
+    fp4_pair p0 = fp4_sqr_v(a.c0.c0, a.c1.c1), p1 = fp4_sqr_v(a.c1.c0, a.c0.c2), p2 = fp4_sqr_v(a.c0.c1, a.c1.c2);
+    fp2 n00 = cyclo_comb_v(p0.t0, fp2_neg(a.c0.c0)), n11 = cyclo_comb_v(p0.t1, a.c1.c1);
+    fp2 n10 = cyclo_comb_v(fp2_mul_xi(p2.t1), a.c1.c0), n02 = cyclo_comb_v(p2.t0, fp2_neg(a.c0.c2));
+    fp2 n01 = cyclo_comb_v(p1.t0, fp2_neg(a.c0.c1)), n12 = cyclo_comb_v(p1.t1, a.c1.c2);
+    r.c0.c0 = n00; r.c1.c1 = n11; r.c1.c0 = n10; r.c0.c2 = n02; r.c0.c1 = n01; r.c1.c2 = n12;
+}
+#else
 BLS_HD void fp4_sqr(fp2& t0, fp2& t1, const fp2& a, const fp2& b) {    // (a + b y)^2, y^2 = xi
     fp2 ab = fp2_mul(a, b);
     fp2 s = fp2_mul(fp2_add(a, b), fp2_add(a, fp2_mul_xi(b)));
@@ -195,5 +218,7 @@ BLS_NOINLINE void fp12_cyclo_sqr(fp12& r, const fp12& a) {
     z = fp2_sub(t2, a.c0.c1); z = fp2_dbl(z); r.c0.c1 = fp2_add(z, t2);
     z = fp2_add(t3, a.c1.c2); z = fp2_dbl(z); r.c1.c2 = fp2_add(z, t3);
 }
+
+#endif
 
 }  // namespace bls

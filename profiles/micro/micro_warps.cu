@@ -1,6 +1,6 @@
 // How many resident warps per SM sub-partition does the IMAD.WIDE pipe need?  (sm_100a)
 // Each kernel is launched as sms * w blocks of 128 threads (w warps per sub-partition, one block wave), w = 1, 2, 3, 4.
-//   B   two independent 8-long IMAD.WIDE.U32.X carry chains per step (no ALU work)
+//   B   two independent carry chains of 8 IMAD.WIDE.U32.X each per step (16 mad.lo/madc.hi pairs fuse to 8 IMAD.WIDE; no ALU work)
 //   M   dependent chain of out-of-line Montgomery products (csrc/fp.cuh fp_mul)
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I bls_verify_gadget_b200/csrc -o build/micro/micro_warps profiles/micro/micro_warps.cu
 #include <cstdio>
@@ -65,8 +65,8 @@ template <class K> void run(K k, uint32_t* sink, int sms, int w, int iters, doub
 int main() {
     int sms, khz; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0); cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
     uint32_t* sink; cudaMalloc(&sink, 64); double g = khz / 1e6;
-    for (int w = 1; w <= 4; w++) run(kB, sink, sms, w, 4096, 32, "B  2 chains x 16 IMAD.WIDE.X", g);
-    for (int w = 1; w <= 4; w++) run(kB4, sink, sms, w, 4096, 64, "B4 4 chains x 16 IMAD.WIDE.X", g);
+    for (int w = 1; w <= 4; w++) run(kB, sink, sms, w, 4096, 16, "B  2 chains x 8 IMAD.WIDE.X", g);
+    for (int w = 1; w <= 4; w++) run(kB4, sink, sms, w, 4096, 32, "B4 4 chains x 8 IMAD.WIDE.X (iterations serialised by a, b updates)", g);
     for (int w = 1; w <= 4; w++) run(kM, sink, sms, w, 2048, 300, "M  fp_mul chain (300 IMAD)", g);
     for (int w = 1; w <= 4; w++) run(kM2, sink, sms, w, 1024, 600, "M2 two inlined fp_mul (600 IMAD)", g);
     return 0;
