@@ -77,11 +77,18 @@ def aggregate_verify_circuit(pks48, bitmap, message, sig96):
     c = Circuit(h, result=bool(res.value) if h >= 0 else None); c.count = cnt.value
     return c
 
-def verify_witnesses(triples, threads=None):
+def verify_witnesses(triples, threads=None, ncols=None):
     """assignments of the verify circuit for a list of (pk48, msg, sig96) (all with the same message length), synthesised on
-    `threads` host threads; returns (z [n, ncols*48] u8, results [n] bool).  The matrices do not depend on the inputs."""
+    `threads` host threads in witness-only mode (no matrices: they do not depend on the inputs); returns
+    (z [n, ncols*48] u8, results [n] bool).  `ncols` comes from one full synthesis (done here when not given)."""
     from concurrent.futures import ThreadPoolExecutor
-    def one(t):
-        c = verify_circuit(*t); z = c.assignment(); r = c.result; c.free(); return z, r
-    with ThreadPoolExecutor(max_workers=threads or os.cpu_count() or 1) as ex: out = list(ex.map(one, triples))
-    return np.stack([o[0] for o in out]), np.array([o[1] for o in out])
+    if ncols is None:
+        c = verify_circuit(*triples[0]); ncols = c.ncols; c.free()
+    z = np.empty((len(triples), ncols * 48), np.uint8); res = np.zeros(len(triples), bool)
+    def one(i):
+        pk, m, sg = (_u8(x) for x in triples[i]); r = ctypes.c_int(-1)
+        rc = lib().blsgadget_verify_assignment(_p(pk), _p(m), ctypes.c_size_t(len(triples[i][1])), _p(sg), _p(z[i]), ctypes.c_size_t(ncols), ctypes.byref(r))
+        if rc != 0: raise RuntimeError(f"blsgadget_verify_assignment failed ({rc})")
+        res[i] = bool(r.value)
+    with ThreadPoolExecutor(max_workers=threads or os.cpu_count() or 1) as ex: list(ex.map(one, range(len(triples))))
+    return z, res

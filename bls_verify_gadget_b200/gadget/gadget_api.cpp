@@ -58,6 +58,20 @@ int blsgadget_aggregate_verify(const uint8_t* pks48, size_t n, const uint8_t* bi
         return put(std::move(c));
     } catch (...) { return -1; }
 }
+// assignment only (witness-only synthesis: no matrices are built): z48 must hold ncols * 48 bytes, ncols from a full synthesis
+int blsgadget_verify_assignment(const uint8_t pk48[48], const uint8_t* msg, size_t len, const uint8_t sig96[96], uint8_t* z48, size_t ncols, int* result) {
+    struct Guard { Guard() { witness_only_mode() = true; } ~Guard() { witness_only_mode() = false; } } guard;
+    try {
+        g1_aff pk; g2_aff sig;
+        if (g1_decode(pk, pk48) != DEC_OK || g2_decode(sig, sig96) != DEC_OK) return -2;
+        ConstraintSystem cs;
+        bool r = synthesize_verify(cs, pk, msg, len, sig);
+        if (cs.z.size() != ncols) return -3;
+        for (size_t i = 0; i < cs.z.size(); i++) le48(z48 + 48 * i, cs.z[i]);
+        if (result) *result = r ? 1 : 0;
+        return 0;
+    } catch (...) { return -1; }
+}
 int blsgadget_shape(int h, uint64_t* nrows, uint64_t* ncols, uint64_t* ninstance, uint64_t nnz[3]) {
     Circuit* c = get(h); if (!c) return -1;
     *nrows = c->cs.num_constraints(); *ncols = c->cs.num_variables(); *ninstance = c->cs.num_instance;

@@ -30,16 +30,21 @@ inline std::vector<uint8_t> bytes_from_hex(const std::string& h) {
     std::vector<uint8_t> o(h.size() / 2); for (size_t i = 0; i < o.size(); i++) o[i] = (uint8_t)(nib(h[2 * i]) << 4 | nib(h[2 * i + 1])); return o;
 }
 
+// Witness-only synthesis: the matrices do not depend on the inputs, so after the first synthesis only the assignment is
+// needed.  With this flag set (per thread) linear combinations stay empty and no rows are emitted; variables are allocated
+// in the same order with the same values, so z is identical (checked by tests/test_gadget_circuit.py).
+inline bool& witness_only_mode() { static thread_local bool f = false; return f; }
+
 struct Term { uint32_t v; fp c; };
 // linear combination over the variables (index 0 is the constant ONE); kept unsorted, merged when a row is emitted
 struct LC {
     std::vector<Term> t;
-    static LC var(uint32_t v) { LC l; l.t.push_back({v, fp_one()}); return l; }
-    static LC constant(const fp& c) { LC l; if (!fp_is_zero(c)) l.t.push_back({0u, c}); return l; }
+    static LC var(uint32_t v) { LC l; if (!witness_only_mode()) l.t.push_back({v, fp_one()}); return l; }
+    static LC constant(const fp& c) { LC l; if (!witness_only_mode() && !fp_is_zero(c)) l.t.push_back({0u, c}); return l; }
     // duplicates are merged once a combination grows (x + x style doubling would otherwise double the list every step)
     LC& operator+=(const LC& o) { t.insert(t.end(), o.t.begin(), o.t.end()); if (t.size() > 12) compact(); return *this; }
     LC operator+(const LC& o) const { LC r = *this; r += o; return r; }
-    LC scaled(const fp& k) const { LC r; if (fp_is_zero(k)) return r; r.t.reserve(t.size()); for (auto& x : t) r.t.push_back({x.v, fp_mul(x.c, k)}); return r; }
+    LC scaled(const fp& k) const { LC r; if (t.empty() || fp_is_zero(k)) return r; r.t.reserve(t.size()); for (auto& x : t) r.t.push_back({x.v, fp_mul(x.c, k)}); return r; }
     LC neg() const { LC r; r.t.reserve(t.size()); for (auto& x : t) r.t.push_back({x.v, fp_neg(x.c)}); return r; }
     LC operator-(const LC& o) const { LC r = *this; r += o.neg(); return r; }
     inline void compact();
@@ -70,7 +75,7 @@ struct ConstraintSystem {
     size_t num_variables() const { return z.size(); }
     fp eval(const LC& l) const { fp s = fp_zero(); for (auto& x : l.t) s = fp_add(s, fp_mul(x.c, z[x.v])); return s; }
     void push_row(int m, LC l) { l.compact(); for (auto& x : l.t) { col[m].push_back(x.v); val[m].push_back(x.c); } rowptr[m].push_back(col[m].size()); }
-    void enforce(const LC& a, const LC& b, const LC& c) { push_row(0, a); push_row(1, b); push_row(2, c); }
+    void enforce(const LC& a, const LC& b, const LC& c) { if (witness_only_mode()) return; push_row(0, a); push_row(1, b); push_row(2, c); }
     // host self-check (builder tests): first unsatisfied row or -1
     long first_unsatisfied(const std::vector<fp>* zz = nullptr) const {
         const std::vector<fp>& w = zz ? *zz : z;

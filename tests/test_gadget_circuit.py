@@ -51,6 +51,8 @@ def test_verify_circuit_reference_cases():
 def test_verify_circuit_oracle_check_and_perturbation():
     c = G.verify_circuit(PK, CASES[0][0], SIG)
     z = c.assignment().reshape(c.ncols, 48).copy()
+    zw, rw = G.verify_witnesses([(PK, CASES[0][0], SIG), (PK, CASES[2][0], SIG)], threads=2, ncols=c.ncols)      # witness-only synthesis
+    assert np.array_equal(zw[0], z.reshape(-1)) and list(rw) == [True, False]
     rng = np.random.default_rng(3)
     bad = z.copy(); victims = sorted(int(v) for v in rng.integers(1, c.ncols, size=3))
     for v in victims: bad[v, 0] ^= 1
