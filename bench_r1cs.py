@@ -1,0 +1,100 @@
+#!/usr/bin/env python3
+"""bench_r1cs.py -- the second half of BASELINE.json's metric: gadget R1CS constraints checked per second at 1/2/4/8 B200.
+
+Workload (BASELINE configs[4]): satisfaction check of the constraints.rs verify circuit (714,250 rows; matrices and assignments
+from the host-side builder bls_verify_gadget_b200/gadget) over assignments sharded across the ranks, 512 per GPU by default
+(4096 on 8 GPUs; weak scaling: the per-GPU share is fixed).  The matrices are replicated; the data path has no collective;
+the one exchange step is an all-gather of the per-assignment flags.  A step = one pass over the rank's
+assignments, resident in HBM (`value`), or staged from pinned host memory through the host-pointer C ABI (`e2e`).
+
+  python bench_r1cs.py [--gpus N] [--steps K] [--warmup W] [--per-gpu 512] [--distinct 16]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench_r1cs.py --gpus N
+"""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
+import numpy as np
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=3); ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--per-gpu", type=int, default=512); ap.add_argument("--distinct", type=int, default=16, help="distinct (pk, msg, sig) assignments synthesised per rank")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args(); args.warmup = max(args.warmup, 3)
+    import torch, torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world > 1: dist.init_process_group("nccl", device_id=dev)
+    from bls_verify_gadget_b200 import Context, synth, gadget as G
+    from bls_verify_gadget_b200.dist import witness_shard, gather_flags
+    ctx = Context(local); stream = torch.cuda.current_stream(dev); ctx.set_stream(stream.cuda_stream)
+    nwit_total = args.per_gpu * world; lo, hi = witness_shard(nwit_total, world, rank); nwit = hi - lo
+    # ---- distinct assignments of this rank (untimed): keys / signatures from the library's own kernels, assignments from the host builder
+    nb = max(2, min(args.distinct, nwit))
+    pk, msg, sig, exp = synth.verify_batch_inputs(ctx, nb * world, every=4, fast=False)
+    triples = []
+    for k in range(nb):
+        i = rank * nb + k; j = i if exp[i] in (0, 1) else rank * nb           # undecodable corruptions fall back to a valid point pair (wrong message)
+        triples.append((pk[48 * j:48 * j + 48].tobytes(), msg[32 * i:32 * i + 32].tobytes(), sig[96 * j:96 * j + 96].tobytes()))
+    c = G.verify_circuit(*triples[0]); mats = c.matrices(); nrows, ncols, nnz = c.nrows, c.ncols, sum(c.nnz); c.free()
+    threads = max(1, (os.cpu_count() or 1) // world)
+    t0 = time.perf_counter(); zb, res = G.verify_witnesses(triples, threads=threads, ncols=ncols); t_syn = time.perf_counter() - t0
+    ctx.set_pointer_mode(False)
+    h = ctx.r1cs_load([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], nrows, ncols)
+    dz = torch.from_numpy(zb).to(dev).repeat((nwit + nb - 1) // nb, 1)[:nwit].contiguous()
+    bad = list(range(5, nwit, 32))
+    for w in bad: dz[w, 48 * (((lo + w) * 7919) % ncols)] ^= 1                  # one perturbed variable per 32 assignments
+    ne = min(nwit, 128)                                                         # e2e leg: the first 128 assignments of the shard from pinned host memory (4.3 GB)
+    h_z = dz[:ne].cpu().pin_memory(); dz = dz.reshape(-1)
+    words = (nrows + 63) // 64
+    bits = torch.zeros(nwit * words, dtype=torch.int64, device=dev); allsat = torch.zeros(nwit, dtype=torch.uint8, device=dev)
+    h_bits = torch.zeros(ne * words, dtype=torch.int64).pin_memory(); h_all = torch.zeros(ne, dtype=torch.uint8).pin_memory()
+    out = {}
+    def step_device():
+        ctx.set_pointer_mode(True)
+        ctx.r1cs_check_ptr(h, dz.data_ptr(), nwit, bits.data_ptr(), allsat.data_ptr())
+        if world > 1: out["flags"] = gather_flags(allsat, nwit_total)
+    def step_e2e():
+        ctx.set_pointer_mode(False)
+        ctx.r1cs_check_ptr(h, h_z.numpy().reshape(-1), ne, h_bits.numpy().view(np.uint64), h_all.numpy())
+    def barrier():
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize(dev)
+    def timed(fn, steps):
+        barrier(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps): fn()
+        e1.record(stream); barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    for _ in range(args.warmup): step_device()
+    torch.cuda.synchronize(dev)
+    a = allsat.cpu().numpy(); assert sorted(np.nonzero(a == 0)[0].tolist()) == bad, "all_sat flags differ from the planted pattern"
+    if world > 1: assert int(out["flags"].sum().item()) == nwit_total - sum(len(range(5, witness_shard(nwit_total, world, r)[1] - witness_shard(nwit_total, world, r)[0], 32)) for r in range(world))
+    l0 = ctx.launch_count(); ms = timed(step_device, args.steps); launches = ctx.launch_count() - l0
+    step_e2e(); assert np.array_equal(h_all.numpy(), a[:ne])
+    ke = max(1, args.steps // 2); ms_e2e = timed(step_e2e, ke)
+    if rank == 0:
+        value = nrows * nwit_total * args.steps / (ms * 1e-3)
+        line = {"metric": "r1cs_constraints_checked_per_sec", "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit modular integer)", "data": "synthetic keys/messages, real circuit",
+                "config": {"workload": f"R1CS check of the constraints.rs:90-128 verify circuit ({nrows} rows, {ncols} cols, nnz {nnz}) over {nwit_total} assignments (BASELINE configs[4])",
+                           "per_rank": nwit, "distinct_per_rank": nb, "parallelism": f"shard{world}", "l2": f"assignments ({ncols * 48} B each, {nwit * ncols * 48 / 1e9:.1f} GB per rank) exceed the 126 MB L2"},
+                "assignments_per_sec": nwit_total * args.steps / (ms * 1e-3),
+                "e2e": {"value": nrows * ne * world * ke / (ms_e2e * 1e-3), "unit": "constraints/s", "h2d_bytes_per_step": ne * ncols * 48, "d2h_bytes_per_step": ne * (8 * words + 1),
+                        "sample": f"{ne} assignments per rank per step through the host-pointer C ABI (pinned host buffers)"},
+                "gpu_launches": launches, "host_synthesis_s_per_assignment_per_thread": t_syn / nb * min(threads, nb),
+                "roofline": {"bound": "hbm", "achieved": nwit * ncols * 48 * 2 * args.steps / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                             "note": "algorithmic bytes = each assignment read once and written once by the transpose (2 x 48 B x ncols); the gather of z by the row kernels re-reads the transposed copy (nnz x 48 B per assignment) -- see profiles/r01_summary.md"}}
+        if not args.no_cpu:
+            from oracle import cwrap as C
+            thr = C.hw_threads(); ns = 2; zs = dz[:ns * ncols * 48].cpu().numpy()
+            t0 = time.perf_counter(); ob, oa = C.r1cs_check([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], nrows, ncols, zs, ns, threads=thr); dt = time.perf_counter() - t0
+            assert np.array_equal(bits.cpu().numpy().view(np.uint64).reshape(nwit, words)[:ns], ob)
+            line["cpu_baseline"] = {"value": nrows * ns / dt, "unit": "constraints/s", "cores": thr, "kind": "port", "sample": f"{ns} assignments, C++ oracle port"}
+        print(json.dumps(line), flush=True)
+    ctx.r1cs_free(h)
+    if world > 1: dist.destroy_process_group()
+
+if __name__ == "__main__":
+    main()

@@ -27,3 +27,23 @@ def exchange(bitmap_shard, gt_partial, fold, group=None):
     dist.all_gather_into_tensor(bm, bitmap_shard, group=group)
     dist.all_gather_into_tensor(gt, gt_partial, group=group)
     return bm, fold(gt)
+
+
+def witness_shard(nwit, world, rank):
+    """R1CS check: the matrices are replicated, the assignments are split into contiguous equal shards
+    (the last ranks may hold one fewer); returns [lo, hi)"""
+    base, extra = divmod(nwit, world)
+    lo = rank * base + min(rank, extra); hi = lo + base + (1 if rank < extra else 0)
+    return lo, hi
+
+def gather_flags(all_sat_shard, nwit, group=None):
+    """all_sat_shard: uint8[hi - lo] of this rank; returns uint8[nwit] on every rank (one all-gather of padded shards --
+    the per-constraint bit vectors stay with the rank that owns the assignment)"""
+    world = dist.get_world_size(group); per = -(-nwit // world)
+    pad = torch.zeros(per, dtype=torch.uint8, device=all_sat_shard.device); pad[:all_sat_shard.numel()] = all_sat_shard
+    out = torch.empty(world * per, dtype=torch.uint8, device=all_sat_shard.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    parts = []
+    for r in range(world):
+        lo, hi = witness_shard(nwit, world, r); parts.append(out[r * per: r * per + (hi - lo)])
+    return torch.cat(parts)
