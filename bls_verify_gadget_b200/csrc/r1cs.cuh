@@ -104,20 +104,25 @@ __device__ __forceinline__ bool r1cs_product_ok(const fp& a, const fp& b, const 
     fp ab = fp_mul(fp_to_mont(a), b);                             // (aR)(b)/R = ab, canonical
     return fp_eq(ab, c);
 }
-// one warp per block of 64 rows; lane = witness in the group.  Long rows are left to the segment kernels (bit 0 here).
+// one warp per block of R1_ROWS consecutive rows (a fraction of a 64-row word: finer blocks balance better and keep more
+// gathers in flight; the bits are OR-ed into the word, which the host zeroes first); lane = witness in the group.
+// Long rows are left to the segment kernels.
+#ifndef R1_ROWS
+#define R1_ROWS 8
+#endif
 __global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_rows(r1cs_sys s, const u32x4* zt, const uint8_t* zbool, size_t w0, size_t g, size_t words, uint64_t* sat_bits) {
-    size_t rb = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
-    if (rb >= words) return;
+    size_t blk = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
+    size_t r0 = blk * R1_ROWS; if (r0 >= s.nrows) return;
     uint64_t bits = 0;
-    size_t r_end = rb * 64 + 64 < s.nrows ? rb * 64 + 64 : s.nrows;
-    for (size_t row = rb * 64; row < r_end; row++) {
+    size_t r_end = r0 + R1_ROWS < s.nrows ? r0 + R1_ROWS : s.nrows;
+    for (size_t row = r0; row < r_end; row++) {
         if (s.is_long[row]) continue;
         fp a = r1cs_range_dot(s, 0, s.rowptr[0][row], s.rowptr[0][row + 1], zt, zbool, lane);
         fp b = r1cs_range_dot(s, 1, s.rowptr[1][row], s.rowptr[1][row + 1], zt, zbool, lane);
         fp c = r1cs_range_dot(s, 2, s.rowptr[2][row], s.rowptr[2][row + 1], zt, zbool, lane);
         if (r1cs_product_ok(a, b, c)) bits |= 1ull << (row & 63);
     }
-    if ((size_t)lane < g) sat_bits[(w0 + lane) * words + rb] = bits;
+    if ((size_t)lane < g && bits) atomicOr((unsigned long long*)&sat_bits[(w0 + lane) * words + (r0 >> 6)], bits);
 }
 // one warp per segment of a long row: partial dot product of 32 witnesses -> part (limb-SoA over n_seg * 32 slots)
 __global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_segments(r1cs_sys s, const u32x4* zt, const uint8_t* zbool, u32x4* part) {
@@ -227,13 +232,14 @@ int blsgpu_r1cs_check(blsgpu_ctx* ctx, int handle, const uint8_t* z48, size_t nw
     u32x4* part = ws_take<u32x4>(ctx, part_bytes / 16);
     uint64_t* dbits = host ? ws_take<uint64_t>(ctx, words * nwit) : sat_bits;
     uint8_t* dall = all_sat ? (host ? ws_take<uint8_t>(ctx, nwit) : all_sat) : nullptr;
+    CU(cudaMemsetAsync(dbits, 0, 8 * words * nwit, ctx->stream));
     for (size_t w0 = 0; w0 < nwit; w0 += R1_GROUP) {
         size_t g = nwit - w0 < R1_GROUP ? nwit - w0 : R1_GROUP;
         const u32x4* zsrc; size_t wbase;
         if (host) { CU(cudaMemcpyAsync(zstage, z48 + w0 * s.ncols * 48, g * s.ncols * 48, cudaMemcpyHostToDevice, ctx->stream)); zsrc = zstage; wbase = 0; }
         else { zsrc = (const u32x4*)z48; wbase = w0; }
         LAUNCH(k_r1cs_transpose, nblk(s.ncols, 8), 256, zsrc, s.ncols, wbase, g, zt, zbool);
-        LAUNCH(k_r1cs_rows, nblk(words, TPB / 32), TPB, s, (const u32x4*)zt, (const uint8_t*)zbool, w0, g, words, dbits);
+        LAUNCH(k_r1cs_rows, nblk((s.nrows + R1_ROWS - 1) / R1_ROWS, TPB / 32), TPB, s, (const u32x4*)zt, (const uint8_t*)zbool, w0, g, words, dbits);
         if (s.n_long) {
             LAUNCH(k_r1cs_segments, nblk(s.n_seg, TPB / 32), TPB, s, (const u32x4*)zt, (const uint8_t*)zbool, part);
             LAUNCH(k_r1cs_combine, nblk(s.n_long, TPB / 32), TPB, s, (const u32x4*)part, w0, g, words, dbits);
