@@ -33,7 +33,7 @@ def lib():
     return _lib
 
 EXPORTS = ["blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_set_stream", "blsgpu_set_pointer_mode", "blsgpu_synchronize",
-           "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_set_coop", "blsgpu_verify_batch", "blsgpu_fast_aggregate_verify_batch", "blsgpu_pool_create", "blsgpu_pool_free", "blsgpu_pool_fast_aggregate_verify", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
+           "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_set_coop", "blsgpu_verify_batch", "blsgpu_verify_batch_rlc", "blsgpu_fast_aggregate_verify_batch", "blsgpu_pool_create", "blsgpu_pool_free", "blsgpu_pool_fast_aggregate_verify", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
            "blsgpu_g2_aggregate", "blsgpu_deserialize_g1", "blsgpu_deserialize_g2", "blsgpu_sk_to_pk_batch", "blsgpu_sign_batch", "blsgpu_pairing_gt",
            "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free"]
 
@@ -81,6 +81,16 @@ class Context:
     # ---- raw pointer entry points (host numpy arrays or device pointers as ints, matching the pointer mode)
     def verify_ptr(self, pk, msg, off, sig, n, status, bitmap=None, gt=None):
         self._ck(lib().blsgpu_verify_batch(self._h, _p(pk), _p(msg), _p(off), _p(sig), _sz(n), _p(status), _p(bitmap), _p(gt)))
+    def verify_rlc_ptr(self, pk, msg, off, sig, n, seed16, status, all_ok):
+        self._ck(lib().blsgpu_verify_batch_rlc(self._h, _p(pk), _p(msg), _p(off), _p(sig), _sz(n), _p(seed16), _p(status), _p(all_ok)))
+    def verify_rlc(self, pk48, msgs, sig96, seed16, fixed32=False):
+        """random-linear-combination batch check (host mode): returns (all_ok bool, per-item decode status)"""
+        pk = _u8(pk48); sg = _u8(sig96); n = sg.size // 96
+        if fixed32: flat, off = _u8(msgs), None
+        else: flat, off = pack_msgs(msgs)
+        st = np.empty(max(n, 1), np.uint8); ok = np.zeros(1, np.uint8); seed = _u8(seed16); assert seed.size == 16
+        self.verify_rlc_ptr(pk, flat, off, sg, n, seed, st, ok)
+        return bool(ok[0]), st[:n]
     def hash_to_g2_ptr(self, msg, off, n, out): self._ck(lib().blsgpu_hash_to_g2_batch(self._h, _p(msg), _p(off), _sz(n), _p(out)))
     def fast_aggregate_verify_ptr(self, pks, bitmap, k, msg, sig, ncomm, status, agg=None):
         self._ck(lib().blsgpu_fast_aggregate_verify_batch(self._h, _p(pks), _p(bitmap), _sz(k), _p(msg), _p(sig), _sz(ncomm), _p(status), _p(agg)))

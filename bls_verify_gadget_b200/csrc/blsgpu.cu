@@ -336,6 +336,66 @@ __global__ void k_fav_status(const uint8_t* agg_status, const uint8_t* agg_inf, 
     code_pk_out[i] = (agg_status[i] != ST_OK || agg_inf[i]) ? DEC_BAD_FLAGS : DEC_OK;
 }
 
+// ---- random-linear-combination batch check: prod_i e(r_i pk_i, H(m_i)) * e(-g1, sum_i r_i sig_i) == 1
+// r_i: 64 non-zero bits of SHA-256(seed16 || le64(global index))
+__device__ __forceinline__ uint64_t rlc_scalar(const uint8_t* seed16, uint64_t idx) {
+    sha256_ctx c; sha256_init(c);
+    for (int i = 0; i < 16; i++) sha256_put(c, seed16[i]);
+    for (int i = 0; i < 8; i++) sha256_put(c, (uint32_t)(idx >> (8 * i)) & 0xffu);
+    uint32_t d[8]; sha256_final(c, d);
+    uint64_t r = ((uint64_t)d[0] << 32) | d[1];
+    return r ? r : 1;
+}
+template <class F> __device__ __forceinline__ void jac_mul_u64(jac<F>& r, const aff<F>& p, uint64_t k) {
+    jac_set_identity(r);
+    for (int i = 63; i >= 0; i--) { jac_dbl(r, r); if ((k >> i) & 1) jac_add_mixed(r, r, p); }
+}
+// pk <- [r] pk (affine, in place); rsig <- [r] sig (Jacobian); pair 0 of the Miller loop is switched off for the item
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_rlc_scale(u32x4* pk_soa, const u32x4* sig_soa, uint8_t* flags, const uint8_t* status, size_t n, size_t idx0,
+                                                              const uint8_t* seed16, u32x4* rsig_jac) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    g2_jac rs; jac_set_identity(rs);
+    if (status[i] == ST_OK) {
+        uint64_t r = rlc_scalar(seed16, idx0 + i);
+        g1_aff pk; soa_load_g1(pk, pk_soa, n, i);
+        g1_jac rp; jac_mul_u64(rp, pk, r);
+        g1_aff a; jac_to_aff(a, rp); soa_store_g1(pk_soa, n, i, a);          // pk has prime order r > 2^64: [r]pk is never the identity
+        if (!(flags[i] & FL_SIG_INF)) { g2_aff sg; soa_load_g2(sg, sig_soa, n, i); jac_mul_u64(rs, sg, r); }
+        flags[i] |= FL_SIG_INF;
+    }
+    segsum_traits<fp2>::storej(rsig_jac, n, i, rs);
+}
+// out[t] = sum_{i = t, t+T, ...} in[i] (Jacobian G2)
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_g2_jac_reduce(const u32x4* in_jac, size_t n, u32x4* out_jac, size_t T) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (t >= T) return;
+    g2_jac acc, x; jac_set_identity(acc);
+    for (size_t i = t; i < n; i += T) { segsum_traits<fp2>::loadj(x, in_jac, n, i); jac_add(acc, acc, x); }
+    segsum_traits<fp2>::storej(out_jac, T, t, acc);
+}
+__global__ void k_g2_jac_add_into(u32x4* acc_jac, const u32x4* x_jac) {
+    if (threadIdx.x || blockIdx.x) return;
+    g2_jac a, x; segsum_traits<fp2>::loadj(a, acc_jac, 1, 0); segsum_traits<fp2>::loadj(x, x_jac, 1, 0); jac_add(a, a, x); segsum_traits<fp2>::storej(acc_jac, 1, 0, a);
+}
+__global__ void k_g2_jac_set_identity(u32x4* acc_jac) { if (threadIdx.x || blockIdx.x) return; g2_jac a; jac_set_identity(a); segsum_traits<fp2>::storej(acc_jac, 1, 0, a); }
+// bad[0] |= any status other than OK
+__global__ void k_any_bad(const uint8_t* status, size_t n, uint32_t* bad) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    bool b = i < n && status[i] != ST_OK;
+    if (__any_sync(0xffffffffu, b) && (threadIdx.x & 31) == 0) atomicOr(bad, 1u);
+}
+// single thread: F * miller(-g1, S), final exponentiation, is_one
+__global__ void __launch_bounds__(32, 1) k_rlc_finish(const u32x4* f_acc, const u32x4* s_jac, const uint32_t* bad, uint8_t* all_ok) {
+    if (threadIdx.x || blockIdx.x) return;
+    fp12 F, f2, gt; soa_load_fp12(F, f_acc, 1, 0);
+    g2_jac S; segsum_traits<fp2>::loadj(S, s_jac, 1, 0);
+    g2_aff sa; bool have = jac_to_aff(sa, S);
+    g1_aff ng; ng.x = fp_const(C_G1X); ng.y = fp_const(C_G1Y_NEG);
+    miller_loop2(f2, ng, sa, have, ng, sa, false);
+    fp12_mul(F, F, f2);
+    final_exponentiation(gt, F);
+    all_ok[0] = (fp12_is_one(gt) && !bad[0]) ? 1 : 0;
+}
+
 // ================================================================================================ context
 struct blsgpu_ctx {
     int device; cudaStream_t own_stream, stream; int ptr_mode; char err[512];
@@ -684,6 +744,69 @@ int blsgpu_verify_batch(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg
         if (ctx->ptr_mode == BLSGPU_HOST || n > ctx->chunk) CU(cudaStreamSynchronize(ctx->stream));
     }
     return 0;
+}
+
+// Random-linear-combination batch check: see include/blsgpu.h.  Single stream, passes of <= ctx->chunk items.
+int blsgpu_verify_batch_rlc(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg, const uint32_t* msg_off, const uint8_t* sig96, size_t n,
+                            const uint8_t seed16[16], uint8_t* status, uint8_t* all_ok) {
+    ENTER(); if (!pk48 || !msg || !sig96 || !seed16 || !all_ok) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    int rc = 0;
+    const uint32_t* off_host = ctx->ptr_mode == BLSGPU_HOST ? msg_off : nullptr;
+    size_t total_mb = 0;
+    if (msg_off && !off_host) { total_mb = msg_bytes_total(ctx, msg_off, n, rc); if (rc) return fail(ctx, rc, "reading msg_off failed"); }
+    // accumulators that live across passes are separate allocations (the workspace is re-carved per pass)
+    u32x4 *f_acc, *s_acc; uint32_t* bad; uint8_t* dseed; uint8_t* dok;
+    CU(cudaMalloc(&f_acc, 36 * 16)); CU(cudaMalloc(&s_acc, 18 * 16)); CU(cudaMalloc(&bad, 4)); CU(cudaMalloc(&dseed, 16)); CU(cudaMalloc(&dok, 1));
+    auto release = [&]() { cudaFree(f_acc); cudaFree(s_acc); cudaFree(bad); cudaFree(dseed); cudaFree(dok); };
+    cudaMemcpyKind in_kind = ctx->ptr_mode == BLSGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cudaMemcpyAsync(dseed, seed16, 16, in_kind, ctx->stream); cudaMemsetAsync(bad, 0, 4, ctx->stream);
+    k_gt_set_one<<<1, 32, 0, ctx->stream>>>(f_acc); k_g2_jac_set_identity<<<1, 32, 0, ctx->stream>>>(s_acc); ctx->launches += 2;
+    for (size_t base = 0; base < n && !rc; base += ctx->chunk) {
+        size_t m = n - base < ctx->chunk ? n - base : ctx->chunk;
+        size_t mb0 = msg_off ? (off_host ? off_host[base] : 0) : 32 * base;
+        size_t mb = msg_off ? (off_host ? off_host[base + m] - off_host[base] : total_mb) : 32 * m;
+        if ((rc = ws_reserve(ctx, verify_ws_bytes(m, ctx->ptr_mode == BLSGPU_HOST ? mb : 0) + al(288 * m) + al(288 * ((m + 7) / 8)) + al(288 * ((m + 63) / 64)) + al(288) + 65536))) break;
+        const uint8_t *dpk, *dsig, *dmsg; const uint32_t* doff;
+        if ((rc = stage_in(ctx, dpk, pk48 + 48 * base, 48 * m))) break;
+        if ((rc = stage_in(ctx, dsig, sig96 + 96 * base, 96 * m))) break;
+        if (ctx->ptr_mode == BLSGPU_HOST) { if ((rc = stage_in(ctx, dmsg, msg + mb0, mb ? mb : 1))) break; dmsg -= msg_off ? mb0 : 0; }
+        else dmsg = msg_off ? msg : msg + mb0;
+        if ((rc = stage_in(ctx, doff, msg_off ? msg_off + base : nullptr, m + 1))) break;
+        uint8_t* dstatus = status ? stage_out(ctx, status + base, m) : ws_take<uint8_t>(ctx, m);
+        u32x4* pk_soa = ws_take<u32x4>(ctx, 6 * m); uint8_t* code_pk = ws_take<uint8_t>(ctx, m);
+        u32x4* sig_soa = ws_take<u32x4>(ctx, 12 * m); u32x4* hm_soa = ws_take<u32x4>(ctx, 12 * m); u32x4* f_soa = ws_take<u32x4>(ctx, 36 * m);
+        uint8_t* code_sig = ws_take<uint8_t>(ctx, m); uint8_t* flags = ws_take<uint8_t>(ctx, m);
+        u32x4* rs = ws_take<u32x4>(ctx, 18 * m); u32x4* ja = ws_take<u32x4>(ctx, 18 * ((m + 7) / 8)); u32x4* jb = ws_take<u32x4>(ctx, 18 * ((m + 63) / 64)); u32x4* jone = ws_take<u32x4>(ctx, 18);
+        u32x4* ta = ws_take<u32x4>(ctx, 36 * ((m + 7) / 8)); u32x4* tb = ws_take<u32x4>(ctx, 36 * ((m + 63) / 64)); u32x4* one = ws_take<u32x4>(ctx, 36);
+        LAUNCH(k_decode_g1, nblk(m), TPB, dpk, m, pk_soa, code_pk);
+        LAUNCH(k_decode_g2, nblk(m), TPB, dsig, m, sig_soa, code_sig);
+        LAUNCH(k_hash_to_g2, nblk(m), TPB, dmsg, doff, m, (const uint8_t*)code_pk, (const uint8_t*)code_sig, hm_soa, flags, dstatus);
+        LAUNCH(k_any_bad, nblk(((m + 31) / 32) * 32, 256), 256, (const uint8_t*)dstatus, m, bad);
+        LAUNCH(k_rlc_scale, nblk(m), TPB, pk_soa, (const u32x4*)sig_soa, flags, (const uint8_t*)dstatus, m, base, (const uint8_t*)dseed, rs);
+        {   // sum of the scaled signatures (radix-8 tree, like the GT product)
+            const u32x4* cur = rs; size_t cnt = m; u32x4* bufs[2] = {ja, jb}; int which = 0;
+            while (true) {
+                size_t T = (cnt + 7) / 8; u32x4* out = T == 1 ? jone : bufs[which];
+                LAUNCH(k_g2_jac_reduce, nblk(T), TPB, cur, cnt, out, T);
+                if (T == 1) break;
+                cur = out; cnt = T; which ^= 1;
+            }
+            LAUNCH(k_g2_jac_add_into, 1, 32, s_acc, (const u32x4*)jone);
+        }
+        LAUNCH(k_miller, nblk(m), TPB, (const u32x4*)pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, m, f_soa);
+        if ((rc = gt_product(ctx, f_soa, dstatus, m, ta, tb, one))) break;
+        LAUNCH(k_gt_mul_into, 1, 32, f_acc, (const u32x4*)one);
+        if (status && (rc = finish_out(ctx, status + base, dstatus, m))) break;
+        if (ctx->ptr_mode == BLSGPU_HOST || n > ctx->chunk) { cudaError_t e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) { rc = fail(ctx, BLSGPU_ERR_CUDA, "sync failed: %s", cudaGetErrorString(e)); break; } }
+    }
+    if (!rc) {
+        k_rlc_finish<<<1, 32, 0, ctx->stream>>>(f_acc, s_acc, bad, dok); ctx->launches++;
+        cudaError_t e = cudaMemcpyAsync(all_ok, dok, 1, ctx->ptr_mode == BLSGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);              // the accumulators are freed below
+        if (e != cudaSuccess) rc = fail(ctx, BLSGPU_ERR_CUDA, "rlc finish failed: %s", cudaGetErrorString(e));
+    } else cudaStreamSynchronize(ctx->stream);
+    release();
+    return rc;
 }
 
 int blsgpu_gt_fold(blsgpu_ctx* ctx, const uint8_t* parts, size_t nparts, uint8_t* out) {

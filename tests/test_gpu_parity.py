@@ -295,6 +295,36 @@ def test_r1cs_verify_circuit_on_gpu(ctx, C):
     obits, oall = C.r1cs_check([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], c.nrows, c.ncols, zz, 3, threads=C.hw_threads())
     assert np.array_equal(bits, obits) and list(allsat) == list(oall) == [1, 1, 0]
 
+def test_rlc_batch_check_agrees_with_per_item_verify(ctx):
+    """blsgpu_verify_batch_rlc (one pairing-product equation per batch): true exactly when every item of the
+    batch verifies, for every corruption kind, several seeds, ragged messages, and across internal passes."""
+    from bls_verify_gadget_b200 import synth
+    n = 200
+    pk, msg, sig, exp = synth.verify_batch_inputs(ctx, n, every=10 ** 9, fast=False)          # all valid
+    msgs = [msg[32 * i:32 * i + 32].tobytes() for i in range(n)]
+    assert not ctx.verify(pk, msgs, sig).any()
+    for seed in (bytes(16), bytes(range(16)), b"\xff" * 16):
+        ok, st = ctx.verify_rlc(pk, msgs, sig, seed); assert ok and not st.any()
+    ctx.set_chunk(64)
+    try: ok, st = ctx.verify_rlc(pk, msgs, sig, bytes(range(16))); assert ok and not st.any()      # 4 passes: accumulators carried across
+    finally: ctx.set_chunk(1 << 20)
+    P, S = pk.reshape(n, 48), sig.reshape(n, 96)
+    def check(p, m, s, want_status=None):
+        ok, st = ctx.verify_rlc(p.reshape(-1), m, s.reshape(-1), b"seed-seed-seed-16"[:16])
+        full = ctx.verify(p.reshape(-1), m, s.reshape(-1))
+        assert ok == (not full.any()) and not ok
+        if want_status is not None: assert st[want_status[0]] == want_status[1]
+    m2 = list(msgs); m2[17] = m2[17][:-1] + bytes([m2[17][-1] ^ 1]); check(P, m2, S)                    # wrong message
+    p2 = P.copy(); p2[[3, 4]] = p2[[4, 3]]; check(p2, msgs, S)                                             # swapped keys: both items false, products do not cancel
+    s2 = S.copy(); s2[[100, 101]] = s2[[101, 100]]; check(P, msgs, s2)                                     # swapped signatures (valid subgroup points)
+    s3 = S.copy(); s3[7, 92:] = 0xff; check(P, msgs, s3, (7, 3))                                           # undecodable signature
+    p3 = P.copy(); p3[0] = 0; p3[0, 0] = 0xc0; check(p3, msgs, S, (0, 2))                                  # identity public key
+    # ragged messages through the offsets path
+    rng = np.random.default_rng(9); rag = [rng.bytes(int(l)) for l in rng.integers(0, 90, size=24)]
+    sk = synth.secret_keys(24); rpk, _ = ctx.sk_to_pk(sk); rsig, _ = ctx.sign(sk, rag)
+    ok, st = ctx.verify_rlc(rpk, rag, rsig, bytes(16)); assert ok
+    ok, st = ctx.verify_rlc(rpk, rag[1:] + rag[:1], rsig, bytes(16)); assert not ok
+
 # ------------------------------------------------------------------------------------------ the reference-shaped API (src/bls.rs)
 def test_bls_api_like_reference_tests(ctx, eth):
     from bls_verify_gadget_b200 import BLS, PrivateKey, PublicKey, Signature, BLSError, hash_to_g2
