@@ -11,7 +11,13 @@ struct Circuit { ConstraintSystem cs; uint8_t out[96]; int out_len = 0; int resu
 std::mutex g_mu; std::vector<std::unique_ptr<Circuit>> g_tab;
 int put(std::unique_ptr<Circuit> c) { std::lock_guard<std::mutex> l(g_mu); for (size_t i = 0; i < g_tab.size(); i++) if (!g_tab[i]) { g_tab[i] = std::move(c); return (int)i; } g_tab.push_back(std::move(c)); return (int)g_tab.size() - 1; }
 Circuit* get(int h) { std::lock_guard<std::mutex> l(g_mu); return h >= 0 && (size_t)h < g_tab.size() ? g_tab[h].get() : nullptr; }
-void le48(uint8_t* o, const fp& m) { fp a = fp_from_mont(m); memcpy(o, a.l, 48); }
+// Montgomery -> canonical little-endian; 93 % of an assignment is 0 / 1 (boolean variables): those skip the Montgomery product
+void le48(uint8_t* o, const fp& m) {
+    static const fp one = fp_one();
+    if (fp_is_zero(m)) { memset(o, 0, 48); return; }
+    if (fp_eq(m, one)) { memset(o, 0, 48); o[0] = 1; return; }
+    fp a = fp_from_mont(m); memcpy(o, a.l, 48);
+}
 }
 
 extern "C" {
