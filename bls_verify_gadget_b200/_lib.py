@@ -35,7 +35,7 @@ def lib():
 EXPORTS = ["blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_set_stream", "blsgpu_set_pointer_mode", "blsgpu_synchronize",
            "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_set_coop", "blsgpu_verify_batch", "blsgpu_verify_batch_rlc", "blsgpu_fast_aggregate_verify_batch", "blsgpu_pool_create", "blsgpu_pool_free", "blsgpu_pool_fast_aggregate_verify", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
            "blsgpu_g2_aggregate", "blsgpu_deserialize_g1", "blsgpu_deserialize_g2", "blsgpu_sk_to_pk_batch", "blsgpu_sign_batch", "blsgpu_pairing_gt",
-           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free"]
+           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_free"]
 
 _sz = ctypes.c_size_t; _vp = ctypes.c_void_p
 def _u8(a):
@@ -164,3 +164,15 @@ class Context:
         self._ck(lib().blsgpu_r1cs_check(self._h, int(handle), _p(z), _sz(nwit), _p(bits), _p(allsat))); return bits.reshape(nwit, words), allsat
     def r1cs_check_ptr(self, handle, z, nwit, bits, allsat): self._ck(lib().blsgpu_r1cs_check(self._h, int(handle), _p(z), _sz(nwit), _p(bits), _p(allsat)))
     def r1cs_free(self, handle): lib().blsgpu_r1cs_free(self._h, int(handle))
+    # ---- GPU witness generation (program from bls_verify_gadget_b200.gadget.verify_program)
+    def witness_load(self, rules16, lc_ptr, lc_col, lc_coef48):
+        r = np.ascontiguousarray(rules16, dtype=np.uint8); lp = np.ascontiguousarray(lc_ptr, dtype=np.uint64); lc = np.ascontiguousarray(lc_col, dtype=np.uint32); cf = np.ascontiguousarray(lc_coef48, dtype=np.uint8)
+        h = ctypes.c_int(-1)
+        self._ck(lib().blsgpu_witness_load(self._h, _p(r), _p(lp), _p(lc), _p(cf), _sz(r.size // 16), _sz(lp.size - 1), _sz(lc.size), ctypes.byref(h)))
+        return h.value
+    def witness_gen(self, handle, pk48, msg32, sig96, nvars):
+        pk = _u8(pk48); m = _u8(msg32); sg = _u8(sig96); n = sg.size // 96
+        z = np.empty(n * nvars * 48, np.uint8); st = np.empty(n, np.uint8)
+        self._ck(lib().blsgpu_witness_gen(self._h, int(handle), _p(pk), _p(m), _p(sg), _sz(n), _p(z), _p(st))); return z.reshape(n, nvars * 48), st
+    def witness_gen_ptr(self, handle, pk, msg, sig, n, z, status=None): self._ck(lib().blsgpu_witness_gen(self._h, int(handle), _p(pk), _p(msg), _p(sig), _sz(n), _p(z), _p(status)))
+    def witness_free(self, handle): lib().blsgpu_witness_free(self._h, int(handle))

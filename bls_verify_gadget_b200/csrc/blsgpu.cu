@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(32, 1) k_rlc_finish(const u32x4* f_acc, const 
 struct blsgpu_ctx {
     int device; cudaStream_t own_stream, stream; int ptr_mode; char err[512];
     uint8_t* ws; size_t ws_bytes, ws_used; unsigned long long launches;
-    struct r1cs_sys* r1cs[16];
+    struct r1cs_sys* r1cs[16]; struct wit_prog* wit[4];
     struct { u32x4* soa; uint8_t* code; size_t n; } pool[16];   // resident decoded validator pools
     int coop;                           // 1 = warp-cooperative hard part of the final exponentiation (coop.cuh)
     int lanes; cudaStream_t lane_stream[4]; cudaEvent_t lane_done[4], fork;   // concurrent sub-ranges of a verify pass
@@ -495,6 +495,7 @@ void blsgpu_destroy(blsgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 16; i++) if (ctx->r1cs[i]) blsgpu_r1cs_free(ctx, i);
+    for (int i = 0; i < 4; i++) if (ctx->wit[i]) blsgpu_witness_free(ctx, i);
     for (int i = 0; i < 16; i++) if (ctx->pool[i].soa) { cudaFree(ctx->pool[i].soa); cudaFree(ctx->pool[i].code); }
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ev[0]) for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
@@ -981,3 +982,4 @@ int blsgpu_pool_fast_aggregate_verify(blsgpu_ctx* ctx, int handle, const uint32_
 }  // extern "C"
 
 #include "r1cs.cuh"
+#include "witness.cuh"

@@ -1,0 +1,181 @@
+// GPU witness generation for the verify circuit: replays the witness program recorded by the host-side
+// builder (bls_verify_gadget_b200/gadget: one rule per variable, in allocation order) for 32 assignments per warp and
+// writes them straight into the layout the satisfaction kernels gather from -- so (pk, msg, sig) bytes go in and the
+// per-constraint bits come out without the 34 MB-per-assignment host synthesis and PCIe transfer.
+//
+// The reference has no counterpart (its witnesses come from running the gadget code under ark-relations'
+// ConstraintSystem in "prove" mode, src/constraints.rs:335-370); the values are checked bit for bit against the host
+// builder's assignment, which is pinned by the reference's own expectations (tests/test_gadget_circuit.py).
+//
+// Mapping: lane <-> assignment, warp <-> group of 32, rules strictly in order (a rule reads variables written by earlier
+// rules of the same lane: program order makes them visible).  Every branch is warp-uniform (rule kind, coefficient class).
+// Included after r1cs.cuh in blsgpu.cu.
+#pragma once
+
+enum { WR_MULADD = 0, WR_INV = 1, WR_NEQ = 2, WR_NEQMULT = 3, WR_BIT = 4, WR_FP2INV = 5, WR_FP12INV = 6, WR_INPUT = 7 };
+struct wit_rule { uint8_t kind, pad; uint16_t aux; uint32_t a, b, d; };
+struct wit_prog {
+    size_t nvars, nlc, nterms;
+    wit_rule* rules; uint64_t* lc_ptr; uint32_t* col; fp* coeff; fp* coeffc; uint8_t* cls;
+};
+#define WIT_INPUTS 262          // 256 message bits, pk.x, pk.y, sig x.c0, x.c1, y.c0, y.c1
+
+__device__ __forceinline__ void wit_store(u32x4* zt, size_t col, int lane, const fp& v) {
+    u32x4 a, b, c;
+    a.x = v.l[0]; a.y = v.l[1]; a.z = v.l[2]; a.w = v.l[3]; b.x = v.l[4]; b.y = v.l[5]; b.z = v.l[6]; b.w = v.l[7]; c.x = v.l[8]; c.y = v.l[9]; c.z = v.l[10]; c.w = v.l[11];
+    zt[(col * 3) * 32 + lane] = a; zt[(col * 3 + 1) * 32 + lane] = b; zt[(col * 3 + 2) * 32 + lane] = c;
+}
+// value of linear combination `id` (0 = empty) on this lane's assignment, canonical
+__device__ __forceinline__ fp wit_lc(const wit_prog& p, uint32_t id, const u32x4* zt, int lane) {
+    fp acc = fp_zero();
+    if (!id) return acc;
+    for (uint64_t k = p.lc_ptr[id - 1], e = p.lc_ptr[id]; k < e; k++) {
+        uint32_t cj = p.col[k]; uint8_t c = p.cls[k];
+        fp zv = r1cs_load_z(zt, cj, lane);
+        if (c == R1_PLUS_ONE) acc = fp_add(acc, zv);
+        else if (c == R1_MINUS_ONE) acc = fp_sub(acc, zv);
+        else {
+            bool small = zv.l[0] < 2 && !(zv.l[1] | zv.l[2] | zv.l[3] | zv.l[4] | zv.l[5] | zv.l[6] | zv.l[7] | zv.l[8] | zv.l[9] | zv.l[10] | zv.l[11]);
+            if (__all_sync(0xffffffffu, small)) acc = fp_add(acc, fp_select(0u - zv.l[0], p.coeffc[k], fp_zero()));       // coefficient times a 0/1 value
+            else acc = fp_add(acc, fp_mul(p.coeff[k], zv));
+        }
+    }
+    return acc;
+}
+__device__ __forceinline__ fp wit_inv_canon(const fp& a) { return fp_from_mont(fp_inv(fp_to_mont(a))); }
+// a b for canonical a, b: small-integer shortcut as in r1cs_product_ok
+__device__ __forceinline__ fp wit_mul_canon(const fp& a, const fp& b) {
+    uint32_t ah = a.l[2] | a.l[3] | a.l[4] | a.l[5] | a.l[6] | a.l[7] | a.l[8] | a.l[9] | a.l[10] | a.l[11];
+    uint32_t bh = b.l[2] | b.l[3] | b.l[4] | b.l[5] | b.l[6] | b.l[7] | b.l[8] | b.l[9] | b.l[10] | b.l[11];
+    bool small = (ah | bh) == 0 && (a.l[1] == 0 || b.l[1] == 0);
+    if (__all_sync(0xffffffffu, small)) {
+        uint64_t x = ((uint64_t)a.l[1] << 32) | a.l[0], y = ((uint64_t)b.l[1] << 32) | b.l[0];
+        uint64_t lo = x * y, hi = __umul64hi(x, y);
+        fp r = fp_zero(); r.l[0] = (uint32_t)lo; r.l[1] = (uint32_t)(lo >> 32); r.l[2] = (uint32_t)hi; r.l[3] = (uint32_t)(hi >> 32);
+        return r;                                                     // < 2^96 < p
+    }
+    return fp_mul(fp_to_mont(a), b);
+}
+// inputs: fp [WIT_INPUTS][nwit_padded] canonical (slot-major, so a warp reads 32 consecutive elements)
+__global__ void __launch_bounds__(32) k_witness_gen(wit_prog p, const fp* inputs, size_t nwit_padded, u32x4* zt_all) {
+    size_t group = blockIdx.x; int lane = threadIdx.x;
+    u32x4* zt = zt_all + group * p.nvars * 96;                        // 3 chunks x 32 lanes per variable
+    size_t w = group * 32 + lane;
+    fp one = fp_zero(); one.l[0] = 1;
+    wit_store(zt, 0, lane, one);
+    for (size_t v = 1; v < p.nvars; v++) {
+        wit_rule r = p.rules[v];
+        fp out;
+        switch (r.kind) {
+            case WR_MULADD: {
+                fp d = wit_lc(p, r.d, zt, lane);
+                if (r.a) { fp a = wit_lc(p, r.a, zt, lane), b = wit_lc(p, r.b, zt, lane); out = fp_add(wit_mul_canon(a, b), d); }
+                else out = d;
+                break;
+            }
+            case WR_INV: out = wit_inv_canon(wit_lc(p, r.a, zt, lane)); break;
+            case WR_NEQ: { fp a = wit_lc(p, r.a, zt, lane); out = fp_zero(); out.l[0] = fp_is_zero(a) ? 0u : 1u; break; }
+            case WR_NEQMULT: { fp a = wit_lc(p, r.a, zt, lane); out = fp_is_zero(a) ? one : wit_inv_canon(a); break; }
+            case WR_BIT: { fp a = wit_lc(p, r.a, zt, lane); out = fp_zero(); out.l[0] = (a.l[r.aux >> 5] >> (r.aux & 31)) & 1u; break; }
+            case WR_FP2INV: {
+                fp2 x; x.c0 = fp_to_mont(wit_lc(p, r.a, zt, lane)); x.c1 = fp_to_mont(wit_lc(p, r.b, zt, lane));
+                fp2 iv = fp2_inv(x); out = fp_from_mont(r.aux ? iv.c1 : iv.c0); break;
+            }
+            case WR_FP12INV: {
+                fp12 x, iv; fp* xf = &x.c0.c0.c0;
+                for (int k = 0; k < 12; k++) xf[k] = fp_to_mont(wit_lc(p, r.a + k, zt, lane));
+                fp12_inv(iv, x); out = fp_from_mont((&iv.c0.c0.c0)[r.aux]); break;
+            }
+            default: out = inputs[(size_t)r.aux * nwit_padded + w]; break;                 // WR_INPUT
+        }
+        wit_store(zt, v, lane, out);
+    }
+}
+// input slots from the decoded points and the message bytes; items whose key or signature does not decode get all-zero inputs
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_witness_inputs(const u32x4* pk_soa, const uint8_t* code_pk, const u32x4* sig_soa, const uint8_t* code_sig, const uint8_t* msg32,
+                                                                  size_t nwit, size_t nwit_padded, fp* inputs, uint8_t* status) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= nwit_padded) return;
+    bool live = i < nwit; uint8_t st = ST_OK;
+    if (live) { if (code_pk[i] != DEC_OK) st = ST_BAD_PK; else if (code_sig[i] != DEC_OK) st = ST_BAD_SIG; }      // the circuit inverts z of both points: the identity has no assignment
+    bool ok = live && st == ST_OK;
+    fp zero = fp_zero();
+    for (int k = 0; k < 256; k++) { fp b = zero; if (ok) b.l[0] = (msg32[32 * i + (k >> 3)] >> (k & 7)) & 1u; inputs[(size_t)k * nwit_padded + i] = b; }
+    g1_aff pk; g2_aff sg;
+    if (ok) { soa_load_g1(pk, pk_soa, nwit, i); soa_load_g2(sg, sig_soa, nwit, i); }
+    inputs[(size_t)256 * nwit_padded + i] = ok ? fp_from_mont(pk.x) : zero; inputs[(size_t)257 * nwit_padded + i] = ok ? fp_from_mont(pk.y) : zero;
+    inputs[(size_t)258 * nwit_padded + i] = ok ? fp_from_mont(sg.x.c0) : zero; inputs[(size_t)259 * nwit_padded + i] = ok ? fp_from_mont(sg.x.c1) : zero;
+    inputs[(size_t)260 * nwit_padded + i] = ok ? fp_from_mont(sg.y.c0) : zero; inputs[(size_t)261 * nwit_padded + i] = ok ? fp_from_mont(sg.y.c1) : zero;
+    if (live && status) status[i] = st;
+}
+// transposed group -> z[w][col] (48-byte LE canonical), the layout of blsgpu_r1cs_check
+__global__ void __launch_bounds__(256) k_witness_untranspose(const u32x4* zt_all, size_t ncols, size_t nwit, u32x4* z) {
+    size_t col = blockIdx.x * (size_t)8 + (threadIdx.x >> 5); int lane = threadIdx.x & 31; size_t group = blockIdx.y;
+    size_t w = group * 32 + lane;
+    if (col >= ncols || w >= nwit) return;
+    const u32x4* zt = zt_all + group * ncols * 96;
+    u32x4* dst = z + (w * ncols + col) * 3;
+    dst[0] = zt[(col * 3) * 32 + lane]; dst[1] = zt[(col * 3 + 1) * 32 + lane]; dst[2] = zt[(col * 3 + 2) * 32 + lane];
+}
+
+struct wit_prog_host { wit_prog d; };
+
+extern "C" {
+int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t* lc_ptr, const uint32_t* lc_col, const uint8_t* lc_coef48, size_t nvars, size_t nlc, size_t nterms, int* handle) {
+    ENTER(); if (!rules16 || !lc_ptr || !lc_col || !lc_coef48 || !handle || !nvars) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
+    int h = -1; for (int i = 0; i < 4; i++) if (!ctx->wit[i]) { h = i; break; }
+    if (h < 0) return fail(ctx, BLSGPU_ERR_ARG, "too many witness programs loaded");
+    wit_prog* p = new (std::nothrow) wit_prog(); if (!p) return fail(ctx, BLSGPU_ERR_ALLOC, "out of host memory");
+    memset(p, 0, sizeof *p); p->nvars = nvars; p->nlc = nlc; p->nterms = nterms; ctx->wit[h] = p;
+    cudaMemcpyKind kind = ctx->ptr_mode == BLSGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    size_t nt = nterms ? nterms : 1;
+    CU(cudaMalloc(&p->rules, 16 * nvars)); CU(cudaMalloc(&p->lc_ptr, 8 * (nlc + 1))); CU(cudaMalloc(&p->col, 4 * nt));
+    CU(cudaMalloc(&p->coeff, 48 * nt)); CU(cudaMalloc(&p->coeffc, 48 * nt)); CU(cudaMalloc(&p->cls, nt));
+    CU(cudaMemcpyAsync(p->rules, rules16, 16 * nvars, kind, ctx->stream)); CU(cudaMemcpyAsync(p->lc_ptr, lc_ptr, 8 * (nlc + 1), kind, ctx->stream));
+    if (nterms) {
+        CU(cudaMemcpyAsync(p->col, lc_col, 4 * nterms, kind, ctx->stream));
+        uint8_t* raw; CU(cudaMalloc(&raw, 48 * nterms));
+        CU(cudaMemcpyAsync(raw, lc_coef48, 48 * nterms, kind, ctx->stream));
+        LAUNCH(k_r1cs_prepare, nblk(nterms), TPB, (const uint8_t*)raw, nterms, p->coeff, p->coeffc, p->cls);
+        CU(cudaStreamSynchronize(ctx->stream)); cudaFree(raw);
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    *handle = h; return 0;
+}
+int blsgpu_witness_free(blsgpu_ctx* ctx, int handle) {
+    if (!ctx || handle < 0 || handle >= 4 || !ctx->wit[handle]) return BLSGPU_ERR_ARG;
+    cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+    wit_prog* p = ctx->wit[handle];
+    cudaFree(p->rules); cudaFree(p->lc_ptr); cudaFree(p->col); cudaFree(p->coeff); cudaFree(p->coeffc); cudaFree(p->cls);
+    delete p; ctx->wit[handle] = nullptr; return 0;
+}
+// assignments of the verify circuit for nwit (pk48, msg32, sig96) triples: z48 = nwit * nvars * 48 bytes (the layout of
+// blsgpu_r1cs_check), status[i] = 0, or 2 / 3 when the key / signature does not decode to a non-identity point (its assignment
+// is then all zeros except z[0] = 1 and the constants).  Pointers follow the context's pointer mode.
+int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, size_t nwit, uint8_t* z48, uint8_t* status) {
+    ENTER(); if (handle < 0 || handle >= 4 || !ctx->wit[handle] || !pk48 || !msg32 || !sig96 || !z48) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
+    if (!nwit) return 0;
+    wit_prog p = *ctx->wit[handle];
+    size_t groups = (nwit + 31) / 32, np = groups * 32;
+    bool host = ctx->ptr_mode == BLSGPU_HOST;
+    size_t zbytes = nwit * p.nvars * 48;
+    if (int rc = ws_reserve(ctx, al(48 * nwit) + al(96 * nwit) + al(32 * nwit) + al(96 * nwit) + al(192 * nwit) + 3 * al(np) + al(48 * WIT_INPUTS * np) + al(groups * p.nvars * 1536) + (host ? al(zbytes) : 0) + 65536)) return rc;
+    const uint8_t *dpk, *dsig, *dmsg;
+    if (int rc = stage_in(ctx, dpk, pk48, 48 * nwit)) return rc;
+    if (int rc = stage_in(ctx, dsig, sig96, 96 * nwit)) return rc;
+    if (int rc = stage_in(ctx, dmsg, msg32, 32 * nwit)) return rc;
+    u32x4* pk_soa = ws_take<u32x4>(ctx, 6 * nwit); u32x4* sig_soa = ws_take<u32x4>(ctx, 12 * nwit);
+    uint8_t* code_pk = ws_take<uint8_t>(ctx, np); uint8_t* code_sig = ws_take<uint8_t>(ctx, np);
+    uint8_t* dstatus = status ? stage_out(ctx, status, nwit) : nullptr;
+    fp* inputs = ws_take<fp>(ctx, (size_t)WIT_INPUTS * np);
+    u32x4* zt_all = ws_take<u32x4>(ctx, groups * p.nvars * 96);
+    uint8_t* dz = host ? ws_take<uint8_t>(ctx, zbytes) : z48;
+    LAUNCH(k_decode_g1, nblk(nwit), TPB, dpk, nwit, pk_soa, code_pk);
+    LAUNCH(k_decode_g2, nblk(nwit), TPB, dsig, nwit, sig_soa, code_sig);
+    LAUNCH(k_witness_inputs, nblk(np), TPB, (const u32x4*)pk_soa, (const uint8_t*)code_pk, (const u32x4*)sig_soa, (const uint8_t*)code_sig, dmsg, nwit, np, inputs, dstatus);
+    LAUNCH(k_witness_gen, (unsigned)groups, 32, p, (const fp*)inputs, np, zt_all);
+    { dim3 grid(nblk(p.nvars, 8), (unsigned)groups); k_witness_untranspose<<<grid, 256, 0, ctx->stream>>>((const u32x4*)zt_all, p.nvars, nwit, (u32x4*)dz); ctx->launches++; CU(cudaGetLastError()); }
+    if (host) CU(cudaMemcpyAsync(z48, dz, zbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) { if (int rc = finish_out(ctx, status, dstatus, nwit)) return rc; }
+    return finish_call(ctx);
+}
+}

@@ -77,6 +77,17 @@ def aggregate_verify_circuit(pks48, bitmap, message, sig96):
     c = Circuit(h, result=bool(res.value) if h >= 0 else None); c.count = cnt.value
     return c
 
+def verify_program(pk48, msg32, sig96):
+    """the witness program of the verify circuit (input-independent; recorded on the given sample triple, 32-byte message):
+    (rules16 u8[nvars*16], lc_ptr u64[nlc+1], lc_col u32[nterms], lc_coef48 u8[nterms*48], nvars) for Context.witness_load"""
+    pk = _u8(pk48); m = _u8(msg32); sg = _u8(sig96); assert len(msg32) == 32
+    h = lib().blsgadget_verify_program(_p(pk), _p(m), _p(sg))
+    if h < 0: raise RuntimeError(f"blsgadget_verify_program failed ({h})")
+    nv = ctypes.c_uint64(); nl = ctypes.c_uint64(); nt = ctypes.c_uint64(); lib().blsgadget_program_shape(h, ctypes.byref(nv), ctypes.byref(nl), ctypes.byref(nt))
+    rules = np.empty(16 * nv.value, np.uint8); lp = np.empty(nl.value + 1, np.uint64); lc = np.empty(max(nt.value, 1), np.uint32); cf = np.empty(48 * max(nt.value, 1), np.uint8)
+    lib().blsgadget_program_export(h, _p(rules), _p(lp), _p(lc), _p(cf)); lib().blsgadget_free(h)
+    return rules, lp, lc[:nt.value], cf[:48 * nt.value], nv.value
+
 def verify_witnesses(triples, threads=None, ncols=None):
     """assignments of the verify circuit for a list of (pk48, msg, sig96) (all with the same message length), synthesised on
     `threads` host threads in witness-only mode (no matrices: they do not depend on the inputs); returns

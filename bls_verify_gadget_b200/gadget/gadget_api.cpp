@@ -64,6 +64,33 @@ int blsgadget_aggregate_verify(const uint8_t* pks48, size_t n, const uint8_t* bi
         return put(std::move(c));
     } catch (...) { return -1; }
 }
+// The witness program of the verify circuit (32-byte messages): a full synthesis with rule recording on a sample input.  The
+// program is input-independent; it is exported with blsgadget_program_export and replayed on the GPU by blsgpu_witness_gen.
+int blsgadget_verify_program(const uint8_t pk48[48], const uint8_t* msg32, const uint8_t sig96[96]) {
+    try {
+        g1_aff pk; g2_aff sig;
+        if (g1_decode(pk, pk48) != DEC_OK || g2_decode(sig, sig96) != DEC_OK) return -2;
+        auto c = std::make_unique<Circuit>();
+        c->cs.record_rules = true;
+        c->result = synthesize_verify(c->cs, pk, msg32, 32, sig) ? 1 : 0;
+        if (c->cs.rules.size() != c->cs.z.size()) return -3;
+        return put(std::move(c));
+    } catch (...) { return -1; }
+}
+int blsgadget_program_shape(int h, uint64_t* nvars, uint64_t* nlc, uint64_t* nterms) {
+    Circuit* c = get(h); if (!c || c->cs.rules.size() != c->cs.z.size()) return -1;
+    *nvars = c->cs.rules.size(); *nlc = c->cs.lc_ptr.size() - 1; *nterms = c->cs.lc_col.size(); return 0;
+}
+// rules16: nvars records {u8 kind, u8 0, u16 aux, u32 a, u32 b, u32 d}; lc_ptr: nlc + 1; lc_col / lc_coef48: nterms
+int blsgadget_program_export(int h, uint8_t* rules16, uint64_t* lc_ptr, uint32_t* lc_col, uint8_t* lc_coef48) {
+    Circuit* c = get(h); if (!c || c->cs.rules.size() != c->cs.z.size()) return -1;
+    static_assert(sizeof(Rule) == 16, "rule record layout");
+    if (rules16) memcpy(rules16, c->cs.rules.data(), 16 * c->cs.rules.size());
+    if (lc_ptr) memcpy(lc_ptr, c->cs.lc_ptr.data(), 8 * c->cs.lc_ptr.size());
+    if (lc_col) memcpy(lc_col, c->cs.lc_col.data(), 4 * c->cs.lc_col.size());
+    if (lc_coef48) for (size_t k = 0; k < c->cs.lc_val.size(); k++) le48(lc_coef48 + 48 * k, c->cs.lc_val[k]);
+    return 0;
+}
 // assignment only (witness-only synthesis: no matrices are built): z48 must hold ncols * 48 bytes, ncols from a full synthesis
 int blsgadget_verify_assignment(const uint8_t pk48[48], const uint8_t* msg, size_t len, const uint8_t sig96[96], uint8_t* z48, size_t ncols, int* result) {
     struct Guard { Guard() { witness_only_mode() = true; } ~Guard() { witness_only_mode() = false; } } guard;

@@ -62,15 +62,48 @@ inline void LC::compact() {
         t.resize(w);
 }
 
+// Witness program (GPU witness generation): with `record_rules` set, every allocated variable also records HOW its
+// value follows from earlier variables -- the circuit's gadgets allocate witnesses through a dozen primitives only, each with
+// one rule kind.  The rules, replayed in allocation order by csrc/witness.cuh, reproduce the assignment on the GPU for any
+// input; LC ids index a flat table (0 = the empty combination).
+enum RuleKind : uint8_t {
+    RULE_MULADD = 0,     // (A z)(B z) + D z            products, AND / XOR, select, packing, constants (A empty)
+    RULE_INV = 1,        // 1 / (A z)                   (0 -> 0)
+    RULE_NEQ = 2,        // A z != 0 ? 1 : 0
+    RULE_NEQMULT = 3,    // A z != 0 ? 1 / (A z) : 1
+    RULE_BIT = 4,        // bit `aux` of the canonical integer A z       (addmany results, to_bits_le)
+    RULE_FP2INV = 5,     // component `aux` of 1 / (A z + u B z)
+    RULE_FP12INV = 6,    // coefficient `aux` (0..11, tower order) of the inverse of the Fp12 element given by LC ids a .. a+11
+    RULE_INPUT = 7       // external input slot `aux`: 0..255 message bits, 256/257 pk.x/y, 258..261 sig x.c0 x.c1 y.c0 y.c1
+};
+struct Rule { uint8_t kind; uint8_t pad; uint16_t aux; uint32_t a, b, d; };
+
 // z = [1, instance.., witness..] (instances must be allocated before the first witness, as in ark-relations' layout)
 struct ConstraintSystem {
+    bool record_rules = false; std::vector<Rule> rules; std::vector<uint64_t> lc_ptr; std::vector<uint32_t> lc_col; std::vector<fp> lc_val;
+    Rule pending; bool has_pending = false;
+    uint32_t add_lc(LC l) {                          // id >= 1 covers terms [lc_ptr[id-1], lc_ptr[id])
+        l.compact(); if (l.t.empty()) return 0;
+        for (auto& x : l.t) { lc_col.push_back(x.v); lc_val.push_back(x.c); }
+        lc_ptr.push_back(lc_col.size()); return (uint32_t)(lc_ptr.size() - 1);
+    }
+    void set_rule_ids(uint8_t kind, uint16_t aux, uint32_t a, uint32_t b, uint32_t d) { if (!record_rules) return; pending = Rule{kind, 0, aux, a, b, d}; has_pending = true; }
+    void set_rule(uint8_t kind, uint16_t aux, const LC* a, const LC* b = nullptr, const LC* d = nullptr) {
+        if (!record_rules) return;
+        set_rule_ids(kind, aux, a ? add_lc(*a) : 0, b ? add_lc(*b) : 0, d ? add_lc(*d) : 0);
+    }
+    void take_rule() {
+        if (!record_rules) return;
+        if (!has_pending) throw std::logic_error("witness allocated without a rule while recording the witness program");
+        rules.push_back(pending); has_pending = false;
+    }
     std::vector<fp> z;
     size_t num_instance = 1;                          // including the constant ONE
     std::vector<uint64_t> rowptr[3]; std::vector<uint32_t> col[3]; std::vector<fp> val[3];
     bool witness_started = false;
-    ConstraintSystem() { z.push_back(fp_one()); for (int m = 0; m < 3; m++) rowptr[m].push_back(0); }
-    uint32_t new_input(const fp& v) { if (witness_started) throw std::logic_error("instance variable after a witness"); z.push_back(v); num_instance++; return (uint32_t)(z.size() - 1); }
-    uint32_t new_witness(const fp& v) { witness_started = true; z.push_back(v); return (uint32_t)(z.size() - 1); }
+    ConstraintSystem() { z.push_back(fp_one()); for (int m = 0; m < 3; m++) rowptr[m].push_back(0); lc_ptr.push_back(0); rules.push_back(Rule{RULE_INPUT, 0, 0xffff, 0, 0, 0}); }
+    uint32_t new_input(const fp& v) { if (witness_started) throw std::logic_error("instance variable after a witness"); take_rule(); z.push_back(v); num_instance++; return (uint32_t)(z.size() - 1); }
+    uint32_t new_witness(const fp& v) { witness_started = true; take_rule(); z.push_back(v); return (uint32_t)(z.size() - 1); }
     size_t num_constraints() const { return rowptr[0].size() - 1; }
     size_t num_variables() const { return z.size(); }
     fp eval(const LC& l) const { fp s = fp_zero(); for (auto& x : l.t) s = fp_add(s, fp_mul(x.c, z[x.v])); return s; }
@@ -97,6 +130,8 @@ struct FpVar {
     static FpVar zero() { return constant(fp_zero()); }
     static FpVar one() { return constant(fp_one()); }
     static FpVar witness(ConstraintSystem& cs, const fp& v) { FpVar r; r.lc = LC::var(cs.new_witness(v)); r.val = v; r.cst = false; return r; }
+    static FpVar witness_const(ConstraintSystem& cs, const fp& v) { LC c = LC::constant(v); cs.set_rule(RULE_MULADD, 0, nullptr, nullptr, &c); return witness(cs, v); }     // a witness whose value is a constant (z = 1 of a point, lib_str)
+    static FpVar witness_input(ConstraintSystem& cs, const fp& v, uint16_t slot) { cs.set_rule(RULE_INPUT, slot, nullptr); return witness(cs, v); }
     static FpVar input(ConstraintSystem& cs, const fp& v) { FpVar r; r.lc = LC::var(cs.new_input(v)); r.val = v; r.cst = false; return r; }
     FpVar operator+(const FpVar& o) const { FpVar r; r.lc = lc + o.lc; r.val = fp_add(val, o.val); r.cst = cst && o.cst; if (r.cst) r.lc = LC::constant(r.val); return r; }
     FpVar operator-(const FpVar& o) const { FpVar r; r.lc = lc - o.lc; r.val = fp_sub(val, o.val); r.cst = cst && o.cst; if (r.cst) r.lc = LC::constant(r.val); return r; }
@@ -107,8 +142,9 @@ struct FpVar {
     FpVar mul(ConstraintSystem& cs, const FpVar& o) const {
         if (cst) return o.scaled(val);
         if (o.cst) return scaled(o.val);
-        FpVar r = witness(cs, fp_mul(val, o.val));
         LC a = lc, b = o.lc; a.compact(); b.compact();
+        cs.set_rule(RULE_MULADD, 0, &a, &b);
+        FpVar r = witness(cs, fp_mul(val, o.val));
         cs.enforce(a, b, r.lc);
         return r;
     }
@@ -116,6 +152,7 @@ struct FpVar {
     // witness-hinted inverse: a * inv = 1 (unsatisfiable for a = 0, like AllocatedFp::inverse)
     FpVar inverse(ConstraintSystem& cs) const {
         if (cst) return constant(fp_inv(val));
+        cs.set_rule(RULE_INV, 0, &lc);
         FpVar r = witness(cs, fp_inv(val));
         cs.enforce(lc, r.lc, LC::constant(fp_one()));
         return r;
@@ -144,6 +181,7 @@ struct Boolean {
     Boolean and_(ConstraintSystem& cs, const Boolean& o) const {
         if (cst) return val ? o : constant(false);
         if (o.cst) return o.val ? *this : constant(false);
+        cs.set_rule(RULE_MULADD, 0, &lc, &o.lc);
         Boolean r = from_var(cs.new_witness((val && o.val) ? fp_one() : fp_zero()), val && o.val);
         cs.enforce(lc, o.lc, r.lc);
         return r;
@@ -153,6 +191,7 @@ struct Boolean {
     Boolean xor_(ConstraintSystem& cs, const Boolean& o) const {
         if (cst) return val ? o.not_() : o;
         if (o.cst) return o.val ? not_() : *this;
+        if (cs.record_rules) { LC m2 = (lc + lc).neg(), sum = lc + o.lc; cs.set_rule(RULE_MULADD, 0, &m2, &o.lc, &sum); }          // a + b - 2ab
         Boolean r = from_var(cs.new_witness((val != o.val) ? fp_one() : fp_zero()), val != o.val);
         cs.enforce(lc + lc, o.lc, lc + o.lc - r.lc);
         return r;
@@ -163,6 +202,7 @@ struct Boolean {
     FpVar select(ConstraintSystem& cs, const FpVar& t, const FpVar& f) const {
         if (cst) return val ? t : f;
         if (t.cst && f.cst) { FpVar r; r.lc = f.lc + lc.scaled(fp_sub(t.val, f.val)); r.val = val ? t.val : f.val; r.cst = false; return r; }
+        if (cs.record_rules) { LC df = t.lc - f.lc; cs.set_rule(RULE_MULADD, 0, &lc, &df, &f.lc); }                                 // f + cond (t - f)
         FpVar r = FpVar::witness(cs, val ? t.val : f.val);
         cs.enforce(lc, t.lc - f.lc, r.lc - f.lc);
         return r;
@@ -174,9 +214,11 @@ inline Boolean kary_and(ConstraintSystem& cs, const std::vector<Boolean>& v) { B
 inline Boolean fp_is_eq(ConstraintSystem& cs, const FpVar& a, const FpVar& b) {
     if (a.cst && b.cst) return Boolean::constant(fp_eq(a.val, b.val));
     fp d = fp_sub(a.val, b.val); bool neq = !fp_is_zero(d);
-    Boolean is_neq = Boolean::witness(cs, neq);
-    FpVar mult = FpVar::witness(cs, neq ? fp_inv(d) : fp_one());
     LC diff = a.lc - b.lc;
+    cs.set_rule(RULE_NEQ, 0, &diff);
+    Boolean is_neq = Boolean::witness(cs, neq);
+    cs.set_rule(RULE_NEQMULT, 0, &diff);
+    FpVar mult = FpVar::witness(cs, neq ? fp_inv(d) : fp_one());
     cs.enforce(diff, mult.lc, is_neq.lc);                                     // (a - b) m = is_neq
     cs.enforce(diff, is_neq.not_().lc, LC());                                 // (a - b)(1 - is_neq) = 0
     return is_neq.not_();
@@ -189,7 +231,9 @@ inline std::vector<Boolean> fp_to_bits_le(ConstraintSystem& cs, const FpVar& a) 
     std::vector<Boolean> bits(381);
     if (a.cst) { for (int i = 0; i < 381; i++) bits[i] = Boolean::constant((canon.l[i >> 5] >> (i & 31)) & 1); return bits; }
     LC sum; fp pw = fp_one();
+    uint32_t src_id = cs.record_rules ? cs.add_lc(a.lc) : 0;                  // one copy of the source combination for all 381 bit rules
     for (int i = 0; i < 381; i++) {
+        cs.set_rule_ids(RULE_BIT, (uint16_t)i, src_id, 0, 0);
         bits[i] = Boolean::witness(cs, (canon.l[i >> 5] >> (i & 31)) & 1);
         sum += bits[i].lc.scaled(pw); pw = fp_add(pw, pw);
     }
@@ -212,6 +256,8 @@ inline std::vector<Boolean> fp_to_bits_le(ConstraintSystem& cs, const FpVar& a) 
 struct UInt8 { std::array<Boolean, 8> b; uint8_t value() const { uint8_t v = 0; for (int i = 0; i < 8; i++) v |= (uint8_t)(b[i].val << i); return v; } };   // little-endian bits
 inline UInt8 u8_constant(uint8_t v) { UInt8 r; for (int i = 0; i < 8; i++) r.b[i] = Boolean::constant((v >> i) & 1); return r; }
 inline UInt8 u8_witness(ConstraintSystem& cs, uint8_t v) { UInt8 r; for (int i = 0; i < 8; i++) r.b[i] = Boolean::witness(cs, (v >> i) & 1); return r; }
+inline UInt8 u8_witness_input(ConstraintSystem& cs, uint8_t v, uint16_t slot0) { UInt8 r; for (int i = 0; i < 8; i++) { cs.set_rule(RULE_INPUT, (uint16_t)(slot0 + i), nullptr); r.b[i] = Boolean::witness(cs, (v >> i) & 1); } return r; }
+inline UInt8 u8_witness_const(ConstraintSystem& cs, uint8_t v) { UInt8 r; for (int i = 0; i < 8; i++) { LC c = LC::constant(((v >> i) & 1) ? fp_one() : fp_zero()); cs.set_rule(RULE_MULADD, 0, nullptr, nullptr, &c); r.b[i] = Boolean::witness(cs, (v >> i) & 1); } return r; }
 inline UInt8 u8_input(ConstraintSystem& cs, uint8_t v) { UInt8 r; for (int i = 0; i < 8; i++) r.b[i] = Boolean::input(cs, (v >> i) & 1); return r; }
 inline UInt8 u8_xor(ConstraintSystem& cs, const UInt8& a, const UInt8& c) { UInt8 r; for (int i = 0; i < 8; i++) r.b[i] = a.b[i].xor_(cs, c.b[i]); return r; }
 inline std::vector<UInt8> u8_constant_vec(const uint8_t* p, size_t n) { std::vector<UInt8> v(n); for (size_t i = 0; i < n; i++) v[i] = u8_constant(p[i]); return v; }
@@ -237,7 +283,9 @@ inline UInt32 u32_addmany(ConstraintSystem& cs, const std::vector<UInt32>& ops) 
     int nbits = 32; { size_t n = ops.size(); uint64_t maxv = n * 0xffffffffull; while ((maxv >> nbits) != 0) nbits++; }
     LC sum; for (auto& o : ops) sum += o.lc();
     LC res; fp pw = fp_one(); UInt32 r;
+    uint32_t sum_id = cs.record_rules ? cs.add_lc(sum) : 0;
     for (int i = 0; i < nbits; i++) {
+        cs.set_rule_ids(RULE_BIT, (uint16_t)i, sum_id, 0, 0);
         Boolean bit = Boolean::witness(cs, (total >> i) & 1);
         res += bit.lc.scaled(pw); pw = fp_add(pw, pw);
         if (i < 32) r.b[i] = bit;

@@ -82,7 +82,9 @@ struct Fp2Var {
     // witness-hinted inverse, a * inv = 1 (3 constraints); the inverse of zero is unsatisfiable, callers substitute
     Fp2Var inverse(ConstraintSystem& cs) const {
         if (is_constant()) return constant(fp2_inv(value()));
-        Fp2Var inv = witness(cs, fp2_inv(value()));
+        fp2 iv = fp2_inv(value()); Fp2Var inv;
+        cs.set_rule(RULE_FP2INV, 0, &c0.lc, &c1.lc); inv.c0 = FpVar::witness(cs, iv.c0);
+        cs.set_rule(RULE_FP2INV, 1, &c0.lc, &c1.lc); inv.c1 = FpVar::witness(cs, iv.c1);
         Fp2Var prod = mul(cs, inv);
         prod.c0.enforce_equal(cs, FpVar::one()); prod.c1.enforce_equal(cs, FpVar::zero());
         return inv;
@@ -165,8 +167,8 @@ struct DefaultFieldHasherWithCons {                                  // hasher.r
         std::vector<UInt8> dst_prime = dst; dst_prime.push_back(u8_constant((uint8_t)dst.size()));
         std::vector<UInt8> msg_prime(64, u8_constant(0));                                             // z_pad
         msg_prime.insert(msg_prime.end(), message.begin(), message.end());
-        msg_prime.push_back(u8_witness(cs, (uint8_t)(len_in_bytes >> 8)));                             // lib_str is a WITNESS in the reference (hasher.rs:131-132)
-        msg_prime.push_back(u8_witness(cs, (uint8_t)len_in_bytes));
+        msg_prime.push_back(u8_witness_const(cs, (uint8_t)(len_in_bytes >> 8)));                       // lib_str is a WITNESS in the reference (hasher.rs:131-132)
+        msg_prime.push_back(u8_witness_const(cs, (uint8_t)len_in_bytes));
         msg_prime.push_back(u8_constant(0));
         msg_prime.insert(msg_prime.end(), dst_prime.begin(), dst_prime.end());
         std::vector<UInt8> b0 = Sha256Gadget::digest(cs, msg_prime);
@@ -194,6 +196,7 @@ struct DefaultFieldHasherWithCons {                                  // hasher.r
             pw = fp_add(pw, pw);
         }
         if (all_const) return FpVar::constant(val);
+        cs.set_rule(RULE_MULADD, 0, nullptr, nullptr, &sum);
         FpVar v = FpVar::witness(cs, val);
         cs.enforce(sum, LC::constant(fp_one()), v.lc);
         return v;

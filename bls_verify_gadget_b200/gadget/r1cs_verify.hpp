@@ -59,7 +59,12 @@ struct Fp12Var {
     Fp12Var unitary_inverse() const { Fp12Var r; r.c0 = c0; r.c1 = c1.neg(); return r; }                 // conjugation
     Fp12Var inverse(ConstraintSystem& cs) const {                                    // witness-hinted: a * inv = 1
         fp12 v = value(), iv; fp12_inv(iv, v);
-        Fp12Var inv = witness(cs, iv), prod = mul(cs, inv), o = one();
+        Fp12Var inv, me = *this; uint32_t first = 0;
+        if (cs.record_rules) for (int k = 0; k < 6; k++) { LC l0 = me.coeff(k)->c0.lc, l1 = me.coeff(k)->c1.lc; l0.compact(); l1.compact();
+            // ids must be consecutive and non-empty: an (impossible here) empty combination would break the 12-id window
+            uint32_t i0 = cs.add_lc(l0), i1 = cs.add_lc(l1); if (!i0 || !i1) throw std::logic_error("Fp12 inverse of a value with a constant-zero coefficient"); if (!k) first = i0; }
+        { const fp* ivf = &iv.c0.c0.c0; for (int k = 0; k < 6; k++) for (int j = 0; j < 2; j++) { cs.set_rule_ids(RULE_FP12INV, (uint16_t)(2 * k + j), first, 0, 0); (j ? inv.coeff(k)->c1 : inv.coeff(k)->c0) = FpVar::witness(cs, ivf[2 * k + j]); } }
+        Fp12Var prod = mul(cs, inv), o = one();
         for (int k = 0; k < 6; k++) prod.coeff(k)->enforce_equal(cs, *o.coeff(k));
         return inv;
     }
@@ -182,7 +187,9 @@ struct G1Var {
     FpVar x, y, z;
     static G1Var make(const FpVar& x, const FpVar& y, const FpVar& z) { G1Var r; r.x = x; r.y = y; r.z = z; return r; }
     static G1Var zero() { return make(FpVar::zero(), FpVar::one(), FpVar::zero()); }
-    static G1Var witness(ConstraintSystem& cs, const g1_aff& p) { return make(FpVar::witness(cs, p.x), FpVar::witness(cs, p.y), FpVar::witness(cs, fp_one())); }
+    static G1Var witness(ConstraintSystem& cs, const g1_aff& p) {                      // input slots 256 / 257; z = 1
+        FpVar x = FpVar::witness_input(cs, p.x, 256), y = FpVar::witness_input(cs, p.y, 257); return make(x, y, FpVar::witness_const(cs, fp_one()));
+    }
     G1Var add(ConstraintSystem& cs, const G1Var& q) const {
         fp b3 = fp_from_u64(12);
         FpVar t0 = x.mul(cs, q.x), t1 = y.mul(cs, q.y), t2 = z.mul(cs, q.z);
@@ -199,7 +206,10 @@ inline G1Var select_g1(ConstraintSystem& cs, const Boolean& c, const G1Var& t, c
 // BlsSignatureVerifyGadget::verify (constraints.rs:90-128) on an already allocated public key; message bytes and the
 // signature are allocated as witnesses (the modes of the reference's tests, constraints.rs:335-366), parameters constant.
 inline bool verify_gadget(ConstraintSystem& cs, const G1Var& pk, const std::vector<UInt8>& m, const g2_aff& sig, fp12* gt) {
-    G2Var sg = G2Var::make(Fp2Var::witness(cs, sig.x), Fp2Var::witness(cs, sig.y), Fp2Var::witness(cs, fp2_one()));
+    G2Var sg;                                                                          // input slots 258..261; z = (1, 0)
+    sg.x.c0 = FpVar::witness_input(cs, sig.x.c0, 258); sg.x.c1 = FpVar::witness_input(cs, sig.x.c1, 259);
+    sg.y.c0 = FpVar::witness_input(cs, sig.y.c0, 260); sg.y.c1 = FpVar::witness_input(cs, sig.y.c1, 261);
+    sg.z.c0 = FpVar::witness_const(cs, fp_one()); sg.z.c1 = FpVar::witness_const(cs, fp_zero());
     // public_key.enforce_not_equal(zero) and prepare_g1: z has an inverse, affine coordinates by two products
     FpVar zi = pk.z.inverse(cs);
     G1AffineVar P1; P1.x = pk.x.mul(cs, zi); P1.y = pk.y.mul(cs, zi);
@@ -215,7 +225,7 @@ inline bool verify_gadget(ConstraintSystem& cs, const G1Var& pk, const std::vect
 // (constraints.rs:101-106).  Returns the value of the output Boolean; *gt (nullable) receives the GT element.
 inline bool synthesize_verify(ConstraintSystem& cs, const g1_aff& pk, const uint8_t* msg, size_t len, const g2_aff& sig, fp12* gt = nullptr) {
     G1Var pkv = G1Var::witness(cs, pk);
-    std::vector<UInt8> m(len); for (size_t i = 0; i < len; i++) m[i] = u8_witness(cs, msg[i]);
+    std::vector<UInt8> m(len); for (size_t i = 0; i < len; i++) m[i] = u8_witness_input(cs, msg[i], (uint16_t)(8 * i));     // input slots 0 .. 8 len - 1 (the program assumes len = 32)
     return verify_gadget(cs, pkv, m, sig, gt);
 }
 // aggregate_verify / mapped_aggregate (constraints.rs:153-191): keys masked by a witness bitmap (select key or zero), summed

@@ -295,6 +295,28 @@ def test_r1cs_verify_circuit_on_gpu(ctx, C):
     obits, oall = C.r1cs_check([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], c.nrows, c.ncols, zz, 3, threads=C.hw_threads())
     assert np.array_equal(bits, obits) and list(allsat) == list(oall) == [1, 1, 0]
 
+def test_gpu_witness_generation_matches_host_builder(ctx, C):
+    """blsgpu_witness_gen replays the builder's witness program on the GPU: the assignments must equal the host
+    synthesis byte for byte for valid and invalid signatures and distinct keys, satisfy every row of the verify circuit, and
+    undecodable inputs must be flagged."""
+    from bls_verify_gadget_b200 import gadget as G, synth
+    n = 37                                                                                    # two groups, the second ragged
+    pk, msg, sig, exp = synth.verify_batch_inputs(ctx, n, every=5, fast=False)                # wrong msg / swaps / tampered sig / identity pk
+    triples = [(pk[48 * i:48 * i + 48].tobytes(), msg[32 * i:32 * i + 32].tobytes(), sig[96 * i:96 * i + 96].tobytes()) for i in range(n)]
+    rules, lp, lc, cf, nvars = G.verify_program(*triples[0])
+    h = ctx.witness_load(rules, lp, lc, cf)
+    z, st = ctx.witness_gen(h, pk, msg, sig, nvars)
+    ctx.witness_free(h)
+    assert list(st) == [0 if e in (0, 1) else e for e in exp]                                 # 2: identity key, 3: undecodable signature
+    good = [i for i in range(n) if exp[i] in (0, 1)]
+    zh, res = G.verify_witnesses([triples[i] for i in good], ncols=nvars)
+    assert list(res) == [exp[i] == 0 for i in good]
+    for k, i in enumerate(good): assert np.array_equal(z[i], zh[k]), f"assignment {i} differs from the host synthesis"
+    c = G.verify_circuit(*triples[good[0]]); mats = c.matrices(); assert c.ncols == nvars
+    hh = ctx.r1cs_load([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], c.nrows, c.ncols)
+    bits, allsat = ctx.r1cs_check(hh, z.reshape(-1), n, c.nrows); ctx.r1cs_free(hh)
+    assert list(allsat) == [1 if e in (0, 1) else 0 for e in exp]                             # flagged items carry no assignment
+
 def test_rlc_batch_check_agrees_with_per_item_verify(ctx):
     """blsgpu_verify_batch_rlc (one pairing-product equation per batch): true exactly when every item of the
     batch verifies, for every corruption kind, several seeds, ragged messages, and across internal passes."""
