@@ -165,10 +165,13 @@ class Context:
     def r1cs_check_ptr(self, handle, z, nwit, bits, allsat): self._ck(lib().blsgpu_r1cs_check(self._h, int(handle), _p(z), _sz(nwit), _p(bits), _p(allsat)))
     def r1cs_free(self, handle): lib().blsgpu_r1cs_free(self._h, int(handle))
     # ---- GPU witness generation (program from bls_verify_gadget_b200.gadget.verify_program)
-    def witness_load(self, rules16, lc_ptr, lc_col, lc_coef48):
-        r = np.ascontiguousarray(rules16, dtype=np.uint8); lp = np.ascontiguousarray(lc_ptr, dtype=np.uint64); lc = np.ascontiguousarray(lc_col, dtype=np.uint32); cf = np.ascontiguousarray(lc_coef48, dtype=np.uint8)
+    def witness_load(self, program, levels=True):
+        """program: the dict of gadget.verify_program; levels=False keeps the strictly sequential replay (one warp per 32 assignments)"""
+        r = np.ascontiguousarray(program["rules16"], dtype=np.uint8); lp = np.ascontiguousarray(program["lc_ptr"], dtype=np.uint64)
+        lc = np.ascontiguousarray(program["lc_col"], dtype=np.uint32); cf = np.ascontiguousarray(program["lc_coef48"], dtype=np.uint8)
+        od = np.ascontiguousarray(program["order"], dtype=np.uint32) if levels else None; lv = np.ascontiguousarray(program["level_ptr"], dtype=np.uint64) if levels else None
         h = ctypes.c_int(-1)
-        self._ck(lib().blsgpu_witness_load(self._h, _p(r), _p(lp), _p(lc), _p(cf), _sz(r.size // 16), _sz(lp.size - 1), _sz(lc.size), ctypes.byref(h)))
+        self._ck(lib().blsgpu_witness_load(self._h, _p(r), _p(lp), _p(lc), _p(cf), _sz(r.size // 16), _sz(program["nvars"]), _sz(lp.size - 1), _sz(lc.size), _p(od), _p(lv), _sz(lv.size - 1 if levels else 0), ctypes.byref(h)))
         return h.value
     def witness_gen(self, handle, pk48, msg32, sig96, nvars):
         pk = _u8(pk48); m = _u8(msg32); sg = _u8(sig96); n = sg.size // 96

@@ -11,12 +11,17 @@
 // rules of the same lane: program order makes them visible).  Every branch is warp-uniform (rule kind, coefficient class).
 // Included after r1cs.cuh in blsgpu.cu.
 #pragma once
+#include <cooperative_groups.h>
 
 enum { WR_MULADD = 0, WR_INV = 1, WR_NEQ = 2, WR_NEQMULT = 3, WR_BIT = 4, WR_FP2INV = 5, WR_FP12INV = 6, WR_INPUT = 7 };
 struct wit_rule { uint8_t kind, pad; uint16_t aux; uint32_t a, b, d; };
+// rule in level order with its term ranges resolved (one dependent load less per combination); for WR_FP12INV a_lo is the
+// id of the first of twelve consecutive combinations
+struct wit_xrule { uint8_t kind, pad; uint16_t aux; uint32_t var; uint32_t a_lo, a_hi, b_lo, b_hi, d_lo, d_hi; };
 struct wit_prog {
-    size_t nvars, nlc, nterms;
+    size_t nvars, nout, nlc, nterms, nlevels;          // nvars: columns of the program (circuit variables, then scratch values); nout: circuit variables
     wit_rule* rules; uint64_t* lc_ptr; uint32_t* col; fp* coeff; fp* coeffc; uint8_t* cls;
+    wit_xrule* xrules; uint64_t* level_ptr;          // dependency levels: rules of one level are independent
 };
 #define WIT_INPUTS 262          // 256 message bits, pk.x, pk.y, sig x.c0, x.c1, y.c0, y.c1
 
@@ -26,10 +31,9 @@ __device__ __forceinline__ void wit_store(u32x4* zt, size_t col, int lane, const
     zt[(col * 3) * 32 + lane] = a; zt[(col * 3 + 1) * 32 + lane] = b; zt[(col * 3 + 2) * 32 + lane] = c;
 }
 // value of linear combination `id` (0 = empty) on this lane's assignment, canonical
-__device__ __forceinline__ fp wit_lc(const wit_prog& p, uint32_t id, const u32x4* zt, int lane) {
+__device__ __forceinline__ fp wit_lc_range(const wit_prog& p, uint64_t lo, uint64_t hi, const u32x4* zt, int lane) {
     fp acc = fp_zero();
-    if (!id) return acc;
-    for (uint64_t k = p.lc_ptr[id - 1], e = p.lc_ptr[id]; k < e; k++) {
+    for (uint64_t k = lo, e = hi; k < e; k++) {
         uint32_t cj = p.col[k]; uint8_t c = p.cls[k];
         fp zv = r1cs_load_z(zt, cj, lane);
         if (c == R1_PLUS_ONE) acc = fp_add(acc, zv);
@@ -41,6 +45,10 @@ __device__ __forceinline__ fp wit_lc(const wit_prog& p, uint32_t id, const u32x4
         }
     }
     return acc;
+}
+__device__ __forceinline__ fp wit_lc(const wit_prog& p, uint32_t id, const u32x4* zt, int lane) {
+    if (!id) return fp_zero();
+    return wit_lc_range(p, p.lc_ptr[id - 1], p.lc_ptr[id], zt, lane);
 }
 __device__ __forceinline__ fp wit_inv_canon(const fp& a) { return fp_from_mont(fp_inv(fp_to_mont(a))); }
 // a b for canonical a, b: small-integer shortcut as in r1cs_product_ok
@@ -91,6 +99,46 @@ __global__ void __launch_bounds__(32) k_witness_gen(wit_prog p, const fp* inputs
         wit_store(zt, v, lane, out);
     }
 }
+// Level-synchronous form: one warp per (rule of the current level, group of 32 assignments); a grid-wide barrier between
+// levels (cooperative launch).  The verify circuit has 8,816 levels of ~80 rules: with 16 groups a level is ~1,300 independent
+// warp tasks, against ONE warp per group walking 707,809 rules in sequence in k_witness_gen (7.3 s, latency bound).
+__global__ void __launch_bounds__(128, 2) k_witness_levels(wit_prog p, const fp* inputs, size_t nwit_padded, u32x4* zt_all, size_t groups) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * (size_t)blockDim.x) >> 5; int lane = threadIdx.x & 31;
+    fp one = fp_zero(); one.l[0] = 1;
+    for (size_t level = 0; level < p.nlevels; level++) {
+        uint64_t lo = p.level_ptr[level], n = p.level_ptr[level + 1] - lo;
+        for (size_t t = warp; t < n * groups; t += nwarps) {
+            wit_xrule r = p.xrules[lo + t / groups]; size_t group = t % groups;
+            u32x4* zt = zt_all + group * p.nvars * 96;
+            fp out;
+            switch (r.kind) {
+                case WR_MULADD: {
+                    fp d = wit_lc_range(p, r.d_lo, r.d_hi, zt, lane);
+                    if (r.a_hi > r.a_lo) { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, lane), b = wit_lc_range(p, r.b_lo, r.b_hi, zt, lane); out = fp_add(wit_mul_canon(a, b), d); }
+                    else out = d;
+                    break;
+                }
+                case WR_INV: out = wit_inv_canon(wit_lc_range(p, r.a_lo, r.a_hi, zt, lane)); break;
+                case WR_NEQ: { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, lane); out = fp_zero(); out.l[0] = fp_is_zero(a) ? 0u : 1u; break; }
+                case WR_NEQMULT: { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, lane); out = fp_is_zero(a) ? one : wit_inv_canon(a); break; }
+                case WR_BIT: { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, lane); out = fp_zero(); out.l[0] = (a.l[r.aux >> 5] >> (r.aux & 31)) & 1u; break; }
+                case WR_FP2INV: {
+                    fp2 x; x.c0 = fp_to_mont(wit_lc_range(p, r.a_lo, r.a_hi, zt, lane)); x.c1 = fp_to_mont(wit_lc_range(p, r.b_lo, r.b_hi, zt, lane));
+                    fp2 iv = fp2_inv(x); out = fp_from_mont(r.aux ? iv.c1 : iv.c0); break;
+                }
+                case WR_FP12INV: {
+                    fp12 x, iv; fp* xf = &x.c0.c0.c0;
+                    for (int k = 0; k < 12; k++) xf[k] = fp_to_mont(wit_lc(p, r.a_lo + k, zt, lane));
+                    fp12_inv(iv, x); out = fp_from_mont((&iv.c0.c0.c0)[r.aux]); break;
+                }
+                default: out = r.aux == 0xffff ? one : inputs[(size_t)r.aux * nwit_padded + group * 32 + lane]; break;       // WR_INPUT; 0xffff: the constant ONE (variable 0)
+            }
+            wit_store(zt, r.var, lane, out);
+        }
+        grid.sync();
+    }
+}
 // input slots from the decoded points and the message bytes; items whose key or signature does not decode get all-zero inputs
 __global__ void __launch_bounds__(TPB, BLS_MINB) k_witness_inputs(const u32x4* pk_soa, const uint8_t* code_pk, const u32x4* sig_soa, const uint8_t* code_sig, const uint8_t* msg32,
                                                                   size_t nwit, size_t nwit_padded, fp* inputs, uint8_t* status) {
@@ -108,24 +156,26 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_witness_inputs(const u32x4* p
     if (live && status) status[i] = st;
 }
 // transposed group -> z[w][col] (48-byte LE canonical), the layout of blsgpu_r1cs_check
-__global__ void __launch_bounds__(256) k_witness_untranspose(const u32x4* zt_all, size_t ncols, size_t nwit, u32x4* z) {
+__global__ void __launch_bounds__(256) k_witness_untranspose(const u32x4* zt_all, size_t ncols, size_t nout, size_t nwit, u32x4* z) {
     size_t col = blockIdx.x * (size_t)8 + (threadIdx.x >> 5); int lane = threadIdx.x & 31; size_t group = blockIdx.y;
     size_t w = group * 32 + lane;
-    if (col >= ncols || w >= nwit) return;
+    if (col >= nout || w >= nwit) return;
     const u32x4* zt = zt_all + group * ncols * 96;
-    u32x4* dst = z + (w * ncols + col) * 3;
+    u32x4* dst = z + (w * nout + col) * 3;
     dst[0] = zt[(col * 3) * 32 + lane]; dst[1] = zt[(col * 3 + 1) * 32 + lane]; dst[2] = zt[(col * 3 + 2) * 32 + lane];
 }
 
 struct wit_prog_host { wit_prog d; };
 
 extern "C" {
-int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t* lc_ptr, const uint32_t* lc_col, const uint8_t* lc_coef48, size_t nvars, size_t nlc, size_t nterms, int* handle) {
-    ENTER(); if (!rules16 || !lc_ptr || !lc_col || !lc_coef48 || !handle || !nvars) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
+int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t* lc_ptr, const uint32_t* lc_col, const uint8_t* lc_coef48, size_t nvars, size_t nout, size_t nlc, size_t nterms,
+                        const uint32_t* order, const uint64_t* level_ptr, size_t nlevels, int* handle) {
+    ENTER(); if (!rules16 || !lc_ptr || !lc_col || !lc_coef48 || !handle || !nvars || !nout || nout > nvars) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
+    if (ctx->ptr_mode != BLSGPU_HOST) return fail(ctx, BLSGPU_ERR_ARG, "blsgpu_witness_load takes host pointers (the level-ordered rule table is built on the host)");
     int h = -1; for (int i = 0; i < 4; i++) if (!ctx->wit[i]) { h = i; break; }
     if (h < 0) return fail(ctx, BLSGPU_ERR_ARG, "too many witness programs loaded");
     wit_prog* p = new (std::nothrow) wit_prog(); if (!p) return fail(ctx, BLSGPU_ERR_ALLOC, "out of host memory");
-    memset(p, 0, sizeof *p); p->nvars = nvars; p->nlc = nlc; p->nterms = nterms; ctx->wit[h] = p;
+    memset(p, 0, sizeof *p); p->nvars = nvars; p->nout = nout; p->nlc = nlc; p->nterms = nterms; ctx->wit[h] = p;
     cudaMemcpyKind kind = ctx->ptr_mode == BLSGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     size_t nt = nterms ? nterms : 1;
     CU(cudaMalloc(&p->rules, 16 * nvars)); CU(cudaMalloc(&p->lc_ptr, 8 * (nlc + 1))); CU(cudaMalloc(&p->col, 4 * nt));
@@ -138,6 +188,22 @@ int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t*
         LAUNCH(k_r1cs_prepare, nblk(nterms), TPB, (const uint8_t*)raw, nterms, p->coeff, p->coeffc, p->cls);
         CU(cudaStreamSynchronize(ctx->stream)); cudaFree(raw);
     }
+    if (order && level_ptr && nlevels) {                   // level-ordered rules with resolved term ranges
+        const wit_rule* hr = reinterpret_cast<const wit_rule*>(rules16);
+        std::vector<wit_xrule> xr(nvars);
+        auto lo_of = [&](uint32_t id) { return id ? (uint32_t)lc_ptr[id - 1] : 0u; }; auto hi_of = [&](uint32_t id) { return id ? (uint32_t)lc_ptr[id] : 0u; };
+        for (size_t k = 0; k < nvars; k++) {
+            const wit_rule& r = hr[order[k]]; wit_xrule& x = xr[k];
+            x.kind = r.kind; x.pad = 0; x.aux = r.aux; x.var = order[k];
+            if (r.kind == WR_FP12INV) { x.a_lo = r.a; x.a_hi = r.a + 12; x.b_lo = x.b_hi = x.d_lo = x.d_hi = 0; }
+            else { x.a_lo = lo_of(r.a); x.a_hi = hi_of(r.a); x.b_lo = lo_of(r.b); x.b_hi = hi_of(r.b); x.d_lo = lo_of(r.d); x.d_hi = hi_of(r.d); }
+        }
+        p->nlevels = nlevels;
+        CU(cudaMalloc(&p->xrules, sizeof(wit_xrule) * nvars)); CU(cudaMalloc(&p->level_ptr, 8 * (nlevels + 1)));
+        CU(cudaMemcpyAsync(p->xrules, xr.data(), sizeof(wit_xrule) * nvars, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(p->level_ptr, level_ptr, 8 * (nlevels + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     *handle = h; return 0;
 }
@@ -146,9 +212,10 @@ int blsgpu_witness_free(blsgpu_ctx* ctx, int handle) {
     cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
     wit_prog* p = ctx->wit[handle];
     cudaFree(p->rules); cudaFree(p->lc_ptr); cudaFree(p->col); cudaFree(p->coeff); cudaFree(p->coeffc); cudaFree(p->cls);
+    if (p->xrules) cudaFree(p->xrules); if (p->level_ptr) cudaFree(p->level_ptr);
     delete p; ctx->wit[handle] = nullptr; return 0;
 }
-// assignments of the verify circuit for nwit (pk48, msg32, sig96) triples: z48 = nwit * nvars * 48 bytes (the layout of
+// assignments of the verify circuit for nwit (pk48, msg32, sig96) triples: z48 = nwit * nout * 48 bytes (the layout of
 // blsgpu_r1cs_check), status[i] = 0, or 2 / 3 when the key / signature does not decode to a non-identity point (its assignment
 // is then all zeros except z[0] = 1 and the constants).  Pointers follow the context's pointer mode.
 int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, size_t nwit, uint8_t* z48, uint8_t* status) {
@@ -157,7 +224,7 @@ int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const u
     wit_prog p = *ctx->wit[handle];
     size_t groups = (nwit + 31) / 32, np = groups * 32;
     bool host = ctx->ptr_mode == BLSGPU_HOST;
-    size_t zbytes = nwit * p.nvars * 48;
+    size_t zbytes = nwit * p.nout * 48;
     if (int rc = ws_reserve(ctx, al(48 * nwit) + al(96 * nwit) + al(32 * nwit) + al(96 * nwit) + al(192 * nwit) + 3 * al(np) + al(48 * WIT_INPUTS * np) + al(groups * p.nvars * 1536) + (host ? al(zbytes) : 0) + 65536)) return rc;
     const uint8_t *dpk, *dsig, *dmsg;
     if (int rc = stage_in(ctx, dpk, pk48, 48 * nwit)) return rc;
@@ -172,8 +239,17 @@ int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const u
     LAUNCH(k_decode_g1, nblk(nwit), TPB, dpk, nwit, pk_soa, code_pk);
     LAUNCH(k_decode_g2, nblk(nwit), TPB, dsig, nwit, sig_soa, code_sig);
     LAUNCH(k_witness_inputs, nblk(np), TPB, (const u32x4*)pk_soa, (const uint8_t*)code_pk, (const u32x4*)sig_soa, (const uint8_t*)code_sig, dmsg, nwit, np, inputs, dstatus);
-    LAUNCH(k_witness_gen, (unsigned)groups, 32, p, (const fp*)inputs, np, zt_all);
-    { dim3 grid(nblk(p.nvars, 8), (unsigned)groups); k_witness_untranspose<<<grid, 256, 0, ctx->stream>>>((const u32x4*)zt_all, p.nvars, nwit, (u32x4*)dz); ctx->launches++; CU(cudaGetLastError()); }
+    if (p.xrules) {                                        // level-synchronous, cooperative launch: every block must be resident
+        int per_sm = 0, sms = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_witness_levels, 128, 0)); CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        if (per_sm < 1) return fail(ctx, BLSGPU_ERR_CUDA, "k_witness_levels does not fit on an SM");
+        const fp* in_c = inputs; void* args[] = {(void*)&p, (void*)&in_c, (void*)&np, (void*)&zt_all, (void*)&groups};
+        CU(cudaLaunchCooperativeKernel((void*)k_witness_levels, dim3((unsigned)(per_sm * sms)), dim3(128), args, 0, ctx->stream)); ctx->launches++;
+    } else {
+        if (p.nvars != p.nout) return fail(ctx, BLSGPU_ERR_ARG, "the sequential replay needs a program without scratch columns (load it with its level order)");
+        LAUNCH(k_witness_gen, (unsigned)groups, 32, p, (const fp*)inputs, np, zt_all);
+    }
+    { dim3 grid(nblk(p.nout, 8), (unsigned)groups); k_witness_untranspose<<<grid, 256, 0, ctx->stream>>>((const u32x4*)zt_all, p.nvars, p.nout, nwit, (u32x4*)dz); ctx->launches++; CU(cudaGetLastError()); }
     if (host) CU(cudaMemcpyAsync(z48, dz, zbytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (status) { if (int rc = finish_out(ctx, status, dstatus, nwit)) return rc; }
     return finish_call(ctx);

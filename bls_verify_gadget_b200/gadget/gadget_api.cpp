@@ -3,6 +3,7 @@
 // blsgpu_r1cs_load / blsgpu_r1cs_check (include/blsgpu.h) consume.  Host code only: no CUDA, no oracle.
 #include "r1cs_verify.hpp"
 #include <memory>
+#include <functional>
 #include <mutex>
 using namespace gadget;
 
@@ -77,19 +78,61 @@ int blsgadget_verify_program(const uint8_t pk48[48], const uint8_t* msg32, const
         return put(std::move(c));
     } catch (...) { return -1; }
 }
-int blsgadget_program_shape(int h, uint64_t* nvars, uint64_t* nlc, uint64_t* nterms) {
+// nvars: circuit variables (the assignment's length); ncols = nvars + scratch columns (the rule count of the program)
+int blsgadget_program_shape(int h, uint64_t* nvars, uint64_t* ncols, uint64_t* nlc, uint64_t* nterms) {
     Circuit* c = get(h); if (!c || c->cs.rules.size() != c->cs.z.size()) return -1;
-    *nvars = c->cs.rules.size(); *nlc = c->cs.lc_ptr.size() - 1; *nterms = c->cs.lc_col.size(); return 0;
+    *nvars = c->cs.rules.size(); *ncols = c->cs.rules.size() + c->cs.scratch_rules.size(); *nlc = c->cs.lc_ptr.size() - 1; *nterms = c->cs.lc_col.size(); return 0;
 }
-// rules16: nvars records {u8 kind, u8 0, u16 aux, u32 a, u32 b, u32 d}; lc_ptr: nlc + 1; lc_col / lc_coef48: nterms
+// rules16: ncols records (variables, then scratch columns) {u8 kind, u8 0, u16 aux, u32 a, u32 b, u32 d}; lc_ptr: nlc + 1; lc_col / lc_coef48: nterms
 int blsgadget_program_export(int h, uint8_t* rules16, uint64_t* lc_ptr, uint32_t* lc_col, uint8_t* lc_coef48) {
     Circuit* c = get(h); if (!c || c->cs.rules.size() != c->cs.z.size()) return -1;
     static_assert(sizeof(Rule) == 16, "rule record layout");
-    if (rules16) memcpy(rules16, c->cs.rules.data(), 16 * c->cs.rules.size());
+    size_t nv = c->cs.rules.size();
+    if (rules16) { memcpy(rules16, c->cs.rules.data(), 16 * nv); memcpy(rules16 + 16 * nv, c->cs.scratch_rules.data(), 16 * c->cs.scratch_rules.size()); }
     if (lc_ptr) memcpy(lc_ptr, c->cs.lc_ptr.data(), 8 * c->cs.lc_ptr.size());
-    if (lc_col) memcpy(lc_col, c->cs.lc_col.data(), 4 * c->cs.lc_col.size());
+    if (lc_col) for (size_t k = 0; k < c->cs.lc_col.size(); k++) { uint32_t v = c->cs.lc_col[k]; lc_col[k] = v >= ConstraintSystem::SCRATCH_BASE ? (uint32_t)(nv + (v - ConstraintSystem::SCRATCH_BASE)) : v; }
     if (lc_coef48) for (size_t k = 0; k < c->cs.lc_val.size(); k++) le48(lc_coef48 + 48 * k, c->cs.lc_val[k]);
     return 0;
+}
+// Dependency levels of the witness program: level(v) = 1 + max level of the variables its rule reads (inputs and z[0]: level 0).
+// Rules of one level are independent, so the GPU evaluates a level with many warps and synchronises between levels.
+// order[nvars]: variable indices sorted by level (stable); level_ptr[nlevels + 1]; returns nlevels (or < 0).
+long blsgadget_program_levels(int h, uint32_t* order, uint64_t* level_ptr, uint64_t level_cap) {
+    Circuit* c = get(h); if (!c || c->cs.rules.size() != c->cs.z.size()) return -1;
+    const ConstraintSystem& cs = c->cs; size_t nv = cs.rules.size(), n = nv + cs.scratch_rules.size();
+    std::vector<uint32_t> lvl(n, 0); uint32_t maxl = 0;
+    auto col_of = [&](uint32_t v) { return v >= ConstraintSystem::SCRATCH_BASE ? (uint32_t)(nv + (v - ConstraintSystem::SCRATCH_BASE)) : v; };
+    auto lc_level = [&](uint32_t id) { uint32_t m = 0; if (!id) return m; for (uint64_t k = cs.lc_ptr[id - 1]; k < cs.lc_ptr[id]; k++) m = std::max(m, lvl[col_of(cs.lc_col[k])]); return m; };
+    // a scratch column only reads variables allocated before the rules that read it, and is read only by later variables: a
+    // single pass in allocation order works if scratch levels are resolved on first use
+    std::vector<uint8_t> done(cs.scratch_rules.size(), 0);
+    std::function<void(uint32_t)> resolve_scratch = [&](uint32_t id) {
+        if (!id) return;
+        for (uint64_t k = cs.lc_ptr[id - 1]; k < cs.lc_ptr[id]; k++) {
+            uint32_t v = cs.lc_col[k]; if (v < ConstraintSystem::SCRATCH_BASE) continue;
+            size_t si = v - ConstraintSystem::SCRATCH_BASE; if (done[si]) continue;
+            done[si] = 1; resolve_scratch(cs.scratch_rules[si].d);                   // partial sums first
+            lvl[nv + si] = lc_level(cs.scratch_rules[si].d) + 1; maxl = std::max(maxl, lvl[nv + si]);
+        }
+    };
+    for (size_t v = 1; v < nv; v++) {
+        const Rule& r = cs.rules[v]; uint32_t m = 0;
+        if (r.kind != RULE_INPUT && r.kind != RULE_FP12INV) { resolve_scratch(r.a); resolve_scratch(r.b); resolve_scratch(r.d); }
+        if (r.kind == RULE_INPUT) { lvl[v] = 0; continue; }
+        if (r.kind == RULE_FP12INV) { for (uint32_t k = 0; k < 12; k++) m = std::max(m, lc_level(r.a + k)); }
+        else m = std::max(lc_level(r.a), std::max(lc_level(r.b), lc_level(r.d)));
+        lvl[v] = m + 1; maxl = std::max(maxl, lvl[v]);
+    }
+    size_t nlev = (size_t)maxl + 1;
+    if (!order || !level_ptr) return (long)nlev;
+    if (level_cap < nlev + 1) return -2;
+    std::vector<uint64_t> cnt(nlev + 1, 0);
+    for (size_t v = 0; v < n; v++) cnt[lvl[v] + 1]++;
+    for (size_t l = 0; l < nlev; l++) cnt[l + 1] += cnt[l];
+    memcpy(level_ptr, cnt.data(), 8 * (nlev + 1));
+    std::vector<uint64_t> pos(cnt.begin(), cnt.end() - 1);
+    for (size_t v = 0; v < n; v++) order[pos[lvl[v]]++] = (uint32_t)v;
+    return (long)nlev;
 }
 // assignment only (witness-only synthesis: no matrices are built): z48 must hold ncols * 48 bytes, ncols from a full synthesis
 int blsgadget_verify_assignment(const uint8_t pk48[48], const uint8_t* msg, size_t len, const uint8_t sig96[96], uint8_t* z48, size_t ncols, int* result) {

@@ -87,10 +87,42 @@ struct ConstraintSystem {
         for (auto& x : l.t) { lc_col.push_back(x.v); lc_val.push_back(x.c); }
         lc_ptr.push_back(lc_col.size()); return (uint32_t)(lc_ptr.size() - 1);
     }
+    // scratch values of the witness program: a long combination read by many rules (the 35 result bits of an addmany, the 381
+    // bits of to_bits_le) is evaluated ONCE into a scratch column (index >= SCRATCH_BASE here, remapped behind the variables at
+    // export); scratch columns are not circuit variables and never reach the matrices
+    static constexpr uint32_t SCRATCH_BASE = 0x80000000u;
+    std::vector<Rule> scratch_rules;
+    uint32_t scratch_column(const LC& l) {            // scratch column holding the value of l; returns its (unmapped) column index
+        uint32_t src = add_lc(l);
+        scratch_rules.push_back(Rule{RULE_MULADD, 0, 0, 0, 0, src});
+        return SCRATCH_BASE + (uint32_t)(scratch_rules.size() - 1);
+    }
+    uint32_t scratch_of(LC l) {                       // returns the id of the one-term combination "1 * scratch"
+        l.compact(); if (l.t.empty()) return 0;
+        // a combination of n terms costs n dependent gathers for ONE warp: cut long ones into 32-term partial sums (independent
+        // tasks of one level) and add the partials in the next level
+        uint32_t col;
+        if (l.t.size() > 48) {
+            LC total;
+            for (size_t i = 0; i < l.t.size(); i += 32) { LC part; part.t.assign(l.t.begin() + i, l.t.begin() + std::min(l.t.size(), i + 32)); total.t.push_back({scratch_column(part), fp_one()}); }
+            col = scratch_column_raw(total);
+        } else col = scratch_column(l);
+        lc_col.push_back(col); lc_val.push_back(fp_one());
+        lc_ptr.push_back(lc_col.size()); return (uint32_t)(lc_ptr.size() - 1);
+    }
+    uint32_t scratch_column_raw(const LC& l) {        // like scratch_column, but the terms are already final (may reference scratch columns; no sorting by variable needed)
+        for (auto& x : l.t) { lc_col.push_back(x.v); lc_val.push_back(x.c); }
+        lc_ptr.push_back(lc_col.size());
+        scratch_rules.push_back(Rule{RULE_MULADD, 0, 0, 0, 0, (uint32_t)(lc_ptr.size() - 1)});
+        return SCRATCH_BASE + (uint32_t)(scratch_rules.size() - 1);
+    }
     void set_rule_ids(uint8_t kind, uint16_t aux, uint32_t a, uint32_t b, uint32_t d) { if (!record_rules) return; pending = Rule{kind, 0, aux, a, b, d}; has_pending = true; }
     void set_rule(uint8_t kind, uint16_t aux, const LC* a, const LC* b = nullptr, const LC* d = nullptr) {
         if (!record_rules) return;
-        set_rule_ids(kind, aux, a ? add_lc(*a) : 0, b ? add_lc(*b) : 0, d ? add_lc(*d) : 0);
+        // long combinations go through scratch columns (partial sums in parallel) so that no single rule walks hundreds of terms
+        auto id = [&](const LC* l) { if (!l) return 0u; LC t = *l; t.compact(); return t.t.size() > 48 ? scratch_of(t) : add_lc(t); };
+        uint32_t ia = id(a), ib = id(b), idd = id(d);
+        set_rule_ids(kind, aux, ia, ib, idd);
     }
     void take_rule() {
         if (!record_rules) return;
@@ -231,7 +263,7 @@ inline std::vector<Boolean> fp_to_bits_le(ConstraintSystem& cs, const FpVar& a) 
     std::vector<Boolean> bits(381);
     if (a.cst) { for (int i = 0; i < 381; i++) bits[i] = Boolean::constant((canon.l[i >> 5] >> (i & 31)) & 1); return bits; }
     LC sum; fp pw = fp_one();
-    uint32_t src_id = cs.record_rules ? cs.add_lc(a.lc) : 0;                  // one copy of the source combination for all 381 bit rules
+    uint32_t src_id = cs.record_rules ? cs.scratch_of(a.lc) : 0;              // the source combination is evaluated once, all 381 bit rules read the scratch value
     for (int i = 0; i < 381; i++) {
         cs.set_rule_ids(RULE_BIT, (uint16_t)i, src_id, 0, 0);
         bits[i] = Boolean::witness(cs, (canon.l[i >> 5] >> (i & 31)) & 1);
@@ -283,7 +315,7 @@ inline UInt32 u32_addmany(ConstraintSystem& cs, const std::vector<UInt32>& ops) 
     int nbits = 32; { size_t n = ops.size(); uint64_t maxv = n * 0xffffffffull; while ((maxv >> nbits) != 0) nbits++; }
     LC sum; for (auto& o : ops) sum += o.lc();
     LC res; fp pw = fp_one(); UInt32 r;
-    uint32_t sum_id = cs.record_rules ? cs.add_lc(sum) : 0;
+    uint32_t sum_id = cs.record_rules ? cs.scratch_of(sum) : 0;
     for (int i = 0; i < nbits; i++) {
         cs.set_rule_ids(RULE_BIT, (uint16_t)i, sum_id, 0, 0);
         Boolean bit = Boolean::witness(cs, (total >> i) & 1);

@@ -156,11 +156,13 @@ int blsgpu_r1cs_free(blsgpu_ctx* ctx, int handle);
 /* ---- GPU witness generation for the verify circuit (no counterpart in the reference, whose assignments come from
  *      running the gadget code of src/constraints.rs:335-370 under ark-relations) -------------------------------------------------
  * blsgpu_witness_load takes the witness program exported by the host-side builder (libblsgadget.so, blsgadget_program_export):
- * rules16 = nvars records {u8 kind, u8 0, u16 aux, u32 a, u32 b, u32 d}, lc_ptr[nlc + 1], lc_col / lc_coef48 (canonical LE) [nterms].
+ * rules16 = ncols records {u8 kind, u8 0, u16 aux, u32 a, u32 b, u32 d}, lc_ptr[nlc + 1], lc_col / lc_coef48 (canonical LE) [nterms].
  * blsgpu_witness_gen replays it for nwit (pk48, msg32, sig96) triples: z48 = nwit * nvars * 48 bytes in the layout of
  * blsgpu_r1cs_check; status[i] (nullable) = 0, or 2 / 3 when the key / signature does not decode to a non-identity point. */
 int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t* lc_ptr, const uint32_t* lc_col, const uint8_t* lc_coef48,
-                        size_t nvars, size_t nlc, size_t nterms, int* handle);
+                        size_t ncols /* rules: circuit variables, then scratch columns */, size_t nvars /* circuit variables */, size_t nlc, size_t nterms,
+                        const uint32_t* order /* nullable: variables sorted by dependency level */, const uint64_t* level_ptr /* nlevels + 1 */, size_t nlevels,
+                        int* handle);   /* host pointers; with `order` the rules of one level run in parallel (blsgadget_program_levels) */
 int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, size_t nwit,
                        uint8_t* z48, uint8_t* status);
 int blsgpu_witness_free(blsgpu_ctx* ctx, int handle);

@@ -303,10 +303,11 @@ def test_gpu_witness_generation_matches_host_builder(ctx, C):
     n = 37                                                                                    # two groups, the second ragged
     pk, msg, sig, exp = synth.verify_batch_inputs(ctx, n, every=5, fast=False)                # wrong msg / swaps / tampered sig / identity pk
     triples = [(pk[48 * i:48 * i + 48].tobytes(), msg[32 * i:32 * i + 32].tobytes(), sig[96 * i:96 * i + 96].tobytes()) for i in range(n)]
-    rules, lp, lc, cf, nvars = G.verify_program(*triples[0])
-    h = ctx.witness_load(rules, lp, lc, cf)
+    prog = G.verify_program(*triples[0]); nvars = prog["nvars"]
+    h = ctx.witness_load(prog)                                                                # level-synchronous replay (cooperative launch)
     z, st = ctx.witness_gen(h, pk, msg, sig, nvars)
     ctx.witness_free(h)
+    assert prog["ncols"] > nvars and prog["level_ptr"].size - 1 > 1000                        # scratch columns exist; thousands of dependency levels
     assert list(st) == [0 if e in (0, 1) else e for e in exp]                                 # 2: identity key, 3: undecodable signature
     good = [i for i in range(n) if exp[i] in (0, 1)]
     zh, res = G.verify_witnesses([triples[i] for i in good], ncols=nvars)
