@@ -102,7 +102,13 @@ __global__ void __launch_bounds__(32) k_witness_gen(wit_prog p, const fp* inputs
 // Level-synchronous form: one warp per (rule of the current level, group of 32 assignments); a grid-wide barrier between
 // levels (cooperative launch).  The verify circuit has 8,816 levels of ~80 rules: with 16 groups a level is ~1,300 independent
 // warp tasks, against ONE warp per group walking 707,809 rules in sequence in k_witness_gen (7.3 s, latency bound).
-__global__ void __launch_bounds__(128, 2) k_witness_levels(wit_prog p, const fp* inputs, size_t nwit_padded, u32x4* zt_all, size_t groups) {
+#ifndef WIT_TPB
+#define WIT_TPB 128
+#endif
+#ifndef WIT_BPS
+#define WIT_BPS 2
+#endif
+__global__ void __launch_bounds__(WIT_TPB, WIT_BPS) k_witness_levels(wit_prog p, const fp* inputs, size_t nwit_padded, u32x4* zt_all, size_t groups) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * (size_t)blockDim.x) >> 5; int lane = threadIdx.x & 31;
     fp one = fp_zero(); one.l[0] = 1;
@@ -241,10 +247,10 @@ int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const u
     LAUNCH(k_witness_inputs, nblk(np), TPB, (const u32x4*)pk_soa, (const uint8_t*)code_pk, (const u32x4*)sig_soa, (const uint8_t*)code_sig, dmsg, nwit, np, inputs, dstatus);
     if (p.xrules) {                                        // level-synchronous, cooperative launch: every block must be resident
         int per_sm = 0, sms = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_witness_levels, 128, 0)); CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_witness_levels, WIT_TPB, 0)); if (per_sm > WIT_BPS) per_sm = WIT_BPS; CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
         if (per_sm < 1) return fail(ctx, BLSGPU_ERR_CUDA, "k_witness_levels does not fit on an SM");
         const fp* in_c = inputs; void* args[] = {(void*)&p, (void*)&in_c, (void*)&np, (void*)&zt_all, (void*)&groups};
-        CU(cudaLaunchCooperativeKernel((void*)k_witness_levels, dim3((unsigned)(per_sm * sms)), dim3(128), args, 0, ctx->stream)); ctx->launches++;
+        CU(cudaLaunchCooperativeKernel((void*)k_witness_levels, dim3((unsigned)(per_sm * sms)), dim3(WIT_TPB), args, 0, ctx->stream)); ctx->launches++;
     } else {
         if (p.nvars != p.nout) return fail(ctx, BLSGPU_ERR_ARG, "the sequential replay needs a program without scratch columns (load it with its level order)");
         LAUNCH(k_witness_gen, (unsigned)groups, 32, p, (const fp*)inputs, np, zt_all);

@@ -97,16 +97,24 @@ struct ConstraintSystem {
         scratch_rules.push_back(Rule{RULE_MULADD, 0, 0, 0, 0, src});
         return SCRATCH_BASE + (uint32_t)(scratch_rules.size() - 1);
     }
+#ifndef BLS_WIT_CHUNK
+#define BLS_WIT_CHUNK 8
+#endif
+    // scratch column holding the value of a (compacted) combination, as a tree of BLS_WIT_CHUNK-term partial sums: a rule is
+    // evaluated by ONE warp, and a general coefficient on a field-sized value costs a full Montgomery product (~1 us at one warp
+    // per task), so the depth of a level is set by its longest combination
+    uint32_t scratch_tree(const LC& l, bool final_terms) {
+        if (l.t.size() <= BLS_WIT_CHUNK) return final_terms ? scratch_column_raw(l) : scratch_column(l);
+        LC total;
+        for (size_t i = 0; i < l.t.size(); i += BLS_WIT_CHUNK) {
+            LC part; part.t.assign(l.t.begin() + i, l.t.begin() + std::min(l.t.size(), i + (size_t)BLS_WIT_CHUNK));
+            total.t.push_back({final_terms ? scratch_column_raw(part) : scratch_column(part), fp_one()});
+        }
+        return scratch_tree(total, true);
+    }
     uint32_t scratch_of(LC l) {                       // returns the id of the one-term combination "1 * scratch"
         l.compact(); if (l.t.empty()) return 0;
-        // a combination of n terms costs n dependent gathers for ONE warp: cut long ones into 32-term partial sums (independent
-        // tasks of one level) and add the partials in the next level
-        uint32_t col;
-        if (l.t.size() > 48) {
-            LC total;
-            for (size_t i = 0; i < l.t.size(); i += 32) { LC part; part.t.assign(l.t.begin() + i, l.t.begin() + std::min(l.t.size(), i + 32)); total.t.push_back({scratch_column(part), fp_one()}); }
-            col = scratch_column_raw(total);
-        } else col = scratch_column(l);
+        uint32_t col = scratch_tree(l, false);
         lc_col.push_back(col); lc_val.push_back(fp_one());
         lc_ptr.push_back(lc_col.size()); return (uint32_t)(lc_ptr.size() - 1);
     }
@@ -120,7 +128,7 @@ struct ConstraintSystem {
     void set_rule(uint8_t kind, uint16_t aux, const LC* a, const LC* b = nullptr, const LC* d = nullptr) {
         if (!record_rules) return;
         // long combinations go through scratch columns (partial sums in parallel) so that no single rule walks hundreds of terms
-        auto id = [&](const LC* l) { if (!l) return 0u; LC t = *l; t.compact(); return t.t.size() > 48 ? scratch_of(t) : add_lc(t); };
+        auto id = [&](const LC* l) { if (!l) return 0u; LC t = *l; t.compact(); return t.t.size() > 2 * BLS_WIT_CHUNK ? scratch_of(t) : add_lc(t); };
         uint32_t ia = id(a), ib = id(b), idd = id(d);
         set_rule_ids(kind, aux, ia, ib, idd);
     }
