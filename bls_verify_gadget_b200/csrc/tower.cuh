@@ -100,11 +100,19 @@ BLS_HD bool fp12_is_one(const fp12& a) {
 BLS_HD void fp12_conj(fp12& r, const fp12& a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }
 
 // 3 Fp6 products
+#ifndef BLS_LAZY_FE
+#define BLS_LAZY_FE 0        // 1: the final exponentiation's Fp12 products also use the lazy Fp6 product (measured: profiles/r01_tuning.md)
+#endif
+#if BLS_LAZY_FE
+#define BLS_FP6_MUL_FE fp6_mul_lz
+#else
+#define BLS_FP6_MUL_FE fp6_mul
+#endif
 BLS_NOINLINE void fp12_mul(fp12& r, const fp12& a, const fp12& b) {
     fp6 t0, t1, t2, s0, s1;
-    fp6_mul(t0, a.c0, b.c0); fp6_mul(t1, a.c1, b.c1);
+    BLS_FP6_MUL_FE(t0, a.c0, b.c0); BLS_FP6_MUL_FE(t1, a.c1, b.c1);
     fp6_add(s0, a.c0, a.c1); fp6_add(s1, b.c0, b.c1);
-    fp6_mul(t2, s0, s1);
+    BLS_FP6_MUL_FE(t2, s0, s1);
     fp6_sub(t2, t2, t0); fp6_sub(r.c1, t2, t1);
     fp6_mul_v(t1, t1); fp6_add(r.c0, t0, t1);
 }
@@ -175,12 +183,12 @@ BLS_NOINLINE void fp12_frob2(fp12& r, const fp12& a) {
     r.c1.c2 = fp2_mul_fp(a.c1.c2, FROB2[5]);
 }
 // Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part): 3 Fp4 squarings.
-// BLS_CYCLO_COMPACT: the Fp4 squaring and the 3t +- 2a combination are out-of-line functions with operands and results BY
-// VALUE in registers -- inlined three / six times the routine was 52 KB, and with a 32 KB instruction cache behind L0
-// nearly half of its stall samples were `no_instruction`.  (A first compact form that passed the operands by reference
-// was slower: the round trip through local memory cost more than the instruction fetches.)
+// BLS_CYCLO_COMPACT (off): the Fp4 squaring and the 3t +- 2a combination as out-of-line functions with operands and results
+// BY VALUE in registers.  Inlined three / six times the routine is 52 KB and nearly half of its stall samples are
+// `no_instruction` (32 KB instruction cache behind L0), yet both compact forms measured slower at 2^20 items: by reference
+// +25 % (local-memory round trips), by value +5.6 % (466 vs 441 ms; argument marshalling) -- profiles/r01_tuning.md.
 #ifndef BLS_CYCLO_COMPACT
-#define BLS_CYCLO_COMPACT 1
+#define BLS_CYCLO_COMPACT 0
 #endif
 #if BLS_CYCLO_COMPACT && defined(__CUDACC__)
 struct fp4_pair { fp2 t0, t1; };
