@@ -401,6 +401,7 @@ struct blsgpu_ctx {
     int device; cudaStream_t own_stream, stream; int ptr_mode; char err[512];
     uint8_t* ws; size_t ws_bytes, ws_used; unsigned long long launches;
     struct r1cs_sys* r1cs[16]; struct wit_prog* wit[4];
+    uint8_t* rlc_acc;                   // accumulators of blsgpu_verify_batch_rlc that live across passes (allocated on first use)
     struct { u32x4* soa; uint8_t* code; size_t n; } pool[16];   // resident decoded validator pools
     int coop;                           // 1 = warp-cooperative hard part of the final exponentiation (coop.cuh)
     int lanes; cudaStream_t lane_stream[4]; cudaEvent_t lane_done[4], fork;   // concurrent sub-ranges of a verify pass
@@ -498,6 +499,7 @@ void blsgpu_destroy(blsgpu_ctx* ctx) {
     for (int i = 0; i < 4; i++) if (ctx->wit[i]) blsgpu_witness_free(ctx, i);
     for (int i = 0; i < 16; i++) if (ctx->pool[i].soa) { cudaFree(ctx->pool[i].soa); cudaFree(ctx->pool[i].code); }
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->rlc_acc) cudaFree(ctx->rlc_acc);
     if (ctx->ev[0]) for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
     if (ctx->lane_stream[0]) { for (int l = 0; l < 4; l++) { cudaStreamDestroy(ctx->lane_stream[l]); cudaEventDestroy(ctx->lane_done[l]); } cudaEventDestroy(ctx->fork); }
     cudaStreamDestroy(ctx->own_stream);
@@ -756,9 +758,10 @@ int blsgpu_verify_batch_rlc(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t*
     size_t total_mb = 0;
     if (msg_off && !off_host) { total_mb = msg_bytes_total(ctx, msg_off, n, rc); if (rc) return fail(ctx, rc, "reading msg_off failed"); }
     // accumulators that live across passes are separate allocations (the workspace is re-carved per pass)
-    u32x4 *f_acc, *s_acc; uint32_t* bad; uint8_t* dseed; uint8_t* dok;
-    CU(cudaMalloc(&f_acc, 36 * 16)); CU(cudaMalloc(&s_acc, 18 * 16)); CU(cudaMalloc(&bad, 4)); CU(cudaMalloc(&dseed, 16)); CU(cudaMalloc(&dok, 1));
-    auto release = [&]() { cudaFree(f_acc); cudaFree(s_acc); cudaFree(bad); cudaFree(dseed); cudaFree(dok); };
+    if (!ctx->rlc_acc) CU(cudaMalloc(&ctx->rlc_acc, 2048));
+    u32x4* f_acc = reinterpret_cast<u32x4*>(ctx->rlc_acc); u32x4* s_acc = f_acc + 36; uint32_t* bad = reinterpret_cast<uint32_t*>(ctx->rlc_acc + 1024);
+    uint8_t* dseed = ctx->rlc_acc + 1040; uint8_t* dok = ctx->rlc_acc + 1056;
+    auto release = [&]() {};
     cudaMemcpyKind in_kind = ctx->ptr_mode == BLSGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     cudaMemcpyAsync(dseed, seed16, 16, in_kind, ctx->stream); cudaMemsetAsync(bad, 0, 4, ctx->stream);
     k_gt_set_one<<<1, 32, 0, ctx->stream>>>(f_acc); k_g2_jac_set_identity<<<1, 32, 0, ctx->stream>>>(s_acc); ctx->launches += 2;
@@ -803,9 +806,9 @@ int blsgpu_verify_batch_rlc(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t*
     if (!rc) {
         k_rlc_finish<<<1, 32, 0, ctx->stream>>>(f_acc, s_acc, bad, dok); ctx->launches++;
         cudaError_t e = cudaMemcpyAsync(all_ok, dok, 1, ctx->ptr_mode == BLSGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);              // the accumulators are freed below
+        if (e == cudaSuccess && ctx->ptr_mode == BLSGPU_HOST) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(ctx, BLSGPU_ERR_CUDA, "rlc finish failed: %s", cudaGetErrorString(e));
-    } else cudaStreamSynchronize(ctx->stream);
+    }
     release();
     return rc;
 }

@@ -48,6 +48,26 @@ BLS_FP6_LIN void fp6_mul_v(fp6& r, const fp6& a) { fp2 t = fp2_mul_xi(a.c2); fp2
 #define BLS_LAZY 1
 #endif
 // 6 Fp2 products (Karatsuba over the cubic extension)
+// BLS_FP6_LOOP: the three diagonal and the three cross products as two 3-iteration loops (one copy of each body: a third of the
+// code; the instruction cache behind L0 holds 32 KB and the inlined form is 27 KB)
+#ifndef BLS_FP6_LOOP
+#define BLS_FP6_LOOP 1
+#endif
+#if BLS_FP6_LOOP
+BLS_NOINLINE void fp6_mul(fp6& r, const fp6& a, const fp6& b) {
+    const fp2* A = &a.c0; const fp2* B = &b.c0; fp2 v[3], t[3];
+#pragma unroll 1
+    for (int i = 0; i < 3; i++) v[i] = fp2_mul(A[i], B[i]);
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {                                  // (i, j) = (1, 2), (0, 1), (0, 2)
+        int i = k == 0 ? 1 : 0, j = k == 1 ? 1 : 2;
+        t[k] = fp2_sub(fp2_sub(fp2_mul(fp2_add(A[i], A[j]), fp2_add(B[i], B[j])), v[i]), v[j]);
+    }
+    r.c0 = fp2_add(v[0], fp2_mul_xi(t[0]));
+    r.c1 = fp2_add(t[1], fp2_mul_xi(v[2]));
+    r.c2 = fp2_add(t[2], v[1]);
+}
+#else
 BLS_NOINLINE void fp6_mul(fp6& r, const fp6& a, const fp6& b) {
     fp2 v0 = fp2_mul(a.c0, b.c0), v1 = fp2_mul(a.c1, b.c1), v2 = fp2_mul(a.c2, b.c2);
     fp2 t0 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c1, a.c2), fp2_add(b.c1, b.c2)), v1), v2);
@@ -57,6 +77,7 @@ BLS_NOINLINE void fp6_mul(fp6& r, const fp6& a, const fp6& b) {
     r.c1 = fp2_add(t1, fp2_mul_xi(v2));
     r.c2 = fp2_add(t2, v1);
 }
+#endif
 // schoolbook over the cubic extension, each output coefficient one 3-term dot product (27 wide products + 6 reductions =
 // 4,824 IMAD.WIDE against 5,400 for six separately reduced Karatsuba products)
 BLS_NOINLINE void fp6_mul_lz(fp6& r, const fp6& a, const fp6& b) {
@@ -183,14 +204,32 @@ BLS_NOINLINE void fp12_frob2(fp12& r, const fp12& a) {
     r.c1.c2 = fp2_mul_fp(a.c1.c2, FROB2[5]);
 }
 // Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part): 3 Fp4 squarings.
-// BLS_CYCLO_COMPACT (off): the Fp4 squaring and the 3t +- 2a combination as out-of-line functions with operands and results
-// BY VALUE in registers.  Inlined three / six times the routine is 52 KB and nearly half of its stall samples are
-// `no_instruction` (32 KB instruction cache behind L0), yet both compact forms measured slower at 2^20 items: by reference
-// +25 % (local-memory round trips), by value +5.6 % (466 vs 441 ms; argument marshalling) -- profiles/r01_tuning.md.
+// Inlined three / six times the routine is 52 KB and nearly half of its stall samples are `no_instruction` (32 KB instruction
+// cache behind L0).  BLS_CYCLO_COMPACT = 2 (default): ONE copy of the Fp4 squaring and of the two combinations inside a
+// 3-iteration loop over the coefficient pairs (20 KB, operands indexed in the thread's local memory where they live anyway):
+// final exponentiation 442 -> 423 ms at 2^20.  = 1: out-of-line helpers with operands and results by value: +5.6 % (argument
+// marshalling); helpers with operands by reference: +25 % (local-memory round trips).  = 0: fully inlined.  profiles/r01_tuning.md
 #ifndef BLS_CYCLO_COMPACT
-#define BLS_CYCLO_COMPACT 0
+#define BLS_CYCLO_COMPACT 2
 #endif
-#if BLS_CYCLO_COMPACT && defined(__CUDACC__)
+#if BLS_CYCLO_COMPACT == 2
+// loop form: one copy of the Fp4 squaring and of the two combinations, the three coefficient pairs selected by index
+BLS_NOINLINE void fp12_cyclo_sqr(fp12& r, const fp12& a) {
+    const fp2* A = &a.c0.c0; fp12 out; fp2* R = &out.c0.c0;           // tower order: c0.c0 c0.c1 c0.c2 c1.c0 c1.c1 c1.c2
+#pragma unroll 1
+    for (int p = 0; p < 3; p++) {
+        int ia = p == 0 ? 0 : (p == 1 ? 3 : 1), ib = p == 0 ? 4 : (p == 1 ? 2 : 5), oe = p, oo = p == 0 ? 4 : (p == 1 ? 5 : 3);
+        fp2 x = A[ia], y = A[ib];
+        fp2 ab = fp2_mul(x, y);
+        fp2 s = fp2_mul(fp2_add(x, y), fp2_add(x, fp2_mul_xi(y)));
+        fp2 te = fp2_sub(fp2_sub(s, ab), fp2_mul_xi(ab)), to = fp2_dbl(ab);
+        if (p == 2) to = fp2_mul_xi(to);
+        fp2 z = fp2_sub(te, A[oe]); z = fp2_dbl(z); R[oe] = fp2_add(z, te);
+        z = fp2_add(to, A[oo]); z = fp2_dbl(z); R[oo] = fp2_add(z, to);
+    }
+    r = out;
+}
+#elif BLS_CYCLO_COMPACT && defined(__CUDACC__)
 struct fp4_pair { fp2 t0, t1; };
 BLS_NOINLINE fp4_pair fp4_sqr_v(fp2 a, fp2 b) {                       // (a + b y)^2, y^2 = xi
     fp2 ab = fp2_mul(a, b);
