@@ -4,7 +4,7 @@
 // BlsSignatureVerifyGadget::verify (src/constraints.rs:90-128); unlike arkworks' serial early-exit loop every row
 // is reported.  Included at the end of blsgpu.cu (same translation unit: one copy of the Fp core).
 //
-// Mapping: lane <-> witness, warp <-> 64 consecutive rows.  All lanes of a warp walk the same CSR row, so column
+// Mapping: lane <-> witness, warp <-> R1_ROWS (8) consecutive rows, OR-ed into the 64-row word.  All lanes of a warp walk the same CSR row, so column
 // indices and coefficients are warp-uniform broadcast loads and the only divergent traffic is the gather of z,
 // which is coalesced by transposing each group of 32 witnesses to  uint4 [col][3][32]  first.
 //
