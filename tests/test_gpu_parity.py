@@ -295,6 +295,24 @@ def test_r1cs_verify_circuit_on_gpu(ctx, C):
     obits, oall = C.r1cs_check([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], c.nrows, c.ncols, zz, 3, threads=C.hw_threads())
     assert np.array_equal(bits, obits) and list(allsat) == list(oall) == [1, 1, 0]
 
+def test_r1cs_aggregate_verify_circuit_on_gpu(ctx, C):
+    """K8 on the aggregate_verify system (constraints.rs:153-191: 512 masked keys + participant count, 739,876 rows): both of the
+    reference's cases (bitmap {0,1}: true; all set: false) are satisfying assignments of the SAME matrices; GPU bits = oracle bits."""
+    from bls_verify_gadget_b200 import gadget as G
+    pk1 = bytes.fromhex("a491d1b0ecd9bb917989f0e74f0dea0422eac4a873e5e2644f368dffb9a6e20fd6e10c1b77654d067c0618f6e5a7f79a")
+    pk2 = bytes.fromhex("b301803f8b5ac4a1133581fc676dfedc60d891dd5fa99028805e5ea5b08d3491af75d0707adab3b70c6a6a580217bf81")
+    sig = bytes.fromhex("912c3615f69575407db9392eb21fee18fff797eeb2fbe1816366ca2a08ae574d8824dbfafb4c9eaa1cf61b63c6f9b69911f269b664c42947dd1b53ef1081926c"
+                        "1e82bb2a465f927124b08391a5249036146d6f3f1e17ff5f162f779746d830d1")
+    msg = bytes.fromhex("56" * 32)
+    c1 = G.aggregate_verify_circuit(pk1 + pk2 * 511, [1, 1] + [0] * 510, msg, sig); c2 = G.aggregate_verify_circuit(pk1 + pk2 * 511, [1] * 512, msg, sig)
+    assert (c1.result, c1.count, c2.result, c2.count) == (True, 2, False, 512) and (c1.nrows, c1.ncols) == (c2.nrows, c2.ncols)
+    z1 = c1.assignment(); z2 = c2.assignment(); bad = z1.reshape(c1.ncols, 48).copy(); bad[c1.ncols // 2, 0] ^= 1  # (a masked-out key coordinate would be unconstrained: the circuit multiplies it by its bit)
+    zz = np.concatenate([z1, z2, bad.reshape(-1)]); mats = c1.matrices()
+    h = ctx.r1cs_load([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], c1.nrows, c1.ncols)
+    bits, allsat = ctx.r1cs_check(h, zz, 3, c1.nrows); ctx.r1cs_free(h)
+    obits, oall = C.r1cs_check([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], c1.nrows, c1.ncols, zz, 3, threads=C.hw_threads())
+    assert np.array_equal(bits, obits) and list(allsat) == list(oall) == [1, 1, 0]
+
 def test_gpu_witness_generation_matches_host_builder(ctx, C):
     """blsgpu_witness_gen replays the builder's witness program on the GPU: the assignments must equal the host
     synthesis byte for byte for valid and invalid signatures and distinct keys, satisfy every row of the verify circuit, and
