@@ -384,7 +384,143 @@ BLS_CONST uint32_t EXP_P_MINUS_2[12] = BLS_C_EXP_PM2;
 // (p-3)/4 ; note (p+1)/4 = (p-3)/4 + 1
 BLS_CONST uint32_t EXP_P_MINUS_3_DIV_4[12] = BLS_C_EXP_PM3D4;
 
-BLS_HD fp fp_inv(const fp& a) { return fp_pow(a, EXP_P_MINUS_2, 12); }          // 0 -> 0
+// c z mod p for a canonical z and a 32-bit c (canonical result, no Montgomery factor): 12 MACs for the product, a 64 x 34-bit
+// Barrett estimate of the quotient from the top 63 bits (q or q - 1: T = floor(t / 2^350) < 2^63, mu = floor(2^414 / p), so
+// floor(T mu / 2^64) > t/p - 1/2 - 2^-30), 12 MACs for q p and one conditional subtraction.  Used for the small coefficients of the
+// R1CS matrices (80 % of the non-unit ones in the verify circuit: 2, 3, 4, 12, 2^k ...): 24 MACs instead of 300.
+BLS_HD fp fp_mul_small(const fp& z, uint32_t c) {
+    const uint32_t PL[12] = BLS_C_P;
+    uint32_t t[13]; uint64_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { uint64_t v = (uint64_t)z.l[i] * c + carry; t[i] = (uint32_t)v; carry = v >> 32; }
+    t[12] = (uint32_t)carry;
+    uint64_t T = ((uint64_t)t[12] << 34) | ((uint64_t)t[11] << 2) | (uint64_t)(t[10] >> 30);
+#if defined(__CUDA_ARCH__)
+    uint32_t q = (uint32_t)__umul64hi(T, BLS_C_MU414);
+#else
+    uint32_t q = (uint32_t)(((unsigned __int128)T * BLS_C_MU414) >> 64);
+#endif
+    fp r; uint64_t mc = 0; int64_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint64_t m = (uint64_t)PL[i] * q + mc; mc = m >> 32;
+        int64_t d = (int64_t)(uint64_t)t[i] - (int64_t)(uint64_t)(uint32_t)m + br; r.l[i] = (uint32_t)d; br = d >> 32;
+    }
+    return fp_reduce_once(r);                                 // t - q p < 2p < 2^382: the thirteenth limb cancels
+}
+
+BLS_HD fp fp_inv_fermat(const fp& a) { return fp_pow(a, EXP_P_MINUS_2, 12); }          // 0 -> 0
+
+// ------------------------------------------------------------------------------------------------ inversion by divsteps
+// Bernstein-Yang "safegcd" (delta = 1 form): (delta, f, g) -> (1 - delta, g, (g - f) / 2) when delta > 0 and g is odd, else
+// (1 + delta, f, (g + (g mod 2) f) / 2).  62 divsteps at a time on the low words give a 2x2 transition matrix (entries < 2^62
+// in magnitude), which is then applied to the full-width (f, g) exactly and to the Bezout pair (d, e) modulo p.  The published
+// bound for 381-bit inputs is floor((49 * 381 + 57) / 17) = 1,101 divsteps <= 18 batches; random inputs end after 13-14 (the loop
+// stops when g = 0, a lane that finishes early idles).  Branch-free inside a batch, ALU-pipe work only: ~35 k simple instructions
+// against ~490 Montgomery products (150 k IMAD.WIDE) for a^(p-2).  Values are 7 limbs of 62 bits, the top limb signed.
+// The same value as the Fermat form for every input (the inverse is unique; 0 -> 0), checked in tests/devcheck.
+struct inv_mat { int64_t u, v, q, r; };
+BLS_HD int64_t inv_divsteps62(int64_t eta, uint64_t f, uint64_t g, inv_mat& t) {     // eta = -delta
+    uint64_t u = 1, v = 0, q = 0, r = 1;
+#pragma unroll 2
+    for (int i = 0; i < 62; i++) {
+        uint64_t c1 = (uint64_t)(eta >> 63), c2 = 0 - (g & 1);                        // delta > 0; g odd
+        uint64_t x = (f ^ c1) - c1, y = (u ^ c1) - c1, z = (v ^ c1) - c1;             // (f, u, v) negated when delta > 0
+        g += x & c2; q += y & c2; r += z & c2;
+        c1 &= c2;
+        eta = (int64_t)(((uint64_t)eta ^ c1) - (c1 + 1));                             // swap: delta -> 1 - delta, else delta + 1
+        f += g & c1; u += q & c1; v += r & c1;
+        g >>= 1; u <<= 1; v <<= 1;
+    }
+    t.u = (int64_t)u; t.v = (int64_t)v; t.q = (int64_t)q; t.r = (int64_t)r;          // 2^62 times the transition matrix
+    return eta;
+}
+#define BLS_INV_M62 ((int64_t)0x3fffffffffffffffLL)
+BLS_HD void inv_to62(int64_t* o, const uint32_t* l) {
+    uint64_t w[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) w[i] = (uint64_t)l[2 * i] | ((uint64_t)l[2 * i + 1] << 32);
+    o[0] = (int64_t)(w[0] & (uint64_t)BLS_INV_M62);
+#pragma unroll
+    for (int i = 1; i < 6; i++) o[i] = (int64_t)(((w[i - 1] >> (64 - 2 * i)) | (w[i] << (2 * i))) & (uint64_t)BLS_INV_M62);
+    o[6] = (int64_t)(w[5] >> 52);
+}
+// (f, g) <- t (f, g) / 2^62 (exact)
+BLS_HD void inv_update_fg(int64_t* f, int64_t* g, const inv_mat& t) {
+    __int128 cf = (__int128)t.u * f[0] + (__int128)t.v * g[0], cg = (__int128)t.q * f[0] + (__int128)t.r * g[0];
+    cf >>= 62; cg >>= 62;
+#pragma unroll
+    for (int i = 1; i < 7; i++) {
+        cf += (__int128)t.u * f[i] + (__int128)t.v * g[i]; cg += (__int128)t.q * f[i] + (__int128)t.r * g[i];
+        f[i - 1] = (int64_t)cf & BLS_INV_M62; g[i - 1] = (int64_t)cg & BLS_INV_M62; cf >>= 62; cg >>= 62;
+    }
+    f[6] = (int64_t)cf; g[6] = (int64_t)cg;
+}
+// (d, e) <- t (d, e) / 2^62 mod p, both kept in (-2p, p): a multiple of p is added that clears the low 62 bits
+BLS_HD void inv_update_de(int64_t* d, int64_t* e, const inv_mat& t, const int64_t* m) {
+    int64_t sd = d[6] >> 63, se = e[6] >> 63;
+    int64_t md = (t.u & sd) + (t.v & se), me = (t.q & sd) + (t.r & se);
+    __int128 cd = (__int128)t.u * d[0] + (__int128)t.v * e[0], ce = (__int128)t.q * d[0] + (__int128)t.r * e[0];
+    md -= (int64_t)((BLS_C_P_INV62 * (uint64_t)cd + (uint64_t)md) & (uint64_t)BLS_INV_M62);
+    me -= (int64_t)((BLS_C_P_INV62 * (uint64_t)ce + (uint64_t)me) & (uint64_t)BLS_INV_M62);
+    cd += (__int128)m[0] * md; ce += (__int128)m[0] * me;
+    cd >>= 62; ce >>= 62;
+#pragma unroll
+    for (int i = 1; i < 7; i++) {
+        cd += (__int128)t.u * d[i] + (__int128)t.v * e[i] + (__int128)m[i] * md; ce += (__int128)t.q * d[i] + (__int128)t.r * e[i] + (__int128)m[i] * me;
+        d[i - 1] = (int64_t)cd & BLS_INV_M62; e[i - 1] = (int64_t)ce & BLS_INV_M62; cd >>= 62; ce >>= 62;
+    }
+    d[6] = (int64_t)cd; e[6] = (int64_t)ce;
+}
+// x^-1 mod p of the RAW limbs (no Montgomery factor involved; canonical in, canonical out); 0 -> 0
+BLS_NOINLINE fp fp_inv_raw(const fp& x) {
+    const uint32_t PL[12] = BLS_C_P;
+    int64_t m[7], f[7], g[7], d[7], e[7];
+    inv_to62(m, PL); inv_to62(g, x.l);
+#pragma unroll
+    for (int i = 0; i < 7; i++) { f[i] = m[i]; d[i] = 0; e[i] = 0; }
+    e[0] = 1;
+    int64_t eta = -1;
+#pragma unroll 1
+    for (int it = 0; it < 18; it++) {
+        if ((g[0] | g[1] | g[2] | g[3] | g[4] | g[5] | g[6]) == 0) break;
+        inv_mat t;
+        eta = inv_divsteps62(eta, (uint64_t)f[0] | ((uint64_t)f[1] << 62), (uint64_t)g[0] | ((uint64_t)g[1] << 62), t);
+        inv_update_de(d, e, t, m); inv_update_fg(f, g, t);
+    }
+    // f = +-gcd, d = +-x^-1 in (-2p, p): bring into (-p, p), apply the sign of f, bring into [0, p)
+    int64_t ca = d[6] >> 63, cn = f[6] >> 63;
+#pragma unroll
+    for (int i = 0; i < 7; i++) { d[i] += m[i] & ca; d[i] = (d[i] ^ cn) - cn; }
+#pragma unroll
+    for (int i = 0; i < 6; i++) { d[i + 1] += d[i] >> 62; d[i] &= BLS_INV_M62; }
+    ca = d[6] >> 63;
+#pragma unroll
+    for (int i = 0; i < 7; i++) d[i] += m[i] & ca;
+#pragma unroll
+    for (int i = 0; i < 6; i++) { d[i + 1] += d[i] >> 62; d[i] &= BLS_INV_M62; }
+    uint64_t w[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) w[i] = ((uint64_t)d[i] >> (2 * i)) | ((uint64_t)d[i + 1] << (62 - 2 * i));
+    fp r;
+#pragma unroll
+    for (int i = 0; i < 6; i++) { r.l[2 * i] = (uint32_t)w[i]; r.l[2 * i + 1] = (uint32_t)(w[i] >> 32); }
+    return r;
+}
+#ifndef BLS_INV_GCD
+#define BLS_INV_GCD 1
+#endif
+// Montgomery form in and out: (aR)^-1 R^3 R^-1 = a^-1 R
+BLS_HD fp fp_inv(const fp& a) {
+#if BLS_INV_GCD
+    const uint32_t O[12] = BLS_C_R3; fp r3;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r3.l[i] = O[i];
+    return fp_mul(fp_inv_raw(a), r3);
+#else
+    return fp_inv_fermat(a);
+#endif
+}
 // t = a^((p-3)/4).  Then a*t = a^((p+1)/4) is the candidate square root and (a*t)*t = a^((p-1)/2) the Legendre symbol.
 BLS_HD fp fp_pow_pm3d4(const fp& a) { return fp_pow(a, EXP_P_MINUS_3_DIV_4, 12); }
 

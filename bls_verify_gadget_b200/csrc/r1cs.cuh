@@ -16,7 +16,8 @@
 //    squarings): rows longer than R1_LONG are cut into R1_SEG-entry segments, one warp each, and combined afterwards --
 //    otherwise one warp serialises ~10^7 instructions while the rest of the GPU idles (measured: 34 ms per group -> see
 //    profiles/r01_summary.md).
-// Coefficients +1 / -1 (the bulk of boolean/uint gadget rows) skip the multiply; z stays canonical:
+// Coefficients +1 / -1 (the bulk of boolean/uint gadget rows) skip the multiply; coefficients of magnitude below 2^32 (2, 3, 4, 12,
+// 2^k ...: 80 % of the remaining ones in the verify circuit) take fp_mul_small (24 MACs); z stays canonical:
 // coeff(Montgomery) x z(canonical) -> canonical, no conversion of z needed.
 #pragma once
 #include <vector>
@@ -29,7 +30,7 @@ struct r1cs_sys {
     uint32_t* seg_ptr;             // [n_long * 3 + 1] first segment of (long row, matrix)
     uint64_t* seg_lo; uint64_t* seg_hi; uint8_t* seg_mat;     // [n_seg] non-zero range and matrix of a segment
 };
-enum { R1_GENERAL = 0, R1_PLUS_ONE = 1, R1_MINUS_ONE = 2 };
+enum { R1_GENERAL = 0, R1_PLUS_ONE = 1, R1_MINUS_ONE = 2, R1_SMALL_POS = 3, R1_SMALL_NEG = 4 };      // SMALL: |c| < 2^32 (fp_mul_small), c = +|c| or p - |c|
 #define R1_GROUP 32
 #ifndef R1_LONG
 #define R1_LONG 32
@@ -38,7 +39,7 @@ enum { R1_GENERAL = 0, R1_PLUS_ONE = 1, R1_MINUS_ONE = 2 };
 // The row kernels are bound by the latency of the z gather (1.5 KB per non-zero and 32 witnesses, from HBM: a group's
 // transposed z is 1 GB), not by registers: more resident warps than the pairing kernels' 8 per SM
 #ifndef R1_MINB
-#define R1_MINB 4
+#define R1_MINB 6
 #endif
 
 // coefficient -> Montgomery image (for general z), canonical copy (for 0/1-valued z) and class byte
@@ -48,12 +49,17 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_r1cs_prepare(const uint8_t* c
     for (int w = 0; w < 12; w++) v.l[w] = b[4 * w] | ((uint32_t)b[4 * w + 1] << 8) | ((uint32_t)b[4 * w + 2] << 16) | ((uint32_t)b[4 * w + 3] << 24);
     fp one = fp_zero(); one.l[0] = 1;
     fp m1; fp_sub_raw(m1, fp_modulus(), one);
-    cls[i] = fp_eq(v, one) ? R1_PLUS_ONE : (fp_eq(v, m1) ? R1_MINUS_ONE : R1_GENERAL);
+    fp nv; fp_sub_raw(nv, fp_modulus(), v);                      // p - v
+    uint32_t hi = 0, nhi = 0;
+    for (int w = 1; w < 12; w++) { hi |= v.l[w]; nhi |= nv.l[w]; }
+    cls[i] = fp_eq(v, one) ? R1_PLUS_ONE : fp_eq(v, m1) ? R1_MINUS_ONE : !hi ? R1_SMALL_POS : !nhi ? R1_SMALL_NEG : R1_GENERAL;
     out[i] = fp_to_mont(v); outc[i] = v;
 }
 // z[w][col] (48-byte LE canonical) for witnesses w0 .. w0+g-1  ->  zt[(col*3 + c)*32 + lane];
-// zbool[col] = 1 when the column is 0/1-valued in every witness of the group
-__global__ void __launch_bounds__(256) k_r1cs_transpose(const u32x4* z, size_t ncols, size_t w0, size_t g, u32x4* zt, uint8_t* zbool) {
+// zbool[col] = (bits of the 32 witnesses, 1) when the column is 0/1-valued in every witness of the group, else (0, 0): such a column
+// (bits, bytes and words of the SHA-256 / decomposition gadgets: most non-zeros of the circuit) is then read as ONE broadcast 8-byte
+// load instead of a 1.5 KB gather, and its +-1 / small coefficients accumulate in a 64-bit integer beside the field accumulator
+__global__ void __launch_bounds__(256) k_r1cs_transpose(const u32x4* z, size_t ncols, size_t w0, size_t g, u32x4* zt, uint2* zbool) {
     size_t col = blockIdx.x * (size_t)8 + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
     if (col >= ncols) return;
     u32x4 zero; zero.x = zero.y = zero.z = zero.w = 0;
@@ -63,30 +69,44 @@ __global__ void __launch_bounds__(256) k_r1cs_transpose(const u32x4* z, size_t n
     zt[(col * 3) * 32 + lane] = a; zt[(col * 3 + 1) * 32 + lane] = b; zt[(col * 3 + 2) * 32 + lane] = c;
     bool small = a.x < 2 && !(a.y | a.z | a.w | b.x | b.y | b.z | b.w | c.x | c.y | c.z | c.w);
     bool all = __all_sync(0xffffffffu, small);
-    if (lane == 0) zbool[col] = all ? 1 : 0;
+    uint32_t pack = __ballot_sync(0xffffffffu, a.x & 1u);        // the column's 32 values as one word when they are all 0 / 1
+    if (lane == 0) zbool[col] = make_uint2(all ? pack : 0u, all ? 1u : 0u);
 }
 __device__ __forceinline__ fp r1cs_load_z(const u32x4* zt, uint32_t col, int lane) {
     u32x4 a = zt[((size_t)col * 3) * 32 + lane], b = zt[((size_t)col * 3 + 1) * 32 + lane], c = zt[((size_t)col * 3 + 2) * 32 + lane];
     fp v; v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w; v.l[8] = c.x; v.l[9] = c.y; v.l[10] = c.z; v.l[11] = c.w;
     return v;
 }
-// sum over the non-zeros [lo, hi) of one matrix row; every branch is warp-uniform (class per non-zero, zbool per column)
-__device__ __forceinline__ fp r1cs_range_dot(const r1cs_sys& s, int m, uint64_t lo, uint64_t hi, const u32x4* zt, const uint8_t* zbool, int lane) {
+// sum over the non-zeros [lo, hi) of one matrix row; every branch is warp-uniform (class per non-zero, zbool per column).
+// Terms on 0/1 columns with coefficient +-1 or |c| < 2^32 go to the integer side sum (at most R1_SEG terms: |sum| < 2^39).
+__device__ __forceinline__ fp r1cs_range_dot(const r1cs_sys& s, int m, uint64_t lo, uint64_t hi, const u32x4* zt, const uint2* zbool, int lane) {
     const uint32_t* col = s.col[m]; const uint8_t* cls = s.cls[m];
-    fp acc = fp_zero();
+    fp acc = fp_zero(); int64_t side = 0;
+    uint32_t cj_n = 0; uint8_t c_n = 0; uint2 zb_n = make_uint2(0u, 0u);
+    if (lo < hi) { cj_n = col[lo]; c_n = cls[lo]; zb_n = zbool[cj_n]; }
     for (uint64_t k = lo; k < hi; k++) {
-        uint32_t cj = col[k]; uint8_t c = cls[k];
-        if (c == R1_GENERAL && zbool[cj]) {                       // coefficient times a 0/1 column: masked addition
-            uint32_t bit = zt[((size_t)cj * 3) * 32 + lane].x;
-            acc = fp_add(acc, fp_select(0u - bit, s.coeffc[m][k], fp_zero()));
+        uint32_t cj = cj_n; uint8_t c = c_n; uint2 zb = zb_n;
+        if (k + 1 < hi) { cj_n = col[k + 1]; c_n = cls[k + 1]; zb_n = zbool[cj_n]; }      // the next term's metadata travels while this term's gather does
+        if (zb.y) {
+            uint32_t bit = (zb.x >> lane) & 1u;
+            if (c == R1_PLUS_ONE) side += bit;
+            else if (c == R1_MINUS_ONE) side -= bit;
+            else if (c == R1_SMALL_POS) side += (int64_t)((uint64_t)bit * s.coeffc[m][k].l[0]);
+            else if (c == R1_SMALL_NEG) side -= (int64_t)((uint64_t)bit * (BLS_P0 - s.coeffc[m][k].l[0]));
+            else acc = fp_add(acc, fp_select(0u - bit, s.coeffc[m][k], fp_zero()));      // general coefficient: masked addition
             continue;
         }
         fp zv = r1cs_load_z(zt, cj, lane);
         if (c == R1_PLUS_ONE) acc = fp_add(acc, zv);
         else if (c == R1_MINUS_ONE) acc = fp_sub(acc, zv);
+        else if (c == R1_SMALL_POS) acc = fp_add(acc, fp_mul_small(zv, s.coeffc[m][k].l[0]));
+        else if (c == R1_SMALL_NEG) acc = fp_sub(acc, fp_mul_small(zv, BLS_P0 - s.coeffc[m][k].l[0]));      // |c| = p - c: low words suffice
         else acc = fp_add(acc, fp_mul(s.coeff[m][k], zv));
     }
-    return acc;
+    uint64_t mag = side < 0 ? (uint64_t)(-side) : (uint64_t)side;
+    fp t = fp_zero(); t.l[0] = (uint32_t)mag; t.l[1] = (uint32_t)(mag >> 32);
+    fp up = fp_add(acc, t), dn = fp_sub(acc, t);
+    return fp_select(side < 0 ? 0xffffffffu : 0u, dn, up);
 }
 // a b == c (all canonical).  In the boolean / uint32 gadget rows (95 % of the verify circuit) a and b are small integers
 // (bits, 35-bit word sums): when one fits 64 bits and the other 32 bits in every lane the product is a 96-bit integer
@@ -110,7 +130,7 @@ __device__ __forceinline__ bool r1cs_product_ok(const fp& a, const fp& b, const 
 #ifndef R1_ROWS
 #define R1_ROWS 8
 #endif
-__global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_rows(r1cs_sys s, const u32x4* zt, const uint8_t* zbool, size_t w0, size_t g, size_t words, uint64_t* sat_bits) {
+__global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_rows(r1cs_sys s, const u32x4* zt, const uint2* zbool, size_t w0, size_t g, size_t words, uint64_t* sat_bits) {
     size_t blk = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
     size_t r0 = blk * R1_ROWS; if (r0 >= s.nrows) return;
     uint64_t bits = 0;
@@ -125,7 +145,7 @@ __global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_rows(r1cs_sys s, const u3
     if ((size_t)lane < g && bits) atomicOr((unsigned long long*)&sat_bits[(w0 + lane) * words + (r0 >> 6)], bits);
 }
 // one warp per segment of a long row: partial dot product of 32 witnesses -> part (limb-SoA over n_seg * 32 slots)
-__global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_segments(r1cs_sys s, const u32x4* zt, const uint8_t* zbool, u32x4* part) {
+__global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_segments(r1cs_sys s, const u32x4* zt, const uint2* zbool, u32x4* part) {
     size_t sg = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
     if (sg >= s.n_seg) return;
     fp v = r1cs_range_dot(s, s.seg_mat[sg], s.seg_lo[sg], s.seg_hi[sg], zt, zbool, lane);
@@ -225,10 +245,10 @@ int blsgpu_r1cs_check(blsgpu_ctx* ctx, int handle, const uint8_t* z48, size_t nw
     bool host = ctx->ptr_mode == BLSGPU_HOST;
     // host mode stages one group of 32 witnesses at a time (32 * ncols * 48 bytes) so the workspace stays bounded
     size_t zgroup = (size_t)R1_GROUP * s.ncols * 48, part_bytes = (s.n_seg ? s.n_seg : 1) * 32 * 48;
-    if (int rc = ws_reserve(ctx, (host ? al(zgroup) : 0) + al(zgroup) + al(s.ncols) + al(part_bytes) + (host ? al(8 * words * nwit) + al(nwit) : 0) + 8192)) return rc;
+    if (int rc = ws_reserve(ctx, (host ? al(zgroup) : 0) + al(zgroup) + al(8 * s.ncols) + al(part_bytes) + (host ? al(8 * words * nwit) + al(nwit) : 0) + 8192)) return rc;
     u32x4* zstage = host ? ws_take<u32x4>(ctx, zgroup / 16) : nullptr;
     u32x4* zt = ws_take<u32x4>(ctx, zgroup / 16);
-    uint8_t* zbool = ws_take<uint8_t>(ctx, s.ncols);
+    uint2* zbool = ws_take<uint2>(ctx, s.ncols);
     u32x4* part = ws_take<u32x4>(ctx, part_bytes / 16);
     uint64_t* dbits = host ? ws_take<uint64_t>(ctx, words * nwit) : sat_bits;
     uint8_t* dall = all_sat ? (host ? ws_take<uint8_t>(ctx, nwit) : all_sat) : nullptr;
@@ -239,9 +259,9 @@ int blsgpu_r1cs_check(blsgpu_ctx* ctx, int handle, const uint8_t* z48, size_t nw
         if (host) { CU(cudaMemcpyAsync(zstage, z48 + w0 * s.ncols * 48, g * s.ncols * 48, cudaMemcpyHostToDevice, ctx->stream)); zsrc = zstage; wbase = 0; }
         else { zsrc = (const u32x4*)z48; wbase = w0; }
         LAUNCH(k_r1cs_transpose, nblk(s.ncols, 8), 256, zsrc, s.ncols, wbase, g, zt, zbool);
-        LAUNCH(k_r1cs_rows, nblk((s.nrows + R1_ROWS - 1) / R1_ROWS, TPB / 32), TPB, s, (const u32x4*)zt, (const uint8_t*)zbool, w0, g, words, dbits);
+        LAUNCH(k_r1cs_rows, nblk((s.nrows + R1_ROWS - 1) / R1_ROWS, TPB / 32), TPB, s, (const u32x4*)zt, (const uint2*)zbool, w0, g, words, dbits);
         if (s.n_long) {
-            LAUNCH(k_r1cs_segments, nblk(s.n_seg, TPB / 32), TPB, s, (const u32x4*)zt, (const uint8_t*)zbool, part);
+            LAUNCH(k_r1cs_segments, nblk(s.n_seg, TPB / 32), TPB, s, (const u32x4*)zt, (const uint2*)zbool, part);
             LAUNCH(k_r1cs_combine, nblk(s.n_long, TPB / 32), TPB, s, (const u32x4*)part, w0, g, words, dbits);
         }
     }

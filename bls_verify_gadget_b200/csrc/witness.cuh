@@ -41,6 +41,8 @@ __device__ __forceinline__ fp wit_lc_range(const wit_prog& p, uint64_t lo, uint6
         else {
             bool small = zv.l[0] < 2 && !(zv.l[1] | zv.l[2] | zv.l[3] | zv.l[4] | zv.l[5] | zv.l[6] | zv.l[7] | zv.l[8] | zv.l[9] | zv.l[10] | zv.l[11]);
             if (__all_sync(0xffffffffu, small)) acc = fp_add(acc, fp_select(0u - zv.l[0], p.coeffc[k], fp_zero()));       // coefficient times a 0/1 value
+            else if (c == R1_SMALL_POS) acc = fp_add(acc, fp_mul_small(zv, p.coeffc[k].l[0]));
+            else if (c == R1_SMALL_NEG) acc = fp_sub(acc, fp_mul_small(zv, BLS_P0 - p.coeffc[k].l[0]));
             else acc = fp_add(acc, fp_mul(p.coeff[k], zv));
         }
     }
@@ -50,7 +52,7 @@ __device__ __forceinline__ fp wit_lc(const wit_prog& p, uint32_t id, const u32x4
     if (!id) return fp_zero();
     return wit_lc_range(p, p.lc_ptr[id - 1], p.lc_ptr[id], zt, lane);
 }
-__device__ __forceinline__ fp wit_inv_canon(const fp& a) { return fp_from_mont(fp_inv(fp_to_mont(a))); }
+__device__ __forceinline__ fp wit_inv_canon(const fp& a) { return fp_inv_raw(a); }                 // canonical in and out: the divsteps inverse needs no Montgomery factor
 // a b for canonical a, b: small-integer shortcut as in r1cs_product_ok
 __device__ __forceinline__ fp wit_mul_canon(const fp& a, const fp& b) {
     uint32_t ah = a.l[2] | a.l[3] | a.l[4] | a.l[5] | a.l[6] | a.l[7] | a.l[8] | a.l[9] | a.l[10] | a.l[11];

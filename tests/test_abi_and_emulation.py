@@ -46,6 +46,32 @@ def test_emu_fp_mul(E, C):
     a[:, 47] &= 0x0f; b[:, 47] &= 0x0f
     assert np.array_equal(E.fp_mul_raw(a, b), C.fp_mul_raw(a, b))
 
+def test_emu_divsteps_inversion_equals_fermat_and_python(E):
+    """fp_inv (Bernstein-Yang divsteps, csrc/fp.cuh) against a^(p-2) in the same library and against Python's pow, on edge values and random elements"""
+    P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab; R = 1 << 384
+    rng = np.random.default_rng(11)
+    vals = [0, 1, 2, 3, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, (1 << 380) - 1, 1 << 380, 1 << 62, (1 << 62) - 1, 1 << 124, P - (1 << 62), R % P, pow(R, -1, P)]
+    vals += [int.from_bytes(rng.bytes(48), "little") % P for _ in range(2000)] + [1 << k for k in range(0, 381, 7)] + [P - (1 << k) for k in range(0, 380, 7)]
+    x = np.frombuffer(b"".join(v.to_bytes(48, "little") for v in vals), np.uint8)
+    out = E.run_op(34, x).reshape(len(vals), 2, 48)
+    assert np.array_equal(out[:, 0], out[:, 1])
+    for v, o in zip(vals, out[:, 0]):                      # Montgomery images: input a R, output a^-1 R
+        a = v * pow(R, -1, P) % P
+        assert int.from_bytes(o.tobytes(), "little") == (pow(a, -1, P) * R % P if a else 0)
+
+def test_emu_mul_small_equals_python(E):
+    """fp_mul_small (32-bit coefficient times canonical element, Barrett quotient estimate) against Python on edge values x edge coefficients"""
+    P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    rng = np.random.default_rng(12)
+    zs = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, (1 << 380) - 1, 1 << 380, P - (1 << 32), P >> 1, (P // 3) + 1, P // 0xffffffff, P // 0xffffffff + 1]
+    cs = [0, 1, 2, 3, 4, 12, 0xffff, 0x10000, 0x7fffffff, 0x80000000, 0xfffffffe, 0xffffffff]
+    pairs = [(z, c) for z in zs for c in cs] + [(int.from_bytes(rng.bytes(48), "little") % P, int(rng.integers(0, 1 << 32))) for _ in range(20000)]
+    pairs += [(P - 1 - int(rng.integers(0, 1 << 20)), 0xffffffff - int(rng.integers(0, 1 << 10))) for _ in range(2000)]
+    pairs += [((k * P) // c + d, c) for c in (3, 5, 0xffffffff, 0x80000001, 12345677) for k in (1, 2, c - 1) for d in (0, 1) if (k * P) // c + d < P]     # products next to multiples of p
+    x = np.frombuffer(b"".join(z.to_bytes(48, "little") + c.to_bytes(48, "little") for z, c in pairs), np.uint8)
+    out = E.run_op(35, x).reshape(len(pairs), 48)
+    for (z, c), o in zip(pairs, out): assert int.from_bytes(o.tobytes(), "little") == z * c % P, (z, c)
+
 def test_emu_fixtures(E, eth, pyv):
     k = eth["inline_kats"]
     assert E.hash_to_g2([bytes(32)]).tobytes().hex() == k["hash_to_g2_zero32"]
