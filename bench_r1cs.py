@@ -6,8 +6,8 @@ from the host-side builder bls_verify_gadget_b200/gadget) over assignments shard
 (4096 on 8 GPUs; weak scaling: the per-GPU share is fixed).  The matrices are replicated; the data path has no collective;
 the one exchange step is an all-gather of the per-assignment flags.  A step = one pass over the rank's
 assignments, resident in HBM (`value`).  `e2e` is the whole pipeline a caller runs: (pk, msg, sig) bytes in pinned host memory ->
-H2D -> GPU witness generation (blsgpu_witness_gen, the builder's witness program replayed on the device) -> satisfaction check ->
-per-assignment flags back on the host; no assignment ever crosses PCIe.
+H2D -> blsgpu_witness_check (the builder's witness program replayed on the device, then the satisfaction kernels on the same
+transposed buffers) -> per-assignment flags back on the host; no assignment ever crosses PCIe or is copied row-major.
 
   python bench_r1cs.py [--gpus N] [--steps K] [--warmup W] [--per-gpu 512] [--distinct 16]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench_r1cs.py --gpus N
@@ -51,7 +51,7 @@ def main():
     epk, emsg, esig, eexp = synth.verify_batch_inputs(ctx, nwit * world, every=16)
     sl = slice(rank * nwit, (rank + 1) * nwit)
     h_in = [torch.from_numpy(x.reshape(nwit * world, -1)[sl].copy().reshape(-1)).pin_memory() for x in (epk, emsg, esig)]; eexp = eexp[sl]
-    d_in = [torch.empty_like(x, device=dev) for x in h_in]; ez = torch.empty(nwit * ncols * 48, dtype=torch.uint8, device=dev); est = torch.empty(nwit, dtype=torch.uint8, device=dev)
+    d_in = [torch.empty_like(x, device=dev) for x in h_in]; est = torch.empty(nwit, dtype=torch.uint8, device=dev)
     ebits = torch.zeros(nwit * ((nrows + 63) // 64), dtype=torch.int64, device=dev); eall = torch.zeros(nwit, dtype=torch.uint8, device=dev); h_flags = torch.zeros(2 * nwit, dtype=torch.uint8).pin_memory()
     words = (nrows + 63) // 64
     bits = torch.zeros(nwit * words, dtype=torch.int64, device=dev); allsat = torch.zeros(nwit, dtype=torch.uint8, device=dev)
@@ -63,8 +63,7 @@ def main():
     def step_e2e():
         ctx.set_pointer_mode(True)
         for d, hsrc in zip(d_in, h_in): d.copy_(hsrc, non_blocking=True)                                  # 176 B per assignment over PCIe
-        ctx.witness_gen_ptr(wh, d_in[0].data_ptr(), d_in[1].data_ptr(), d_in[2].data_ptr(), nwit, ez.data_ptr(), est.data_ptr())
-        ctx.r1cs_check_ptr(h, ez.data_ptr(), nwit, ebits.data_ptr(), eall.data_ptr())
+        ctx.witness_check_ptr(wh, h, d_in[0].data_ptr(), d_in[1].data_ptr(), d_in[2].data_ptr(), nwit, ebits.data_ptr(), eall.data_ptr(), est.data_ptr())
         h_flags[:nwit].copy_(eall, non_blocking=True); h_flags[nwit:].copy_(est, non_blocking=True)
     def barrier():
         if world > 1: dist.barrier()
@@ -95,7 +94,7 @@ def main():
                 "assignments_per_sec": nwit_total * args.steps / (ms * 1e-3),
                 "e2e": {"value": nrows * nwit_total * ke / (ms_e2e * 1e-3), "unit": "constraints/s", "h2d_bytes_per_step": 176 * nwit, "d2h_bytes_per_step": 2 * nwit,
                         "assignments_per_sec": nwit_total * ke / (ms_e2e * 1e-3),
-                        "pipeline": "pinned host (pk,msg,sig) bytes -> GPU witness generation -> satisfaction check -> flags to host"},
+                        "pipeline": "pinned host (pk,msg,sig) bytes -> blsgpu_witness_check (GPU witness generation + satisfaction check) -> flags to host"},
                 "gpu_launches": launches, "host_synthesis_s_per_assignment_per_thread": t_syn / nb * min(threads, nb),
                 "roofline": {"bound": "hbm", "achieved": nwit * ncols * 48 * 2 * args.steps / (ms * 1e-3) / 1e9, "unit": "GB/s",
                              "note": "algorithmic bytes = each assignment read once and written once by the transpose (2 x 48 B x ncols); the gather of z by the row kernels re-reads the transposed copy (nnz x 48 B per assignment) -- see profiles/r01_summary.md"}}

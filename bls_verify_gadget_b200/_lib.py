@@ -35,7 +35,7 @@ def lib():
 EXPORTS = ["blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_set_stream", "blsgpu_set_pointer_mode", "blsgpu_synchronize",
            "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_set_coop", "blsgpu_verify_batch", "blsgpu_verify_batch_rlc", "blsgpu_fast_aggregate_verify_batch", "blsgpu_pool_create", "blsgpu_pool_free", "blsgpu_pool_fast_aggregate_verify", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
            "blsgpu_g2_aggregate", "blsgpu_deserialize_g1", "blsgpu_deserialize_g2", "blsgpu_sk_to_pk_batch", "blsgpu_sign_batch", "blsgpu_pairing_gt",
-           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_free"]
+           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_check", "blsgpu_witness_free"]
 
 _sz = ctypes.c_size_t; _vp = ctypes.c_void_p
 def _u8(a):
@@ -178,4 +178,11 @@ class Context:
         z = np.empty(n * nvars * 48, np.uint8); st = np.empty(n, np.uint8)
         self._ck(lib().blsgpu_witness_gen(self._h, int(handle), _p(pk), _p(m), _p(sg), _sz(n), _p(z), _p(st))); return z.reshape(n, nvars * 48), st
     def witness_gen_ptr(self, handle, pk, msg, sig, n, z, status=None): self._ck(lib().blsgpu_witness_gen(self._h, int(handle), _p(pk), _p(msg), _p(sig), _sz(n), _p(z), _p(status)))
+    def witness_check(self, wit_handle, r1cs_handle, pk, msgs32, sig, nrows):
+        """host buffers: generation + satisfaction check in one call -> (bits uint64[n, words], all_sat uint8[n], status uint8[n])"""
+        pk = _u8(pk); sg = _u8(sig); m = _u8(msgs32); n = pk.size // 48; words = (nrows + 63) // 64
+        bits = np.zeros((n, words), np.uint64); allsat = np.zeros(n, np.uint8); st = np.empty(n, np.uint8)
+        self._ck(lib().blsgpu_witness_check(self._h, int(wit_handle), int(r1cs_handle), _p(pk), _p(m), _p(sg), _sz(n), _p(bits), _p(allsat), _p(st))); return bits, allsat, st
+    def witness_check_ptr(self, wit_handle, r1cs_handle, pk, msg, sig, n, bits, allsat=None, status=None):
+        self._ck(lib().blsgpu_witness_check(self._h, int(wit_handle), int(r1cs_handle), _p(pk), _p(msg), _p(sig), _sz(n), _p(bits), _p(allsat), _p(status)))
     def witness_free(self, handle): lib().blsgpu_witness_free(self._h, int(handle))

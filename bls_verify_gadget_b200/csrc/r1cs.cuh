@@ -33,9 +33,11 @@ struct r1cs_sys {
 enum { R1_GENERAL = 0, R1_PLUS_ONE = 1, R1_MINUS_ONE = 2, R1_SMALL_POS = 3, R1_SMALL_NEG = 4 };      // SMALL: |c| < 2^32 (fp_mul_small), c = +|c| or p - |c|
 #define R1_GROUP 32
 #ifndef R1_LONG
-#define R1_LONG 32
+#define R1_LONG 16
 #endif
-#define R1_SEG 64
+#ifndef R1_SEG
+#define R1_SEG 32
+#endif
 // The row kernels are bound by the latency of the z gather (1.5 KB per non-zero and 32 witnesses, from HBM: a group's
 // transposed z is 1 GB), not by registers: more resident warps than the pairing kernels' 8 per SM
 #ifndef R1_MINB
@@ -59,18 +61,27 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_r1cs_prepare(const uint8_t* c
 // zbool[col] = (bits of the 32 witnesses, 1) when the column is 0/1-valued in every witness of the group, else (0, 0): such a column
 // (bits, bytes and words of the SHA-256 / decomposition gadgets: most non-zeros of the circuit) is then read as ONE broadcast 8-byte
 // load instead of a 1.5 KB gather, and its +-1 / small coefficients accumulate in a 64-bit integer beside the field accumulator
+// One warp per PAIR of columns: a lane reads the 96 contiguous bytes of its assignment (three whole 32-byte sectors; a single
+// 48-byte column would touch two sectors for 1.5 sectors of data) and writes two 1.5 KB rows of the transposed copy.
 __global__ void __launch_bounds__(256) k_r1cs_transpose(const u32x4* z, size_t ncols, size_t w0, size_t g, u32x4* zt, uint2* zbool) {
-    size_t col = blockIdx.x * (size_t)8 + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
+    size_t col = (blockIdx.x * (size_t)8 + (threadIdx.x >> 5)) * 2; int lane = threadIdx.x & 31;
     if (col >= ncols) return;
     u32x4 zero; zero.x = zero.y = zero.z = zero.w = 0;
     const u32x4* src = z + ((w0 + lane) * ncols + col) * 3;
-    bool live = (size_t)lane < g;
-    u32x4 a = live ? src[0] : zero, b = live ? src[1] : zero, c = live ? src[2] : zero;
-    zt[(col * 3) * 32 + lane] = a; zt[(col * 3 + 1) * 32 + lane] = b; zt[(col * 3 + 2) * 32 + lane] = c;
-    bool small = a.x < 2 && !(a.y | a.z | a.w | b.x | b.y | b.z | b.w | c.x | c.y | c.z | c.w);
-    bool all = __all_sync(0xffffffffu, small);
-    uint32_t pack = __ballot_sync(0xffffffffu, a.x & 1u);        // the column's 32 values as one word when they are all 0 / 1
-    if (lane == 0) zbool[col] = make_uint2(all ? pack : 0u, all ? 1u : 0u);
+    bool live = (size_t)lane < g, two = col + 1 < ncols;
+    u32x4 v[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) v[k] = (live && (k < 3 || two)) ? src[k] : zero;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        if (h && !two) break;
+        u32x4 a = v[3 * h], b = v[3 * h + 1], c = v[3 * h + 2];
+        zt[((col + h) * 3) * 32 + lane] = a; zt[((col + h) * 3 + 1) * 32 + lane] = b; zt[((col + h) * 3 + 2) * 32 + lane] = c;
+        bool small = a.x < 2 && !(a.y | a.z | a.w | b.x | b.y | b.z | b.w | c.x | c.y | c.z | c.w);
+        bool all = __all_sync(0xffffffffu, small);
+        uint32_t pack = __ballot_sync(0xffffffffu, a.x & 1u);        // the column's 32 values as one word when they are all 0 / 1
+        if (lane == 0) zbool[col + h] = make_uint2(all ? pack : 0u, all ? 1u : 0u);
+    }
 }
 __device__ __forceinline__ fp r1cs_load_z(const u32x4* zt, uint32_t col, int lane) {
     u32x4 a = zt[((size_t)col * 3) * 32 + lane], b = zt[((size_t)col * 3 + 1) * 32 + lane], c = zt[((size_t)col * 3 + 2) * 32 + lane];
@@ -165,14 +176,16 @@ __global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_combine(r1cs_sys s, const
     if ((size_t)lane < g && r1cs_product_ok(v[0], v[1], v[2]))
         atomicOr((unsigned long long*)&sat_bits[(w0 + lane) * words + (row >> 6)], 1ull << (row & 63));
 }
-__global__ void k_r1cs_all(const uint64_t* sat_bits, size_t nwit, size_t words, size_t nrows, uint8_t* all_sat) {
-    size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (w >= nwit) return;
+// one warp per assignment: AND over its bit words (coalesced), lane 0 writes the flag
+__global__ void __launch_bounds__(256) k_r1cs_all(const uint64_t* sat_bits, size_t nwit, size_t words, size_t nrows, uint8_t* all_sat) {
+    size_t w = blockIdx.x * (size_t)8 + (threadIdx.x >> 5); int lane = threadIdx.x & 31; if (w >= nwit) return;
     bool all = true;
-    for (size_t i = 0; i < words; i++) {
+    for (size_t i = lane; i < words; i += 32) {
         uint64_t want = (i + 1 == words && (nrows & 63)) ? ((1ull << (nrows & 63)) - 1) : ~0ull;
         all &= sat_bits[w * words + i] == want;
     }
-    all_sat[w] = all ? 1 : 0;
+    all = __all_sync(0xffffffffu, all);
+    if (lane == 0) all_sat[w] = all ? 1 : 0;
 }
 
 template <class T> static int r1cs_upload(blsgpu_ctx* ctx, T** dst, const std::vector<T>& v) {
@@ -237,6 +250,17 @@ int blsgpu_r1cs_free(blsgpu_ctx* ctx, int handle) {
     cudaFree(s->is_long); cudaFree(s->long_row); cudaFree(s->seg_ptr); cudaFree(s->seg_lo); cudaFree(s->seg_hi); cudaFree(s->seg_mat);
     delete s; ctx->r1cs[handle] = nullptr; return 0;
 }
+}
+// rows, segments and combination of one group of <= 32 assignments given in the transposed layout (zt, zbool)
+static int r1cs_check_group(blsgpu_ctx* ctx, const r1cs_sys& s, const u32x4* zt, const uint2* zbool, u32x4* part, size_t w0, size_t g, size_t words, uint64_t* dbits) {
+    LAUNCH(k_r1cs_rows, nblk((s.nrows + R1_ROWS - 1) / R1_ROWS, TPB / 32), TPB, s, zt, zbool, w0, g, words, dbits);
+    if (s.n_long) {
+        LAUNCH(k_r1cs_segments, nblk(s.n_seg, TPB / 32), TPB, s, zt, zbool, part);
+        LAUNCH(k_r1cs_combine, nblk(s.n_long, TPB / 32), TPB, s, (const u32x4*)part, w0, g, words, dbits);
+    }
+    return 0;
+}
+extern "C" {
 int blsgpu_r1cs_check(blsgpu_ctx* ctx, int handle, const uint8_t* z48, size_t nwit, uint64_t* sat_bits, uint8_t* all_sat) {
     ENTER(); if (handle < 0 || handle >= 16 || !ctx->r1cs[handle] || !z48 || !sat_bits) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
     if (!nwit) return 0;
@@ -258,14 +282,10 @@ int blsgpu_r1cs_check(blsgpu_ctx* ctx, int handle, const uint8_t* z48, size_t nw
         const u32x4* zsrc; size_t wbase;
         if (host) { CU(cudaMemcpyAsync(zstage, z48 + w0 * s.ncols * 48, g * s.ncols * 48, cudaMemcpyHostToDevice, ctx->stream)); zsrc = zstage; wbase = 0; }
         else { zsrc = (const u32x4*)z48; wbase = w0; }
-        LAUNCH(k_r1cs_transpose, nblk(s.ncols, 8), 256, zsrc, s.ncols, wbase, g, zt, zbool);
-        LAUNCH(k_r1cs_rows, nblk((s.nrows + R1_ROWS - 1) / R1_ROWS, TPB / 32), TPB, s, (const u32x4*)zt, (const uint2*)zbool, w0, g, words, dbits);
-        if (s.n_long) {
-            LAUNCH(k_r1cs_segments, nblk(s.n_seg, TPB / 32), TPB, s, (const u32x4*)zt, (const uint2*)zbool, part);
-            LAUNCH(k_r1cs_combine, nblk(s.n_long, TPB / 32), TPB, s, (const u32x4*)part, w0, g, words, dbits);
-        }
+        LAUNCH(k_r1cs_transpose, nblk((s.ncols + 1) / 2, 8), 256, zsrc, s.ncols, wbase, g, zt, zbool);
+        if (int rc = r1cs_check_group(ctx, s, zt, zbool, part, w0, g, words, dbits)) return rc;
     }
-    if (dall) LAUNCH(k_r1cs_all, nblk(nwit), TPB, (const uint64_t*)dbits, nwit, words, s.nrows, dall);
+    if (dall) LAUNCH(k_r1cs_all, nblk(nwit, 8), 256, (const uint64_t*)dbits, nwit, words, s.nrows, dall);
     if (host) {
         CU(cudaMemcpyAsync(sat_bits, dbits, 8 * words * nwit, cudaMemcpyDeviceToHost, ctx->stream));
         if (all_sat) CU(cudaMemcpyAsync(all_sat, dall, nwit, cudaMemcpyDeviceToHost, ctx->stream));

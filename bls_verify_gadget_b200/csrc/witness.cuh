@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(32) k_witness_gen(wit_prog p, const fp* inputs
 #ifndef WIT_BPS
 #define WIT_BPS 2
 #endif
-__global__ void __launch_bounds__(WIT_TPB, WIT_BPS) k_witness_levels(wit_prog p, const fp* inputs, size_t nwit_padded, u32x4* zt_all, size_t groups) {
+__global__ void __launch_bounds__(WIT_TPB, WIT_BPS) k_witness_levels(wit_prog p, const fp* inputs, size_t nwit_padded, u32x4* zt_all, size_t groups, uint2* zbool_all) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * (size_t)blockDim.x) >> 5; int lane = threadIdx.x & 31;
     fp one = fp_zero(); one.l[0] = 1;
@@ -143,6 +143,11 @@ __global__ void __launch_bounds__(WIT_TPB, WIT_BPS) k_witness_levels(wit_prog p,
                 default: out = r.aux == 0xffff ? one : inputs[(size_t)r.aux * nwit_padded + group * 32 + lane]; break;       // WR_INPUT; 0xffff: the constant ONE (variable 0)
             }
             wit_store(zt, r.var, lane, out);
+            if (zbool_all) {                                  // the packed 0/1 view the satisfaction kernels read (r1cs.cuh: k_r1cs_transpose writes the same)
+                bool small = out.l[0] < 2 && !(out.l[1] | out.l[2] | out.l[3] | out.l[4] | out.l[5] | out.l[6] | out.l[7] | out.l[8] | out.l[9] | out.l[10] | out.l[11]);
+                bool all = __all_sync(0xffffffffu, small); uint32_t pack = __ballot_sync(0xffffffffu, out.l[0] & 1u);
+                if (lane == 0) zbool_all[group * p.nvars + r.var] = make_uint2(all ? pack : 0u, all ? 1u : 0u);
+            }
         }
         grid.sync();
     }
@@ -223,17 +228,15 @@ int blsgpu_witness_free(blsgpu_ctx* ctx, int handle) {
     if (p->xrules) cudaFree(p->xrules); if (p->level_ptr) cudaFree(p->level_ptr);
     delete p; ctx->wit[handle] = nullptr; return 0;
 }
-// assignments of the verify circuit for nwit (pk48, msg32, sig96) triples: z48 = nwit * nout * 48 bytes (the layout of
-// blsgpu_r1cs_check), status[i] = 0, or 2 / 3 when the key / signature does not decode to a non-identity point (its assignment
-// is then all zeros except z[0] = 1 and the constants).  Pointers follow the context's pointer mode.
-int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, size_t nwit, uint8_t* z48, uint8_t* status) {
-    ENTER(); if (handle < 0 || handle >= 4 || !ctx->wit[handle] || !pk48 || !msg32 || !sig96 || !z48) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
-    if (!nwit) return 0;
-    wit_prog p = *ctx->wit[handle];
+}
+// decode, input slots and the level-synchronous replay for nwit triples: leaves the assignments in the transposed group layout
+// (group stride nvars * 96 u32x4) in the workspace; `extra` bytes of workspace are reserved for the caller's own buffers, which it
+// takes AFTER this returns.  want_zbool: also the packed 0/1 view per (group, variable).
+static int witness_run(blsgpu_ctx* ctx, const wit_prog& p, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, size_t nwit, uint8_t* status, size_t extra,
+                       bool want_zbool, u32x4** zt_out, uint2** zbool_out, uint8_t** dstatus_out) {
     size_t groups = (nwit + 31) / 32, np = groups * 32;
-    bool host = ctx->ptr_mode == BLSGPU_HOST;
-    size_t zbytes = nwit * p.nout * 48;
-    if (int rc = ws_reserve(ctx, al(48 * nwit) + al(96 * nwit) + al(32 * nwit) + al(96 * nwit) + al(192 * nwit) + 3 * al(np) + al(48 * WIT_INPUTS * np) + al(groups * p.nvars * 1536) + (host ? al(zbytes) : 0) + 65536)) return rc;
+    if (int rc = ws_reserve(ctx, al(48 * nwit) + al(96 * nwit) + al(32 * nwit) + al(96 * nwit) + al(192 * nwit) + 3 * al(np) + al(48 * WIT_INPUTS * np) + al(groups * p.nvars * 1536) +
+                                 (want_zbool ? al(groups * p.nvars * 8) : 0) + extra + 65536)) return rc;
     const uint8_t *dpk, *dsig, *dmsg;
     if (int rc = stage_in(ctx, dpk, pk48, 48 * nwit)) return rc;
     if (int rc = stage_in(ctx, dsig, sig96, 96 * nwit)) return rc;
@@ -243,7 +246,7 @@ int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const u
     uint8_t* dstatus = status ? stage_out(ctx, status, nwit) : nullptr;
     fp* inputs = ws_take<fp>(ctx, (size_t)WIT_INPUTS * np);
     u32x4* zt_all = ws_take<u32x4>(ctx, groups * p.nvars * 96);
-    uint8_t* dz = host ? ws_take<uint8_t>(ctx, zbytes) : z48;
+    uint2* zbool_all = want_zbool ? ws_take<uint2>(ctx, groups * p.nvars) : nullptr;
     LAUNCH(k_decode_g1, nblk(nwit), TPB, dpk, nwit, pk_soa, code_pk);
     LAUNCH(k_decode_g2, nblk(nwit), TPB, dsig, nwit, sig_soa, code_sig);
     LAUNCH(k_witness_inputs, nblk(np), TPB, (const u32x4*)pk_soa, (const uint8_t*)code_pk, (const u32x4*)sig_soa, (const uint8_t*)code_sig, dmsg, nwit, np, inputs, dstatus);
@@ -251,14 +254,62 @@ int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const u
         int per_sm = 0, sms = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_witness_levels, WIT_TPB, 0)); if (per_sm > WIT_BPS) per_sm = WIT_BPS; CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
         if (per_sm < 1) return fail(ctx, BLSGPU_ERR_CUDA, "k_witness_levels does not fit on an SM");
-        const fp* in_c = inputs; void* args[] = {(void*)&p, (void*)&in_c, (void*)&np, (void*)&zt_all, (void*)&groups};
+        wit_prog pc = p; const fp* in_c = inputs; void* args[] = {(void*)&pc, (void*)&in_c, (void*)&np, (void*)&zt_all, (void*)&groups, (void*)&zbool_all};
         CU(cudaLaunchCooperativeKernel((void*)k_witness_levels, dim3((unsigned)(per_sm * sms)), dim3(WIT_TPB), args, 0, ctx->stream)); ctx->launches++;
     } else {
-        if (p.nvars != p.nout) return fail(ctx, BLSGPU_ERR_ARG, "the sequential replay needs a program without scratch columns (load it with its level order)");
+        if (p.nvars != p.nout || want_zbool) return fail(ctx, BLSGPU_ERR_ARG, "the sequential replay needs a program without scratch columns (load it with its level order)");
         LAUNCH(k_witness_gen, (unsigned)groups, 32, p, (const fp*)inputs, np, zt_all);
     }
+    *zt_out = zt_all; if (zbool_out) *zbool_out = zbool_all; *dstatus_out = dstatus;
+    return 0;
+}
+extern "C" {
+// assignments of the verify circuit for nwit (pk48, msg32, sig96) triples: z48 = nwit * nout * 48 bytes (the layout of
+// blsgpu_r1cs_check), status[i] = 0, or 2 / 3 when the key / signature does not decode to a non-identity point (its assignment
+// is then all zeros except z[0] = 1 and the constants).  Pointers follow the context's pointer mode.
+int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, size_t nwit, uint8_t* z48, uint8_t* status) {
+    ENTER(); if (handle < 0 || handle >= 4 || !ctx->wit[handle] || !pk48 || !msg32 || !sig96 || !z48) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
+    if (!nwit) return 0;
+    wit_prog p = *ctx->wit[handle];
+    size_t groups = (nwit + 31) / 32;
+    bool host = ctx->ptr_mode == BLSGPU_HOST;
+    size_t zbytes = nwit * p.nout * 48;
+    u32x4* zt_all; uint8_t* dstatus;
+    if (int rc = witness_run(ctx, p, pk48, msg32, sig96, nwit, status, host ? al(zbytes) : 0, false, &zt_all, nullptr, &dstatus)) return rc;
+    uint8_t* dz = host ? ws_take<uint8_t>(ctx, zbytes) : z48;
     { dim3 grid(nblk(p.nout, 8), (unsigned)groups); k_witness_untranspose<<<grid, 256, 0, ctx->stream>>>((const u32x4*)zt_all, p.nvars, p.nout, nwit, (u32x4*)dz); ctx->launches++; CU(cudaGetLastError()); }
     if (host) CU(cudaMemcpyAsync(z48, dz, zbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) { if (int rc = finish_out(ctx, status, dstatus, nwit)) return rc; }
+    return finish_call(ctx);
+}
+// Generation and satisfaction check in one call: the assignments never leave the transposed group layout (no 48-byte row-major
+// copy, no second transpose; 34 MB per assignment stay out of the caller's memory).  sat_bits / all_sat as blsgpu_r1cs_check,
+// status as blsgpu_witness_gen; the R1CS system must be the one the program was recorded with (same column count).
+int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, size_t nwit,
+                         uint64_t* sat_bits, uint8_t* all_sat, uint8_t* status) {
+    ENTER(); if (wit_handle < 0 || wit_handle >= 4 || !ctx->wit[wit_handle] || r1cs_handle < 0 || r1cs_handle >= 16 || !ctx->r1cs[r1cs_handle] || !pk48 || !msg32 || !sig96 || !sat_bits)
+        return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
+    if (!nwit) return 0;
+    wit_prog p = *ctx->wit[wit_handle]; r1cs_sys s = *ctx->r1cs[r1cs_handle];
+    if (p.nout != s.ncols) return fail(ctx, BLSGPU_ERR_ARG, "witness program and R1CS system have different column counts");
+    if (!p.xrules) return fail(ctx, BLSGPU_ERR_ARG, "blsgpu_witness_check needs a program loaded with its level order");
+    size_t groups = (nwit + 31) / 32, words = (s.nrows + 63) / 64, part_bytes = (s.n_seg ? s.n_seg : 1) * 32 * 48;
+    bool host = ctx->ptr_mode == BLSGPU_HOST;
+    u32x4* zt_all; uint2* zbool_all; uint8_t* dstatus;
+    if (int rc = witness_run(ctx, p, pk48, msg32, sig96, nwit, status, al(part_bytes) + (host ? al(8 * words * nwit) + al(nwit) : 0), true, &zt_all, &zbool_all, &dstatus)) return rc;
+    u32x4* part = ws_take<u32x4>(ctx, part_bytes / 16);
+    uint64_t* dbits = host ? ws_take<uint64_t>(ctx, words * nwit) : sat_bits;
+    uint8_t* dall = all_sat ? (host ? ws_take<uint8_t>(ctx, nwit) : all_sat) : nullptr;
+    CU(cudaMemsetAsync(dbits, 0, 8 * words * nwit, ctx->stream));
+    for (size_t gi = 0; gi < groups; gi++) {
+        size_t w0 = gi * 32, g = nwit - w0 < 32 ? nwit - w0 : 32;
+        if (int rc = r1cs_check_group(ctx, s, zt_all + gi * p.nvars * 96, zbool_all + gi * p.nvars, part, w0, g, words, dbits)) return rc;
+    }
+    if (dall) LAUNCH(k_r1cs_all, nblk(nwit, 8), 256, (const uint64_t*)dbits, nwit, words, s.nrows, dall);
+    if (host) {
+        CU(cudaMemcpyAsync(sat_bits, dbits, 8 * words * nwit, cudaMemcpyDeviceToHost, ctx->stream));
+        if (all_sat) CU(cudaMemcpyAsync(all_sat, dall, nwit, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (status) { if (int rc = finish_out(ctx, status, dstatus, nwit)) return rc; }
     return finish_call(ctx);
 }

@@ -165,6 +165,12 @@ int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t*
                         int* handle);   /* host pointers; with `order` the rules of one level run in parallel (blsgadget_program_levels) */
 int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, size_t nwit,
                        uint8_t* z48, uint8_t* status);
+/* Generation and satisfaction check in one call: (pk, msg, sig) bytes in, per-constraint bits (words64 per assignment) and the
+ * per-assignment flag out, as blsgpu_r1cs_check would report them for blsgpu_witness_gen's output -- but the assignments stay in
+ * the device-side transposed layout (no row-major copy of 34 MB per assignment, no second transpose).  r1cs_handle must be the
+ * system of the circuit the program was recorded with; all_sat and status are nullable. */
+int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, size_t nwit,
+                         uint64_t* sat_bits, uint8_t* all_sat, uint8_t* status);
 int blsgpu_witness_free(blsgpu_ctx* ctx, int handle);
 
 #ifdef __cplusplus

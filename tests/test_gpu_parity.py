@@ -324,7 +324,6 @@ def test_gpu_witness_generation_matches_host_builder(ctx, C):
     prog = G.verify_program(*triples[0]); nvars = prog["nvars"]
     h = ctx.witness_load(prog)                                                                # level-synchronous replay (cooperative launch)
     z, st = ctx.witness_gen(h, pk, msg, sig, nvars)
-    ctx.witness_free(h)
     assert prog["ncols"] > nvars and prog["level_ptr"].size - 1 > 1000                        # scratch columns exist; thousands of dependency levels
     assert list(st) == [0 if e in (0, 1) else e for e in exp]                                 # 2: identity key, 3: undecodable signature
     good = [i for i in range(n) if exp[i] in (0, 1)]
@@ -333,8 +332,11 @@ def test_gpu_witness_generation_matches_host_builder(ctx, C):
     for k, i in enumerate(good): assert np.array_equal(z[i], zh[k]), f"assignment {i} differs from the host synthesis"
     c = G.verify_circuit(*triples[good[0]]); mats = c.matrices(); assert c.ncols == nvars
     hh = ctx.r1cs_load([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], c.nrows, c.ncols)
-    bits, allsat = ctx.r1cs_check(hh, z.reshape(-1), n, c.nrows); ctx.r1cs_free(hh)
+    bits, allsat = ctx.r1cs_check(hh, z.reshape(-1), n, c.nrows)
     assert list(allsat) == [1 if e in (0, 1) else 0 for e in exp]                             # flagged items carry no assignment
+    fbits, fall, fst = ctx.witness_check(h, hh, pk, msg, sig, c.nrows)                        # fused: generation + check without the row-major copy
+    assert np.array_equal(fbits, bits) and np.array_equal(fall, allsat) and np.array_equal(fst, st)
+    ctx.r1cs_free(hh); ctx.witness_free(h)
 
 def test_rlc_batch_check_agrees_with_per_item_verify(ctx):
     """blsgpu_verify_batch_rlc (one pairing-product equation per batch): true exactly when every item of the
