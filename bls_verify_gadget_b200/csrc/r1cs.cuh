@@ -61,26 +61,34 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_r1cs_prepare(const uint8_t* c
 // zbool[col] = (bits of the 32 witnesses, 1) when the column is 0/1-valued in every witness of the group, else (0, 0): such a column
 // (bits, bytes and words of the SHA-256 / decomposition gadgets: most non-zeros of the circuit) is then read as ONE broadcast 8-byte
 // load instead of a 1.5 KB gather, and its +-1 / small coefficients accumulate in a 64-bit integer beside the field accumulator
-// One warp per PAIR of columns: a lane reads the 96 contiguous bytes of its assignment (three whole 32-byte sectors; a single
-// 48-byte column would touch two sectors for 1.5 sectors of data) and writes two 1.5 KB rows of the transposed copy.
+// Tiled through shared memory: a CTA takes R1_TT consecutive columns of the 32 assignments.  Phase 1 reads, per assignment, the
+// R1_TT * 48 contiguous bytes of its row (coalesced 16-byte loads; the direct form -- each lane fetching 48 bytes from rows 34 MB
+// apart -- ran at half of the HBM rate); phase 2 hands each column to a warp, lane = assignment, which writes the three 512-byte
+// rows of the transposed copy (the tile's output is one contiguous R1_TT * 1.5 KB block) and the packed 0/1 view.  The row
+// stride of the tile is padded by one 16-byte slot so that the 32 lanes of phase 2 fall into distinct bank groups.
+#define R1_TT 16
 __global__ void __launch_bounds__(256) k_r1cs_transpose(const u32x4* z, size_t ncols, size_t w0, size_t g, u32x4* zt, uint2* zbool) {
-    size_t col = (blockIdx.x * (size_t)8 + (threadIdx.x >> 5)) * 2; int lane = threadIdx.x & 31;
-    if (col >= ncols) return;
+    __shared__ u32x4 tile[32][R1_TT * 3 + 1];
+    size_t col0 = blockIdx.x * (size_t)R1_TT; int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    size_t ncol_here = ncols - col0 < R1_TT ? ncols - col0 : R1_TT;
     u32x4 zero; zero.x = zero.y = zero.z = zero.w = 0;
-    const u32x4* src = z + ((w0 + lane) * ncols + col) * 3;
-    bool live = (size_t)lane < g, two = col + 1 < ncols;
-    u32x4 v[6];
 #pragma unroll
-    for (int k = 0; k < 6; k++) v[k] = (live && (k < 3 || two)) ? src[k] : zero;
+    for (int k = 0; k < (32 * R1_TT * 3) / 256; k++) {
+        int i = threadIdx.x + 256 * k, w = i / (R1_TT * 3), j = i % (R1_TT * 3);
+        bool live = (size_t)w < g && (size_t)j < ncol_here * 3;
+        tile[w][j] = live ? z[((w0 + w) * ncols + col0) * 3 + j] : zero;
+    }
+    __syncthreads();
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        if (h && !two) break;
-        u32x4 a = v[3 * h], b = v[3 * h + 1], c = v[3 * h + 2];
-        zt[((col + h) * 3) * 32 + lane] = a; zt[((col + h) * 3 + 1) * 32 + lane] = b; zt[((col + h) * 3 + 2) * 32 + lane] = c;
+    for (int h = 0; h < R1_TT / 8; h++) {
+        int cl = warp + 8 * h; size_t col = col0 + cl;
+        if ((size_t)cl >= ncol_here) break;
+        u32x4 a = tile[lane][3 * cl], b = tile[lane][3 * cl + 1], c = tile[lane][3 * cl + 2];
+        zt[(col * 3) * 32 + lane] = a; zt[(col * 3 + 1) * 32 + lane] = b; zt[(col * 3 + 2) * 32 + lane] = c;
         bool small = a.x < 2 && !(a.y | a.z | a.w | b.x | b.y | b.z | b.w | c.x | c.y | c.z | c.w);
         bool all = __all_sync(0xffffffffu, small);
         uint32_t pack = __ballot_sync(0xffffffffu, a.x & 1u);        // the column's 32 values as one word when they are all 0 / 1
-        if (lane == 0) zbool[col + h] = make_uint2(all ? pack : 0u, all ? 1u : 0u);
+        if (lane == 0) zbool[col] = make_uint2(all ? pack : 0u, all ? 1u : 0u);
     }
 }
 __device__ __forceinline__ fp r1cs_load_z(const u32x4* zt, uint32_t col, int lane) {
@@ -88,36 +96,51 @@ __device__ __forceinline__ fp r1cs_load_z(const u32x4* zt, uint32_t col, int lan
     fp v; v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w; v.l[8] = c.x; v.l[9] = c.y; v.l[10] = c.z; v.l[11] = c.w;
     return v;
 }
-// sum over the non-zeros [lo, hi) of one matrix row; every branch is warp-uniform (class per non-zero, zbool per column).
-// Terms on 0/1 columns with coefficient +-1 or |c| < 2^32 go to the integer side sum (at most R1_SEG terms: |sum| < 2^39).
-__device__ __forceinline__ fp r1cs_range_dot(const r1cs_sys& s, int m, uint64_t lo, uint64_t hi, const u32x4* zt, const uint2* zbool, int lane) {
+// One non-zero: class c, column cj with its packed 0/1 view zb, |coefficient| low word cf (small classes).  Every branch is
+// warp-uniform (class per non-zero, zbool per column).  Terms on 0/1 columns with coefficient +-1 or |c| < 2^32 go to the integer
+// side sum (at most R1_SEG terms: |sum| < 2^39); `touched` records whether the field accumulator was used at all.
+__device__ __forceinline__ void r1cs_term(const r1cs_sys& s, int m, uint64_t k, uint32_t cj, uint32_t c, uint2 zb, uint32_t cf, const u32x4* zt, int lane,
+                                          fp& acc, int64_t& side, bool& touched) {
+    if (zb.y) {
+        uint32_t bit = (zb.x >> lane) & 1u;
+        if (c == R1_PLUS_ONE) side += bit;
+        else if (c == R1_MINUS_ONE) side -= bit;
+        else if (c == R1_SMALL_POS) side += (int64_t)((uint64_t)bit * cf);
+        else if (c == R1_SMALL_NEG) side -= (int64_t)((uint64_t)bit * (BLS_P0 - cf));                  // |c| = p - c: the low words suffice
+        else { acc = fp_add(acc, fp_select(0u - bit, s.coeffc[m][k], fp_zero())); touched = true; }   // general coefficient: masked addition
+        return;
+    }
+    touched = true;
+    fp zv = r1cs_load_z(zt, cj, lane);
+    if (c == R1_PLUS_ONE) acc = fp_add(acc, zv);
+    else if (c == R1_MINUS_ONE) acc = fp_sub(acc, zv);
+    else if (c == R1_SMALL_POS) acc = fp_add(acc, fp_mul_small(zv, cf));
+    else if (c == R1_SMALL_NEG) acc = fp_sub(acc, fp_mul_small(zv, BLS_P0 - cf));
+    else acc = fp_add(acc, fp_mul(s.coeff[m][k], zv));
+}
+// sum over the non-zeros [lo, hi) of one matrix (a segment of a long row): field part returned, integer part in side_out
+__device__ __forceinline__ fp r1cs_range_dot(const r1cs_sys& s, int m, uint64_t lo, uint64_t hi, const u32x4* zt, const uint2* zbool, int lane, int64_t& side_out, bool& touched) {
     const uint32_t* col = s.col[m]; const uint8_t* cls = s.cls[m];
-    fp acc = fp_zero(); int64_t side = 0;
+    fp acc = fp_zero(); int64_t side = 0; touched = false;
     uint32_t cj_n = 0; uint8_t c_n = 0; uint2 zb_n = make_uint2(0u, 0u);
     if (lo < hi) { cj_n = col[lo]; c_n = cls[lo]; zb_n = zbool[cj_n]; }
     for (uint64_t k = lo; k < hi; k++) {
         uint32_t cj = cj_n; uint8_t c = c_n; uint2 zb = zb_n;
         if (k + 1 < hi) { cj_n = col[k + 1]; c_n = cls[k + 1]; zb_n = zbool[cj_n]; }      // the next term's metadata travels while this term's gather does
-        if (zb.y) {
-            uint32_t bit = (zb.x >> lane) & 1u;
-            if (c == R1_PLUS_ONE) side += bit;
-            else if (c == R1_MINUS_ONE) side -= bit;
-            else if (c == R1_SMALL_POS) side += (int64_t)((uint64_t)bit * s.coeffc[m][k].l[0]);
-            else if (c == R1_SMALL_NEG) side -= (int64_t)((uint64_t)bit * (BLS_P0 - s.coeffc[m][k].l[0]));
-            else acc = fp_add(acc, fp_select(0u - bit, s.coeffc[m][k], fp_zero()));      // general coefficient: masked addition
-            continue;
-        }
-        fp zv = r1cs_load_z(zt, cj, lane);
-        if (c == R1_PLUS_ONE) acc = fp_add(acc, zv);
-        else if (c == R1_MINUS_ONE) acc = fp_sub(acc, zv);
-        else if (c == R1_SMALL_POS) acc = fp_add(acc, fp_mul_small(zv, s.coeffc[m][k].l[0]));
-        else if (c == R1_SMALL_NEG) acc = fp_sub(acc, fp_mul_small(zv, BLS_P0 - s.coeffc[m][k].l[0]));      // |c| = p - c: low words suffice
-        else acc = fp_add(acc, fp_mul(s.coeff[m][k], zv));
+        uint32_t cf = (c == R1_SMALL_POS || c == R1_SMALL_NEG) ? s.coeffc[m][k].l[0] : 0u;
+        r1cs_term(s, m, k, cj, c, zb, cf, zt, lane, acc, side, touched);
     }
+    side_out = side; return acc;
+}
+// field part + integer part as one canonical element
+__device__ __forceinline__ fp r1cs_finalize(const fp& acc, int64_t side, bool touched) {
     uint64_t mag = side < 0 ? (uint64_t)(-side) : (uint64_t)side;
     fp t = fp_zero(); t.l[0] = (uint32_t)mag; t.l[1] = (uint32_t)(mag >> 32);
+    uint32_t neg = side < 0 ? 0xffffffffu : 0u;
+    if (!touched) { fp n; fp_sub_raw(n, fp_modulus(), t); return fp_select(neg, n, t); }      // side != 0 when neg, so p - |side| < p
+    if (__all_sync(0xffffffffu, side == 0)) return acc;
     fp up = fp_add(acc, t), dn = fp_sub(acc, t);
-    return fp_select(side < 0 ? 0xffffffffu : 0u, dn, up);
+    return fp_select(neg, dn, up);
 }
 // a b == c (all canonical).  In the boolean / uint32 gadget rows (95 % of the verify circuit) a and b are small integers
 // (bits, 35-bit word sums): when one fits 64 bits and the other 32 bits in every lane the product is a 96-bit integer
@@ -137,7 +160,8 @@ __device__ __forceinline__ bool r1cs_product_ok(const fp& a, const fp& b, const 
 }
 // one warp per block of R1_ROWS consecutive rows (a fraction of a 64-row word: finer blocks balance better and keep more
 // gathers in flight; the bits are OR-ed into the word, which the host zeroes first); lane = witness in the group.
-// Long rows are left to the segment kernels.
+// Long rows are left to the segment kernels.  (A variant that fetched a row's metadata with one lane per non-zero and evaluated
+// it from register broadcasts was 12 % slower: the kernel is not bound by the CSR walk -- profiles/r01_tuning.md.)
 #ifndef R1_ROWS
 #define R1_ROWS 8
 #endif
@@ -148,10 +172,14 @@ __global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_rows(r1cs_sys s, const u3
     size_t r_end = r0 + R1_ROWS < s.nrows ? r0 + R1_ROWS : s.nrows;
     for (size_t row = r0; row < r_end; row++) {
         if (s.is_long[row]) continue;
-        fp a = r1cs_range_dot(s, 0, s.rowptr[0][row], s.rowptr[0][row + 1], zt, zbool, lane);
-        fp b = r1cs_range_dot(s, 1, s.rowptr[1][row], s.rowptr[1][row + 1], zt, zbool, lane);
-        fp c = r1cs_range_dot(s, 2, s.rowptr[2][row], s.rowptr[2][row + 1], zt, zbool, lane);
-        if (r1cs_product_ok(a, b, c)) bits |= 1ull << (row & 63);
+        int64_t sa, sb, sc; bool ta, tb, tc;
+        fp a = r1cs_range_dot(s, 0, s.rowptr[0][row], s.rowptr[0][row + 1], zt, zbool, lane, sa, ta);
+        fp b = r1cs_range_dot(s, 1, s.rowptr[1][row], s.rowptr[1][row + 1], zt, zbool, lane, sb, tb);
+        fp c = r1cs_range_dot(s, 2, s.rowptr[2][row], s.rowptr[2][row + 1], zt, zbool, lane, sc, tc);
+        bool ok;
+        if (!(ta | tb | tc)) ok = (__int128)sa * (__int128)sb == (__int128)sc;      // only 0/1 columns with small coefficients: |a b - c| < 2^80 < p, so equality mod p is equality
+        else ok = r1cs_product_ok(r1cs_finalize(a, sa, ta), r1cs_finalize(b, sb, tb), r1cs_finalize(c, sc, tc));
+        if (ok) bits |= 1ull << (row & 63);
     }
     if ((size_t)lane < g && bits) atomicOr((unsigned long long*)&sat_bits[(w0 + lane) * words + (r0 >> 6)], bits);
 }
@@ -159,7 +187,9 @@ __global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_rows(r1cs_sys s, const u3
 __global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_segments(r1cs_sys s, const u32x4* zt, const uint2* zbool, u32x4* part) {
     size_t sg = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
     if (sg >= s.n_seg) return;
-    fp v = r1cs_range_dot(s, s.seg_mat[sg], s.seg_lo[sg], s.seg_hi[sg], zt, zbool, lane);
+    int64_t side; bool touched;
+    fp v = r1cs_range_dot(s, s.seg_mat[sg], s.seg_lo[sg], s.seg_hi[sg], zt, zbool, lane, side, touched);
+    v = r1cs_finalize(v, side, touched);
     soa_store_fp(part, s.n_seg * 32, sg * 32 + lane, 0, v);
 }
 // one warp per long row: add the partial sums of each matrix, test the product, OR the bit into the row's word
@@ -282,7 +312,7 @@ int blsgpu_r1cs_check(blsgpu_ctx* ctx, int handle, const uint8_t* z48, size_t nw
         const u32x4* zsrc; size_t wbase;
         if (host) { CU(cudaMemcpyAsync(zstage, z48 + w0 * s.ncols * 48, g * s.ncols * 48, cudaMemcpyHostToDevice, ctx->stream)); zsrc = zstage; wbase = 0; }
         else { zsrc = (const u32x4*)z48; wbase = w0; }
-        LAUNCH(k_r1cs_transpose, nblk((s.ncols + 1) / 2, 8), 256, zsrc, s.ncols, wbase, g, zt, zbool);
+        LAUNCH(k_r1cs_transpose, nblk(s.ncols, R1_TT), 256, zsrc, s.ncols, wbase, g, zt, zbool);
         if (int rc = r1cs_check_group(ctx, s, zt, zbool, part, w0, g, words, dbits)) return rc;
     }
     if (dall) LAUNCH(k_r1cs_all, nblk(nwit, 8), 256, (const uint64_t*)dbits, nwit, words, s.nrows, dall);
