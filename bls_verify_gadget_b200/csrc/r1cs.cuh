@@ -10,8 +10,10 @@
 //
 // What the real verify circuit (714 k rows, built by bls_verify_gadget_b200/gadget) needed beyond the synthetic one:
 //  * 93 % of its columns are boolean variables (SHA-256 bits) and 40 % of its "general" coefficients (powers of two of the
-//    bit-packing rows) multiply such a column: the transpose marks columns that are 0/1 in all 32 witnesses and the
-//    product becomes a masked addition of the canonical coefficient (warp-uniform branch);
+//    bit-packing rows) multiply such a column: the transpose packs a column that is 0/1 in all 32 witnesses into one word
+//    (+ a flag); the row kernels read that word instead of gathering 1.5 KB, add +-1 / small coefficients into a 64-bit integer
+//    side sum, a larger coefficient as a masked addition of its canonical value (warp-uniform branches), and test a row that
+//    touched nothing else as a * b == c on integers;
 //  * a few hundred rows carry 300-760 general coefficients (linear combinations that grow through runs of cyclotomic
 //    squarings): rows longer than R1_LONG are cut into R1_SEG-entry segments, one warp each, and combined afterwards --
 //    otherwise one warp serialises ~10^7 instructions while the rest of the GPU idles (measured: 34 ms per group -> see
