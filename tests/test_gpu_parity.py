@@ -275,6 +275,54 @@ def test_r1cs_differential(ctx, C):
     unsat = lambda w: [i for i in range(nrows) if not (int(bits[w, i // 64]) >> (i % 64)) & 1]
     assert unsat(3) == [0, 63, 64, 199] and unsat(36) == [100]
 
+def test_r1cs_coefficient_classes_and_packed_columns(ctx, C):
+    """Crafted system for the kernel's special cases: coefficients on both sides of every class boundary (0, +-1, 2, 2^32 - 1 | 2^32,
+    p - (2^32 - 1) | p - 2^32, random), columns that are 0/1 in one group of 32 assignments but not in the next, rows of 1..120
+    non-zeros (short rows, the integer-only path, 32-entry segments of long rows), satisfied and unsatisfied rows, a ragged second
+    group -- every per-constraint bit must equal the oracle's."""
+    rng = np.random.default_rng(23); nwit = 45; nbool = 24; nfld = 40; nrows = 300
+    special = [0, 1, 2, 3, 12, (1 << 32) - 1, 1 << 32, (1 << 32) + 1, P - 1, P - 2, P - ((1 << 32) - 1), P - (1 << 32), P - (1 << 32) - 1, 1 << 200, (P - 1) // 2]
+    def coeff(): return special[int(rng.integers(0, len(special)))] if rng.random() < 0.8 else int.from_bytes(rng.bytes(48), "little") % P
+    ncols = 1 + nbool + nfld + nrows                      # constant, 0/1 columns, field columns, one product column per row
+    rows = []
+    for r in range(nrows):
+        mats = []
+        for m in range(2):
+            n = int(rng.choice([1, 2, 3, 5, 9, 17, 40, 120], p=[.2, .2, .15, .15, .1, .1, .05, .05]))
+            only_bool = rng.random() < 0.5                # rows that touch only 0/1 columns take the integer-only test
+            cols = rng.choice(np.arange(0, 1 + nbool) if only_bool else np.arange(0, 1 + nbool + nfld), size=min(n, (1 + nbool) if only_bool else 1 + nbool + nfld), replace=False)
+            mats.append([(int(c), coeff() if not only_bool or rng.random() < 0.3 else int(rng.choice([1, P - 1, 2, 5, P - 3, (1 << 32) - 1]))) for c in sorted(cols)])
+        if r < 20: mats = [[(1 + (3 * r) % nbool, 1)], [(1 + (5 * r + 1) % nbool, 1)]]      # AND gates: all three combinations stay on 0/1 columns
+        mats.append([(1 + nbool + nfld + r, 1)])          # C row: the product column
+        rows.append(mats)
+    z = np.zeros((nwit, ncols), dtype=object); z[:, 0] = 1
+    z[:, 1:1 + nbool] = rng.integers(0, 2, size=(nwit, nbool))
+    z[35, 5] = 7; z[40, 9] = P - 1                          # columns 5 and 9 stop being 0/1 in the second group only
+    edge = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, 1 << 380, (1 << 64) - 1]
+    for w in range(nwit):
+        for c in range(1 + nbool, 1 + nbool + nfld): z[w, c] = edge[int(rng.integers(0, len(edge)))] if rng.random() < 0.3 else int.from_bytes(rng.bytes(48), "little") % P
+    z[:, 30] = rng.integers(0, 2, size=nwit)              # a "field" column that happens to be 0/1 everywhere
+    for r, (A, B, Cc) in enumerate(rows):
+        for w in range(nwit):
+            a = sum(cf * z[w, c] for c, cf in A) % P; b = sum(cf * z[w, c] for c, cf in B) % P
+            z[w, 1 + nbool + nfld + r] = a * b % P
+    bad = [(3, 0), (3, 299), (17, 64), (40, 128), (44, 7)]
+    for w, r in bad: z[w, 1 + nbool + nfld + r] = (z[w, 1 + nbool + nfld + r] + 1) % P
+    def csr(m):
+        rp = [0]; cl = []; cf = []
+        for row in rows:
+            for c, v in row[m]: cl.append(c); cf.append(v.to_bytes(48, "little"))
+            rp.append(len(cl))
+        return np.array(rp, np.uint64), np.array(cl, np.uint32), np.frombuffer(b"".join(cf), np.uint8)
+    mats = [csr(m) for m in range(3)]
+    zb = np.frombuffer(b"".join(int(v).to_bytes(48, "little") for v in z.reshape(-1)), np.uint8)
+    h = ctx.r1cs_load([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], nrows, ncols)
+    bits, allsat = ctx.r1cs_check(h, zb, nwit, nrows); ctx.r1cs_free(h)
+    obits, oall = C.r1cs_check([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], nrows, ncols, zb, nwit, threads=4)
+    assert np.array_equal(bits, obits) and list(allsat) == list(oall)
+    unsat = {(w, r) for w in range(nwit) for r in range(nrows) if not (int(bits[w, r // 64]) >> (r % 64)) & 1}
+    assert unsat == set(bad)
+
 def test_r1cs_verify_circuit_on_gpu(ctx, C):
     """K8 on the REAL system: the matrices and assignments of BlsSignatureVerifyGadget::verify (constraints.rs:90-128) built
     by the host-side builder (714 k rows).  Assignments of a valid and an invalid signature are both satisfying (the gadget
