@@ -86,6 +86,8 @@ def main():
     assert np.array_equal(fl[nwit:], want_st) and np.array_equal(fl[:nwit], (want_st == 0).astype(np.uint8)), "e2e flags differ from the recipe"
     ke = max(1, args.steps // 2); ms_e2e = timed(step_e2e, ke)
     if rank == 0:
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json"); peaks = json.load(open(pk_path)) if os.path.exists(pk_path) else {}
+        hbm_peak = float(peaks.get("hbm_gbs") or 6549.4)
         value = nrows * nwit_total * args.steps / (ms * 1e-3)
         line = {"metric": "r1cs_constraints_checked_per_sec", "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit modular integer)", "data": "synthetic keys/messages, real circuit",
@@ -96,7 +98,10 @@ def main():
                         "assignments_per_sec": nwit_total * ke / (ms_e2e * 1e-3),
                         "pipeline": "pinned host (pk,msg,sig) bytes -> blsgpu_witness_check (GPU witness generation + satisfaction check) -> flags to host"},
                 "gpu_launches": launches, "host_synthesis_s_per_assignment_per_thread": t_syn / nb * min(threads, nb),
-                "roofline": {"bound": "hbm", "achieved": nwit * ncols * 48 * 2 * args.steps / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "achieved": nwit * ncols * 48 * 2 * args.steps / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": nwit * ncols * 48 * 2 * args.steps / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6549.4 GB/s (the value MEASURED_PEAKS.json held when this was written)",
+                             "kernel_note": "whole step; the transpose kernel alone moves these bytes at the HBM peak (0.32 ms per 32 assignments, profiles/launches_cfg5r_r01c.csv); the row kernels are issue / gather-latency bound",
                              "note": "algorithmic bytes = each assignment read once and written once by the transpose (2 x 48 B x ncols); the gather of z by the row kernels re-reads the transposed copy (nnz x 48 B per assignment) -- see profiles/r01_summary.md"}}
         if not args.no_cpu:
             from oracle import cwrap as C
