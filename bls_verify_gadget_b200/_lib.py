@@ -6,8 +6,8 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("BLSGPU_SO") or os.path.join(_PKG, "libblsgpu.so")      # BLSGPU_SO: tuning builds (profiles/), never a fallback
-_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("blsgpu.cu", "r1cs.cuh", "stages.cuh", "pairing.cuh", "h2c.cuh", "curve.cuh", "tower.cuh",
-                                                    "fp2.cuh", "fp.cuh", "consts.cuh", "coop.cuh", "wide.cuh")] + [os.path.join(_ROOT, "include", "blsgpu.h")]
+import glob
+_SOURCES = [os.path.join(_PKG, "csrc", "blsgpu.cu")] + sorted(glob.glob(os.path.join(_PKG, "csrc", "*.cuh"))) + sorted(glob.glob(os.path.join(_ROOT, "include", "*.h")))      # every header the one translation unit includes
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
 class BlsGpuError(RuntimeError): pass
@@ -35,7 +35,7 @@ def lib():
 EXPORTS = ["blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_set_stream", "blsgpu_set_pointer_mode", "blsgpu_synchronize",
            "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_set_coop", "blsgpu_verify_batch", "blsgpu_verify_batch_rlc", "blsgpu_fast_aggregate_verify_batch", "blsgpu_pool_create", "blsgpu_pool_free", "blsgpu_pool_fast_aggregate_verify", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
            "blsgpu_g2_aggregate", "blsgpu_deserialize_g1", "blsgpu_deserialize_g2", "blsgpu_sk_to_pk_batch", "blsgpu_sign_batch", "blsgpu_pairing_gt",
-           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_check", "blsgpu_witness_free"]
+           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_r1cs_row_classes", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_check", "blsgpu_witness_free"]
 
 _sz = ctypes.c_size_t; _vp = ctypes.c_void_p
 def _u8(a):
@@ -46,6 +46,9 @@ def _p(a):
     if isinstance(a, int): return _vp(a)                      # raw device pointer
     if a.size == 0: a = np.zeros(1, dtype=a.dtype)
     return a.ctypes.data_as(_vp)
+def _need(name, a, nbytes):
+    """the C side trusts the sizes it is given: a short host buffer would be read past its end, so the wrappers check"""
+    if a is not None and a.size * a.itemsize != nbytes: raise ValueError(f"{name}: expected {nbytes} bytes, got {a.size * a.itemsize}")
 def pack_msgs(msgs):
     off = np.zeros(len(msgs) + 1, dtype=np.uint32)
     if len(msgs): off[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
@@ -88,7 +91,10 @@ class Context:
         pk = _u8(pk48); sg = _u8(sig96); n = sg.size // 96
         if fixed32: flat, off = _u8(msgs), None
         else: flat, off = pack_msgs(msgs)
-        st = np.empty(max(n, 1), np.uint8); ok = np.zeros(1, np.uint8); seed = _u8(seed16); assert seed.size == 16
+        _need("sig96", sg, 96 * n); _need("pk48", pk, 48 * n)
+        if fixed32: _need("msgs", flat, 32 * n)
+        elif len(msgs) != n: raise ValueError(f"{len(msgs)} messages for {n} signatures")
+        st = np.empty(max(n, 1), np.uint8); ok = np.zeros(1, np.uint8); seed = _u8(seed16); _need("seed16", seed, 16)
         self.verify_rlc_ptr(pk, flat, off, sg, n, seed, st, ok)
         return bool(ok[0]), st[:n]
     def hash_to_g2_ptr(self, msg, off, n, out): self._ck(lib().blsgpu_hash_to_g2_batch(self._h, _p(msg), _p(off), _sz(n), _p(out)))
@@ -99,6 +105,9 @@ class Context:
         pk = _u8(pk48); sg = _u8(sig96); n = sg.size // 96
         if fixed32: flat, off = _u8(msgs), None
         else: flat, off = pack_msgs(msgs)
+        _need("sig96", sg, 96 * n); _need("pk48", pk, 48 * n)
+        if fixed32: _need("msgs", flat, 32 * n)
+        elif len(msgs) != n: raise ValueError(f"{len(msgs)} messages for {n} signatures")
         st = np.empty(n, np.uint8); bm = np.zeros((n + 63) // 64, np.uint64) if want_bitmap else None; gt = np.empty(576, np.uint8) if want_gt else None
         self.verify_ptr(pk, flat, off, sg, n, st, bm, gt)
         out = (st,) + ((bm,) if want_bitmap else ()) + ((gt,) if want_gt else ())
@@ -107,6 +116,7 @@ class Context:
         pk = _u8(pks48); m = _u8(msg32); sg = _u8(sig96); nc = sg.size // 96
         st = np.empty(nc, np.uint8); agg = np.empty(48 * nc, np.uint8) if want_agg else None
         bm = np.ascontiguousarray(bitmap, dtype=np.uint64) if bitmap is not None else None
+        _need("sig96", sg, 96 * nc); _need("msg32", m, 32 * nc); _need("pks48", pk, 48 * nc * k); _need("bitmap", bm, 8 * ((nc * k + 63) // 64))
         self.fast_aggregate_verify_ptr(pk, bm, k, m, sg, nc, st, agg)
         return (st, agg) if want_agg else st
     def pool_create(self, pks48):
@@ -119,6 +129,7 @@ class Context:
         ix = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1); m = _u8(msg32); sg = _u8(sig96); nc = sg.size // 96
         st = np.empty(nc, np.uint8); agg = np.empty(48 * nc, np.uint8) if want_agg else None
         bm = np.ascontiguousarray(bitmap, dtype=np.uint64) if bitmap is not None else None
+        _need("sig96", sg, 96 * nc); _need("msg32", m, 32 * nc); _need("idx", ix, 4 * nc * k); _need("bitmap", bm, 8 * ((nc * k + 63) // 64))
         self.pool_fast_aggregate_verify_ptr(handle, ix, bm, k, m, sg, nc, st, agg)
         return (st, agg) if want_agg else st
     def hash_to_g2(self, msgs):
@@ -126,10 +137,14 @@ class Context:
     def g1_aggregate(self, pts48, seg_off):
         a = _u8(pts48); seg = np.ascontiguousarray(seg_off, dtype=np.uint32); ns = seg.size - 1
         out = np.empty(48 * ns, np.uint8); st = np.empty(ns, np.uint8)
+        if ns < 0 or (ns > 0 and (np.any(np.diff(seg.astype(np.int64)) < 0) or seg[0] != 0)): raise ValueError("seg_off must start at 0 and be non-decreasing")
+        _need("pts48", a, 48 * int(seg[-1]) if ns >= 0 and seg.size else 0)
         self._ck(lib().blsgpu_g1_aggregate(self._h, _p(a), _p(seg), _sz(ns), _p(out), _p(st))); return out, st
     def g2_aggregate(self, pts96, seg_off):
         a = _u8(pts96); seg = np.ascontiguousarray(seg_off, dtype=np.uint32); ns = seg.size - 1
         out = np.empty(96 * ns, np.uint8); st = np.empty(ns, np.uint8)
+        if ns < 0 or (ns > 0 and (np.any(np.diff(seg.astype(np.int64)) < 0) or seg[0] != 0)): raise ValueError("seg_off must start at 0 and be non-decreasing")
+        _need("pts96", a, 96 * int(seg[-1]) if ns >= 0 and seg.size else 0)
         self._ck(lib().blsgpu_g2_aggregate(self._h, _p(a), _p(seg), _sz(ns), _p(out), _p(st))); return out, st
     def deserialize_g1(self, in48):
         a = _u8(in48); n = a.size // 48; st = np.empty(n, np.uint8); self._ck(lib().blsgpu_deserialize_g1(self._h, _p(a), _sz(n), _p(st))); return st
@@ -142,10 +157,13 @@ class Context:
         sk = _u8(sk_le); n = sk.size // 32
         if fixed32: flat, off = _u8(msgs), None
         else: flat, off = pack_msgs(msgs)
+        _need("sk32", sk, 32 * n)
+        if fixed32: _need("msgs", flat, 32 * n)
+        elif len(msgs) != n: raise ValueError(f"{len(msgs)} messages for {n} secret keys")
         out = np.empty(96 * n, np.uint8); st = np.empty(n, np.uint8)
         self._ck(lib().blsgpu_sign_batch(self._h, _p(sk), _p(flat), _p(off), _sz(n), _p(out), _p(st))); return out, st
     def pairing_gt(self, g1_48, g2_96, npairs):
-        a = _u8(g1_48); b = _u8(g2_96); nprod = a.size // 48 // npairs; out = np.empty(576 * nprod, np.uint8); st = np.empty(nprod, np.uint8)
+        a = _u8(g1_48); b = _u8(g2_96); nprod = a.size // 48 // npairs; _need("g1_48", a, 48 * npairs * nprod); _need("g2_96", b, 96 * npairs * nprod); out = np.empty(576 * nprod, np.uint8); st = np.empty(nprod, np.uint8)
         self._ck(lib().blsgpu_pairing_gt(self._h, _p(a), _p(b), _sz(npairs), _sz(nprod), _p(out), _p(st))); return out.reshape(nprod, 576), st
     def gt_fold(self, parts):
         a = _u8(parts); out = np.empty(576, np.uint8); self._ck(lib().blsgpu_gt_fold(self._h, _p(a), _sz(a.size // 576), _p(out))); return out
@@ -157,13 +175,21 @@ class Context:
     def r1cs_load(self, rowptr, col, coeff48, nrows, ncols):
         rp = [np.ascontiguousarray(x, dtype=np.uint64) for x in rowptr]; cl = [np.ascontiguousarray(x, dtype=np.uint32) for x in col]
         cf = [np.ascontiguousarray(x, dtype=np.uint8) for x in coeff48]; P3 = _vp * 3; h = ctypes.c_int(-1)
+        for m in range(3):
+            if rp[m].size != nrows + 1: raise ValueError(f"rowptr[{m}] must hold nrows + 1 entries")
+            nnz = int(rp[m][-1])
+            if cl[m].size < nnz or cf[m].size < 48 * nnz: raise ValueError(f"matrix {m}: rowptr announces {nnz} non-zeros, col / coeff48 hold fewer")
         self._ck(lib().blsgpu_r1cs_load(self._h, P3(*[_p(x) for x in rp]), P3(*[_p(x) for x in cl]), P3(*[_p(x) for x in cf]), _sz(nrows), _sz(ncols), ctypes.byref(h)))
         return h.value
     def r1cs_check(self, handle, z48, nwit, nrows):
         z = _u8(z48); words = (nrows + 63) // 64; bits = np.zeros(nwit * words, np.uint64); allsat = np.zeros(nwit, np.uint8)
+        if nwit and z.size % (48 * nwit): raise ValueError("z48 must hold nwit * ncols * 48 bytes")
         self._ck(lib().blsgpu_r1cs_check(self._h, int(handle), _p(z), _sz(nwit), _p(bits), _p(allsat))); return bits.reshape(nwit, words), allsat
     def r1cs_check_ptr(self, handle, z, nwit, bits, allsat): self._ck(lib().blsgpu_r1cs_check(self._h, int(handle), _p(z), _sz(nwit), _p(bits), _p(allsat)))
     def r1cs_free(self, handle): lib().blsgpu_r1cs_free(self._h, int(handle))
+    def r1cs_row_classes(self, handle):
+        c = (ctypes.c_uint64 * 4)(); self._ck(lib().blsgpu_r1cs_row_classes(self._h, int(handle), c))
+        return dict(zip(("truth_table", "generic", "long", "segments"), [int(x) for x in c]))
     # ---- GPU witness generation (program from bls_verify_gadget_b200.gadget.verify_program)
     def witness_load(self, program, levels=True):
         """program: the dict of gadget.verify_program; levels=False keeps the strictly sequential replay (one warp per 32 assignments)"""
@@ -175,12 +201,14 @@ class Context:
         return h.value
     def witness_gen(self, handle, pk48, msg32, sig96, nvars):
         pk = _u8(pk48); m = _u8(msg32); sg = _u8(sig96); n = sg.size // 96
+        _need("sig96", sg, 96 * n); _need("pk48", pk, 48 * n); _need("msg32", m, 32 * n)
         z = np.empty(n * nvars * 48, np.uint8); st = np.empty(n, np.uint8)
         self._ck(lib().blsgpu_witness_gen(self._h, int(handle), _p(pk), _p(m), _p(sg), _sz(n), _p(z), _p(st))); return z.reshape(n, nvars * 48), st
     def witness_gen_ptr(self, handle, pk, msg, sig, n, z, status=None): self._ck(lib().blsgpu_witness_gen(self._h, int(handle), _p(pk), _p(msg), _p(sig), _sz(n), _p(z), _p(status)))
     def witness_check(self, wit_handle, r1cs_handle, pk, msgs32, sig, nrows):
         """host buffers: generation + satisfaction check in one call -> (bits uint64[n, words], all_sat uint8[n], status uint8[n])"""
         pk = _u8(pk); sg = _u8(sig); m = _u8(msgs32); n = pk.size // 48; words = (nrows + 63) // 64
+        _need("pk", pk, 48 * n); _need("sig", sg, 96 * n); _need("msgs32", m, 32 * n)
         bits = np.zeros((n, words), np.uint64); allsat = np.zeros(n, np.uint8); st = np.empty(n, np.uint8)
         self._ck(lib().blsgpu_witness_check(self._h, int(wit_handle), int(r1cs_handle), _p(pk), _p(m), _p(sg), _sz(n), _p(bits), _p(allsat), _p(st))); return bits, allsat, st
     def witness_check_ptr(self, wit_handle, r1cs_handle, pk, msg, sig, n, bits, allsat=None, status=None):

@@ -408,6 +408,8 @@ struct blsgpu_ctx {
     size_t chunk;                       // items per internal pass of verify_batch (bounds the workspace); multiple of 64
     int prof; cudaEvent_t ev[8];        // stage boundaries of the last verify_batch chunk: g1 | g2 | hash | miller | final | epilogue
 };
+// every entry point runs on the context's device and leaves the caller's current device as it found it
+struct dev_guard { int prev; dev_guard() : prev(-1) { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } } ~dev_guard() { if (prev >= 0) cudaSetDevice(prev); } };
 #define STAGE_MARK(k) do { if (ctx->prof) CU(cudaEventRecord(ctx->ev[k], ctx->stream)); } while (0)
 static int fail(blsgpu_ctx* c, int code, const char* fmt, ...) {
     if (c) { va_list ap; va_start(ap, fmt); vsnprintf(c->err, sizeof c->err, fmt, ap); va_end(ap); }
@@ -481,6 +483,7 @@ int blsgpu_create(blsgpu_ctx** out, int device) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return BLSGPU_ERR_CUDA; }
     if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) return BLSGPU_ERR_CUDA; }
     if (device >= ndev) return BLSGPU_ERR_ARG;
+    dev_guard guard_;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BLSGPU_ERR_CUDA;
     if (prop.major != 10) return BLSGPU_ERR_CUDA;                         // sm_100a cubin only: no other device can run it
@@ -493,7 +496,7 @@ int blsgpu_create(blsgpu_ctx** out, int device) {
 }
 void blsgpu_destroy(blsgpu_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    dev_guard guard_; cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 16; i++) if (ctx->r1cs[i]) blsgpu_r1cs_free(ctx, i);
     for (int i = 0; i < 4; i++) if (ctx->wit[i]) blsgpu_witness_free(ctx, i);
@@ -508,25 +511,25 @@ void blsgpu_destroy(blsgpu_ctx* ctx) {
 const char* blsgpu_last_error(blsgpu_ctx* ctx) { return ctx ? ctx->err : "no context (no usable sm_100 CUDA device, or bad device ordinal)"; }
 int blsgpu_set_stream(blsgpu_ctx* ctx, void* s, int use_own) { if (!ctx) return BLSGPU_ERR_ARG; ctx->stream = use_own ? ctx->own_stream : (cudaStream_t)s; return 0; }
 int blsgpu_set_pointer_mode(blsgpu_ctx* ctx, int mode) { if (!ctx || (mode != BLSGPU_HOST && mode != BLSGPU_DEVICE)) return BLSGPU_ERR_ARG; ctx->ptr_mode = mode; return 0; }
-int blsgpu_synchronize(blsgpu_ctx* ctx) { if (!ctx) return BLSGPU_ERR_ARG; CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); return 0; }
+int blsgpu_synchronize(blsgpu_ctx* ctx) { if (!ctx) return BLSGPU_ERR_ARG; dev_guard guard_; CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); return 0; }
 uint64_t blsgpu_launch_count(blsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int blsgpu_set_coop(blsgpu_ctx* ctx, int on) { if (!ctx) return BLSGPU_ERR_ARG; ctx->coop = on ? 1 : 0; return 0; }
 int blsgpu_set_lanes(blsgpu_ctx* ctx, int lanes) { if (!ctx || lanes < 1 || lanes > 4) return BLSGPU_ERR_ARG; ctx->lanes = lanes; return 0; }
 int blsgpu_set_chunk(blsgpu_ctx* ctx, size_t items) { if (!ctx || items < 64 || (items & 63)) return BLSGPU_ERR_ARG; ctx->chunk = items; return 0; }
 int blsgpu_set_profiling(blsgpu_ctx* ctx, int on) {
     if (!ctx) return BLSGPU_ERR_ARG;
-    CU(cudaSetDevice(ctx->device));
+    dev_guard guard_; CU(cudaSetDevice(ctx->device));
     if (on && !ctx->ev[0]) for (int i = 0; i < 8; i++) CU(cudaEventCreate(&ctx->ev[i]));
     ctx->prof = on ? 1 : 0; return 0;
 }
 int blsgpu_stage_times(blsgpu_ctx* ctx, float* ms6) {
     if (!ctx || !ms6 || !ctx->ev[0]) return BLSGPU_ERR_ARG;
-    CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream));
+    dev_guard guard_; CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 6; i++) CU(cudaEventElapsedTime(&ms6[i], ctx->ev[i], ctx->ev[i + 1]));
     return 0;
 }
 
-#define ENTER() do { if (!ctx) return BLSGPU_ERR_ARG; CU(cudaSetDevice(ctx->device)); } while (0)
+#define ENTER() if (!ctx) return BLSGPU_ERR_ARG; dev_guard guard_; CU(cudaSetDevice(ctx->device))
 
 int blsgpu_fp_mul_raw(blsgpu_ctx* ctx, const uint8_t* a48, const uint8_t* b48, size_t n, uint8_t* out48, int reps) {
     ENTER(); if (!a48 || !b48 || !out48) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
@@ -763,8 +766,8 @@ int blsgpu_verify_batch_rlc(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t*
     uint8_t* dseed = ctx->rlc_acc + 1040; uint8_t* dok = ctx->rlc_acc + 1056;
     auto release = [&]() {};
     cudaMemcpyKind in_kind = ctx->ptr_mode == BLSGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    cudaMemcpyAsync(dseed, seed16, 16, in_kind, ctx->stream); cudaMemsetAsync(bad, 0, 4, ctx->stream);
-    k_gt_set_one<<<1, 32, 0, ctx->stream>>>(f_acc); k_g2_jac_set_identity<<<1, 32, 0, ctx->stream>>>(s_acc); ctx->launches += 2;
+    CU(cudaMemcpyAsync(dseed, seed16, 16, in_kind, ctx->stream)); CU(cudaMemsetAsync(bad, 0, 4, ctx->stream));
+    LAUNCH(k_gt_set_one, 1, 32, f_acc); LAUNCH(k_g2_jac_set_identity, 1, 32, s_acc);
     for (size_t base = 0; base < n && !rc; base += ctx->chunk) {
         size_t m = n - base < ctx->chunk ? n - base : ctx->chunk;
         size_t mb0 = msg_off ? (off_host ? off_host[base] : 0) : 32 * base;
@@ -957,7 +960,7 @@ int blsgpu_pool_create(blsgpu_ctx* ctx, const uint8_t* pks48, size_t n, int* han
 }
 int blsgpu_pool_free(blsgpu_ctx* ctx, int handle) {
     if (!ctx || handle < 0 || handle >= 16 || !ctx->pool[handle].soa) return BLSGPU_ERR_ARG;
-    cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+    dev_guard guard_; cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->pool[handle].soa); cudaFree(ctx->pool[handle].code); ctx->pool[handle].soa = nullptr; ctx->pool[handle].code = nullptr; ctx->pool[handle].n = 0; return 0;
 }
 int blsgpu_pool_fast_aggregate_verify(blsgpu_ctx* ctx, int handle, const uint32_t* idx, const uint64_t* bitmap, size_t k, const uint8_t* msg32, const uint8_t* sig96, size_t ncomm,

@@ -9,6 +9,10 @@
 // chain: 300 IMAD-pipe instructions per product (12*12 product + 12*12 reduction + 12 quotients) and ~70
 // ALU-pipe instructions.  Each carry chain is ONE asm statement, so the compiler cannot interleave chains.
 //
+// Lineage: the even/odd carry-save scheme and the helper shapes (cmad_n, madc_n_rshift, mad_n_redc) follow the public
+// mont_t.cuh of supranational/sppark (Apache-2.0), restated for 12 limbs with one asm statement per carry chain; the
+// reference itself (arkworks' MontBackend) has no GPU code.
+//
 // The same source builds for the host (g++, tests/hostemu) with plain-C fallbacks of every asm block, which
 // is how the algorithm layer above is debugged without a GPU.  The product library is nvcc-only.
 #pragma once

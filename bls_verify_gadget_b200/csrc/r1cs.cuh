@@ -31,6 +31,10 @@ struct r1cs_sys {
     uint32_t* long_row;            // [n_long] row index
     uint32_t* seg_ptr;             // [n_long * 3 + 1] first segment of (long row, matrix)
     uint64_t* seg_lo; uint64_t* seg_hi; uint8_t* seg_mat;     // [n_seg] non-zero range and matrix of a segment
+    // rows specialised at load time (see "row classes" below)
+    uint4* lut_a; uint2* lut_b;    // [nrows] truth-table rows: (col0 | need_b << 31, col1, col2, table) and (col3, col4); col0 = R1_NOT_LUT for other rows
+    uint32_t* gen_rows; size_t n_gen, n_lut;     // short rows that are evaluated term by term (lane = assignment)
+    uint32_t* fb_rows; uint32_t* fb_count;       // truth-table rows that met a non-0/1 column in the current group: evaluated generically afterwards
 };
 enum { R1_GENERAL = 0, R1_PLUS_ONE = 1, R1_MINUS_ONE = 2, R1_SMALL_POS = 3, R1_SMALL_NEG = 4 };      // SMALL: |c| < 2^32 (fp_mul_small), c = +|c| or p - |c|
 #define R1_GROUP 32
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(256) k_r1cs_transpose(const u32x4* z, size_t n
     for (int k = 0; k < (32 * R1_TT * 3) / 256; k++) {
         int i = threadIdx.x + 256 * k, w = i / (R1_TT * 3), j = i % (R1_TT * 3);
         bool live = (size_t)w < g && (size_t)j < ncol_here * 3;
-        tile[w][j] = live ? z[((w0 + w) * ncols + col0) * 3 + j] : zero;
+        tile[w][j] = live ? __ldcs(&z[((w0 + w) * ncols + col0) * 3 + j]) : zero;      // read once: evict-first, so the transposed copy of the non-0/1 columns stays in L2
     }
     __syncthreads();
 #pragma unroll
@@ -86,9 +90,11 @@ __global__ void __launch_bounds__(256) k_r1cs_transpose(const u32x4* z, size_t n
         int cl = warp + 8 * h; size_t col = col0 + cl;
         if ((size_t)cl >= ncol_here) break;
         u32x4 a = tile[lane][3 * cl], b = tile[lane][3 * cl + 1], c = tile[lane][3 * cl + 2];
-        zt[(col * 3) * 32 + lane] = a; zt[(col * 3 + 1) * 32 + lane] = b; zt[(col * 3 + 2) * 32 + lane] = c;
         bool small = a.x < 2 && !(a.y | a.z | a.w | b.x | b.y | b.z | b.w | c.x | c.y | c.z | c.w);
         bool all = __all_sync(0xffffffffu, small);
+        // a 0/1 column is only ever read through its packed word (every reader tests zbool[col].y first): its 1.5 KB of the transposed
+        // copy are not written -- 93 % of the verify circuit's columns, so the transpose writes 0.08 GB per group instead of 1.09 GB
+        if (!all) { zt[(col * 3) * 32 + lane] = a; zt[(col * 3 + 1) * 32 + lane] = b; zt[(col * 3 + 2) * 32 + lane] = c; }
         uint32_t pack = __ballot_sync(0xffffffffu, a.x & 1u);        // the column's 32 values as one word when they are all 0 / 1
         if (lane == 0) zbool[col] = make_uint2(all ? pack : 0u, all ? 1u : 0u);
     }
@@ -160,20 +166,88 @@ __device__ __forceinline__ bool r1cs_product_ok(const fp& a, const fp& b, const 
     fp ab = fp_mul(fp_to_mont(a), b);                             // (aR)(b)/R = ab, canonical
     return fp_eq(ab, c);
 }
-// one warp per block of R1_ROWS consecutive rows (a fraction of a 64-row word: finer blocks balance better and keep more
-// gathers in flight; the bits are OR-ed into the word, which the host zeroes first); lane = witness in the group.
-// Long rows are left to the segment kernels.  (A variant that fetched a row's metadata with one lane per non-zero and evaluated
-// it from register broadcasts was 12 % slower: the kernel is not bound by the CSR walk -- profiles/r01_tuning.md.)
-#ifndef R1_ROWS
-#define R1_ROWS 8
+
+// ---------------------------------------------------------------------------------------------------------------- row classes
+// blsgpu_r1cs_load sorts the rows into three classes ("specialise rows at load time instead of interpreting them"):
+//  * truth-table rows: at most R1_LUT_NNZ non-zeros on at most 5 distinct columns (column 0, the constant, counts).  When all of
+//    those columns are 0/1 in a group of 32 assignments -- booleanity rows a (1 - a) = 0, AND rows a b = c, XOR rows
+//    2a b = a + b - c, the SHA-256 ch / maj forms: 661,550 of the verify circuit's 714,250 rows -- satisfaction is a Boolean
+//    function of <= 5 bits.  Its 32-entry table is computed once at load time with exact field arithmetic (k_r1cs_lut_build);
+//    k_r1cs_lut then evaluates it BIT-SLICED with lane = row on the packed 32-assignment words: no field arithmetic, no CSR walk,
+//    ~40 logic instructions per row and 32 assignments.  A row that meets a column which is not 0/1 in this group is appended to a
+//    fallback list and evaluated generically, so the result is exact for every input.
+//  * long rows (more than R1_LONG non-zeros): segments + combine, as before.
+//  * the rest ("generic" short rows, mostly the field rows of the pairing part): one warp per row, lane = assignment.
+#define R1_NOT_LUT 0xffffffffu
+#define R1_NO_COL 0xffffffffu
+#ifndef R1_LUT_NNZ
+#define R1_LUT_NNZ 16
 #endif
-__global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_rows(r1cs_sys s, const u32x4* zt, const uint2* zbool, size_t w0, size_t g, size_t words, uint64_t* sat_bits) {
-    size_t blk = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
-    size_t r0 = blk * R1_ROWS; if (r0 >= s.nrows) return;
-    uint64_t bits = 0;
-    size_t r_end = r0 + R1_ROWS < s.nrows ? r0 + R1_ROWS : s.nrows;
-    for (size_t row = r0; row < r_end; row++) {
-        if (s.is_long[row]) continue;
+// table[idx] = "the row holds when column c_j has the value bit j of idx"; absent columns never match, so the table does not depend on their bits
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_r1cs_lut_build(r1cs_sys s, const uint32_t* rows, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    uint32_t row = rows[i];
+    uint4 A = s.lut_a[row]; uint2 B = s.lut_b[row];
+    uint32_t c[5] = {A.x & 0x7fffffffu, A.y, A.z, B.x, B.y};
+    uint32_t table = 0;
+    for (uint32_t idx = 0; idx < 32; idx++) {
+        fp v[3];
+        for (int m = 0; m < 3; m++) {
+            fp acc = fp_zero();
+            for (uint64_t k = s.rowptr[m][row]; k < s.rowptr[m][row + 1]; k++) {
+                uint32_t cj = s.col[m][k], bit = 0;
+                for (int j = 0; j < 5; j++) if (c[j] == cj) bit = (idx >> j) & 1u;
+                if (bit) acc = fp_add(acc, s.coeff[m][k]);                       // Montgomery images: (aR)(bR)/R = abR is compared with cR
+            }
+            v[m] = acc;
+        }
+        if (fp_eq(fp_mul(v[0], v[1]), v[2])) table |= 1u << idx;
+    }
+    A.w = table; s.lut_a[row] = A;
+}
+// bitwise (x ? b : a)
+__device__ __forceinline__ uint32_t r1cs_sel(uint32_t x, uint32_t a, uint32_t b) { return (x & b) | (~x & a); }
+__device__ __forceinline__ uint32_t r1cs_tbit(uint32_t T, int i) { return 0u - ((T >> i) & 1u); }
+// the 3-input / 5-input truth table T applied to 32 assignments at once (bit w of x_j = value of column j in assignment w)
+__device__ __forceinline__ uint32_t r1cs_lut3(uint32_t T, uint32_t x0, uint32_t x1, uint32_t x2) {
+    uint32_t m0 = r1cs_sel(x0, r1cs_tbit(T, 0), r1cs_tbit(T, 1)), m1 = r1cs_sel(x0, r1cs_tbit(T, 2), r1cs_tbit(T, 3));
+    uint32_t m2 = r1cs_sel(x0, r1cs_tbit(T, 4), r1cs_tbit(T, 5)), m3 = r1cs_sel(x0, r1cs_tbit(T, 6), r1cs_tbit(T, 7));
+    return r1cs_sel(x2, r1cs_sel(x1, m0, m1), r1cs_sel(x1, m2, m3));
+}
+__device__ __forceinline__ uint32_t r1cs_lut5(uint32_t T, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4) {
+    uint32_t q0 = r1cs_lut3(T, x0, x1, x2), q1 = r1cs_lut3(T >> 8, x0, x1, x2), q2 = r1cs_lut3(T >> 16, x0, x1, x2), q3 = r1cs_lut3(T >> 24, x0, x1, x2);
+    return r1cs_sel(x4, r1cs_sel(x3, q0, q1), r1cs_sel(x3, q2, q3));
+}
+// lane = row (32 consecutive rows per warp), the 32 assignments of the group in the bits of each word.  Writes -- plain stores, no
+// atomics -- the 32-bit half word of every assignment for these rows: this kernel runs first in a group and thereby also
+// initialises the output (rows of the other classes contribute 0 here and are OR-ed in by the later kernels).
+__global__ void __launch_bounds__(256) k_r1cs_lut(r1cs_sys s, const uint2* zbool, size_t w0, size_t g, size_t words, uint32_t* sat32) {
+    size_t row = blockIdx.x * (size_t)256 + threadIdx.x; int lane = threadIdx.x & 31;
+    uint32_t R = 0;
+    if (row < s.nrows) {
+        uint4 A = s.lut_a[row];
+        if (A.x != R1_NOT_LUT) {
+            uint2 z0 = zbool[A.x & 0x7fffffffu], z1 = make_uint2(0u, 1u), z2 = z1, z3 = z1, z4 = z1;
+            if (A.y != R1_NO_COL) z1 = zbool[A.y];
+            if (A.z != R1_NO_COL) z2 = zbool[A.z];
+            if (A.x >> 31) { uint2 B = s.lut_b[row]; z3 = zbool[B.x]; if (B.y != R1_NO_COL) z4 = zbool[B.y]; }
+            if (z0.y & z1.y & z2.y & z3.y & z4.y) R = (A.x >> 31) ? r1cs_lut5(A.w, z0.x, z1.x, z2.x, z3.x, z4.x) : r1cs_lut3(A.w, z0.x, z1.x, z2.x);
+            else s.fb_rows[atomicAdd(s.fb_count, 1u)] = (uint32_t)row;
+        }
+    }
+    uint32_t mine = 0;                                      // 32 x 32 bit transpose: lane w ends up with the 32 rows of assignment w
+#pragma unroll
+    for (int w = 0; w < 32; w++) { uint32_t m = __ballot_sync(0xffffffffu, (R >> w) & 1u); if (lane == w) mine = m; }
+    size_t half = row >> 5;                                 // warp-uniform
+    if ((size_t)lane < g && half < 2 * words) sat32[(w0 + lane) * 2 * words + half] = mine;
+}
+// one warp per listed row, lane = assignment: the generic evaluation (count_dev != NULL: the fallback list, whose length is on the device)
+__global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_rows_list(r1cs_sys s, const uint32_t* list, const uint32_t* count_dev, size_t count_host, const u32x4* zt, const uint2* zbool,
+                                                                  size_t w0, size_t g, size_t words, uint64_t* sat_bits) {
+    size_t warp = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5), nwarps = gridDim.x * (size_t)(TPB / 32); int lane = threadIdx.x & 31;
+    size_t n = count_dev ? (size_t)*count_dev : count_host;
+    for (size_t i = warp; i < n; i += nwarps) {
+        size_t row = list[i];
         int64_t sa, sb, sc; bool ta, tb, tc;
         fp a = r1cs_range_dot(s, 0, s.rowptr[0][row], s.rowptr[0][row + 1], zt, zbool, lane, sa, ta);
         fp b = r1cs_range_dot(s, 1, s.rowptr[1][row], s.rowptr[1][row + 1], zt, zbool, lane, sb, tb);
@@ -181,9 +255,8 @@ __global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_rows(r1cs_sys s, const u3
         bool ok;
         if (!(ta | tb | tc)) ok = (__int128)sa * (__int128)sb == (__int128)sc;      // only 0/1 columns with small coefficients: |a b - c| < 2^80 < p, so equality mod p is equality
         else ok = r1cs_product_ok(r1cs_finalize(a, sa, ta), r1cs_finalize(b, sb, tb), r1cs_finalize(c, sc, tc));
-        if (ok) bits |= 1ull << (row & 63);
+        if ((size_t)lane < g && ok) atomicOr((unsigned long long*)&sat_bits[(w0 + lane) * words + (row >> 6)], 1ull << (row & 63));
     }
-    if ((size_t)lane < g && bits) atomicOr((unsigned long long*)&sat_bits[(w0 + lane) * words + (r0 >> 6)], bits);
 }
 // one warp per segment of a long row: partial dot product of 32 witnesses -> part (limb-SoA over n_seg * 32 slots)
 __global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_segments(r1cs_sys s, const u32x4* zt, const uint2* zbool, u32x4* part) {
@@ -205,8 +278,8 @@ __global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_combine(r1cs_sys s, const
         v[m] = acc;
     }
     size_t row = s.long_row[li];
-    if ((size_t)lane < g && r1cs_product_ok(v[0], v[1], v[2]))
-        atomicOr((unsigned long long*)&sat_bits[(w0 + lane) * words + (row >> 6)], 1ull << (row & 63));
+    bool ok = r1cs_product_ok(v[0], v[1], v[2]);            // all 32 lanes take part in the vote inside; only the store is masked
+    if ((size_t)lane < g && ok) atomicOr((unsigned long long*)&sat_bits[(w0 + lane) * words + (row >> 6)], 1ull << (row & 63));
 }
 // one warp per assignment: AND over its bit words (coalesced), lane 0 writes the flag
 __global__ void __launch_bounds__(256) k_r1cs_all(const uint64_t* sat_bits, size_t nwit, size_t words, size_t nrows, uint8_t* all_sat) {
@@ -220,10 +293,92 @@ __global__ void __launch_bounds__(256) k_r1cs_all(const uint64_t* sat_bits, size
     if (lane == 0) all_sat[w] = all ? 1 : 0;
 }
 
+struct dev_tmp { void* p = nullptr; ~dev_tmp() { if (p) cudaFree(p); } };        // scratch device buffer released on every return path
 template <class T> static int r1cs_upload(blsgpu_ctx* ctx, T** dst, const std::vector<T>& v) {
     size_t n = v.size() ? v.size() : 1;
     CU(cudaMalloc(dst, n * sizeof(T)));
     if (v.size()) CU(cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+static void r1cs_release(r1cs_sys* s) {
+    for (int m = 0; m < 3; m++) { cudaFree(s->rowptr[m]); cudaFree(s->col[m]); cudaFree(s->coeff[m]); cudaFree(s->coeffc[m]); cudaFree(s->cls[m]); }
+    cudaFree(s->is_long); cudaFree(s->long_row); cudaFree(s->seg_ptr); cudaFree(s->seg_lo); cudaFree(s->seg_hi); cudaFree(s->seg_mat);
+    cudaFree(s->lut_a); cudaFree(s->lut_b); cudaFree(s->gen_rows); cudaFree(s->fb_rows); cudaFree(s->fb_count);
+    delete s;
+}
+// builds *s (zero-initialised by the caller, who releases it when this fails): uploads, coefficient classes, row classes, truth tables
+static int r1cs_build(blsgpu_ctx* ctx, r1cs_sys* s, const uint64_t* const rowptr[3], const uint32_t* const col[3], const uint8_t* const coeff48[3], size_t nrows, size_t ncols) {
+    s->nrows = nrows; s->ncols = ncols;
+    bool dev = ctx->ptr_mode == BLSGPU_DEVICE;
+    cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    std::vector<uint64_t> hrp[3]; std::vector<uint32_t> hcol_buf[3]; const uint32_t* hcol[3];      // host copies: the row classes are decided here
+    for (int m = 0; m < 3; m++) {
+        if (!rowptr[m]) return fail(ctx, BLSGPU_ERR_ARG, "null row pointer array");
+        hrp[m].resize(nrows + 1);
+        if (dev) { CU(cudaMemcpyAsync(hrp[m].data(), rowptr[m], 8 * (nrows + 1), cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream)); }
+        else memcpy(hrp[m].data(), rowptr[m], 8 * (nrows + 1));
+        if (hrp[m][0] != 0) return fail(ctx, BLSGPU_ERR_ARG, "rowptr[%d][0] must be 0", m);
+        for (size_t r = 0; r < nrows; r++) if (hrp[m][r + 1] < hrp[m][r]) return fail(ctx, BLSGPU_ERR_ARG, "rowptr[%d] is not monotone at row %zu", m, r);
+        size_t nnz = s->nnz[m] = hrp[m][nrows], na = nnz ? nnz : 1;
+        if (nnz && (!col[m] || !coeff48[m])) return fail(ctx, BLSGPU_ERR_ARG, "null column / coefficient array");
+        if (dev) { hcol_buf[m].resize(na); if (nnz) { CU(cudaMemcpyAsync(hcol_buf[m].data(), col[m], 4 * nnz, cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream)); } hcol[m] = hcol_buf[m].data(); }
+        else hcol[m] = col[m];
+        for (size_t k = 0; k < nnz; k++) if (hcol[m][k] >= ncols) return fail(ctx, BLSGPU_ERR_ARG, "matrix %d: column index %u of non-zero %zu is out of range (ncols = %zu)", m, hcol[m][k], k, ncols);
+        CU(cudaMalloc(&s->rowptr[m], 8 * (nrows + 1))); CU(cudaMalloc(&s->col[m], 4 * na)); CU(cudaMalloc(&s->coeff[m], 48 * na)); CU(cudaMalloc(&s->coeffc[m], 48 * na)); CU(cudaMalloc(&s->cls[m], na));
+        CU(cudaMemcpyAsync(s->rowptr[m], rowptr[m], 8 * (nrows + 1), kind, ctx->stream));
+        if (nnz) {
+            CU(cudaMemcpyAsync(s->col[m], col[m], 4 * nnz, kind, ctx->stream));
+            dev_tmp raw; CU(cudaMalloc(&raw.p, 48 * nnz));
+            CU(cudaMemcpyAsync(raw.p, coeff48[m], 48 * nnz, kind, ctx->stream));
+            LAUNCH(k_r1cs_prepare, nblk(nnz), TPB, (const uint8_t*)raw.p, nnz, s->coeff[m], s->coeffc[m], s->cls[m]);
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    // row classes: long rows with their segments, truth-table rows, generic short rows
+    std::vector<uint8_t> is_long(nrows, 0), seg_mat; std::vector<uint32_t> long_row, seg_ptr, gen_rows, lut_rows; std::vector<uint64_t> seg_lo, seg_hi;
+    std::vector<uint4> lut_a(nrows); std::vector<uint2> lut_b(nrows);
+    for (size_t r = 0; r < nrows; r++) {
+        lut_a[r] = make_uint4(R1_NOT_LUT, R1_NO_COL, R1_NO_COL, 0u); lut_b[r] = make_uint2(R1_NO_COL, R1_NO_COL);
+        size_t len = 0; for (int m = 0; m < 3; m++) len += hrp[m][r + 1] - hrp[m][r];
+        if (len > R1_LONG) {
+            is_long[r] = 1; long_row.push_back((uint32_t)r);
+            for (int m = 0; m < 3; m++) {
+                seg_ptr.push_back((uint32_t)seg_lo.size());
+                for (uint64_t k = hrp[m][r]; k < hrp[m][r + 1]; k += R1_SEG) { seg_lo.push_back(k); seg_hi.push_back(k + R1_SEG < hrp[m][r + 1] ? k + R1_SEG : hrp[m][r + 1]); seg_mat.push_back((uint8_t)m); }
+            }
+            continue;
+        }
+        uint32_t c[5]; int d = 0; bool fits = len <= R1_LUT_NNZ && ncols < 0x7fffffffu;
+        for (int m = 0; m < 3 && fits; m++)
+            for (uint64_t k = hrp[m][r]; k < hrp[m][r + 1] && fits; k++) {
+                uint32_t cj = hcol[m][k]; int j = 0; while (j < d && c[j] != cj) j++;
+                if (j == d) { if (d == 5) fits = false; else c[d++] = cj; }
+            }
+        if (fits && d > 0) {
+            lut_a[r] = make_uint4(c[0] | (d > 3 ? 0x80000000u : 0u), d > 1 ? c[1] : R1_NO_COL, d > 2 ? c[2] : R1_NO_COL, 0u);
+            lut_b[r] = make_uint2(d > 3 ? c[3] : R1_NO_COL, d > 4 ? c[4] : R1_NO_COL);
+            lut_rows.push_back((uint32_t)r);
+        } else gen_rows.push_back((uint32_t)r);
+    }
+    seg_ptr.push_back((uint32_t)seg_lo.size());
+    s->n_long = long_row.size(); s->n_seg = seg_lo.size(); s->n_gen = gen_rows.size(); s->n_lut = lut_rows.size();
+    if (int rc = r1cs_upload(ctx, &s->is_long, is_long)) return rc;
+    if (int rc = r1cs_upload(ctx, &s->long_row, long_row)) return rc;
+    if (int rc = r1cs_upload(ctx, &s->seg_ptr, seg_ptr)) return rc;
+    if (int rc = r1cs_upload(ctx, &s->seg_lo, seg_lo)) return rc;
+    if (int rc = r1cs_upload(ctx, &s->seg_hi, seg_hi)) return rc;
+    if (int rc = r1cs_upload(ctx, &s->seg_mat, seg_mat)) return rc;
+    if (int rc = r1cs_upload(ctx, &s->lut_a, lut_a)) return rc;
+    if (int rc = r1cs_upload(ctx, &s->lut_b, lut_b)) return rc;
+    if (int rc = r1cs_upload(ctx, &s->gen_rows, gen_rows)) return rc;
+    CU(cudaMalloc(&s->fb_rows, 4 * (lut_rows.size() ? lut_rows.size() : 1))); CU(cudaMalloc(&s->fb_count, 4));
+    if (!lut_rows.empty()) {
+        dev_tmp list; CU(cudaMalloc(&list.p, 4 * lut_rows.size()));
+        CU(cudaMemcpyAsync(list.p, lut_rows.data(), 4 * lut_rows.size(), cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(k_r1cs_lut_build, nblk(lut_rows.size()), TPB, *s, (const uint32_t*)list.p, lut_rows.size());
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -233,59 +388,31 @@ int blsgpu_r1cs_load(blsgpu_ctx* ctx, const uint64_t* const rowptr[3], const uin
     int h = -1; for (int i = 0; i < 16; i++) if (!ctx->r1cs[i]) { h = i; break; }
     if (h < 0) return fail(ctx, BLSGPU_ERR_ARG, "too many R1CS systems loaded");
     r1cs_sys* s = new (std::nothrow) r1cs_sys(); if (!s) return fail(ctx, BLSGPU_ERR_ALLOC, "out of host memory");
-    memset(s, 0, sizeof *s); s->nrows = nrows; s->ncols = ncols;
-    cudaMemcpyKind kind = ctx->ptr_mode == BLSGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    ctx->r1cs[h] = s;
-    std::vector<uint64_t> hrp[3];                                 // host copy of the row pointers: the long-row tables are built here
-    for (int m = 0; m < 3; m++) {
-        hrp[m].resize(nrows + 1);
-        if (ctx->ptr_mode == BLSGPU_DEVICE) { CU(cudaMemcpyAsync(hrp[m].data(), rowptr[m], 8 * (nrows + 1), cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream)); }
-        else memcpy(hrp[m].data(), rowptr[m], 8 * (nrows + 1));
-        size_t nnz = s->nnz[m] = hrp[m][nrows], na = nnz ? nnz : 1;
-        CU(cudaMalloc(&s->rowptr[m], 8 * (nrows + 1))); CU(cudaMalloc(&s->col[m], 4 * na)); CU(cudaMalloc(&s->coeff[m], 48 * na)); CU(cudaMalloc(&s->coeffc[m], 48 * na)); CU(cudaMalloc(&s->cls[m], na));
-        CU(cudaMemcpyAsync(s->rowptr[m], rowptr[m], 8 * (nrows + 1), kind, ctx->stream));
-        if (nnz) {
-            CU(cudaMemcpyAsync(s->col[m], col[m], 4 * nnz, kind, ctx->stream));
-            uint8_t* raw; CU(cudaMalloc(&raw, 48 * nnz));
-            CU(cudaMemcpyAsync(raw, coeff48[m], 48 * nnz, kind, ctx->stream));
-            LAUNCH(k_r1cs_prepare, nblk(nnz), TPB, (const uint8_t*)raw, nnz, s->coeff[m], s->coeffc[m], s->cls[m]);
-            CU(cudaStreamSynchronize(ctx->stream)); cudaFree(raw);
-        }
-    }
-    // long rows and their segments
-    std::vector<uint8_t> is_long(nrows, 0), seg_mat; std::vector<uint32_t> long_row, seg_ptr; std::vector<uint64_t> seg_lo, seg_hi;
-    for (size_t r = 0; r < nrows; r++) {
-        size_t len = 0; for (int m = 0; m < 3; m++) len += hrp[m][r + 1] - hrp[m][r];
-        if (len <= R1_LONG) continue;
-        is_long[r] = 1; long_row.push_back((uint32_t)r);
-        for (int m = 0; m < 3; m++) {
-            seg_ptr.push_back((uint32_t)seg_lo.size());
-            for (uint64_t k = hrp[m][r]; k < hrp[m][r + 1]; k += R1_SEG) { seg_lo.push_back(k); seg_hi.push_back(k + R1_SEG < hrp[m][r + 1] ? k + R1_SEG : hrp[m][r + 1]); seg_mat.push_back((uint8_t)m); }
-        }
-    }
-    seg_ptr.push_back((uint32_t)seg_lo.size());
-    s->n_long = long_row.size(); s->n_seg = seg_lo.size();
-    if (int rc = r1cs_upload(ctx, &s->is_long, is_long)) return rc;
-    if (int rc = r1cs_upload(ctx, &s->long_row, long_row)) return rc;
-    if (int rc = r1cs_upload(ctx, &s->seg_ptr, seg_ptr)) return rc;
-    if (int rc = r1cs_upload(ctx, &s->seg_lo, seg_lo)) return rc;
-    if (int rc = r1cs_upload(ctx, &s->seg_hi, seg_hi)) return rc;
-    if (int rc = r1cs_upload(ctx, &s->seg_mat, seg_mat)) return rc;
-    CU(cudaStreamSynchronize(ctx->stream));
-    *handle = h; return 0;
+    memset(s, 0, sizeof *s);
+    if (int rc = r1cs_build(ctx, s, rowptr, col, coeff48, nrows, ncols)) { cudaStreamSynchronize(ctx->stream); r1cs_release(s); return rc; }      // nothing half-built stays behind
+    ctx->r1cs[h] = s; *handle = h; return 0;
 }
 int blsgpu_r1cs_free(blsgpu_ctx* ctx, int handle) {
     if (!ctx || handle < 0 || handle >= 16 || !ctx->r1cs[handle]) return BLSGPU_ERR_ARG;
-    cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
-    r1cs_sys* s = ctx->r1cs[handle];
-    for (int m = 0; m < 3; m++) { cudaFree(s->rowptr[m]); cudaFree(s->col[m]); cudaFree(s->coeff[m]); cudaFree(s->coeffc[m]); cudaFree(s->cls[m]); }
-    cudaFree(s->is_long); cudaFree(s->long_row); cudaFree(s->seg_ptr); cudaFree(s->seg_lo); cudaFree(s->seg_hi); cudaFree(s->seg_mat);
-    delete s; ctx->r1cs[handle] = nullptr; return 0;
+    dev_guard guard_; cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+    r1cs_release(ctx->r1cs[handle]); ctx->r1cs[handle] = nullptr; return 0;
+}
+// rows per class of a loaded system: counts[0] truth-table rows, [1] generic short rows, [2] long rows, [3] segments of the long rows
+int blsgpu_r1cs_row_classes(blsgpu_ctx* ctx, int handle, uint64_t counts[4]) {
+    if (!ctx || handle < 0 || handle >= 16 || !ctx->r1cs[handle] || !counts) return BLSGPU_ERR_ARG;
+    const r1cs_sys* s = ctx->r1cs[handle]; counts[0] = s->n_lut; counts[1] = s->n_gen; counts[2] = s->n_long; counts[3] = s->n_seg; return 0;
 }
 }
-// rows, segments and combination of one group of <= 32 assignments given in the transposed layout (zt, zbool)
+// one group of <= 32 assignments given in the transposed layout (zt, zbool): truth-table rows first (plain stores: this initialises
+// the group's slice of the output), then the rows that fell back, the generic short rows, and the long rows' segments + combination
+#ifndef R1_FB_BLOCKS
+#define R1_FB_BLOCKS 592
+#endif
 static int r1cs_check_group(blsgpu_ctx* ctx, const r1cs_sys& s, const u32x4* zt, const uint2* zbool, u32x4* part, size_t w0, size_t g, size_t words, uint64_t* dbits) {
-    LAUNCH(k_r1cs_rows, nblk((s.nrows + R1_ROWS - 1) / R1_ROWS, TPB / 32), TPB, s, zt, zbool, w0, g, words, dbits);
+    CU(cudaMemsetAsync(s.fb_count, 0, 4, ctx->stream));
+    LAUNCH(k_r1cs_lut, nblk(words * 64, 256), 256, s, zbool, w0, g, words, (uint32_t*)dbits);
+    if (s.n_lut) LAUNCH(k_r1cs_rows_list, R1_FB_BLOCKS, TPB, s, (const uint32_t*)s.fb_rows, (const uint32_t*)s.fb_count, (size_t)0, zt, zbool, w0, g, words, dbits);
+    if (s.n_gen) LAUNCH(k_r1cs_rows_list, nblk(s.n_gen, TPB / 32), TPB, s, (const uint32_t*)s.gen_rows, (const uint32_t*)nullptr, s.n_gen, zt, zbool, w0, g, words, dbits);
     if (s.n_long) {
         LAUNCH(k_r1cs_segments, nblk(s.n_seg, TPB / 32), TPB, s, zt, zbool, part);
         LAUNCH(k_r1cs_combine, nblk(s.n_long, TPB / 32), TPB, s, (const u32x4*)part, w0, g, words, dbits);
@@ -308,7 +435,6 @@ int blsgpu_r1cs_check(blsgpu_ctx* ctx, int handle, const uint8_t* z48, size_t nw
     u32x4* part = ws_take<u32x4>(ctx, part_bytes / 16);
     uint64_t* dbits = host ? ws_take<uint64_t>(ctx, words * nwit) : sat_bits;
     uint8_t* dall = all_sat ? (host ? ws_take<uint8_t>(ctx, nwit) : all_sat) : nullptr;
-    CU(cudaMemsetAsync(dbits, 0, 8 * words * nwit, ctx->stream));
     for (size_t w0 = 0; w0 < nwit; w0 += R1_GROUP) {
         size_t g = nwit - w0 < R1_GROUP ? nwit - w0 : R1_GROUP;
         const u32x4* zsrc; size_t wbase;

@@ -30,9 +30,22 @@ __device__ __forceinline__ void wit_store(u32x4* zt, size_t col, int lane, const
     a.x = v.l[0]; a.y = v.l[1]; a.z = v.l[2]; a.w = v.l[3]; b.x = v.l[4]; b.y = v.l[5]; b.z = v.l[6]; b.w = v.l[7]; c.x = v.l[8]; c.y = v.l[9]; c.z = v.l[10]; c.w = v.l[11];
     zt[(col * 3) * 32 + lane] = a; zt[(col * 3 + 1) * 32 + lane] = b; zt[(col * 3 + 2) * 32 + lane] = c;
 }
-// value of linear combination `id` (0 = empty) on this lane's assignment, canonical
-__device__ __forceinline__ fp wit_lc_range(const wit_prog& p, uint64_t lo, uint64_t hi, const u32x4* zt, int lane) {
+// value of the combination with terms [lo, hi) on this lane's assignment, canonical.  zb (nullable) = the group's packed 0/1 view: a
+// column that an earlier level found to be 0/1 in all 32 assignments is read as ONE broadcast 8-byte load instead of a 1.5 KB gather and
+// its +-1 / small coefficients go to a 64-bit integer side sum -- the same term rule as the satisfaction kernels (r1cs_term), which is
+// what 93 % of the verify circuit's columns and most of the witness program's 4.0 M terms are.
+__device__ __forceinline__ fp wit_lc_range(const wit_prog& p, uint64_t lo, uint64_t hi, const u32x4* zt, const uint2* zb, int lane) {
     fp acc = fp_zero();
+    if (zb) {
+        r1cs_sys view; view.coeff[0] = p.coeff; view.coeffc[0] = p.coeffc;
+        int64_t side = 0; bool touched = false;
+        for (uint64_t k = lo, e = hi; k < e; k++) {
+            uint32_t cj = p.col[k]; uint8_t c = p.cls[k]; uint2 f = zb[cj];
+            uint32_t cf = (c == R1_SMALL_POS || c == R1_SMALL_NEG) ? p.coeffc[k].l[0] : 0u;
+            r1cs_term(view, 0, k, cj, c, f, cf, zt, lane, acc, side, touched);
+        }
+        return r1cs_finalize(acc, side, touched);
+    }
     for (uint64_t k = lo, e = hi; k < e; k++) {
         uint32_t cj = p.col[k]; uint8_t c = p.cls[k];
         fp zv = r1cs_load_z(zt, cj, lane);
@@ -48,9 +61,9 @@ __device__ __forceinline__ fp wit_lc_range(const wit_prog& p, uint64_t lo, uint6
     }
     return acc;
 }
-__device__ __forceinline__ fp wit_lc(const wit_prog& p, uint32_t id, const u32x4* zt, int lane) {
+__device__ __forceinline__ fp wit_lc(const wit_prog& p, uint32_t id, const u32x4* zt, const uint2* zb, int lane) {
     if (!id) return fp_zero();
-    return wit_lc_range(p, p.lc_ptr[id - 1], p.lc_ptr[id], zt, lane);
+    return wit_lc_range(p, p.lc_ptr[id - 1], p.lc_ptr[id], zt, zb, lane);
 }
 __device__ __forceinline__ fp wit_inv_canon(const fp& a) { return fp_inv_raw(a); }                 // canonical in and out: the divsteps inverse needs no Montgomery factor
 // a b for canonical a, b: small-integer shortcut as in r1cs_product_ok
@@ -78,22 +91,22 @@ __global__ void __launch_bounds__(32) k_witness_gen(wit_prog p, const fp* inputs
         fp out;
         switch (r.kind) {
             case WR_MULADD: {
-                fp d = wit_lc(p, r.d, zt, lane);
-                if (r.a) { fp a = wit_lc(p, r.a, zt, lane), b = wit_lc(p, r.b, zt, lane); out = fp_add(wit_mul_canon(a, b), d); }
+                fp d = wit_lc(p, r.d, zt, nullptr, lane);
+                if (r.a) { fp a = wit_lc(p, r.a, zt, nullptr, lane), b = wit_lc(p, r.b, zt, nullptr, lane); out = fp_add(wit_mul_canon(a, b), d); }
                 else out = d;
                 break;
             }
-            case WR_INV: out = wit_inv_canon(wit_lc(p, r.a, zt, lane)); break;
-            case WR_NEQ: { fp a = wit_lc(p, r.a, zt, lane); out = fp_zero(); out.l[0] = fp_is_zero(a) ? 0u : 1u; break; }
-            case WR_NEQMULT: { fp a = wit_lc(p, r.a, zt, lane); out = fp_is_zero(a) ? one : wit_inv_canon(a); break; }
-            case WR_BIT: { fp a = wit_lc(p, r.a, zt, lane); out = fp_zero(); out.l[0] = (a.l[r.aux >> 5] >> (r.aux & 31)) & 1u; break; }
+            case WR_INV: out = wit_inv_canon(wit_lc(p, r.a, zt, nullptr, lane)); break;
+            case WR_NEQ: { fp a = wit_lc(p, r.a, zt, nullptr, lane); out = fp_zero(); out.l[0] = fp_is_zero(a) ? 0u : 1u; break; }
+            case WR_NEQMULT: { fp a = wit_lc(p, r.a, zt, nullptr, lane); out = fp_is_zero(a) ? one : wit_inv_canon(a); break; }
+            case WR_BIT: { fp a = wit_lc(p, r.a, zt, nullptr, lane); out = fp_zero(); out.l[0] = (a.l[r.aux >> 5] >> (r.aux & 31)) & 1u; break; }
             case WR_FP2INV: {
-                fp2 x; x.c0 = fp_to_mont(wit_lc(p, r.a, zt, lane)); x.c1 = fp_to_mont(wit_lc(p, r.b, zt, lane));
+                fp2 x; x.c0 = fp_to_mont(wit_lc(p, r.a, zt, nullptr, lane)); x.c1 = fp_to_mont(wit_lc(p, r.b, zt, nullptr, lane));
                 fp2 iv = fp2_inv(x); out = fp_from_mont(r.aux ? iv.c1 : iv.c0); break;
             }
             case WR_FP12INV: {
                 fp12 x, iv; fp* xf = &x.c0.c0.c0;
-                for (int k = 0; k < 12; k++) xf[k] = fp_to_mont(wit_lc(p, r.a + k, zt, lane));
+                for (int k = 0; k < 12; k++) xf[k] = fp_to_mont(wit_lc(p, r.a + k, zt, nullptr, lane));
                 fp12_inv(iv, x); out = fp_from_mont((&iv.c0.c0.c0)[r.aux]); break;
             }
             default: out = inputs[(size_t)r.aux * nwit_padded + w]; break;                 // WR_INPUT
@@ -118,34 +131,35 @@ __global__ void __launch_bounds__(WIT_TPB, WIT_BPS) k_witness_levels(wit_prog p,
         uint64_t lo = p.level_ptr[level], n = p.level_ptr[level + 1] - lo;
         for (size_t t = warp; t < n * groups; t += nwarps) {
             wit_xrule r = p.xrules[lo + t / groups]; size_t group = t % groups;
-            u32x4* zt = zt_all + group * p.nvars * 96;
+            u32x4* zt = zt_all + group * p.nvars * 96; const uint2* zb = zbool_all ? zbool_all + group * p.nvars : nullptr;
             fp out;
             switch (r.kind) {
                 case WR_MULADD: {
-                    fp d = wit_lc_range(p, r.d_lo, r.d_hi, zt, lane);
-                    if (r.a_hi > r.a_lo) { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, lane), b = wit_lc_range(p, r.b_lo, r.b_hi, zt, lane); out = fp_add(wit_mul_canon(a, b), d); }
+                    fp d = wit_lc_range(p, r.d_lo, r.d_hi, zt, zb, lane);
+                    if (r.a_hi > r.a_lo) { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, zb, lane), b = wit_lc_range(p, r.b_lo, r.b_hi, zt, zb, lane); out = fp_add(wit_mul_canon(a, b), d); }
                     else out = d;
                     break;
                 }
-                case WR_INV: out = wit_inv_canon(wit_lc_range(p, r.a_lo, r.a_hi, zt, lane)); break;
-                case WR_NEQ: { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, lane); out = fp_zero(); out.l[0] = fp_is_zero(a) ? 0u : 1u; break; }
-                case WR_NEQMULT: { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, lane); out = fp_is_zero(a) ? one : wit_inv_canon(a); break; }
-                case WR_BIT: { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, lane); out = fp_zero(); out.l[0] = (a.l[r.aux >> 5] >> (r.aux & 31)) & 1u; break; }
+                case WR_INV: out = wit_inv_canon(wit_lc_range(p, r.a_lo, r.a_hi, zt, zb, lane)); break;
+                case WR_NEQ: { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, zb, lane); out = fp_zero(); out.l[0] = fp_is_zero(a) ? 0u : 1u; break; }
+                case WR_NEQMULT: { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, zb, lane); out = fp_is_zero(a) ? one : wit_inv_canon(a); break; }
+                case WR_BIT: { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, zb, lane); out = fp_zero(); out.l[0] = (a.l[r.aux >> 5] >> (r.aux & 31)) & 1u; break; }
                 case WR_FP2INV: {
-                    fp2 x; x.c0 = fp_to_mont(wit_lc_range(p, r.a_lo, r.a_hi, zt, lane)); x.c1 = fp_to_mont(wit_lc_range(p, r.b_lo, r.b_hi, zt, lane));
+                    fp2 x; x.c0 = fp_to_mont(wit_lc_range(p, r.a_lo, r.a_hi, zt, zb, lane)); x.c1 = fp_to_mont(wit_lc_range(p, r.b_lo, r.b_hi, zt, zb, lane));
                     fp2 iv = fp2_inv(x); out = fp_from_mont(r.aux ? iv.c1 : iv.c0); break;
                 }
                 case WR_FP12INV: {
                     fp12 x, iv; fp* xf = &x.c0.c0.c0;
-                    for (int k = 0; k < 12; k++) xf[k] = fp_to_mont(wit_lc(p, r.a_lo + k, zt, lane));
+                    for (int k = 0; k < 12; k++) xf[k] = fp_to_mont(wit_lc(p, r.a_lo + k, zt, zb, lane));
                     fp12_inv(iv, x); out = fp_from_mont((&iv.c0.c0.c0)[r.aux]); break;
                 }
                 default: out = r.aux == 0xffff ? one : inputs[(size_t)r.aux * nwit_padded + group * 32 + lane]; break;       // WR_INPUT; 0xffff: the constant ONE (variable 0)
             }
-            wit_store(zt, r.var, lane, out);
-            if (zbool_all) {                                  // the packed 0/1 view the satisfaction kernels read (r1cs.cuh: k_r1cs_transpose writes the same)
+            if (!zbool_all) wit_store(zt, r.var, lane, out);
+            else {                                  // the packed 0/1 view the satisfaction kernels read (r1cs.cuh: k_r1cs_transpose writes the same)
                 bool small = out.l[0] < 2 && !(out.l[1] | out.l[2] | out.l[3] | out.l[4] | out.l[5] | out.l[6] | out.l[7] | out.l[8] | out.l[9] | out.l[10] | out.l[11]);
                 bool all = __all_sync(0xffffffffu, small); uint32_t pack = __ballot_sync(0xffffffffu, out.l[0] & 1u);
+                if (!all) wit_store(zt, r.var, lane, out);           // a 0/1 column lives in its packed word only (every reader tests the flag first)
                 if (lane == 0) zbool_all[group * p.nvars + r.var] = make_uint2(all ? pack : 0u, all ? 1u : 0u);
             }
         }
@@ -178,7 +192,11 @@ __global__ void __launch_bounds__(256) k_witness_untranspose(const u32x4* zt_all
     dst[0] = zt[(col * 3) * 32 + lane]; dst[1] = zt[(col * 3 + 1) * 32 + lane]; dst[2] = zt[(col * 3 + 2) * 32 + lane];
 }
 
-struct wit_prog_host { wit_prog d; };
+static void wit_release(wit_prog* p) {
+    cudaFree(p->rules); cudaFree(p->lc_ptr); cudaFree(p->col); cudaFree(p->coeff); cudaFree(p->coeffc); cudaFree(p->cls);
+    cudaFree(p->xrules); cudaFree(p->level_ptr);
+    delete p;
+}
 
 extern "C" {
 int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t* lc_ptr, const uint32_t* lc_col, const uint8_t* lc_coef48, size_t nvars, size_t nout, size_t nlc, size_t nterms,
@@ -188,7 +206,8 @@ int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t*
     int h = -1; for (int i = 0; i < 4; i++) if (!ctx->wit[i]) { h = i; break; }
     if (h < 0) return fail(ctx, BLSGPU_ERR_ARG, "too many witness programs loaded");
     wit_prog* p = new (std::nothrow) wit_prog(); if (!p) return fail(ctx, BLSGPU_ERR_ALLOC, "out of host memory");
-    memset(p, 0, sizeof *p); p->nvars = nvars; p->nout = nout; p->nlc = nlc; p->nterms = nterms; ctx->wit[h] = p;
+    memset(p, 0, sizeof *p); p->nvars = nvars; p->nout = nout; p->nlc = nlc; p->nterms = nterms;
+    struct guard_t { wit_prog* p; ~guard_t() { if (p) wit_release(p); } } undo{p};          // a failed load leaves nothing behind
     cudaMemcpyKind kind = ctx->ptr_mode == BLSGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     size_t nt = nterms ? nterms : 1;
     CU(cudaMalloc(&p->rules, 16 * nvars)); CU(cudaMalloc(&p->lc_ptr, 8 * (nlc + 1))); CU(cudaMalloc(&p->col, 4 * nt));
@@ -196,10 +215,10 @@ int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t*
     CU(cudaMemcpyAsync(p->rules, rules16, 16 * nvars, kind, ctx->stream)); CU(cudaMemcpyAsync(p->lc_ptr, lc_ptr, 8 * (nlc + 1), kind, ctx->stream));
     if (nterms) {
         CU(cudaMemcpyAsync(p->col, lc_col, 4 * nterms, kind, ctx->stream));
-        uint8_t* raw; CU(cudaMalloc(&raw, 48 * nterms));
-        CU(cudaMemcpyAsync(raw, lc_coef48, 48 * nterms, kind, ctx->stream));
-        LAUNCH(k_r1cs_prepare, nblk(nterms), TPB, (const uint8_t*)raw, nterms, p->coeff, p->coeffc, p->cls);
-        CU(cudaStreamSynchronize(ctx->stream)); cudaFree(raw);
+        dev_tmp raw; CU(cudaMalloc(&raw.p, 48 * nterms));
+        CU(cudaMemcpyAsync(raw.p, lc_coef48, 48 * nterms, kind, ctx->stream));
+        LAUNCH(k_r1cs_prepare, nblk(nterms), TPB, (const uint8_t*)raw.p, nterms, p->coeff, p->coeffc, p->cls);
+        CU(cudaStreamSynchronize(ctx->stream));
     }
     if (order && level_ptr && nlevels) {                   // level-ordered rules with resolved term ranges
         const wit_rule* hr = reinterpret_cast<const wit_rule*>(rules16);
@@ -218,15 +237,12 @@ int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t*
         CU(cudaStreamSynchronize(ctx->stream));
     }
     CU(cudaStreamSynchronize(ctx->stream));
-    *handle = h; return 0;
+    undo.p = nullptr; ctx->wit[h] = p; *handle = h; return 0;
 }
 int blsgpu_witness_free(blsgpu_ctx* ctx, int handle) {
     if (!ctx || handle < 0 || handle >= 4 || !ctx->wit[handle]) return BLSGPU_ERR_ARG;
-    cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
-    wit_prog* p = ctx->wit[handle];
-    cudaFree(p->rules); cudaFree(p->lc_ptr); cudaFree(p->col); cudaFree(p->coeff); cudaFree(p->coeffc); cudaFree(p->cls);
-    if (p->xrules) cudaFree(p->xrules); if (p->level_ptr) cudaFree(p->level_ptr);
-    delete p; ctx->wit[handle] = nullptr; return 0;
+    dev_guard guard_; cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+    wit_release(ctx->wit[handle]); ctx->wit[handle] = nullptr; return 0;
 }
 }
 // decode, input slots and the level-synchronous replay for nwit triples: leaves the assignments in the transposed group layout

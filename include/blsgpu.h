@@ -16,6 +16,10 @@
  *    compressed big-endian with flag bits (src/bls.rs:219-260, 316-357), secret key = 32-byte little-endian
  *    canonical Fr (src/bls.rs:79-121), GT = 12 x 48-byte little-endian canonical in tower order
  *    c0.c0.c0 ... c1.c2.c1 (ark-serialize of Fp12).
+ *  - Host mode copies with cudaMemcpyAsync straight from / to the caller's buffers: pageable memory works (the runtime stages it, the
+ *    copy then is synchronous and slower); PINNED buffers (cudaHostAlloc / cudaHostRegister) give the PCIe rate and are what
+ *    bench.py's e2e figure uses.
+ *  - Every call runs on the context's device and restores the caller's current CUDA device before it returns.
  *  - One context per GPU per process; a context may be used by one host thread at a time.
  *  - There is no CPU fallback: every function fails with BLSGPU_ERR_CUDA if no sm_100 device is usable.
  */
@@ -152,6 +156,9 @@ int blsgpu_r1cs_load(blsgpu_ctx* ctx, const uint64_t* const rowptr[3], const uin
                      size_t nrows, size_t ncols, int* handle);
 int blsgpu_r1cs_check(blsgpu_ctx* ctx, int handle, const uint8_t* z48, size_t nwit, uint64_t* sat_bits, uint8_t* all_sat);
 int blsgpu_r1cs_free(blsgpu_ctx* ctx, int handle);
+/* how blsgpu_r1cs_load classified the rows: counts[0] truth-table rows (<= 16 non-zeros on <= 5 distinct columns: evaluated bit-sliced over
+ * 32 assignments when those columns are 0/1, generically otherwise), [1] generic short rows, [2] long rows, [3] their 32-entry segments */
+int blsgpu_r1cs_row_classes(blsgpu_ctx* ctx, int handle, uint64_t counts[4]);
 
 /* ---- GPU witness generation for the verify circuit (no counterpart in the reference, whose assignments come from
  *      running the gadget code of src/constraints.rs:335-370 under ark-relations) -------------------------------------------------

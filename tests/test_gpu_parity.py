@@ -323,6 +323,72 @@ def test_r1cs_coefficient_classes_and_packed_columns(ctx, C):
     unsat = {(w, r) for w in range(nwit) for r in range(nrows) if not (int(bits[w, r // 64]) >> (r % 64)) & 1}
     assert unsat == set(bad)
 
+def test_r1cs_row_classes(ctx, C):
+    """One test per row class of blsgpu_r1cs_load (truth-table rows evaluated bit-sliced, their generic fallback, generic short rows,
+    long rows): the Boolean gate forms of ark-r1cs-std -- booleanity a(1-a)=0, AND a b = c, XOR 2a b = a + b - c, OR (1-a)(1-b) = 1-c,
+    NOT through the constant column, a conditional select on five columns, a constant row -- with every input combination present in
+    the 70 assignments, deliberately wrong outputs, and columns that stop being 0/1 in the second / third group only."""
+    rng = np.random.default_rng(41); nwit = 70; nb = 12
+    ONE = 0; cols = {"b": list(range(1, 1 + nb))}; nextc = [1 + nb]; rows = []; outs = []
+    def newcol(): nextc[0] += 1; return nextc[0] - 1
+    M = P - 1
+    for i in range(nb): rows.append(([(cols["b"][i], 1)], [(ONE, 1), (cols["b"][i], M)], []))                      # booleanity
+    for i in range(10):
+        a, b = cols["b"][i], cols["b"][(i + 3) % nb]
+        c = newcol(); rows.append(([(a, 1)], [(b, 1)], [(c, 1)])); outs.append((c, "and", (a, b)))                   # AND
+        c = newcol(); rows.append(([(a, 2)], [(b, 1)], [(a, 1), (b, 1), (c, M)])); outs.append((c, "xor", (a, b)))    # XOR
+        c = newcol(); rows.append(([(ONE, 1), (a, M)], [(ONE, 1), (b, M)], [(ONE, 1), (c, M)])); outs.append((c, "or", (a, b)))   # OR
+        s, d = cols["b"][(i + 5) % nb], newcol()                                                                      # select: s (a - b) = d - b on five columns with the constant
+        rows.append(([(s, 1)], [(a, 1), (b, M)], [(d, 1), (b, M), (ONE, 0)])); outs.append((d, "sel", (s, a, b)))
+    rows.append(([(ONE, 3)], [(ONE, 5)], [(ONE, 15)]))                                                                # constant row (satisfied), one column
+    rows.append(([(ONE, 3)], [(ONE, 5)], [(ONE, 16)]))                                                                # constant row (never satisfied)
+    fa, fb = newcol(), newcol(); fc = newcol(); rows.append(([(fa, 1)], [(fb, 1)], [(fc, 1)]))                        # a field product on three columns: truth-table shape, always falls back
+    wide = [newcol() for _ in range(7)]; wc = newcol(); rows.append(([(c, 1 + k) for k, c in enumerate(wide)], [(ONE, 1)], [(wc, 1)]))      # 9 distinct columns: generic short row
+    ncols = nextc[0]; nrows = len(rows)
+    z = np.zeros((nwit, ncols), dtype=object); z[:, 0] = 1; z[:, 1:1 + nb] = rng.integers(0, 2, size=(nwit, nb))
+    fn = {"and": lambda a, b: a & b, "xor": lambda a, b: a ^ b, "or": lambda a, b: a | b, "sel": lambda s, a, b: a if s else b}
+    for w in range(nwit):
+        for c, k, ins in outs: z[w, c] = fn[k](*[int(z[w, i]) for i in ins])
+        z[w, fa] = int.from_bytes(rng.bytes(48), "little") % P; z[w, fb] = int.from_bytes(rng.bytes(48), "little") % P; z[w, fc] = z[w, fa] * z[w, fb] % P
+        for c in wide: z[w, c] = int(rng.integers(0, 2)) if w < 32 else int.from_bytes(rng.bytes(48), "little") % P
+        z[w, wc] = sum((1 + k) * z[w, c] for k, c in enumerate(wide)) % P
+    flips = [(2, outs[0][0]), (31, outs[5][0]), (33, outs[9][0]), (64, outs[39][0]), (69, outs[17][0])]              # wrong gate outputs (still 0/1)
+    for w, c in flips: z[w, c] ^= 1
+    z[40, cols["b"][2]] = 2; z[66, outs[3][0]] = P - 1; z[5, fc] = (z[5, fc] + 1) % P                                 # non-0/1 values: second and third group only
+    def csr(m):
+        rp = [0]; cl = []; cf = []
+        for row in rows:
+            for c, v in row[m]: cl.append(c); cf.append(int(v).to_bytes(48, "little"))
+            rp.append(len(cl))
+        return np.array(rp, np.uint64), np.array(cl, np.uint32), np.frombuffer(b"".join(cf) + b"\0", np.uint8)[:48 * len(cl)]
+    mats = [csr(m) for m in range(3)]
+    zb = np.frombuffer(b"".join(int(v).to_bytes(48, "little") for v in z.reshape(-1)), np.uint8)
+    h = ctx.r1cs_load([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], nrows, ncols)
+    cls = ctx.r1cs_row_classes(h)
+    assert cls == {"truth_table": nrows - 1, "generic": 1, "long": 0, "segments": 0}
+    bits, allsat = ctx.r1cs_check(h, zb, nwit, nrows); ctx.r1cs_free(h)
+    obits, oall = C.r1cs_check([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], nrows, ncols, zb, nwit, threads=4)
+    assert np.array_equal(bits, obits) and list(allsat) == list(oall)
+    sat = lambda w, r: (int(bits[w, r // 64]) >> (r % 64)) & 1
+    # independent expectation: the planted flips break exactly the rows whose gate they belong to, in their assignment only
+    for w in range(nwit):
+        for r, (A, B, Cc) in enumerate(rows):
+            ev = lambda lc: sum(cf * int(z[w, c]) for c, cf in lc) % P
+            assert sat(w, r) == int(ev(A) * ev(B) % P == ev(Cc)), (w, r)
+    assert not allsat.any()                                                                                         # the unsatisfiable constant row
+
+def test_r1cs_load_rejects_bad_systems(ctx):
+    """a column index out of range or a non-monotone row pointer is an argument error and leaves no half-built system behind (all 16 handles stay usable)"""
+    from bls_verify_gadget_b200._lib import BlsGpuError
+    one = (1).to_bytes(48, "little")
+    rp = np.array([0, 1, 2], np.uint64); cf = np.frombuffer(one * 2, np.uint8)
+    for _ in range(20):
+        with pytest.raises(BlsGpuError): ctx.r1cs_load([rp] * 3, [np.array([0, 7], np.uint32)] * 3, [cf] * 3, 2, 3)
+    with pytest.raises(BlsGpuError): ctx.r1cs_load([np.array([0, 2, 1], np.uint64)] * 3, [np.array([0, 1], np.uint32)] * 3, [cf] * 3, 2, 3)
+    hs = [ctx.r1cs_load([rp] * 3, [np.array([0, 1], np.uint32)] * 3, [cf] * 3, 2, 3) for _ in range(16)]
+    assert sorted(hs) == list(range(16))
+    for h in hs: ctx.r1cs_free(h)
+
 def test_r1cs_verify_circuit_on_gpu(ctx, C):
     """K8 on the REAL system: the matrices and assignments of BlsSignatureVerifyGadget::verify (constraints.rs:90-128) built
     by the host-side builder (714 k rows).  Assignments of a valid and an invalid signature are both satisfying (the gadget
