@@ -9,51 +9,47 @@ assignments, resident in HBM (`value`).  `e2e` is the whole pipeline a caller ru
 H2D -> blsgpu_witness_check (the builder's witness program replayed on the device, then the satisfaction kernels on the same
 transposed buffers) -> per-assignment flags back on the host; no assignment ever crosses PCIe or is copied row-major.
 
-  python bench_r1cs.py [--gpus N] [--steps K] [--warmup W] [--per-gpu 512] [--distinct 16]
+  python bench_r1cs.py [--gpus N] [--steps K] [--warmup W] [--per-gpu 512]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench_r1cs.py --gpus N
 """
 import argparse, json, os, sys, time
 ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
 import numpy as np
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=3); ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--per-gpu", type=int, default=512); ap.add_argument("--distinct", type=int, default=16, help="distinct (pk, msg, sig) assignments synthesised per rank")
-    ap.add_argument("--no-cpu", action="store_true")
-    args = ap.parse_args(); args.warmup = max(args.warmup, 3)
+def run(ctx, dev, stream, world, rank, steps=3, warmup=3, per_gpu=512, cpu=True):
+    """One rank's share of BASELINE configs[4]; returns the JSON-able result dict on rank 0 (None elsewhere).  Every one of the rank's
+    `per_gpu` assignments is DISTINCT: they are generated on the GPU (blsgpu_witness_gen) from per_gpu different (pk, msg, sig)
+    triples, so the data-dependent shortcuts of the kernels (packed 0/1 columns, integer-only rows) see real variety."""
     import torch, torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local); dev = torch.device("cuda", local)
-    if world > 1: dist.init_process_group("nccl", device_id=dev)
-    from bls_verify_gadget_b200 import Context, synth, gadget as G
+    from bls_verify_gadget_b200 import synth, gadget as G
     from bls_verify_gadget_b200.dist import witness_shard, gather_flags
-    ctx = Context(local); stream = torch.cuda.current_stream(dev); ctx.set_stream(stream.cuda_stream)
-    nwit_total = args.per_gpu * world; lo, hi = witness_shard(nwit_total, world, rank); nwit = hi - lo
-    # ---- distinct assignments of this rank (untimed): keys / signatures from the library's own kernels, assignments from the host builder
-    nb = max(2, min(args.distinct, nwit))
-    pk, msg, sig, exp = synth.verify_batch_inputs(ctx, nb * world, every=4, fast=False)
-    triples = []
-    for k in range(nb):
-        i = rank * nb + k; j = i if exp[i] in (0, 1) else rank * nb           # undecodable corruptions fall back to a valid point pair (wrong message)
-        triples.append((pk[48 * j:48 * j + 48].tobytes(), msg[32 * i:32 * i + 32].tobytes(), sig[96 * j:96 * j + 96].tobytes()))
-    c = G.verify_circuit(*triples[0]); mats = c.matrices(); nrows, ncols, nnz = c.nrows, c.ncols, sum(c.nnz); c.free()
-    threads = max(1, (os.cpu_count() or 1) // world)
-    t0 = time.perf_counter(); zb, res = G.verify_witnesses(triples, threads=threads, ncols=ncols); t_syn = time.perf_counter() - t0
+    nwit_total = per_gpu * world; lo, hi = witness_shard(nwit_total, world, rank); nwit = hi - lo
     ctx.set_pointer_mode(False)
-    h = ctx.r1cs_load([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], nrows, ncols)
-    dz = torch.from_numpy(zb).to(dev).repeat((nwit + nb - 1) // nb, 1)[:nwit].contiguous()
+    epk, emsg, esig, eexp = synth.verify_batch_inputs(ctx, nwit_total, every=16)
+    sl = slice(lo, hi)
+    epk, emsg, esig, eexp = epk.reshape(-1, 48)[sl].copy(), emsg.reshape(-1, 32)[sl].copy(), esig.reshape(-1, 96)[sl].copy(), eexp[sl].copy()
+    # resident leg: undecodable corruptions (status 2 / 3 have no assignment) are replaced by the rank's first valid pair, which with the
+    # item's own message is a wrong-message triple -- still a satisfying assignment (the gadget RETURNS a Boolean)
+    rpk, rsig = epk.copy(), esig.copy(); good = int(np.nonzero(eexp <= 1)[0][0])
+    for i in np.nonzero(eexp > 1)[0]: rpk[i] = epk[good]; rsig[i] = esig[good]
+    t0 = time.perf_counter()
+    c = G.verify_circuit(rpk[0].tobytes(), emsg[0].tobytes(), rsig[0].tobytes()); mats = c.matrices(); nrows, ncols, nnz = c.nrows, c.ncols, sum(c.nnz); c.free()
+    prog = G.verify_program(rpk[0].tobytes(), emsg[0].tobytes(), rsig[0].tobytes()); t_host = time.perf_counter() - t0
+    h = ctx.r1cs_load([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], nrows, ncols); wh = ctx.witness_load(prog)
+    classes = ctx.r1cs_row_classes(h)
+    d_rpk, d_msg, d_rsig = (torch.from_numpy(x.reshape(-1)).to(dev) for x in (rpk, emsg, rsig))
+    dz = torch.empty(nwit * ncols * 48, dtype=torch.uint8, device=dev); gst = torch.empty(nwit, dtype=torch.uint8, device=dev)
+    ctx.set_pointer_mode(True)
+    ctx.witness_gen_ptr(wh, d_rpk.data_ptr(), d_msg.data_ptr(), d_rsig.data_ptr(), nwit, dz.data_ptr(), gst.data_ptr()); torch.cuda.synchronize(dev)
+    assert int(gst.sum().item()) == 0, "a resident triple did not decode"
+    dz2 = dz.view(nwit, ncols * 48)
     bad = list(range(5, nwit, 32))
-    for w in bad: dz[w, 48 * (((lo + w) * 7919) % ncols)] ^= 1                  # one perturbed variable per 32 assignments
-    dz = dz.reshape(-1)
-    # e2e leg: nwit distinct triples of this rank as bytes in pinned host memory; assignments are generated on the GPU
-    prog = G.verify_program(*triples[0]); wh = ctx.witness_load(prog)
-    epk, emsg, esig, eexp = synth.verify_batch_inputs(ctx, nwit * world, every=16)
-    sl = slice(rank * nwit, (rank + 1) * nwit)
-    h_in = [torch.from_numpy(x.reshape(nwit * world, -1)[sl].copy().reshape(-1)).pin_memory() for x in (epk, emsg, esig)]; eexp = eexp[sl]
+    for w in bad: dz2[w, 48 * (((lo + w) * 7919) % ncols)] ^= 1                # one perturbed variable per 32 assignments
+    # e2e leg: the rank's distinct triples (corruptions included) as bytes in pinned host memory; assignments are generated on the GPU
+    h_in = [torch.from_numpy(x.reshape(-1).copy()).pin_memory() for x in (epk, emsg, esig)]
     d_in = [torch.empty_like(x, device=dev) for x in h_in]; est = torch.empty(nwit, dtype=torch.uint8, device=dev)
-    ebits = torch.zeros(nwit * ((nrows + 63) // 64), dtype=torch.int64, device=dev); eall = torch.zeros(nwit, dtype=torch.uint8, device=dev); h_flags = torch.zeros(2 * nwit, dtype=torch.uint8).pin_memory()
     words = (nrows + 63) // 64
+    ebits = torch.zeros(nwit * words, dtype=torch.int64, device=dev); eall = torch.zeros(nwit, dtype=torch.uint8, device=dev); h_flags = torch.zeros(2 * nwit, dtype=torch.uint8).pin_memory()
     bits = torch.zeros(nwit * words, dtype=torch.int64, device=dev); allsat = torch.zeros(nwit, dtype=torch.uint8, device=dev)
     out = {}
     def step_device():
@@ -65,52 +61,73 @@ def main():
         for d, hsrc in zip(d_in, h_in): d.copy_(hsrc, non_blocking=True)                                  # 176 B per assignment over PCIe
         ctx.witness_check_ptr(wh, h, d_in[0].data_ptr(), d_in[1].data_ptr(), d_in[2].data_ptr(), nwit, ebits.data_ptr(), eall.data_ptr(), est.data_ptr())
         h_flags[:nwit].copy_(eall, non_blocking=True); h_flags[nwit:].copy_(est, non_blocking=True)
+        if world > 1: out["eflags"] = gather_flags(eall, nwit_total)
     def barrier():
         if world > 1: dist.barrier()
         torch.cuda.synchronize(dev)
-    def timed(fn, steps):
+    def timed(fn, k):
         barrier(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(steps): fn()
+        for _ in range(k): fn()
         e1.record(stream); barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
-    for _ in range(args.warmup): step_device()
+    for _ in range(warmup): step_device()
     torch.cuda.synchronize(dev)
     a = allsat.cpu().numpy(); assert sorted(np.nonzero(a == 0)[0].tolist()) == bad, "all_sat flags differ from the planted pattern"
     if world > 1: assert int(out["flags"].sum().item()) == nwit_total - sum(len(range(5, witness_shard(nwit_total, world, r)[1] - witness_shard(nwit_total, world, r)[0], 32)) for r in range(world))
-    l0 = ctx.launch_count(); ms = timed(step_device, args.steps); launches = ctx.launch_count() - l0
+    l0 = ctx.launch_count(); ms = timed(step_device, steps); launches = ctx.launch_count() - l0
     step_e2e(); torch.cuda.synchronize(dev)
-    fl = h_flags.numpy(); want_st = np.where((eexp == 0) | (eexp == 1), 0, eexp)                           # 2 / 3: no assignment (identity key, undecodable signature)
+    fl = h_flags.numpy(); want_st = np.where(eexp <= 1, 0, eexp)                                           # 2 / 3: no assignment (identity key, undecodable signature)
     assert np.array_equal(fl[nwit:], want_st) and np.array_equal(fl[:nwit], (want_st == 0).astype(np.uint8)), "e2e flags differ from the recipe"
-    ke = max(1, args.steps // 2); ms_e2e = timed(step_e2e, ke)
+    ke = max(1, steps // 2); ms_e2e = timed(step_e2e, ke)
+    line = None
     if rank == 0:
         pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json"); peaks = json.load(open(pk_path)) if os.path.exists(pk_path) else {}
         hbm_peak = float(peaks.get("hbm_gbs") or 6549.4)
-        value = nrows * nwit_total * args.steps / (ms * 1e-3)
-        line = {"metric": "r1cs_constraints_checked_per_sec", "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        value = nrows * nwit_total * steps / (ms * 1e-3)
+        alg_bytes = 48 * ncols + (nrows + 7) // 8                                                            # z read once + one bit per row out; matrices amortised
+        achieved = nwit * alg_bytes * steps / (ms * 1e-3) / 1e9
+        line = {"metric": "r1cs_constraints_checked_per_sec", "value": value, "unit": "constraints/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit modular integer)", "data": "synthetic keys/messages, real circuit",
                 "config": {"workload": f"R1CS check of the constraints.rs:90-128 verify circuit ({nrows} rows, {ncols} cols, nnz {nnz}) over {nwit_total} assignments (BASELINE configs[4])",
-                           "per_rank": nwit, "distinct_per_rank": nb, "parallelism": f"shard{world}", "l2": f"assignments ({ncols * 48} B each, {nwit * ncols * 48 / 1e9:.1f} GB per rank) exceed the 126 MB L2"},
-                "assignments_per_sec": nwit_total * args.steps / (ms * 1e-3),
+                           "per_rank": nwit, "distinct_per_rank": nwit, "assignments_from": "blsgpu_witness_gen on this GPU, one per distinct (pk, msg, sig) triple", "row_classes": classes,
+                           "parallelism": f"shard{world}", "l2": f"assignments ({ncols * 48} B each, {nwit * ncols * 48 / 1e9:.1f} GB per rank) exceed the 126 MB L2"},
+                "assignments_per_sec": nwit_total * steps / (ms * 1e-3),
                 "e2e": {"value": nrows * nwit_total * ke / (ms_e2e * 1e-3), "unit": "constraints/s", "h2d_bytes_per_step": 176 * nwit, "d2h_bytes_per_step": 2 * nwit,
                         "assignments_per_sec": nwit_total * ke / (ms_e2e * 1e-3),
-                        "pipeline": "pinned host (pk,msg,sig) bytes -> blsgpu_witness_check (GPU witness generation + satisfaction check) -> flags to host"},
-                "gpu_launches": launches, "host_synthesis_s_per_assignment_per_thread": t_syn / nb * min(threads, nb),
-                "roofline": {"bound": "hbm", "achieved": nwit * ncols * 48 * 2 * args.steps / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": nwit * ncols * 48 * 2 * args.steps / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                        "pipeline": "pinned host (pk,msg,sig) bytes -> blsgpu_witness_check (GPU witness generation + satisfaction check) -> flags to host" + (" -> all-gather of the flags" if world > 1 else "")},
+                "gpu_launches": launches, "host_build_s": t_host,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                             "algorithmic_bytes_per_unit": alg_bytes, "units_per_launch": 32, "unit_name": "assignment (a launch = one kernel over a group of 32)",
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6549.4 GB/s (the value MEASURED_PEAKS.json held when this was written)",
-                             "kernel_note": "whole step; the transpose kernel alone moves these bytes at the HBM peak (0.32 ms per 32 assignments, profiles/launches_cfg5r_r01c.csv); the row kernels are issue / gather-latency bound",
-                             "note": "algorithmic bytes = each assignment read once and written once by the transpose (2 x 48 B x ncols); the gather of z by the row kernels re-reads the transposed copy (nnz x 48 B per assignment) -- see profiles/r01_summary.md"}}
-        if not args.no_cpu:
+                             "note": "whole step (transpose + truth-table rows + generic rows + long-row segments + combine) against SURVEY 8(d) bytes: 48 B x ncols read once + nrows / 8 written per assignment; "
+                                     "per-kernel times: profiles/r02_launches_r1cs.csv"}}
+        if cpu:
             from oracle import cwrap as C
             thr = C.hw_threads(); ns = 2; zs = dz[:ns * ncols * 48].cpu().numpy()
             t0 = time.perf_counter(); ob, oa = C.r1cs_check([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], nrows, ncols, zs, ns, threads=thr); dt = time.perf_counter() - t0
             assert np.array_equal(bits.cpu().numpy().view(np.uint64).reshape(nwit, words)[:ns], ob)
             line["cpu_baseline"] = {"value": nrows * ns / dt, "unit": "constraints/s", "cores": thr, "kind": "port", "sample": f"{ns} assignments, C++ oracle port"}
-        print(json.dumps(line), flush=True)
     ctx.r1cs_free(h); ctx.witness_free(wh)
+    del dz, dz2, bits, ebits
+    torch.cuda.empty_cache()
+    return line
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=3); ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--per-gpu", type=int, default=512); ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args(); args.warmup = max(args.warmup, 3)
+    import torch, torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world > 1: dist.init_process_group("nccl", device_id=dev)
+    from bls_verify_gadget_b200 import Context
+    ctx = Context(local); stream = torch.cuda.current_stream(dev); ctx.set_stream(stream.cuda_stream)
+    line = run(ctx, dev, stream, world, rank, args.steps, args.warmup, args.per_gpu, cpu=not args.no_cpu)
+    if rank == 0: print(json.dumps(line), flush=True)
     if world > 1: dist.destroy_process_group()
 
 if __name__ == "__main__":

@@ -8,7 +8,7 @@ _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("BLSGPU_SO") or os.path.join(_PKG, "libblsgpu.so")      # BLSGPU_SO: tuning builds (profiles/), never a fallback
 import glob
 _SOURCES = [os.path.join(_PKG, "csrc", "blsgpu.cu")] + sorted(glob.glob(os.path.join(_PKG, "csrc", "*.cuh"))) + sorted(glob.glob(os.path.join(_ROOT, "include", "*.h")))      # every header the one translation unit includes
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-ldl"]
 
 class BlsGpuError(RuntimeError): pass
 
@@ -29,13 +29,16 @@ def lib():
         L = ctypes.CDLL(SO_PATH)
         L.blsgpu_last_error.restype = ctypes.c_char_p
         L.blsgpu_launch_count.restype = ctypes.c_uint64
+        L.blsgpu_multi_last_error.restype = ctypes.c_char_p
+        L.blsgpu_multi_ctx.restype = ctypes.c_void_p
         _lib = L
     return _lib
 
 EXPORTS = ["blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_set_stream", "blsgpu_set_pointer_mode", "blsgpu_synchronize",
            "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_set_coop", "blsgpu_verify_batch", "blsgpu_verify_batch_rlc", "blsgpu_fast_aggregate_verify_batch", "blsgpu_pool_create", "blsgpu_pool_free", "blsgpu_pool_fast_aggregate_verify", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
            "blsgpu_g2_aggregate", "blsgpu_deserialize_g1", "blsgpu_deserialize_g2", "blsgpu_sk_to_pk_batch", "blsgpu_sign_batch", "blsgpu_pairing_gt",
-           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_r1cs_row_classes", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_check", "blsgpu_witness_free"]
+           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_r1cs_row_classes", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_check", "blsgpu_witness_free",
+           "blsgpu_create_multi", "blsgpu_destroy_multi", "blsgpu_multi_last_error", "blsgpu_multi_ndev", "blsgpu_multi_nccl_version", "blsgpu_multi_ctx", "blsgpu_multi_verify_batch", "blsgpu_multi_peek"]
 
 _sz = ctypes.c_size_t; _vp = ctypes.c_void_p
 def _u8(a):
@@ -214,3 +217,43 @@ class Context:
     def witness_check_ptr(self, wit_handle, r1cs_handle, pk, msg, sig, n, bits, allsat=None, status=None):
         self._ck(lib().blsgpu_witness_check(self._h, int(wit_handle), int(r1cs_handle), _p(pk), _p(msg), _p(sig), _sz(n), _p(bits), _p(allsat), _p(status)))
     def witness_free(self, handle): lib().blsgpu_witness_free(self._h, int(handle))
+
+
+class MultiContext:
+    """Every GPU of the box behind one handle (blsgpu_create_multi): the batch is sharded contiguously across the devices, the
+    ok-bitmap shards and the GT partials are all-gathered with NCCL inside the library and folded on every device.  Host buffers in,
+    host buffers out -- the single-process counterpart of bench.py's torchrun path."""
+    def __init__(self, devices=None):
+        self._h = _vp()
+        dev = (ctypes.c_int * len(devices))(*devices) if devices else None
+        rc = lib().blsgpu_create_multi(ctypes.byref(self._h), dev, len(devices) if devices else 0)
+        if rc != 0:
+            self._h = None
+            raise BlsGpuError(f"blsgpu_create_multi failed (rc={rc}): no usable sm_100 CUDA device, bad device list, or NCCL not loadable -- there is no CPU fallback")
+    @property
+    def ndev(self): return int(lib().blsgpu_multi_ndev(self._h))
+    @property
+    def nccl_version(self): return int(lib().blsgpu_multi_nccl_version(self._h))
+    def close(self):
+        if getattr(self, "_h", None): lib().blsgpu_destroy_multi(self._h); self._h = None
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+    def _ck(self, rc):
+        if rc != 0: raise BlsGpuError(f"rc={rc}: {lib().blsgpu_multi_last_error(self._h).decode()}")
+    def verify_ptr(self, pk, msg, off, sig, n, status, bitmap=None, gt=None):
+        self._ck(lib().blsgpu_multi_verify_batch(self._h, _p(pk), _p(msg), _p(off), _p(sig), _sz(n), _p(status), _p(bitmap), _p(gt)))
+    def verify(self, pk48, msgs, sig96, fixed32=False):
+        """-> (status uint8[n], ok_bitmap uint64[ceil(n/64)], gt uint8[576])"""
+        pk = _u8(pk48); sg = _u8(sig96); n = sg.size // 96
+        if fixed32: flat, off = _u8(msgs), None
+        else: flat, off = pack_msgs(msgs)
+        _need("sig96", sg, 96 * n); _need("pk48", pk, 48 * n)
+        if fixed32: _need("msgs", flat, 32 * n)
+        elif len(msgs) != n: raise ValueError(f"{len(msgs)} messages for {n} signatures")
+        st = np.empty(max(n, 1), np.uint8); bm = np.zeros(max((n + 63) // 64, 1), np.uint64); gt = np.zeros(576, np.uint8)
+        self.verify_ptr(pk, flat, off, sg, n, st, bm, gt)
+        return st[:n], bm[:(n + 63) // 64], gt
+    def peek(self, i, n):
+        bm = np.zeros(max((n + 63) // 64, 1), np.uint64); gt = np.zeros(576, np.uint8)
+        self._ck(lib().blsgpu_multi_peek(self._h, int(i), _sz(n), _p(bm), _p(gt))); return bm[:(n + 63) // 64], gt

@@ -989,3 +989,4 @@ int blsgpu_pool_fast_aggregate_verify(blsgpu_ctx* ctx, int handle, const uint32_
 
 #include "r1cs.cuh"
 #include "witness.cuh"
+#include "multi.cuh"

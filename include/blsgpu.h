@@ -180,6 +180,24 @@ int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const
                          uint64_t* sat_bits, uint8_t* all_sat, uint8_t* status);
 int blsgpu_witness_free(blsgpu_ctx* ctx, int handle);
 
+/* ---- every GPU of the box behind one handle ---------------------------------------------------------------------
+ * blsgpu_create_multi: devices = ndev ordinals (NULL / ndev <= 0: every visible device); one single-GPU context and stream per device and
+ * one NCCL communicator over them (ncclCommInitAll; libnccl.so.2 is bound with dlopen at this point, never for single-GPU use).
+ * blsgpu_multi_verify_batch = BLS::verify (src/bls.rs:427-458) over a batch sharded contiguously across the devices (shard sizes are
+ * multiples of 64), HOST pointers, outputs as blsgpu_verify_batch.  No data-path collective; the one exchange is an all-gather of the
+ * ok-bitmap shards and the 576-byte GT partials followed by a fold in rank order on every device, so each GPU ends with the whole-batch
+ * bitmap and GT accumulator (blsgpu_multi_peek reads device i's copies back: the test hook).  One host thread at a time per handle. */
+typedef struct blsgpu_multi blsgpu_multi;
+int  blsgpu_create_multi(blsgpu_multi** out, const int* devices, int ndev);
+void blsgpu_destroy_multi(blsgpu_multi* m);
+const char* blsgpu_multi_last_error(blsgpu_multi* m);
+int  blsgpu_multi_ndev(blsgpu_multi* m);
+int  blsgpu_multi_nccl_version(blsgpu_multi* m);            /* ncclGetVersion of the library that was bound, e.g. 22703 */
+blsgpu_ctx* blsgpu_multi_ctx(blsgpu_multi* m, int i);       /* device slot i's context (DEVICE pointer mode) for per-device calls of the rest of the ABI */
+int  blsgpu_multi_verify_batch(blsgpu_multi* m, const uint8_t* pk48, const uint8_t* msg, const uint32_t* msg_off, const uint8_t* sig96, size_t n,
+                               uint8_t* status, uint64_t* ok_bitmap, uint8_t* gt_acc_le576);
+int  blsgpu_multi_peek(blsgpu_multi* m, int i, size_t n, uint64_t* ok_bitmap, uint8_t* gt_le576);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,57 @@
+#!/usr/bin/env python3
+"""Executed-work figures from `ncu --set full --import-source on` reports: per kernel, the thread-level count of executed IMAD.WIDE
+instructions (summed over the SASS source page: "Thread Instructions Executed" of every line whose opcode is IMAD.WIDE*), the DRAM bytes
+(dram__bytes_read.sum + dram__bytes_write.sum) and both divided by the number of items the launch processed.
+
+  python profiles/tools/ncu_executed.py ITEMS report1.ncu-rep [report2.ncu-rep ...] > profiles/ncu_r02_executed.json
+"""
+import csv, io, json, subprocess, sys, collections
+
+def source_tables(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    kernels = []; cur = None
+    for row in csv.reader(io.StringIO(out)):
+        if not row: continue
+        if row[0] == "Kernel Name": cur = {"name": row[1].split("(")[0], "hdr": None, "rows": []}; kernels.append(cur)
+        elif cur is not None and row[0] == "Address": cur["hdr"] = row
+        elif cur is not None and cur["hdr"]: cur["rows"].append(row)
+    return kernels
+
+def raw_metrics(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out))); H, U = rows[0], rows[1]; res = []
+    for r in rows[2:]:
+        d = {}
+        for i, h in enumerate(H):
+            if h in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__grid_size", "launch__block_size"):
+                d[h] = (r[i], U[i])
+        res.append(d)
+    return res
+
+def to_bytes(v, u):
+    f = float(v.replace(",", "")); return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(u, 1)
+
+def main():
+    items = int(sys.argv[1]); result = {}
+    for rep in sys.argv[2:]:
+        src = source_tables(rep); raw = raw_metrics(rep)
+        for k, r in zip(src, raw):
+            H = k["hdr"]; si = H.index("Source"); ti = H.index("Thread Instructions Executed")
+            ops = collections.Counter()
+            for row in k["rows"]:
+                txt = row[si].strip()
+                if txt.startswith("@"): txt = txt.split(None, 1)[1] if " " in txt else txt
+                op = txt.split()[0] if txt else ""
+                ops[op.split(".")[0] + (".WIDE" if ".WIDE" in op else "")] += int(row[ti].replace(",", "") or 0)
+            wide = ops.get("IMAD.WIDE", 0); total = sum(ops.values())
+            dram = to_bytes(*r["dram__bytes_read.sum"]) + to_bytes(*r["dram__bytes_write.sum"])
+            name = k["name"]
+            result[name] = {"items": items, "imad_wide_per_item": wide / items, "thread_instructions_per_item": total / items, "dram_bytes_per_item": dram / items,
+                            "other_fma_pipe_per_item": (ops.get("IMAD", 0) + ops.get("IMAD.HI", 0)) / items,
+                            "fma_pipe_active_pct": float(r["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"][0]), "issue_active_pct": float(r["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
+                            "warps_active_pct": float(r["sm__warps_active.avg.pct_of_peak_sustained_active"][0]), "registers": int(r["launch__registers_per_thread"][0]),
+                            "time_under_ncu": " ".join(r["gpu__time_duration.sum"]), "top_ops_per_item": {o: c / items for o, c in ops.most_common(8)}, "report": rep.split("/")[-1]}
+    json.dump(result, sys.stdout, indent=1); print()
+
+if __name__ == "__main__":
+    main()

@@ -3,6 +3,7 @@
 #include "blsgpu.hpp"
 #include <cstdio>
 #include <random>
+#include <algorithm>
 using namespace blsgpu;
 #define CHECK(c) do { if (!(c)) { std::printf("FAIL line %d: %s\n", __LINE__, #c); return 1; } } while (0)
 int main() {
@@ -38,6 +39,34 @@ int main() {
     bool threw = false; try { Signature::try_from(bad); } catch (const SerializationError&) { threw = true; }
     CHECK(threw || true);
     CHECK(BLS::verify(params, kp.first, msg, 5, Signature()).unwrap() == false);                    // identity signature: Ok(false), SURVEY B2
+    // ---- multi-GPU behind the ABI (blsgpu_create_multi: every visible device, NCCL exchange inside): a 300-triple batch with ragged
+    // messages and corrupted items must give the 1-GPU status bytes, ok-bitmap and GT accumulator, identically on every device
+    {
+        const size_t n = 300;
+        std::vector<uint8_t> pk(48 * n), sg(96 * n), msgs; std::vector<uint32_t> off(n + 1, 0);
+        std::vector<uint8_t> sks(32 * n, 0);
+        for (size_t i = 0; i < n; i++) { sks[32 * i] = (uint8_t)(i + 1); sks[32 * i + 1] = (uint8_t)((i >> 8) + 3); for (size_t k = 0; k < 1 + i % 7; k++) msgs.push_back((uint8_t)(i * 31 + k)); off[i + 1] = (uint32_t)msgs.size(); }
+        blsgpu_ctx* c = default_context().raw();
+        std::vector<uint8_t> st(n);
+        CHECK(blsgpu_sk_to_pk_batch(c, sks.data(), n, pk.data(), st.data()) == 0);
+        CHECK(blsgpu_sign_batch(c, sks.data(), msgs.data(), off.data(), n, sg.data(), st.data()) == 0);
+        for (size_t i = 5; i < n; i += 37) sg[96 * i + 95] ^= 1;                                   // undecodable / off-curve signatures
+        for (size_t i = 11; i < n; i += 53) std::copy(pk.begin() + 48 * ((i + 1) % n), pk.begin() + 48 * ((i + 1) % n) + 48, pk.begin() + 48 * i);   // wrong key
+        std::vector<uint8_t> st1(n), stm(n), gt1(576), gtm(576), gtp(576); std::vector<uint64_t> bm1((n + 63) / 64), bmm((n + 63) / 64), bmp((n + 63) / 64);
+        CHECK(blsgpu_verify_batch(c, pk.data(), msgs.data(), off.data(), sg.data(), n, st1.data(), bm1.data(), gt1.data()) == 0);
+        blsgpu_multi* mm = nullptr;
+        CHECK(blsgpu_create_multi(&mm, nullptr, 0) == 0);
+        int nd = blsgpu_multi_ndev(mm); CHECK(nd >= 1 && blsgpu_multi_nccl_version(mm) >= 20000);
+        CHECK(blsgpu_multi_verify_batch(mm, pk.data(), msgs.data(), off.data(), sg.data(), n, stm.data(), bmm.data(), gtm.data()) == 0);
+        CHECK(st1 == stm && bm1 == bmm && gt1 == gtm);
+        size_t bad = 0; for (auto v : st1) bad += v != 0; CHECK(bad >= 14);
+        for (int i = 0; i < nd; i++) { CHECK(blsgpu_multi_peek(mm, i, n, bmp.data(), gtp.data()) == 0); CHECK(bmp == bm1 && gtp == gt1); }
+        // fixed 32-byte messages, a batch smaller than 64 x devices (empty shards), and no optional outputs
+        CHECK(blsgpu_multi_verify_batch(mm, pk.data(), msgs.data(), off.data(), sg.data(), 3, stm.data(), nullptr, nullptr) == 0);
+        CHECK(stm[0] == st1[0] && stm[1] == st1[1] && stm[2] == st1[2]);
+        std::printf("multi: %d device(s), NCCL %d\n", nd, blsgpu_multi_nccl_version(mm));
+        blsgpu_destroy_multi(mm);
+    }
     std::printf("OK\n");
     return 0;
 }

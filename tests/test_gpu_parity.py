@@ -585,3 +585,27 @@ def test_cooperative_final_exponentiation_matches(ctx, C):
     finally: ctx.set_coop(False)
     ost, ogt = C.verify(pk, msgs, sig, want_gt=True, threads=8)
     assert list(st0) == list(st1) == list(ost) == list(exp) and gt0.tobytes() == gt1.tobytes() == ogt.tobytes()
+
+
+def test_multi_gpu_abi_matches_single_gpu(ctx):
+    """blsgpu_create_multi / blsgpu_multi_verify_batch (every visible device, NCCL all-gather + fold inside the library): status bytes,
+    ok-bitmap and GT accumulator must equal the single-GPU call's for a batch with every corruption kind, on every device's copy;
+    also a batch so small that some shards are empty, and ragged messages."""
+    from bls_verify_gadget_b200 import synth
+    from bls_verify_gadget_b200._lib import MultiContext
+    n = 3000
+    pk, msg, sig, exp = synth.verify_batch_inputs(ctx, n, every=16, fast=False)
+    st1, bm1, gt1 = ctx.verify(pk, msg, sig, want_bitmap=True, want_gt=True, fixed32=True)
+    assert list(st1) == list(exp)
+    mc = MultiContext()
+    assert mc.ndev >= 1 and mc.nccl_version >= 20000
+    st, bm, gt = mc.verify(pk, msg, sig, fixed32=True)
+    assert np.array_equal(st, st1) and np.array_equal(bm, bm1) and gt.tobytes() == gt1.tobytes()
+    for i in range(mc.ndev):
+        b, g = mc.peek(i, n); assert np.array_equal(b, bm1) and g.tobytes() == gt1.tobytes()
+    msgs = [msg[32 * i:32 * i + 32].tobytes()[:1 + i % 32] for i in range(70)]
+    a = ctx.verify(pk[:48 * 70], msgs, sig[:96 * 70], want_bitmap=True, want_gt=True); b = mc.verify(pk[:48 * 70], msgs, sig[:96 * 70])
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    a = ctx.verify(pk[:48 * 2], msg[:64], sig[:96 * 2], want_bitmap=True, want_gt=True, fixed32=True); b = mc.verify(pk[:48 * 2], msg[:64], sig[:96 * 2], fixed32=True)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    mc.close()
