@@ -35,9 +35,9 @@ def lib():
     return _lib
 
 EXPORTS = ["blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_set_stream", "blsgpu_set_pointer_mode", "blsgpu_synchronize",
-           "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_set_coop", "blsgpu_verify_batch", "blsgpu_verify_batch_rlc", "blsgpu_fast_aggregate_verify_batch", "blsgpu_pool_create", "blsgpu_pool_free", "blsgpu_pool_fast_aggregate_verify", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
+           "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_set_coop", "blsgpu_verify_batch", "blsgpu_verify_batch_rlc", "blsgpu_verify_batch_rlc_bisect", "blsgpu_fast_aggregate_verify_batch", "blsgpu_pool_create", "blsgpu_pool_free", "blsgpu_pool_fast_aggregate_verify", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
            "blsgpu_g2_aggregate", "blsgpu_deserialize_g1", "blsgpu_deserialize_g2", "blsgpu_sk_to_pk_batch", "blsgpu_sign_batch", "blsgpu_pairing_gt",
-           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_r1cs_row_classes", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_check", "blsgpu_witness_free",
+           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_r1cs_row_classes", "blsgpu_r1cs_load_file", "blsgpu_r1cs_check_file", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_check", "blsgpu_witness_free",
            "blsgpu_create_multi", "blsgpu_destroy_multi", "blsgpu_multi_last_error", "blsgpu_multi_ndev", "blsgpu_multi_nccl_version", "blsgpu_multi_ctx", "blsgpu_multi_verify_batch", "blsgpu_multi_peek"]
 
 _sz = ctypes.c_size_t; _vp = ctypes.c_void_p
@@ -100,6 +100,17 @@ class Context:
         st = np.empty(max(n, 1), np.uint8); ok = np.zeros(1, np.uint8); seed = _u8(seed16); _need("seed16", seed, 16)
         self.verify_rlc_ptr(pk, flat, off, sg, n, seed, st, ok)
         return bool(ok[0]), st[:n]
+    def verify_rlc_bisect(self, pk48, msgs, sig96, seed16, fixed32=False):
+        """batch check with exact per-item outcome (host mode): -> (status uint8[n], ok_bitmap uint64[ceil(n/64)], items re-run per item)"""
+        pk = _u8(pk48); sg = _u8(sig96); n = sg.size // 96
+        if fixed32: flat, off = _u8(msgs), None
+        else: flat, off = pack_msgs(msgs)
+        _need("sig96", sg, 96 * n); _need("pk48", pk, 48 * n)
+        if fixed32: _need("msgs", flat, 32 * n)
+        elif len(msgs) != n: raise ValueError(f"{len(msgs)} messages for {n} signatures")
+        st = np.empty(max(n, 1), np.uint8); bm = np.zeros(max((n + 63) // 64, 1), np.uint64); seed = _u8(seed16); _need("seed16", seed, 16); rerun = ctypes.c_uint64(0)
+        self._ck(lib().blsgpu_verify_batch_rlc_bisect(self._h, _p(pk), _p(flat), _p(off), _p(sg), _sz(n), _p(seed), _p(st), _p(bm), ctypes.byref(rerun)))
+        return st[:n], bm[:(n + 63) // 64], int(rerun.value)
     def hash_to_g2_ptr(self, msg, off, n, out): self._ck(lib().blsgpu_hash_to_g2_batch(self._h, _p(msg), _p(off), _sz(n), _p(out)))
     def fast_aggregate_verify_ptr(self, pks, bitmap, k, msg, sig, ncomm, status, agg=None):
         self._ck(lib().blsgpu_fast_aggregate_verify_batch(self._h, _p(pks), _p(bitmap), _sz(k), _p(msg), _p(sig), _sz(ncomm), _p(status), _p(agg)))
@@ -190,6 +201,15 @@ class Context:
         self._ck(lib().blsgpu_r1cs_check(self._h, int(handle), _p(z), _sz(nwit), _p(bits), _p(allsat))); return bits.reshape(nwit, words), allsat
     def r1cs_check_ptr(self, handle, z, nwit, bits, allsat): self._ck(lib().blsgpu_r1cs_check(self._h, int(handle), _p(z), _sz(nwit), _p(bits), _p(allsat)))
     def r1cs_free(self, handle): lib().blsgpu_r1cs_free(self._h, int(handle))
+    def r1cs_load_file(self, path):
+        """-> (handle, dict(nrows, ncols, ninstance, nwit)) from a BLSR1CS1 file (gadget.write_r1cs_file / rust/examples/export_r1cs.rs)"""
+        h = ctypes.c_int(-1); shape = (ctypes.c_uint64 * 4)()
+        self._ck(lib().blsgpu_r1cs_load_file(self._h, os.fsencode(path), ctypes.byref(h), shape))
+        return h.value, dict(zip(("nrows", "ncols", "ninstance", "nwit"), [int(x) for x in shape]))
+    def r1cs_check_file(self, handle, path, first, count, nrows):
+        words = (nrows + 63) // 64; bits = np.zeros(max(count, 1) * words, np.uint64); allsat = np.zeros(max(count, 1), np.uint8)
+        self._ck(lib().blsgpu_r1cs_check_file(self._h, int(handle), os.fsencode(path), _sz(first), _sz(count), _p(bits), _p(allsat)))
+        return bits[:count * words].reshape(count, words), allsat[:count]
     def r1cs_row_classes(self, handle):
         c = (ctypes.c_uint64 * 4)(); self._ck(lib().blsgpu_r1cs_row_classes(self._h, int(handle), c))
         return dict(zip(("truth_table", "generic", "long", "segments"), [int(x) for x in c]))

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <cstdarg>
 #include <new>
+#include <vector>
 #include "stages.cuh"
 #include "coop.cuh"
 #include "../../include/blsgpu.h"
@@ -394,6 +395,39 @@ __global__ void __launch_bounds__(32, 1) k_rlc_finish(const u32x4* f_acc, const 
     fp12_mul(F, F, f2);
     final_exponentiation(gt, F);
     all_ok[0] = (fp12_is_one(gt) && !bad[0]) ? 1 : 0;
+}
+
+// ---- per-piece forms for the bisecting batch check: the batch is cut into pieces of L items; products / sums are kept per piece
+// out[p * T + t] = prod_{i = t, t + T, ... < len_p} in[p * L + i]   (len_p = min(L, n - p L); status filter as k_gt_reduce)
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_gt_reduce_seg(const u32x4* in_soa, const uint8_t* status, size_t n, size_t L, u32x4* out_soa, size_t T, size_t P) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x, p = blockIdx.y; if (t >= T) return;
+    size_t lo = p * L, hi = lo + L < n ? lo + L : n;
+    fp12 acc, x; fp12_one(acc);
+    for (size_t i = lo + t; i < hi; i += T) {
+        if (status && status[i] > ST_FALSE) continue;
+        soa_load_fp12(x, in_soa, n, i); fp12_mul(acc, acc, x);
+    }
+    soa_store_fp12(out_soa, P * T, p * T + t, acc);
+}
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_g2_jac_reduce_seg(const u32x4* in_jac, size_t n, size_t L, u32x4* out_jac, size_t T, size_t P) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x, p = blockIdx.y; if (t >= T) return;
+    size_t lo = p * L, hi = lo + L < n ? lo + L : n;
+    g2_jac acc, x; jac_set_identity(acc);
+    for (size_t i = lo + t; i < hi; i += T) { segsum_traits<fp2>::loadj(x, in_jac, n, i); jac_add(acc, acc, x); }
+    segsum_traits<fp2>::storej(out_jac, P * T, p * T + t, acc);
+}
+// one block per piece (thread 0 works): ok[p] = [ F_p * miller(-g1, S_p) ]^((p^12-1)/r) == 1  -- the pieces' finishes run side by side,
+// so locating the failing pieces costs one single-thread latency (~20 ms) whatever their number
+__global__ void __launch_bounds__(32, 1) k_rlc_finish_seg(const u32x4* f_piece, const u32x4* s_piece, size_t P, uint8_t* ok) {
+    size_t p = blockIdx.x; if (threadIdx.x || p >= P) return;
+    fp12 F, f2, gt; soa_load_fp12(F, f_piece, P, p);
+    g2_jac S; segsum_traits<fp2>::loadj(S, s_piece, P, p);
+    g2_aff sa; bool have = jac_to_aff(sa, S);
+    g1_aff ng; ng.x = fp_const(C_G1X); ng.y = fp_const(C_G1Y_NEG);
+    miller_loop2(f2, ng, sa, have, ng, sa, false);
+    fp12_mul(F, F, f2);
+    final_exponentiation(gt, F);
+    ok[p] = fp12_is_one(gt) ? 1 : 0;
 }
 
 // ================================================================================================ context
@@ -814,6 +848,97 @@ int blsgpu_verify_batch_rlc(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t*
     }
     release();
     return rc;
+}
+
+// Batch check that returns the EXACT per-item outcome ("fall back to per-item checks to recover the exact bitmap when
+// the batch fails").  One random-linear-combination equation per PIECE of RLC_PIECE items, all pieces finished side by side; a piece
+// whose equation fails is re-run through the per-item path (blsgpu_verify_batch) inside this call.  status[i] and ok_bitmap equal
+// blsgpu_verify_batch's except with probability <= 2^-64 per failing piece over the seed; fallback_items (nullable, host) = items re-run.
+#define RLC_PIECE 4096
+int blsgpu_verify_batch_rlc_bisect(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg, const uint32_t* msg_off, const uint8_t* sig96, size_t n,
+                                   const uint8_t seed16[16], uint8_t* status, uint64_t* ok_bitmap, uint64_t* fallback_items) {
+    ENTER(); if (!pk48 || !msg || !sig96 || !seed16 || !status) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (fallback_items) *fallback_items = 0;
+    if (!n) return 0;
+    int rc = 0; bool host = ctx->ptr_mode == BLSGPU_HOST;
+    const uint32_t* off_host = host ? msg_off : nullptr;
+    size_t total_mb = 0;
+    if (msg_off && !off_host) { total_mb = msg_bytes_total(ctx, msg_off, n, rc); if (rc) return fail(ctx, rc, "reading msg_off failed"); }
+    if (!ctx->rlc_acc) CU(cudaMalloc(&ctx->rlc_acc, 2048));
+    uint8_t* dseed = ctx->rlc_acc + 1040;
+    CU(cudaMemcpyAsync(dseed, seed16, 16, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+    const size_t L = RLC_PIECE;
+    std::vector<uint8_t> piece_ok((n + L - 1) / L, 1);
+    size_t chunk = ctx->chunk >= L ? ctx->chunk / L * L : L;                 // pieces never straddle passes
+    for (size_t base = 0; base < n; base += chunk) {
+        size_t m = n - base < chunk ? n - base : chunk, P = (m + L - 1) / L, T0 = (L + 7) / 8;
+        size_t mb0 = msg_off ? (off_host ? off_host[base] : 0) : 32 * base;
+        size_t mb = msg_off ? (off_host ? off_host[base + m] - off_host[base] : total_mb) : 32 * m;
+        if ((rc = ws_reserve(ctx, verify_ws_bytes(m, host ? mb : 0) + al(288 * m) + 2 * al(288 * P * T0) + 2 * al(576 * P * T0) + al(P) + 65536))) return rc;
+        const uint8_t *dpk, *dsig, *dmsg; const uint32_t* doff;
+        if ((rc = stage_in(ctx, dpk, pk48 + 48 * base, 48 * m))) return rc;
+        if ((rc = stage_in(ctx, dsig, sig96 + 96 * base, 96 * m))) return rc;
+        if (host) { if ((rc = stage_in(ctx, dmsg, msg + mb0, mb ? mb : 1))) return rc; dmsg -= msg_off ? mb0 : 0; }
+        else dmsg = msg_off ? msg : msg + mb0;
+        if ((rc = stage_in(ctx, doff, msg_off ? msg_off + base : nullptr, m + 1))) return rc;
+        uint8_t* dstatus = stage_out(ctx, status + base, m);
+        u32x4* pk_soa = ws_take<u32x4>(ctx, 6 * m); uint8_t* code_pk = ws_take<uint8_t>(ctx, m);
+        u32x4* sig_soa = ws_take<u32x4>(ctx, 12 * m); u32x4* hm_soa = ws_take<u32x4>(ctx, 12 * m); u32x4* f_soa = ws_take<u32x4>(ctx, 36 * m);
+        uint8_t* code_sig = ws_take<uint8_t>(ctx, m); uint8_t* flags = ws_take<uint8_t>(ctx, m);
+        u32x4* rs = ws_take<u32x4>(ctx, 18 * m); u32x4* ja = ws_take<u32x4>(ctx, 18 * P * T0); u32x4* jb = ws_take<u32x4>(ctx, 18 * P * T0);
+        u32x4* ta = ws_take<u32x4>(ctx, 36 * P * T0); u32x4* tb = ws_take<u32x4>(ctx, 36 * P * T0); uint8_t* dok = ws_take<uint8_t>(ctx, P);
+        LAUNCH(k_decode_g1, nblk(m), TPB, dpk, m, pk_soa, code_pk);
+        LAUNCH(k_decode_g2, nblk(m), TPB, dsig, m, sig_soa, code_sig);
+        LAUNCH(k_hash_to_g2, nblk(m), TPB, dmsg, doff, m, (const uint8_t*)code_pk, (const uint8_t*)code_sig, hm_soa, flags, dstatus);
+        LAUNCH(k_rlc_scale, nblk(m), TPB, pk_soa, (const u32x4*)sig_soa, flags, (const uint8_t*)dstatus, m, base, (const uint8_t*)dseed, rs);
+        const u32x4* s_piece; const u32x4* f_piece;
+        {   // per-piece sums of the scaled signatures: radix-8 trees, all pieces in one launch per level
+            const u32x4* cur = rs; size_t cnt_n = m, len = L; u32x4* bufs[2] = {ja, jb}; int which = 0;
+            while (true) {
+                size_t T = (len + 7) / 8; u32x4* out = bufs[which];
+                k_g2_jac_reduce_seg<<<dim3(nblk(T), (unsigned)P), TPB, 0, ctx->stream>>>(cur, cnt_n, len, out, T, P); ctx->launches++; CU(cudaGetLastError());
+                cur = out; cnt_n = P * T; len = T; which ^= 1;
+                if (T == 1) break;
+            }
+            s_piece = cur;
+        }
+        LAUNCH(k_miller, nblk(m), TPB, (const u32x4*)pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, m, f_soa);
+        {
+            const u32x4* cur = f_soa; const uint8_t* st = dstatus; size_t cnt_n = m, len = L; u32x4* bufs[2] = {ta, tb}; int which = 0;
+            while (true) {
+                size_t T = (len + 7) / 8; u32x4* out = bufs[which];
+                k_gt_reduce_seg<<<dim3(nblk(T), (unsigned)P), TPB, 0, ctx->stream>>>(cur, st, cnt_n, len, out, T, P); ctx->launches++; CU(cudaGetLastError());
+                cur = out; st = nullptr; cnt_n = P * T; len = T; which ^= 1;
+                if (T == 1) break;
+            }
+            f_piece = cur;
+        }
+        LAUNCH(k_rlc_finish_seg, (unsigned)P, 32, f_piece, s_piece, P, dok);
+        if ((rc = finish_out(ctx, status + base, dstatus, m))) return rc;
+        CU(cudaMemcpyAsync(piece_ok.data() + base / L, dok, P, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    // failing pieces: the per-item path on exactly those items (adjacent failing pieces are merged into one call)
+    uint64_t rerun = 0;
+    for (size_t p = 0; p < piece_ok.size(); ) {
+        if (piece_ok[p]) { p++; continue; }
+        size_t q = p; while (q < piece_ok.size() && !piece_ok[q]) q++;
+        size_t lo = p * L, hi = q * L < n ? q * L : n;
+        const uint8_t* m_ptr; const uint32_t* o_ptr;
+        std::vector<uint32_t> rebased;
+        if (!msg_off) { m_ptr = msg + 32 * lo; o_ptr = nullptr; }
+        else if (host) { rebased.resize(hi - lo + 1); for (size_t i = 0; i <= hi - lo; i++) rebased[i] = msg_off[lo + i] - msg_off[lo]; m_ptr = msg + msg_off[lo]; o_ptr = rebased.data(); }
+        else { m_ptr = msg; o_ptr = msg_off + lo; }                       // device offsets are absolute into msg
+        if ((rc = blsgpu_verify_batch(ctx, pk48 + 48 * lo, m_ptr, o_ptr, sig96 + 96 * lo, hi - lo, status + lo, nullptr, nullptr))) return rc;
+        if (!host) CU(cudaStreamSynchronize(ctx->stream));
+        rerun += hi - lo; p = q;
+    }
+    if (fallback_items) *fallback_items = rerun;
+    if (ok_bitmap) {
+        if (host) { size_t words = (n + 63) / 64; for (size_t w = 0; w < words; w++) ok_bitmap[w] = 0; for (size_t i = 0; i < n; i++) if (status[i] == ST_OK) ok_bitmap[i >> 6] |= 1ull << (i & 63); }
+        else { CU(cudaMemsetAsync(ok_bitmap, 0, 8 * ((n + 63) / 64), ctx->stream)); LAUNCH(k_status_bitmap, nblk(((n + 31) / 32) * 32, 256), 256, (const uint8_t*)status, n, (uint32_t*)ok_bitmap); }
+    }
+    return finish_call(ctx);
 }
 
 int blsgpu_gt_fold(blsgpu_ctx* ctx, const uint8_t* parts, size_t nparts, uint8_t* out) {

@@ -397,6 +397,63 @@ int blsgpu_r1cs_free(blsgpu_ctx* ctx, int handle) {
     dev_guard guard_; cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
     r1cs_release(ctx->r1cs[handle]); ctx->r1cs[handle] = nullptr; return 0;
 }
+// ---- on-disk exchange format (written by rust/examples/export_r1cs.rs from arkworks' cs.to_matrices() after
+// src/constraints.rs:335-367, and by bls_verify_gadget_b200/gadget.py from the in-repo builder).  All little-endian:
+//   "BLSR1CS1" | u32 version = 1 | u32 field_bytes = 48 | u64 nrows | u64 ncols | u64 ninstance | u64 nnz[3] | u64 nwit          (72 bytes)
+//   for A, B, C:  rowptr u64[nrows + 1] | col u32[nnz] (zero-padded to a multiple of 8 bytes) | coeff [nnz][48] canonical
+//   nwit assignments of ncols x 48 bytes canonical (z = [1, instance.., witness..])
+struct r1cs_file_hdr { char magic[8]; uint32_t version, field_bytes; uint64_t nrows, ncols, ninstance, nnz[3], nwit; };
+struct file_closer { FILE* f; ~file_closer() { if (f) fclose(f); } };
+static int r1cs_file_open(blsgpu_ctx* ctx, const char* path, file_closer& fc, r1cs_file_hdr& h, uint64_t& z_offset) {
+    fc.f = fopen(path, "rb"); if (!fc.f) return fail(ctx, BLSGPU_ERR_ARG, "cannot open %s", path);
+    if (fread(&h, sizeof h, 1, fc.f) != 1 || memcmp(h.magic, "BLSR1CS1", 8) != 0) return fail(ctx, BLSGPU_ERR_ARG, "%s is not a BLSR1CS1 file", path);
+    if (h.version != 1 || h.field_bytes != 48 || !h.nrows || !h.ncols || h.ncols >= 0x7fffffffu) return fail(ctx, BLSGPU_ERR_ARG, "%s: unsupported header (version %u, field bytes %u)", path, h.version, h.field_bytes);
+    z_offset = sizeof h;
+    for (int m = 0; m < 3; m++) z_offset += 8 * (h.nrows + 1) + ((4 * h.nnz[m] + 7) & ~(uint64_t)7) + 48 * h.nnz[m];
+    return 0;
+}
+extern "C" {
+// shape4 (nullable) = {nrows, ncols, ninstance, nwit}
+int blsgpu_r1cs_load_file(blsgpu_ctx* ctx, const char* path, int* handle, uint64_t* shape4) {
+    ENTER(); if (!path || !handle) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
+    file_closer fc{nullptr}; r1cs_file_hdr h; uint64_t zoff;
+    if (int rc = r1cs_file_open(ctx, path, fc, h, zoff)) return rc;
+    std::vector<uint64_t> rp[3]; std::vector<uint32_t> cl[3]; std::vector<uint8_t> cf[3];
+    for (int m = 0; m < 3; m++) {
+        size_t nnz = h.nnz[m], colb = (4 * nnz + 7) & ~(size_t)7;
+        rp[m].resize(h.nrows + 1); cl[m].resize(colb / 4 + 1); cf[m].resize(48 * nnz + 1);
+        if (fread(rp[m].data(), 8, h.nrows + 1, fc.f) != h.nrows + 1 || (colb && fread(cl[m].data(), 1, colb, fc.f) != colb) || (nnz && fread(cf[m].data(), 48, nnz, fc.f) != nnz))
+            return fail(ctx, BLSGPU_ERR_ARG, "%s: truncated matrix %d", path, m);
+        if (rp[m][h.nrows] != nnz) return fail(ctx, BLSGPU_ERR_ARG, "%s: rowptr of matrix %d ends at %llu, header says %llu non-zeros", path, m, (unsigned long long)rp[m][h.nrows], (unsigned long long)nnz);
+    }
+    const uint64_t* rpp[3] = {rp[0].data(), rp[1].data(), rp[2].data()}; const uint32_t* clp[3] = {cl[0].data(), cl[1].data(), cl[2].data()}; const uint8_t* cfp[3] = {cf[0].data(), cf[1].data(), cf[2].data()};
+    int saved = ctx->ptr_mode; ctx->ptr_mode = BLSGPU_HOST;
+    int rc = blsgpu_r1cs_load(ctx, rpp, clp, cfp, (size_t)h.nrows, (size_t)h.ncols, handle);
+    ctx->ptr_mode = saved;
+    if (!rc && shape4) { shape4[0] = h.nrows; shape4[1] = h.ncols; shape4[2] = h.ninstance; shape4[3] = h.nwit; }
+    return rc;
+}
+// checks assignments [first, first + count) stored in the file against the loaded system `handle` (which must have the file's shape);
+// sat_bits (count x ceil(nrows/64) words) and all_sat (count bytes, nullable) are HOST pointers
+int blsgpu_r1cs_check_file(blsgpu_ctx* ctx, int handle, const char* path, size_t first, size_t count, uint64_t* sat_bits, uint8_t* all_sat) {
+    ENTER(); if (!path || !sat_bits || handle < 0 || handle >= 16 || !ctx->r1cs[handle]) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
+    file_closer fc{nullptr}; r1cs_file_hdr h; uint64_t zoff;
+    if (int rc = r1cs_file_open(ctx, path, fc, h, zoff)) return rc;
+    const r1cs_sys* s = ctx->r1cs[handle];
+    if (h.nrows != s->nrows || h.ncols != s->ncols) return fail(ctx, BLSGPU_ERR_ARG, "%s holds a %llu x %llu system, the handle a %zu x %zu one", path, (unsigned long long)h.nrows, (unsigned long long)h.ncols, s->nrows, s->ncols);
+    if (first + count > h.nwit) return fail(ctx, BLSGPU_ERR_ARG, "%s holds %llu assignments", path, (unsigned long long)h.nwit);
+    size_t words = (s->nrows + 63) / 64, zb = (size_t)h.ncols * 48;
+    std::vector<uint8_t> z; int saved = ctx->ptr_mode, rc = 0;
+    for (size_t w = 0; w < count && !rc; w += R1_GROUP) {               // one group of 32 assignments at a time: bounded host memory
+        size_t g = count - w < R1_GROUP ? count - w : R1_GROUP; z.resize(g * zb);
+        if (fseek(fc.f, (long)(zoff + (first + w) * zb), SEEK_SET) != 0 || fread(z.data(), zb, g, fc.f) != g) return fail(ctx, BLSGPU_ERR_ARG, "%s: truncated assignments", path);
+        ctx->ptr_mode = BLSGPU_HOST;
+        rc = blsgpu_r1cs_check(ctx, handle, z.data(), g, sat_bits + w * words, all_sat ? all_sat + w : nullptr);
+        ctx->ptr_mode = saved;
+    }
+    return rc;
+}
+}
 // rows per class of a loaded system: counts[0] truth-table rows, [1] generic short rows, [2] long rows, [3] segments of the long rows
 int blsgpu_r1cs_row_classes(blsgpu_ctx* ctx, int handle, uint64_t counts[4]) {
     if (!ctx || handle < 0 || handle >= 16 || !ctx->r1cs[handle] || !counts) return BLSGPU_ERR_ARG;

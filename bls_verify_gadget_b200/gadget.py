@@ -109,3 +109,20 @@ def verify_witnesses(triples, threads=None, ncols=None):
         res[i] = bool(r.value)
     with ThreadPoolExecutor(max_workers=threads or os.cpu_count() or 1) as ex: list(ex.map(one, range(len(triples))))
     return z, res
+
+
+def write_r1cs_file(path, nrows, ncols, ninstance, mats, assignments):
+    """the BLSR1CS1 exchange format of blsgpu_r1cs_load_file / blsgpu_r1cs_check_file (layout: csrc/r1cs.cuh); the Rust exporter
+    rust/examples/export_r1cs.rs writes the same bytes from arkworks' cs.to_matrices().  mats = [(rowptr u64, col u32, coeff48 u8)] x 3,
+    assignments = iterable of ncols * 48-byte vectors."""
+    import struct
+    zs = [np.ascontiguousarray(z, dtype=np.uint8).reshape(-1) for z in assignments]
+    with open(path, "wb") as f:
+        f.write(b"BLSR1CS1" + struct.pack("<II", 1, 48) + struct.pack("<QQQ", nrows, ncols, ninstance) + struct.pack("<QQQ", *[int(m[0][-1]) for m in mats]) + struct.pack("<Q", len(zs)))
+        for rp, cl, cf in mats:
+            nnz = int(rp[-1]); assert len(rp) == nrows + 1 and len(cl) >= nnz and len(cf) >= 48 * nnz
+            f.write(np.ascontiguousarray(rp, dtype="<u8").tobytes()); f.write(np.ascontiguousarray(cl[:nnz], dtype="<u4").tobytes())
+            if nnz % 2: f.write(b"\0" * 4)
+            f.write(np.ascontiguousarray(cf[:48 * nnz], dtype=np.uint8).tobytes())
+        for z in zs:
+            assert z.size == ncols * 48; f.write(z.tobytes())

@@ -95,10 +95,17 @@ int blsgpu_verify_batch(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg
  * *all_ok = 1 iff every public key and signature decodes and validates (the checks of src/bls.rs:434-447) and the equation
  * holds; a batch that contains a triple BLS::verify would reject passes with probability <= 2^-64 over the choice of the seed,
  * which must be unpredictable to whoever produced the batch.  status (nullable, n bytes) receives the per-item decode
- * outcome only (0, 2 or 3): to locate a bad item after *all_ok == 0, call blsgpu_verify_batch.  Roughly 1.6x the
+ * outcome only (0, 2 or 3): to locate a bad item after *all_ok == 0, use blsgpu_verify_batch_rlc_bisect (below).  Roughly 1.6x the
  * throughput of blsgpu_verify_batch: one pair per Miller loop and a single final exponentiation per batch. */
 int blsgpu_verify_batch_rlc(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg, const uint32_t* msg_off,
                             const uint8_t* sig96, size_t n, const uint8_t seed16[16], uint8_t* status, uint8_t* all_ok);
+
+/* The batch check with the EXACT per-item outcome: one such equation per piece of 4,096 items, all pieces finished side by
+ * side; every piece whose equation fails is re-run through the per-item path inside the call.  status[n] and ok_bitmap (nullable) equal
+ * blsgpu_verify_batch's, except with probability <= 2^-64 per failing piece over the seed; *fallback_items (nullable, host memory) = number of
+ * items that went through the per-item path. */
+int blsgpu_verify_batch_rlc_bisect(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg, const uint32_t* msg_off,
+                                   const uint8_t* sig96, size_t n, const uint8_t seed16[16], uint8_t* status, uint64_t* ok_bitmap, uint64_t* fallback_items);
 
 /* ---- PublicKey::aggregate + verify  (src/bls.rs:183-195 then 427-458; tests/tests.rs:297-334) ---------------
  * ncomm committees of k keys each; bitmap (nullable): bit c*k+j selects key j of committee c (the gadget's
@@ -156,6 +163,12 @@ int blsgpu_r1cs_load(blsgpu_ctx* ctx, const uint64_t* const rowptr[3], const uin
                      size_t nrows, size_t ncols, int* handle);
 int blsgpu_r1cs_check(blsgpu_ctx* ctx, int handle, const uint8_t* z48, size_t nwit, uint64_t* sat_bits, uint8_t* all_sat);
 int blsgpu_r1cs_free(blsgpu_ctx* ctx, int handle);
+/* The same through a file (format "BLSR1CS1": header, three CSR matrices, nwit assignments -- written by rust/examples/export_r1cs.rs from
+ * arkworks' cs.to_matrices() after src/constraints.rs:335-367, or by bls_verify_gadget_b200/gadget.py; layout in csrc/r1cs.cuh).
+ * shape4 (nullable) = {nrows, ncols, ninstance, nwit}.  blsgpu_r1cs_check_file checks assignments [first, first + count) of the file;
+ * its sat_bits / all_sat are HOST pointers whatever the pointer mode. */
+int blsgpu_r1cs_load_file(blsgpu_ctx* ctx, const char* path, int* handle, uint64_t shape4[4]);
+int blsgpu_r1cs_check_file(blsgpu_ctx* ctx, int handle, const char* path, size_t first, size_t count, uint64_t* sat_bits, uint8_t* all_sat);
 /* how blsgpu_r1cs_load classified the rows: counts[0] truth-table rows (<= 16 non-zeros on <= 5 distinct columns: evaluated bit-sliced over
  * 32 assignments when those columns are 0/1, generically otherwise), [1] generic short rows, [2] long rows, [3] their 32-entry segments */
 int blsgpu_r1cs_row_classes(blsgpu_ctx* ctx, int handle, uint64_t counts[4]);

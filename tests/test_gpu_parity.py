@@ -482,6 +482,38 @@ def test_rlc_batch_check_agrees_with_per_item_verify(ctx):
     ok, st = ctx.verify_rlc(rpk, rag, rsig, bytes(16)); assert ok
     ok, st = ctx.verify_rlc(rpk, rag[1:] + rag[:1], rsig, bytes(16)); assert not ok
 
+def test_rlc_bisect_returns_the_exact_per_item_outcome(ctx):
+    """blsgpu_verify_batch_rlc_bisect ("fall back to per-item checks to recover the exact bitmap"): status bytes and
+    ok-bitmap equal blsgpu_verify_batch's for clean batches, for bad items confined to some pieces of 4,096 (only those are re-run),
+    for every corruption kind, ragged messages, a ragged last piece, and across internal passes."""
+    from bls_verify_gadget_b200 import synth
+    n = 3 * 4096 + 777
+    pk, msg, sig, exp = synth.verify_batch_inputs(ctx, n, every=10 ** 9)                                    # all valid
+    seed = bytes(range(16))
+    st, bm, rerun = ctx.verify_rlc_bisect(pk, msg, sig, seed, fixed32=True)
+    assert not st.any() and rerun == 0 and int(np.unpackbits(bm.view(np.uint8)).sum()) == n
+    P, M, S = pk.reshape(n, 48).copy(), msg.reshape(n, 32).copy(), sig.reshape(n, 96).copy()
+    M[4096 + 5, 0] ^= 1                                                                                      # wrong message          (piece 1)
+    S[[4096 + 900, 4096 + 901]] = S[[4096 + 901, 4096 + 900]]                                                # swapped signatures     (piece 1)
+    S[3 * 4096 + 10, 92:] = 0xff                                                                             # undecodable signature  (piece 3): decode status, no re-run needed
+    P[7] = 0; P[7, 0] = 0xc0                                                                                 # identity public key    (piece 0): decode status
+    P[[3 * 4096 + 700, 3 * 4096 + 701]] = P[[3 * 4096 + 701, 3 * 4096 + 700]]                                # swapped keys           (piece 3, the ragged one)
+    want, wbm = ctx.verify(P.reshape(-1), M.reshape(-1), S.reshape(-1), want_bitmap=True, fixed32=True)
+    assert sorted(np.nonzero(want)[0].tolist()) == [7, 4101, 4996, 4997, 12298, 12988, 12989]
+    st, bm, rerun = ctx.verify_rlc_bisect(P.reshape(-1), M.reshape(-1), S.reshape(-1), seed, fixed32=True)
+    assert np.array_equal(st, want) and np.array_equal(bm, wbm) and rerun == 4096 + 777                      # pieces 1 and 3 only
+    ctx.set_chunk(4096)
+    try: st2, bm2, rerun2 = ctx.verify_rlc_bisect(P.reshape(-1), M.reshape(-1), S.reshape(-1), b"another seed 16b", fixed32=True)
+    finally: ctx.set_chunk(1 << 20)
+    assert np.array_equal(st2, want) and np.array_equal(bm2, wbm) and rerun2 == rerun
+    # ragged messages; a batch smaller than one piece falls back as a whole
+    rng = np.random.default_rng(19); rag = [rng.bytes(int(l)) for l in rng.integers(0, 70, size=150)]
+    sk = synth.secret_keys(150); rpk, _ = ctx.sk_to_pk(sk); rsig, _ = ctx.sign(sk, rag)
+    st, bm, rerun = ctx.verify_rlc_bisect(rpk, rag, rsig, seed); assert not st.any() and rerun == 0
+    rag2 = list(rag); rag2[77] = rag2[77] + b"x"
+    st, bm, rerun = ctx.verify_rlc_bisect(rpk, rag2, rsig, seed); w2, wb2 = ctx.verify(rpk, rag2, rsig, want_bitmap=True)
+    assert np.array_equal(st, w2) and np.array_equal(bm, wb2) and rerun == 150 and sorted(np.nonzero(st)[0].tolist()) == [77]
+
 # ------------------------------------------------------------------------------------------ the reference-shaped API (src/bls.rs)
 def test_bls_api_like_reference_tests(ctx, eth):
     from bls_verify_gadget_b200 import BLS, PrivateKey, PublicKey, Signature, BLSError, hash_to_g2
