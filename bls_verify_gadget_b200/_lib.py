@@ -35,7 +35,7 @@ def lib():
     return _lib
 
 EXPORTS = ["blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_set_stream", "blsgpu_set_pointer_mode", "blsgpu_synchronize",
-           "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_set_coop", "blsgpu_verify_batch", "blsgpu_verify_batch_rlc", "blsgpu_verify_batch_rlc_bisect", "blsgpu_fast_aggregate_verify_batch", "blsgpu_pool_create", "blsgpu_pool_free", "blsgpu_pool_fast_aggregate_verify", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
+           "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_set_coop", "blsgpu_verify_batch", "blsgpu_verify_batch_rlc", "blsgpu_verify_batch_rlc_bisect", "blsgpu_fast_aggregate_verify_batch", "blsgpu_aggregate_verify_batch", "blsgpu_g1_uncompress", "blsgpu_g1_compress", "blsgpu_g2_uncompress", "blsgpu_g2_compress", "blsgpu_pool_create", "blsgpu_pool_free", "blsgpu_pool_fast_aggregate_verify", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
            "blsgpu_g2_aggregate", "blsgpu_deserialize_g1", "blsgpu_deserialize_g2", "blsgpu_sk_to_pk_batch", "blsgpu_sign_batch", "blsgpu_pairing_gt",
            "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_r1cs_row_classes", "blsgpu_r1cs_load_file", "blsgpu_r1cs_check_file", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_check", "blsgpu_witness_free",
            "blsgpu_create_multi", "blsgpu_destroy_multi", "blsgpu_multi_last_error", "blsgpu_multi_ndev", "blsgpu_multi_nccl_version", "blsgpu_multi_ctx", "blsgpu_multi_verify_batch", "blsgpu_multi_peek"]
@@ -133,6 +133,22 @@ class Context:
         _need("sig96", sg, 96 * nc); _need("msg32", m, 32 * nc); _need("pks48", pk, 48 * nc * k); _need("bitmap", bm, 8 * ((nc * k + 63) // 64))
         self.fast_aggregate_verify_ptr(pk, bm, k, m, sg, nc, st, agg)
         return (st, agg) if want_agg else st
+    def aggregate_verify(self, pks48, msgs, pair_off, sig96):
+        """Eth2 AggregateVerify (distinct messages): signature s covers pairs [pair_off[s], pair_off[s+1]) of (pks48[j], msgs[j]) -> status per signature"""
+        pk = _u8(pks48); sg = _u8(sig96); ns = sg.size // 96; po = np.ascontiguousarray(pair_off, dtype=np.uint32)
+        if po.size != ns + 1 or (ns and (po[0] != 0 or np.any(np.diff(po.astype(np.int64)) < 0))): raise ValueError("pair_off must hold nsig + 1 non-decreasing offsets starting at 0")
+        npairs = int(po[-1]) if po.size else 0
+        if len(msgs) != npairs: raise ValueError(f"{len(msgs)} messages for {npairs} pairs")
+        _need("pks48", pk, 48 * npairs); _need("sig96", sg, 96 * ns)
+        flat, off = pack_msgs(msgs); st = np.empty(max(ns, 1), np.uint8)
+        self._ck(lib().blsgpu_aggregate_verify_batch(self._h, _p(pk), _p(flat), _p(off), _p(po), _p(sg), _sz(ns), _p(st))); return st[:ns]
+    def _recode(self, fn, data, in_sz, out_sz):
+        a = _u8(data); n = a.size // in_sz; _need("input", a, in_sz * n); out = np.empty(max(out_sz * n, 1), np.uint8); st = np.empty(max(n, 1), np.uint8)
+        self._ck(fn(self._h, _p(a), _sz(n), _p(out), _p(st))); return out[:out_sz * n], st[:n]
+    def g1_uncompress(self, in48): return self._recode(lib().blsgpu_g1_uncompress, in48, 48, 96)
+    def g1_compress(self, in96): return self._recode(lib().blsgpu_g1_compress, in96, 96, 48)
+    def g2_uncompress(self, in96): return self._recode(lib().blsgpu_g2_uncompress, in96, 96, 192)
+    def g2_compress(self, in192): return self._recode(lib().blsgpu_g2_compress, in192, 192, 96)
     def pool_create(self, pks48):
         a = _u8(pks48); n = a.size // 48; st = np.empty(n, np.uint8); h = ctypes.c_int(-1)
         self._ck(lib().blsgpu_pool_create(self._h, _p(a), _sz(n), ctypes.byref(h), _p(st))); return h.value, st

@@ -430,6 +430,44 @@ __global__ void __launch_bounds__(32, 1) k_rlc_finish_seg(const u32x4* f_piece, 
     ok[p] = fp12_is_one(gt) ? 1 : 0;
 }
 
+// ---- uncompressed <-> compressed point encodings (K7'): status = BLSGPU_DE_* of the INPUT; an undecodable input gives an all-zero output
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_g1_recode(const uint8_t* in, size_t n, uint8_t* out, uint8_t* code, int to_uncompressed) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    g1_aff p; int rc = to_uncompressed ? g1_decode(p, in + 48 * i) : g1_decode_uncompressed(p, in + 96 * i);
+    uint8_t* o = out + (to_uncompressed ? 96 : 48) * i;
+    if (rc > DEC_INF) { for (int k = 0; k < (to_uncompressed ? 96 : 48); k++) o[k] = 0; }
+    else if (to_uncompressed) g1_encode_uncompressed(o, p, rc == DEC_INF); else g1_encode(o, p, rc == DEC_INF);
+    if (code) code[i] = (uint8_t)rc;
+}
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_g2_recode(const uint8_t* in, size_t n, uint8_t* out, uint8_t* code, int to_uncompressed) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    g2_aff p; int rc = to_uncompressed ? g2_decode(p, in + 96 * i) : g2_decode_uncompressed(p, in + 192 * i);
+    uint8_t* o = out + (to_uncompressed ? 192 : 96) * i;
+    if (rc > DEC_INF) { for (int k = 0; k < (to_uncompressed ? 192 : 96); k++) o[k] = 0; }
+    else if (to_uncompressed) g2_encode_uncompressed(o, p, rc == DEC_INF); else g2_encode(o, p, rc == DEC_INF);
+    if (code) code[i] = (uint8_t)rc;
+}
+// ---- aggregate_verify (distinct messages): per-signature glue.  sig_status / sig_flags for the (-g1, sig) Miller loops:
+__global__ void k_aggv_sig_status(const uint8_t* code_sig, size_t nsig, uint8_t* st, uint8_t* flags) {
+    size_t s = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (s >= nsig) return;
+    st[s] = (code_sig[s] == DEC_OK || code_sig[s] == DEC_INF) ? ST_OK : ST_BAD_SIG;
+    flags[s] = FL_HM_INF | (code_sig[s] == DEC_INF ? FL_SIG_INF : 0);            // the (pk, H(m)) slot of k_miller is switched off
+}
+// F_s = f_sig[s] * prod_{j in pairs of s} f_pair[j]; status: a bad key wins over a bad signature (the order of src/bls.rs:434-447), no pairs = ST_EMPTY
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_aggv_combine(const u32x4* f_pair, const uint8_t* pair_status, size_t npairs, const uint32_t* pair_off,
+                                                                 u32x4* f_sig, const uint8_t* sig_status, size_t nsig, uint8_t* status) {
+    size_t s = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (s >= nsig) return;
+    uint32_t lo = pair_off[s], hi = pair_off[s + 1];
+    uint8_t st = sig_status[s];
+    for (uint32_t j = lo; j < hi; j++) if (pair_status[j] != ST_OK) { st = ST_BAD_PK; break; }
+    if (st == ST_OK && lo == hi) st = ST_EMPTY;
+    status[s] = st;
+    if (st != ST_OK) return;
+    fp12 acc, x; soa_load_fp12(acc, f_sig, nsig, s);
+    for (uint32_t j = lo; j < hi; j++) { soa_load_fp12(x, f_pair, npairs, j); fp12_mul(acc, acc, x); }
+    soa_store_fp12(f_sig, nsig, s, acc);
+}
+
 // ================================================================================================ context
 struct blsgpu_ctx {
     int device; cudaStream_t own_stream, stream; int ptr_mode; char err[512];
@@ -1068,6 +1106,64 @@ int blsgpu_fast_aggregate_verify_batch(blsgpu_ctx* ctx, const uint8_t* pks48, co
     if ((rc = finish_out(ctx, status, dstatus, ncomm))) return rc; if ((rc = finish_out(ctx, agg_pk48_out, dagg, 48 * ncomm))) return rc;
     return finish_call(ctx);
 }
+
+// ---- Eth2 AggregateVerify (distinct messages; the category reference tests/readme.md:4-7 names and does not vendor):
+// signature s covers the pairs [pair_off[s], pair_off[s+1]): true iff  e(-g1, sig_s) * prod_j e(pk_j, H(m_j)) == 1  with every key
+// KeyValidate-d (decodes, not the identity, in the subgroup) and the signature in the subgroup.  Every pair's Miller loop is an
+// independent item (full parallelism over npairs + nsig loops, the single-pair form of k_miller); the Miller values of a signature are
+// multiplied and ONE final exponentiation per signature decides.  status[s]: 0 / 1, 2 = a key failed, 3 = the signature failed, 4 = no pairs.
+int blsgpu_aggregate_verify_batch(blsgpu_ctx* ctx, const uint8_t* pks48, const uint8_t* msg, const uint32_t* msg_off, const uint32_t* pair_off,
+                                  const uint8_t* sig96, size_t nsig, uint8_t* status) {
+    ENTER(); if (!pair_off || !sig96 || !status) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (!nsig) return 0;
+    int rc; size_t npairs; if ((rc = seg_total(ctx, pair_off, nsig, npairs))) return rc;
+    if (npairs && (!pks48 || !msg)) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    size_t mb = msg_bytes_total(ctx, msg_off, npairs, rc); if (rc) return fail(ctx, rc, "reading msg_off failed");
+    size_t np1 = npairs ? npairs : 1;
+    if ((rc = ws_reserve(ctx, al(48 * np1) + al(mb + 1) + al(4 * (np1 + 1)) + al(4 * (nsig + 1)) + al(96 * nsig) + al(96 * np1) + 2 * al(192 * np1) + al(576 * np1) + 5 * al(np1) +
+                              al(96 * nsig) + 2 * al(192 * nsig) + al(576 * nsig) + 4 * al(nsig) + 65536))) return rc;
+    const uint8_t *dpk, *dmsg, *dsig; const uint32_t *doff, *dpair;
+    if ((rc = stage_in(ctx, dpk, pks48, 48 * npairs))) return rc; if ((rc = stage_in(ctx, dmsg, msg, mb ? mb : 1))) return rc;
+    if ((rc = stage_in(ctx, doff, msg_off, npairs + 1))) return rc; if ((rc = stage_in(ctx, dpair, pair_off, nsig + 1))) return rc;
+    if ((rc = stage_in(ctx, dsig, sig96, 96 * nsig))) return rc;
+    u32x4* pk_soa = ws_take<u32x4>(ctx, 6 * np1); u32x4* hm_soa = ws_take<u32x4>(ctx, 12 * np1); u32x4* zero_g2 = ws_take<u32x4>(ctx, 12 * np1); u32x4* f_pair = ws_take<u32x4>(ctx, 36 * np1);
+    uint8_t* code_pk = ws_take<uint8_t>(ctx, np1); uint8_t* code_inf = ws_take<uint8_t>(ctx, np1); uint8_t* pflags = ws_take<uint8_t>(ctx, np1); uint8_t* pstatus = ws_take<uint8_t>(ctx, np1);
+    u32x4* sig_soa = ws_take<u32x4>(ctx, 12 * nsig); u32x4* zero_g1 = ws_take<u32x4>(ctx, 6 * nsig); u32x4* zero_hm = ws_take<u32x4>(ctx, 12 * nsig); u32x4* f_sig = ws_take<u32x4>(ctx, 36 * nsig);
+    uint8_t* code_sig = ws_take<uint8_t>(ctx, nsig); uint8_t* sflags = ws_take<uint8_t>(ctx, nsig); uint8_t* sstatus = ws_take<uint8_t>(ctx, nsig);
+    uint8_t* dstatus = stage_out(ctx, status, nsig);
+    if (npairs) {
+        LAUNCH(k_decode_g1, nblk(npairs), TPB, dpk, npairs, pk_soa, code_pk);
+        CU(cudaMemsetAsync(code_inf, DEC_INF, npairs, ctx->stream));          // "signature = identity" for every pair item: k_hash_to_g2 then switches the (-g1, sig) slot off
+        CU(cudaMemsetAsync(zero_g2, 0, 192 * npairs, ctx->stream));
+        LAUNCH(k_hash_to_g2, nblk(npairs), TPB, dmsg, doff, npairs, (const uint8_t*)code_pk, (const uint8_t*)code_inf, hm_soa, pflags, pstatus);
+        LAUNCH(k_miller, nblk(npairs), TPB, (const u32x4*)pk_soa, (const u32x4*)hm_soa, (const u32x4*)zero_g2, (const uint8_t*)pflags, (const uint8_t*)pstatus, npairs, f_pair);
+    }
+    LAUNCH(k_decode_g2, nblk(nsig), TPB, dsig, nsig, sig_soa, code_sig);
+    LAUNCH(k_aggv_sig_status, nblk(nsig), TPB, (const uint8_t*)code_sig, nsig, sstatus, sflags);
+    CU(cudaMemsetAsync(zero_g1, 0, 96 * nsig, ctx->stream)); CU(cudaMemsetAsync(zero_hm, 0, 192 * nsig, ctx->stream));
+    LAUNCH(k_miller, nblk(nsig), TPB, (const u32x4*)zero_g1, (const u32x4*)zero_hm, (const u32x4*)sig_soa, (const uint8_t*)sflags, (const uint8_t*)sstatus, nsig, f_sig);
+    LAUNCH(k_aggv_combine, nblk(nsig), TPB, (const u32x4*)f_pair, (const uint8_t*)pstatus, npairs, dpair, f_sig, (const uint8_t*)sstatus, nsig, dstatus);
+    LAUNCH(k_final_exp, nblk(nsig), TPB, f_sig, (const uint8_t*)dstatus, dstatus, nsig);
+    if ((rc = finish_out(ctx, status, dstatus, nsig))) return rc;
+    return finish_call(ctx);
+}
+
+// ---- the uncompressed wire format: compressed <-> uncompressed with full validation of the input (status: BLSGPU_DE_* per item)
+static int recode(blsgpu_ctx* ctx, const uint8_t* in, size_t n, uint8_t* out, uint8_t* status, size_t in_sz, size_t out_sz, bool g2, int to_unc) {
+    if (!in || !out) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
+    if (!n) return 0;
+    if (int rc = ws_reserve(ctx, al(in_sz * n) + al(out_sz * n) + al(n) + 8192)) return rc;
+    const uint8_t* din; if (int rc = stage_in(ctx, din, in, in_sz * n)) return rc;
+    uint8_t* dout = stage_out(ctx, out, out_sz * n); uint8_t* dst = stage_out(ctx, status, n);
+    if (g2) LAUNCH(k_g2_recode, nblk(n), TPB, din, n, dout, dst, to_unc); else LAUNCH(k_g1_recode, nblk(n), TPB, din, n, dout, dst, to_unc);
+    if (int rc = finish_out(ctx, out, dout, out_sz * n)) return rc;
+    if (int rc = finish_out(ctx, status, dst, n)) return rc;
+    return finish_call(ctx);
+}
+int blsgpu_g1_uncompress(blsgpu_ctx* ctx, const uint8_t* in48, size_t n, uint8_t* out96, uint8_t* status) { ENTER(); return recode(ctx, in48, n, out96, status, 48, 96, false, 1); }
+int blsgpu_g1_compress(blsgpu_ctx* ctx, const uint8_t* in96, size_t n, uint8_t* out48, uint8_t* status) { ENTER(); return recode(ctx, in96, n, out48, status, 96, 48, false, 0); }
+int blsgpu_g2_uncompress(blsgpu_ctx* ctx, const uint8_t* in96, size_t n, uint8_t* out192, uint8_t* status) { ENTER(); return recode(ctx, in96, n, out192, status, 96, 192, true, 1); }
+int blsgpu_g2_compress(blsgpu_ctx* ctx, const uint8_t* in192, size_t n, uint8_t* out96, uint8_t* status) { ENTER(); return recode(ctx, in192, n, out96, status, 192, 96, true, 0); }
 
 // ---- resident validator pool (cfg 3a): keys are decoded and subgroup-checked once and stay in HBM as affine limb-SoA
 int blsgpu_pool_create(blsgpu_ctx* ctx, const uint8_t* pks48, size_t n, int* handle, uint8_t* status) {

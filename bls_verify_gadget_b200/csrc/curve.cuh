@@ -220,4 +220,43 @@ BLS_HD void g2_encode(uint8_t* b, const g2_aff& a, bool inf) {
     b[0] |= 0x80; if (fp2_lex_largest(a.y)) b[0] |= 0x20;
 }
 
+// ------------------------------------------------------------------------------------------------ ZCash uncompressed codec
+// 96 bytes x || y (G1) and 192 bytes x.c1 || x.c0 || y.c1 || y.c0 (G2), big-endian; first byte: bit 7 (compression) must be clear, bit 6 =
+// infinity (rest ignored, lenient like the compressed form: SURVEY B7), bit 5 is ignored like ark-bls12-381 0.4's read_g1_uncompressed.
+// The other wire format of the upstream bls12-381-tests suite (reference tests/readme.md:4-7); validation = on-curve + subgroup
+// (deserialize_uncompressed = Validate::Yes).  Not pinned by a reference fixture (the reference vendors no uncompressed vectors).
+BLS_HD int g1_decode_uncompressed(g1_aff& out, const uint8_t* b) {
+    uint32_t flags = b[0];
+    out.x = fp_zero(); out.y = fp_zero();
+    if (flags & 0x80) return DEC_BAD_FLAGS;
+    if (flags & 0x40) return DEC_INF;
+    fp x, y; bool okx = fp_from_be48(x, b, 0x1f), oky = fp_from_be48(y, b + 48);
+    if (!(okx & oky)) return DEC_RANGE;
+    if (!fp_eq(fp_sqr(y), fp_add(fp_mul(fp_sqr(x), x), g1_b()))) return DEC_NOT_ON_CURVE;
+    out.x = x; out.y = y;
+    if (!g1_in_subgroup(out)) return DEC_NOT_IN_SUBGROUP;
+    return DEC_OK;
+}
+BLS_HD void g1_encode_uncompressed(uint8_t* b, const g1_aff& a, bool inf) {
+    if (inf) { for (int i = 0; i < 96; i++) b[i] = 0; b[0] = 0x40; return; }
+    fp_canon_to_be48(b, fp_from_mont(a.x)); fp_canon_to_be48(b + 48, fp_from_mont(a.y));
+}
+BLS_HD int g2_decode_uncompressed(g2_aff& out, const uint8_t* b) {
+    uint32_t flags = b[0];
+    out.x = fp2_zero(); out.y = fp2_zero();
+    if (flags & 0x80) return DEC_BAD_FLAGS;
+    if (flags & 0x40) return DEC_INF;
+    fp2 x, y; bool ok = fp_from_be48(x.c1, b, 0x1f); ok &= fp_from_be48(x.c0, b + 48); ok &= fp_from_be48(y.c1, b + 96); ok &= fp_from_be48(y.c0, b + 144);
+    if (!ok) return DEC_RANGE;
+    if (!fp2_eq(fp2_sqr(y), fp2_add(fp2_mul(fp2_sqr(x), x), g2_b()))) return DEC_NOT_ON_CURVE;
+    out.x = x; out.y = y;
+    if (!g2_in_subgroup(out)) return DEC_NOT_IN_SUBGROUP;
+    return DEC_OK;
+}
+BLS_HD void g2_encode_uncompressed(uint8_t* b, const g2_aff& a, bool inf) {
+    if (inf) { for (int i = 0; i < 192; i++) b[i] = 0; b[0] = 0x40; return; }
+    fp_canon_to_be48(b, fp_from_mont(a.x.c1)); fp_canon_to_be48(b + 48, fp_from_mont(a.x.c0));
+    fp_canon_to_be48(b + 96, fp_from_mont(a.y.c1)); fp_canon_to_be48(b + 144, fp_from_mont(a.y.c0));
+}
+
 }  // namespace bls

@@ -114,6 +114,15 @@ int blsgpu_fast_aggregate_verify_batch(blsgpu_ctx* ctx, const uint8_t* pks48, co
                                        const uint8_t* msg32, const uint8_t* sig96, size_t ncomm,
                                        uint8_t* status, uint8_t* agg_pk48_out);
 
+/* ---- Eth2 AggregateVerify: one signature over k (public key, message) pairs with DISTINCT messages -- the category the reference's
+ *      tests/readme.md:4-7 names and does not vendor.  nsig signatures; signature s covers the pairs
+ *      [pair_off[s], pair_off[s+1]) of pks48 / msg (msg_off: npairs + 1 offsets, NULL = fixed 32-byte messages).  True iff every key
+ *      decodes, is not the identity and lies in the subgroup (the checks of src/bls.rs:434-442), the signature lies in the subgroup
+ *      (src/bls.rs:443-447) and e(-g1, sig) * prod_j e(pk_j, H(m_j)) == 1.  status[s]: 0 / 1, 2 = a key failed, 3 = the signature failed,
+ *      4 = no pairs (the draft's precondition n >= 1: callers treat it as false). */
+int blsgpu_aggregate_verify_batch(blsgpu_ctx* ctx, const uint8_t* pks48, const uint8_t* msg, const uint32_t* msg_off, const uint32_t* pair_off,
+                                  const uint8_t* sig96, size_t nsig, uint8_t* status);
+
 /* ---- the same with a RESIDENT validator pool (BASELINE configs[2], variant "keys pre-decoded in HBM"): the pool's keys are
  *      decoded and subgroup-checked once (PublicKey::try_from, src/bls.rs:219-223) and kept in HBM as affine Montgomery limb-SoA;
  *      committees are lists of pool indices.  status (nullable) of pool_create: BLSGPU_DE_* per key; an index that is out of range or
@@ -134,6 +143,15 @@ int blsgpu_g2_aggregate(blsgpu_ctx* ctx, const uint8_t* pts96, const uint32_t* s
 /* ---- TryFrom<&[u8]> for PublicKey / Signature  (src/bls.rs:219-223, 316-320) -> BLSGPU_DE_* per item -------- */
 int blsgpu_deserialize_g1(blsgpu_ctx* ctx, const uint8_t* in48, size_t n, uint8_t* status);
 int blsgpu_deserialize_g2(blsgpu_ctx* ctx, const uint8_t* in96, size_t n, uint8_t* status);
+
+/* ---- ZCash UNCOMPRESSED encodings (96-byte G1 = x || y, 192-byte G2 = x.c1 || x.c0 || y.c1 || y.c0; ark-serialize's
+ *      serialize_uncompressed / deserialize_uncompressed of the types of src/bls.rs:135-138, 262-265): conversion in both directions with
+ *      full validation of the input (on curve + subgroup, Validate::Yes).  status (nullable): BLSGPU_DE_* of the input; an input that does
+ *      not decode gives an all-zero output. */
+int blsgpu_g1_uncompress(blsgpu_ctx* ctx, const uint8_t* in48, size_t n, uint8_t* out96, uint8_t* status);
+int blsgpu_g1_compress(blsgpu_ctx* ctx, const uint8_t* in96, size_t n, uint8_t* out48, uint8_t* status);
+int blsgpu_g2_uncompress(blsgpu_ctx* ctx, const uint8_t* in96, size_t n, uint8_t* out192, uint8_t* status);
+int blsgpu_g2_compress(blsgpu_ctx* ctx, const uint8_t* in192, size_t n, uint8_t* out96, uint8_t* status);
 
 /* ---- PublicKey::from(&PrivateKey) / keygen's derivation  (src/bls.rs:210-216, 395-409) ---------------------- */
 int blsgpu_sk_to_pk_batch(blsgpu_ctx* ctx, const uint8_t* sk32_le, size_t n, uint8_t* pk48, uint8_t* status /* nullable; 5 = non-canonical */);

@@ -351,6 +351,35 @@ static void ser_g2(u8* b, const G2A& a) {
     fp_to_be(b, a.x.c1); fp_to_be(b + 48, a.x.c0); b[0] |= 0x80; if (lex_largest(a.y)) b[0] |= 0x20;
 }
 
+// ZCash UNCOMPRESSED codec (96 / 192 bytes; the other wire format of the upstream bls12-381-tests suite, reference tests/readme.md:4-7):
+// bit 7 of the first byte must be clear, bit 6 = infinity (lenient like the compressed form), bit 5 ignored (ark-bls12-381 0.4's
+// read_g1_uncompressed); Validate::Yes = on curve + in the subgroup.  Unpinned: the reference vendors no uncompressed vectors.
+static int deser_g1_unc(G1A& out, const u8* b) {
+    if (b[0] & 0x80) return DE_FLAGS;
+    if (b[0] & 0x40) { out.inf = true; out.x = FP_ZERO; out.y = FP_ZERO; return DE_OK; }
+    u8 t[48]; memcpy(t, b, 48); t[0] &= 0x1f;
+    if (!fp_from_be(out.x, t) || !fp_from_be(out.y, b + 48)) return DE_RANGE;
+    out.inf = false;
+    if (!on_curve(out)) return DE_CURVE;
+    if (!in_subgroup(out)) return DE_SUBGROUP;
+    return DE_OK;
+}
+static void ser_g1_unc(u8* b, const G1A& a) { if (a.inf) { memset(b, 0, 96); b[0] = 0x40; return; } fp_to_be(b, a.x); fp_to_be(b + 48, a.y); }
+static int deser_g2_unc(G2A& out, const u8* b) {
+    if (b[0] & 0x80) return DE_FLAGS;
+    if (b[0] & 0x40) { out.inf = true; out.x = F2_ZERO; out.y = F2_ZERO; return DE_OK; }
+    u8 t[48]; memcpy(t, b, 48); t[0] &= 0x1f;
+    if (!fp_from_be(out.x.c1, t) || !fp_from_be(out.x.c0, b + 48) || !fp_from_be(out.y.c1, b + 96) || !fp_from_be(out.y.c0, b + 144)) return DE_RANGE;
+    out.inf = false;
+    if (!on_curve(out)) return DE_CURVE;
+    if (!in_subgroup(out)) return DE_SUBGROUP;
+    return DE_OK;
+}
+static void ser_g2_unc(u8* b, const G2A& a) {
+    if (a.inf) { memset(b, 0, 192); b[0] = 0x40; return; }
+    fp_to_be(b, a.x.c1); fp_to_be(b + 48, a.x.c0); fp_to_be(b + 96, a.y.c1); fp_to_be(b + 144, a.y.c0);
+}
+
 // ---------------------------------------------------------------------------------------- SHA-256, xmd, hash_to_field
 static const uint32_t K256[64] = {
     0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3,
@@ -707,6 +736,37 @@ int ora_r1cs_check(const uint64_t* const rowptr[3], const uint32_t* const col[3]
         }
         all_sat[w] = all; });
     return bad ? -1 : 0;
+}
+// Eth2 AggregateVerify (draft-irtf-cfrg-bls-signature-05 3.1.1 under the POP scheme; upstream bls12-381-tests "aggregate_verify", the
+// category reference tests/readme.md:4-7 names): signature s covers pairs [pair_off[s], pair_off[s+1]); every key KeyValidate-d, the
+// signature subgroup-checked, then ONE (k+1)-pair product e(-g1, sig) prod e(pk_j, H(m_j)) == 1.  status: 0 / 1, 2 key, 3 signature, 4 no pairs.
+int ora_aggregate_verify(const u8* pks48, const u8* msg, const uint32_t* off, const uint32_t* pair_off, const u8* sig96, size_t nsig, u8* status, int threads) {
+    init();
+    parallel_for(nsig, threads, [&](size_t s) {
+        uint32_t lo = pair_off[s], hi = pair_off[s + 1];
+        std::vector<G1A> ps; std::vector<G2A> qs; bool bad_pk = false;
+        for (uint32_t j = lo; j < hi && !bad_pk; j++) {
+            G1A pk; if (deser_g1(pk, pks48 + 48 * (size_t)j) != DE_OK || pk.inf) { bad_pk = true; break; }
+            size_t len; const u8* m = msg_ptr(msg, off, j, len);
+            ps.push_back(pk); qs.push_back(hash_to_g2(m, len));
+        }
+        if (bad_pk) { status[s] = ST_BAD_PK; return; }
+        G2A sig; if (deser_g2(sig, sig96 + 96 * s) != DE_OK) { status[s] = ST_BAD_SIG; return; }
+        if (lo == hi) { status[s] = ST_EMPTY; return; }
+        if (!sig.inf) { ps.push_back(G1_GEN_NEG); qs.push_back(sig); }                 // ark-ec drops pairs that contain the identity
+        status[s] = final_exp(miller(ps.data(), qs.data(), (int)ps.size())) == F12_ONE ? ST_OK : ST_FALSE; });
+    return 0;
+}
+// compressed <-> uncompressed point encodings; status = DE_* of the input, undecodable input -> all-zero output
+int ora_g1_recode(const u8* in, size_t n, u8* out, u8* status, int to_unc) {
+    init(); for (size_t i = 0; i < n; i++) { G1A a; int rc = to_unc ? deser_g1(a, in + 48 * i) : deser_g1_unc(a, in + 96 * i); status[i] = (u8)rc;
+        u8* o = out + (to_unc ? 96 : 48) * i; if (rc != DE_OK) memset(o, 0, to_unc ? 96 : 48); else if (to_unc) ser_g1_unc(o, a); else ser_g1(o, a); }
+    return 0;
+}
+int ora_g2_recode(const u8* in, size_t n, u8* out, u8* status, int to_unc) {
+    init(); for (size_t i = 0; i < n; i++) { G2A a; int rc = to_unc ? deser_g2(a, in + 96 * i) : deser_g2_unc(a, in + 192 * i); status[i] = (u8)rc;
+        u8* o = out + (to_unc ? 192 : 96) * i; if (rc != DE_OK) memset(o, 0, to_unc ? 192 : 96); else if (to_unc) ser_g2_unc(o, a); else ser_g2(o, a); }
+    return 0;
 }
 int ora_hw_threads() { return (int)std::thread::hardware_concurrency(); }
 }

@@ -79,6 +79,18 @@ def fast_aggregate_verify(pks48, k, msg32, sig96, bitmap=None, want_agg=False, t
     bm = np.ascontiguousarray(bitmap, dtype=np.uint64) if bitmap is not None else None
     lib().ora_fast_aggregate_verify(_p(pk), _p(bm), _sz(k), _p(m), _p(sg), _sz(nc), _p(st), _p(agg), threads)
     return (st, agg) if want_agg else st
+def aggregate_verify(pks48, msgs, pair_off, sig96, threads=1):
+    """Eth2 AggregateVerify: signature s covers pairs [pair_off[s], pair_off[s+1]) of (pks48[j], msgs[j]); status per signature"""
+    pk = _u8(pks48); sg = _u8(sig96); ns = sg.size // 96; flat, off = msgs_pack(msgs); po = np.ascontiguousarray(pair_off, dtype=np.uint32)
+    st = np.empty(ns, dtype=np.uint8)
+    lib().ora_aggregate_verify(_p(pk), _p(flat), _p(off), _p(po), _p(sg), _sz(ns), _p(st), threads)
+    return st
+def g1_recode(data, to_uncompressed):
+    a = _u8(data); n = a.size // (48 if to_uncompressed else 96); out = np.empty((96 if to_uncompressed else 48) * n, dtype=np.uint8); st = np.empty(n, dtype=np.uint8)
+    lib().ora_g1_recode(_p(a), _sz(n), _p(out), _p(st), 1 if to_uncompressed else 0); return out, st
+def g2_recode(data, to_uncompressed):
+    a = _u8(data); n = a.size // (96 if to_uncompressed else 192); out = np.empty((192 if to_uncompressed else 96) * n, dtype=np.uint8); st = np.empty(n, dtype=np.uint8)
+    lib().ora_g2_recode(_p(a), _sz(n), _p(out), _p(st), 1 if to_uncompressed else 0); return out, st
 def pairing_gt(g1_48, g2_96):
     a = _u8(g1_48); b = _u8(g2_96); out = np.empty(576, dtype=np.uint8)
     rc = lib().ora_pairing_gt(_p(a), _p(b), _sz(a.size // 48), _p(out))

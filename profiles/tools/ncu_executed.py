@@ -7,8 +7,8 @@ instructions (summed over the SASS source page: "Thread Instructions Executed" o
 """
 import csv, io, json, subprocess, sys, collections
 
-def source_tables(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+def source_tables(rep, kernel=None):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["-k", kernel] if kernel else []), capture_output=True, text=True).stdout
     kernels = []; cur = None
     for row in csv.reader(io.StringIO(out)):
         if not row: continue
@@ -34,8 +34,12 @@ def to_bytes(v, u):
 def main():
     items = int(sys.argv[1]); result = {}
     for rep in sys.argv[2:]:
-        src = source_tables(rep); raw = raw_metrics(rep)
-        for k, r in zip(src, raw):
+        raw = raw_metrics(rep); last = {}
+        for r in raw: last[r["Kernel Name"][0].split("(")[0]] = r                 # the last captured launch of every kernel
+        for name, r in last.items():
+            tabs = [t for t in source_tables(rep, name) if t["name"] == name and t["hdr"]]
+            if not tabs: continue
+            k = tabs[-1]
             H = k["hdr"]; si = H.index("Source"); ti = H.index("Thread Instructions Executed")
             ops = collections.Counter()
             for row in k["rows"]:

@@ -514,6 +514,60 @@ def test_rlc_bisect_returns_the_exact_per_item_outcome(ctx):
     st, bm, rerun = ctx.verify_rlc_bisect(rpk, rag2, rsig, seed); w2, wb2 = ctx.verify(rpk, rag2, rsig, want_bitmap=True)
     assert np.array_equal(st, w2) and np.array_equal(bm, wb2) and rerun == 150 and sorted(np.nonzero(st)[0].tolist()) == [77]
 
+def test_aggregate_verify_distinct_messages(ctx, C):
+    """Eth2 AggregateVerify (the upstream category reference tests/readme.md:4-7 names): GPU = oracle for valid
+    aggregates of 1..9 (key, message) pairs with ragged messages, a tampered aggregate, a wrong message, a swapped key, an identity key,
+    an undecodable key, an undecodable / identity signature, no pairs -- and a bad key wins over a bad signature (src/bls.rs:434-447 order)."""
+    from bls_verify_gadget_b200 import synth
+    rng = np.random.default_rng(77); R = synth.R_ORDER
+    sizes = [1, 2, 3, 9, 4, 1, 5, 2, 3, 0, 2, 6]; npairs = sum(sizes)
+    sk = synth.secret_keys(npairs); msgs = [rng.bytes(int(l)) for l in rng.integers(0, 80, size=npairs)]
+    pk, _ = ctx.sk_to_pk(sk); sigs, st = ctx.sign(sk, msgs); assert not st.any()
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+    seg = off.copy(); agg, ast = ctx.g2_aggregate(sigs, seg)                               # Signature::aggregate per group (bls.rs:288-300)
+    assert list(ast) == [4 if s == 0 else 0 for s in sizes]
+    P = pk.reshape(npairs, 48).copy(); A = agg.reshape(len(sizes), 96).copy(); M = list(msgs)
+    A[9] = 0; A[9, 0] = 0xc0                                                               # group 9 has no pairs: identity signature
+    want = [0] * len(sizes); want[9] = 4
+    A[1] = A[2]; want[1] = 1                                                               # someone else's (valid) aggregate
+    j = int(off[4]) + 2; M[j] = M[j] + b"!"; want[4] = 1                                   # wrong message
+    j = int(off[6]); P[[j, j + 1]] = P[[j + 1, j]]; want[6] = 1                            # swapped keys inside a group
+    j = int(off[7]) + 1; P[j] = 0; P[j, 0] = 0xc0; want[7] = 2                             # identity key
+    j = int(off[8]); P[j, 47] ^= 1; want[8] = 2                                            # undecodable key (w.h.p. not on the curve / not in the subgroup)
+    A[10, 95] ^= 1; want[10] = 3                                                           # undecodable signature
+    j = int(off[11]) + 3; P[j] = 0; P[j, 0] = 0xc0; A[11, 95] ^= 1; want[11] = 2           # bad key AND bad signature: the key is reported
+    got = ctx.aggregate_verify(P.reshape(-1), M, off, A.reshape(-1))
+    ora = C.aggregate_verify(P.reshape(-1), M, off, A.reshape(-1), threads=8)
+    assert list(got) == list(ora) == want
+    # one pair = BLS::verify; an identity signature over real pairs is false, not an error (SURVEY B2)
+    one = ctx.aggregate_verify(pk[:48], msgs[:1], np.array([0, 1], np.uint32), sigs[:96]); assert list(one) == [0] == list(ctx.verify(pk[:48], msgs[:1], sigs[:96]))
+    ident = np.zeros(96, np.uint8); ident[0] = 0xc0
+    assert list(ctx.aggregate_verify(pk[:96], msgs[:2], np.array([0, 2], np.uint32), ident)) == [1] == list(C.aggregate_verify(pk[:96], msgs[:2], np.array([0, 2], np.uint32), ident))
+
+def test_uncompressed_point_encodings(ctx, C, eth):
+    """compressed <-> uncompressed ZCash encodings: GPU = oracle byte for byte in both directions on generated points, the
+    identity, every deserialisation fixture of the reference (their decode verdict carries over), and crafted bad uncompressed inputs
+    (compression flag set, x >= p, off the curve, on the curve but outside the subgroup)."""
+    from bls_verify_gadget_b200 import synth
+    n = 40; sk = synth.secret_keys(n); pk, _ = ctx.sk_to_pk(sk); sg, _ = ctx.sign(sk, [bytes([i]) * (i % 5) for i in range(n)])
+    pk = np.concatenate([pk, np.frombuffer(bytes([0xc0]) + bytes(47), np.uint8)]); sg = np.concatenate([sg, np.frombuffer(bytes([0xc0]) + bytes(95), np.uint8)])
+    u1, s1 = ctx.g1_uncompress(pk); o1, os1 = C.g1_recode(pk, True); assert np.array_equal(u1, o1) and list(s1[:n]) == [0] * n and s1[n] == 1 and not os1.any()
+    u2, s2 = ctx.g2_uncompress(sg); o2, os2 = C.g2_recode(sg, True); assert np.array_equal(u2, o2) and list(s2[:n]) == [0] * n and s2[n] == 1
+    c1, t1 = ctx.g1_compress(u1); c2, t2 = ctx.g2_compress(u2); assert np.array_equal(c1, pk) and np.array_equal(c2, sg) and list(t1) == list(s1) and list(t2) == list(s2)
+    assert np.array_equal(C.g1_recode(u1, False)[0], pk) and np.array_equal(C.g2_recode(u2, False)[0], sg)
+    for kind, key, size, unc in (("deserialization_G1", "pubkey", 48, ctx.g1_uncompress), ("deserialization_G2", "signature", 96, ctx.g2_uncompress)):
+        for name, case in eth[kind].items():
+            raw = bytes.fromhex(case["input"][key])
+            if len(raw) != size: continue
+            out, st = unc(np.frombuffer(raw, np.uint8)); assert (st[0] <= 1) == case["output"], name
+    P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    good = bytes(u1[:96]); bad = [bytes([good[0] | 0x80]) + good[1:], P.to_bytes(48, "big") + good[48:], good[:95] + bytes([good[95] ^ 1])]
+    x = 4                                                                                  # a curve point outside the subgroup: smallest x >= 4 with x^3 + 4 a square
+    while pow((x ** 3 + 4) % P, (P - 1) // 2, P) != 1: x += 1
+    y = pow((x ** 3 + 4) % P, (P + 1) // 4, P); bad.append(x.to_bytes(48, "big") + y.to_bytes(48, "big"))
+    b = np.frombuffer(b"".join(bad), np.uint8); out, st = ctx.g1_compress(b); oo, ost = C.g1_recode(b, False)
+    assert list(st) == [2, 3, 4, 5] and [int(v) for v in ost] == [1, 2, 3, 4] and not out.any() and not oo.any()
+
 # ------------------------------------------------------------------------------------------ the reference-shaped API (src/bls.rs)
 def test_bls_api_like_reference_tests(ctx, eth):
     from bls_verify_gadget_b200 import BLS, PrivateKey, PublicKey, Signature, BLSError, hash_to_g2
