@@ -31,13 +31,14 @@ def lib():
         L.blsgpu_launch_count.restype = ctypes.c_uint64
         L.blsgpu_multi_last_error.restype = ctypes.c_char_p
         L.blsgpu_multi_ctx.restype = ctypes.c_void_p
+        L.blsgpu_witness_msg_len.restype = ctypes.c_long
         _lib = L
     return _lib
 
 EXPORTS = ["blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_set_stream", "blsgpu_set_pointer_mode", "blsgpu_synchronize",
            "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_set_coop", "blsgpu_verify_batch", "blsgpu_verify_batch_rlc", "blsgpu_verify_batch_rlc_bisect", "blsgpu_fast_aggregate_verify_batch", "blsgpu_aggregate_verify_batch", "blsgpu_g1_uncompress", "blsgpu_g1_compress", "blsgpu_g2_uncompress", "blsgpu_g2_compress", "blsgpu_pool_create", "blsgpu_pool_free", "blsgpu_pool_fast_aggregate_verify", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
            "blsgpu_g2_aggregate", "blsgpu_deserialize_g1", "blsgpu_deserialize_g2", "blsgpu_sk_to_pk_batch", "blsgpu_sign_batch", "blsgpu_pairing_gt",
-           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_r1cs_row_classes", "blsgpu_r1cs_load_file", "blsgpu_r1cs_check_file", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_check", "blsgpu_witness_free",
+           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_r1cs_row_classes", "blsgpu_r1cs_load_file", "blsgpu_r1cs_check_file", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_check", "blsgpu_witness_free", "blsgpu_witness_msg_len", "blsgpu_set_witness_mode",
            "blsgpu_create_multi", "blsgpu_destroy_multi", "blsgpu_multi_last_error", "blsgpu_multi_ndev", "blsgpu_multi_nccl_version", "blsgpu_multi_ctx", "blsgpu_multi_verify_batch", "blsgpu_multi_peek"]
 
 _sz = ctypes.c_size_t; _vp = ctypes.c_void_p
@@ -238,21 +239,27 @@ class Context:
         h = ctypes.c_int(-1)
         self._ck(lib().blsgpu_witness_load(self._h, _p(r), _p(lp), _p(lc), _p(cf), _sz(r.size // 16), _sz(program["nvars"]), _sz(lp.size - 1), _sz(lc.size), _p(od), _p(lv), _sz(lv.size - 1 if levels else 0), ctypes.byref(h)))
         return h.value
-    def witness_gen(self, handle, pk48, msg32, sig96, nvars):
-        pk = _u8(pk48); m = _u8(msg32); sg = _u8(sig96); n = sg.size // 96
-        _need("sig96", sg, 96 * n); _need("pk48", pk, 48 * n); _need("msg32", m, 32 * n)
+    def witness_msg_len(self, handle):
+        L = int(lib().blsgpu_witness_msg_len(self._h, int(handle)))
+        if L < 0: raise BlsGpuError("bad witness program handle")
+        return L
+    def witness_gen(self, handle, pk48, msg, sig96, nvars):
+        """msg: n x L bytes, L = witness_msg_len(handle) (the message length the program was recorded with)"""
+        pk = _u8(pk48); m = _u8(msg); sg = _u8(sig96); n = sg.size // 96
+        _need("sig96", sg, 96 * n); _need("pk48", pk, 48 * n); _need("msg", m, self.witness_msg_len(handle) * n)
         z = np.empty(n * nvars * 48, np.uint8); st = np.empty(n, np.uint8)
         self._ck(lib().blsgpu_witness_gen(self._h, int(handle), _p(pk), _p(m), _p(sg), _sz(n), _p(z), _p(st))); return z.reshape(n, nvars * 48), st
     def witness_gen_ptr(self, handle, pk, msg, sig, n, z, status=None): self._ck(lib().blsgpu_witness_gen(self._h, int(handle), _p(pk), _p(msg), _p(sig), _sz(n), _p(z), _p(status)))
     def witness_check(self, wit_handle, r1cs_handle, pk, msgs32, sig, nrows):
         """host buffers: generation + satisfaction check in one call -> (bits uint64[n, words], all_sat uint8[n], status uint8[n])"""
         pk = _u8(pk); sg = _u8(sig); m = _u8(msgs32); n = pk.size // 48; words = (nrows + 63) // 64
-        _need("pk", pk, 48 * n); _need("sig", sg, 96 * n); _need("msgs32", m, 32 * n)
+        _need("pk", pk, 48 * n); _need("sig", sg, 96 * n); _need("msgs", m, self.witness_msg_len(wit_handle) * n)
         bits = np.zeros((n, words), np.uint64); allsat = np.zeros(n, np.uint8); st = np.empty(n, np.uint8)
         self._ck(lib().blsgpu_witness_check(self._h, int(wit_handle), int(r1cs_handle), _p(pk), _p(m), _p(sg), _sz(n), _p(bits), _p(allsat), _p(st))); return bits, allsat, st
     def witness_check_ptr(self, wit_handle, r1cs_handle, pk, msg, sig, n, bits, allsat=None, status=None):
         self._ck(lib().blsgpu_witness_check(self._h, int(wit_handle), int(r1cs_handle), _p(pk), _p(msg), _p(sig), _sz(n), _p(bits), _p(allsat), _p(status)))
     def witness_free(self, handle): lib().blsgpu_witness_free(self._h, int(handle))
+    def set_witness_mode(self, cluster=True): self._ck(lib().blsgpu_set_witness_mode(self._h, 1 if cluster else 0))
 
 
 class MultiContext:

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_final_easy(u32x4* f_soa, cons
     soa_store_fp12(f_soa, n, i, r);
 }
 __global__ void __launch_bounds__(128, 2) k_final_hard_coop(u32x4* f_soa, const uint8_t* status_in, uint8_t* status_out, size_t n) {
-    __shared__ coop_smem sm[4];
+    __shared__ coop_smem sm[4];                            // 41.5 KB per CTA
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane / 6;
     coop_lane c = coop_init(&sm[warp]);
     size_t item = (blockIdx.x * (size_t)4 + warp) * 5 + g;
@@ -476,6 +476,7 @@ struct blsgpu_ctx {
     uint8_t* rlc_acc;                   // accumulators of blsgpu_verify_batch_rlc that live across passes (allocated on first use)
     struct { u32x4* soa; uint8_t* code; size_t n; } pool[16];   // resident decoded validator pools
     int coop;                           // 1 = warp-cooperative hard part of the final exponentiation (coop.cuh)
+    int wit_cluster;                    // 1 = witness replay with one thread-block cluster per group of 32 assignments; 0 (default) = grid-wide level barrier
     int lanes; cudaStream_t lane_stream[4]; cudaEvent_t lane_done[4], fork;   // concurrent sub-ranges of a verify pass
     size_t chunk;                       // items per internal pass of verify_batch (bounds the workspace); multiple of 64
     int prof; cudaEvent_t ev[8];        // stage boundaries of the last verify_batch chunk: g1 | g2 | hash | miller | final | epilogue
@@ -561,7 +562,7 @@ int blsgpu_create(blsgpu_ctx** out, int device) {
     if (prop.major != 10) return BLSGPU_ERR_CUDA;                         // sm_100a cubin only: no other device can run it
     if (cudaSetDevice(device) != cudaSuccess) return BLSGPU_ERR_CUDA;
     blsgpu_ctx* c = new (std::nothrow) blsgpu_ctx(); if (!c) return BLSGPU_ERR_ALLOC;
-    memset(c, 0, sizeof *c); c->device = device; c->ptr_mode = BLSGPU_HOST; c->chunk = VERIFY_CHUNK_DEFAULT; c->lanes = 2;
+    memset(c, 0, sizeof *c); c->device = device; c->ptr_mode = BLSGPU_HOST; c->chunk = VERIFY_CHUNK_DEFAULT; c->lanes = 2; c->wit_cluster = 0;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return BLSGPU_ERR_CUDA; }
     c->stream = c->own_stream;
     *out = c; return 0;
@@ -586,6 +587,7 @@ int blsgpu_set_pointer_mode(blsgpu_ctx* ctx, int mode) { if (!ctx || (mode != BL
 int blsgpu_synchronize(blsgpu_ctx* ctx) { if (!ctx) return BLSGPU_ERR_ARG; dev_guard guard_; CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); return 0; }
 uint64_t blsgpu_launch_count(blsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int blsgpu_set_coop(blsgpu_ctx* ctx, int on) { if (!ctx) return BLSGPU_ERR_ARG; ctx->coop = on ? 1 : 0; return 0; }
+int blsgpu_set_witness_mode(blsgpu_ctx* ctx, int cluster) { if (!ctx) return BLSGPU_ERR_ARG; ctx->wit_cluster = cluster ? 1 : 0; return 0; }
 int blsgpu_set_lanes(blsgpu_ctx* ctx, int lanes) { if (!ctx || lanes < 1 || lanes > 4) return BLSGPU_ERR_ARG; ctx->lanes = lanes; return 0; }
 int blsgpu_set_chunk(blsgpu_ctx* ctx, size_t items) { if (!ctx || items < 64 || (items & 63)) return BLSGPU_ERR_ARG; ctx->chunk = items; return 0; }
 int blsgpu_set_profiling(blsgpu_ctx* ctx, int on) {

@@ -1,6 +1,7 @@
 // Warp-cooperative Fp12 arithmetic: one Fp12 element is spread over SIX lanes, lane k holding the Fp2 coefficient of w^k
 // (Fp12 = Fp2[w]/(w^6 - xi)), five elements per warp (lanes 30, 31 idle).  Everything an item needs stays in registers
-// (24 limbs per value per lane); operands are exchanged through a small shared-memory window per group.
+// (24 limbs per value per lane); operands are exchanged through small shared-memory windows per group and read from there
+// by the lazy dot products of wide.cuh.
 //
 // Why: in the thread-per-item kernels an item's Fp12 state (576 B per value, 3.6-6 KB per thread with temporaries) lives in
 // local memory, 0.9 MB per SM against 228 KB of L1, and the pairing kernels reach only ~60 % of the IMAD.WIDE pipe
@@ -19,74 +20,41 @@
 namespace bls {
 
 #define COOP_GROUPS 6          // groups addressed per warp (5 active + 1 dummy for lanes 30/31 so that every access is in bounds)
-struct coop_smem { fp2 A[COOP_GROUPS][6]; fp2 B[COOP_GROUPS][6]; };          // 6.75 KB per warp
+// operand windows of one warp: A = left operand coefficients, B = right operand coefficients, XB = xi * B (published by the owner lane,
+// so a product term that wraps around w^6 = xi is an ordinary term of the lazy dot product)
+struct coop_smem { fp2 A[COOP_GROUPS][6]; fp2 B[COOP_GROUPS][6]; fp2 XB[COOP_GROUPS][6]; };          // 10,368 B per warp
 
 __device__ __constant__ int COOP_TOWER_POS[6] = {0, 3, 1, 4, 2, 5};           // Fp2 slot of w^k in the tower-ordered limb-SoA record
 
-struct coop_lane { int k; fp2* A; fp2* B; };                                   // this lane's coefficient index and its group's windows
+struct coop_lane { int k; fp2* A; fp2* B; fp2* XB; };                          // this lane's coefficient index and its group's windows
 
 __device__ __forceinline__ coop_lane coop_init(coop_smem* sm_warp) {
     int lane = threadIdx.x & 31, g = lane / 6;
-    coop_lane c; c.k = lane - 6 * g; c.A = sm_warp->A[g]; c.B = sm_warp->B[g]; return c;
-}
-__device__ __constant__ uint32_t COOP_OFF_RE[6][24] = BLS_C_COOP_OFF_RE;      // (16 - 2k) p^2
-__device__ __constant__ uint32_t COOP_OFF_IM[6][24] = BLS_C_COOP_OFF_IM;      // (5 - k) p^2
-// value in [0, 4p) -> [0, p)
-__device__ __forceinline__ fp fp_reduce_4p(const fp& a) {
-    fp p2; fp_add_raw(p2, fp_modulus(), fp_modulus());
-    fp t; uint32_t br = fp_sub_raw(t, a, p2);
-    return fp_reduce_once(fp_select(br, a, t));
-}
-// Montgomery reduction of X < 24 p^2 to [0, p): (X + m p)/R < 24 p (p/R) + p < 3.5 p
-__device__ __forceinline__ fp fp_redc_wide_4p(const fpw& Xin) {
-    fpw X = Xin; uint32_t C[14];
-#pragma unroll
-    for (int i = 0; i < 14; i++) C[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-        uint32_t m = X.l[i] * BLS_M0;
-        cmad_n(&X.l[i], C[i], BLS_P0, BLS_P2, BLS_P4, BLS_P6, BLS_P8, BLS_P10, m);
-        if (i < 11) cmad_n(&X.l[i + 1], C[i + 1], BLS_P1, BLS_P3, BLS_P5, BLS_P7, BLS_P9, BLS_P11, m);
-        else { uint32_t drop = 0; cmad_n(&X.l[12], drop, BLS_P1, BLS_P3, BLS_P5, BLS_P7, BLS_P9, BLS_P11, m); }
-    }
-    fp hi, cc, t;
-#pragma unroll
-    for (int k = 0; k < 12; k++) { hi.l[k] = X.l[12 + k]; cc.l[k] = C[k]; }
-    fp_add_raw(t, hi, cc);
-    return fp_reduce_4p(t);
+    coop_lane c; c.k = lane - 6 * g; c.A = sm_warp->A[g]; c.B = sm_warp->B[g]; c.XB = sm_warp->XB[g]; return c;
 }
 
-// c = a * b.  Every lane passes its own coefficients a_k, b_k and receives c_k.
-//   c_k = sum_{i+j=k} a_i b_j + xi * sum_{i+j=k+6} a_i b_j ;  with j = s, i = (k - s) mod 6 the term wraps iff s > k.
-//   Per term (Karatsuba on unreduced products T0 = a0 b0, T1 = a1 b1, T2 = (a0+a1)(b0+b1)):
-//     plain:  re += T0 - T1        im += T2 - T0 - T1
-//     * xi :  re += 2 T0 - T2      im += T2 - 2 T1            ((x + y u)(1 + u) = (x - y) + (x + y) u)
-//   Offsets of (16 - 2k) p^2 on re and (5 - k) p^2 on im keep both accumulators in [0, 22 p^2].
+// c = a * b.  Every lane passes its own coefficients a_k, b_k and receives
+//   c_k = sum_{s = 0..5} a_{(k - s) mod 6} * (s > k ? xi b_s : b_s)
+// as two 3-term LAZY dot products (wide.cuh: unreduced 768-bit accumulation, Karatsuba inside each Fp2 product, two Montgomery
+// reductions per dot) whose operands are read straight from the shared-memory windows: 2 x 1,608 IMAD.WIDE per lane, nothing of
+// the item's Fp12 state ever touches local memory.
 __device__ __noinline__ fp2 coop_mul(const coop_lane& c, fp2 a, fp2 b) {
     __syncwarp();
-    c.A[c.k] = a; c.B[c.k] = b;
+    c.A[c.k] = a; c.B[c.k] = b; c.XB[c.k] = fp2_mul_xi(b);
     __syncwarp();
-    fpw re, im;
+    const fp2* x[6]; const fp2* y[6];
 #pragma unroll
-    for (int i = 0; i < 24; i++) { re.l[i] = COOP_OFF_RE[c.k][i]; im.l[i] = COOP_OFF_IM[c.k][i]; }     // offsets keep both sums non-negative
-#pragma unroll 1
     for (int s = 0; s < 6; s++) {
         int i = c.k - s; bool wrap = i < 0; if (wrap) i += 6;
-        fp2 x = c.A[i], y = c.B[s];
-        fpw T0, T1, T2;
-        fp_mul_wide(T0, x.c0, y.c0); fp_mul_wide(T1, x.c1, y.c1);
-        fp sx, sy; fp_add_raw(sx, x.c0, x.c1); fp_add_raw(sy, y.c0, y.c1);
-        fp_mul_wide(T2, sx, sy);
-        fpw_sub(T2, T2, T0); fpw_sub(T2, T2, T1);             // D = a0 b1 + a1 b0  (imaginary part, >= 0)
-        fpw_sub(T0, T0, T1);                                  // E = a0 b0 - a1 b1  (real part, mod 2^768)
-        fpw_add(re, re, T0); fpw_add(im, im, T2);             // plain term: (E, D)
-        if (wrap) { fpw_sub(re, re, T2); fpw_add(im, im, T0); }   // * xi: (E - D, E + D)
+        x[s] = &c.A[i]; y[s] = wrap ? &c.XB[s] : &c.B[s];
     }
-    fp2 r; r.c0 = fp_redc_wide_4p(re); r.c1 = fp_redc_wide_4p(im);
-    return r;
+    fp2 r0, r1;
+    fp2_dot_t<3>(r0, x[0], y[0], x[1], y[1], x[2], y[2]);
+    fp2_dot_t<3>(r1, x[3], y[3], x[4], y[4], x[5], y[5]);
+    return fp2_add(r0, r1);
 }
 
-// Granger-Scott squaring in the cyclotomic subgroup, one Fp2 product per lane.
+// Granger-Scott squaring in the cyclotomic subgroup, one (lazy) Fp2 product per lane.
 // Pairs (w^q, w^(q+3)), q = 0,1,2: low lane q computes T = a b, high lane q+3 computes S = (a + b)(a + xi b); then
 //   t_even[q] = S - T - xi T,  t_odd[q] = 2 T   and (arkworks' cyclotomic_square_in_place, csrc/tower.cuh fp12_cyclo_sqr)
 //   w^0 <- 3 t_even[0] - 2 z   w^3 <- 3 t_odd[0] + 2 z   w^1 <- 3 xi t_odd[2] + 2 z   w^4 <- 3 t_even[2] - 2 z
@@ -99,7 +67,7 @@ __device__ __noinline__ fp2 coop_cyclo_sqr(const coop_lane& c, fp2 z) {
     fp2 a = c.A[q], b = c.A[q + 3];
     fp2 x = high ? fp2_add(a, b) : a;
     fp2 y = high ? fp2_add(a, fp2_mul_xi(b)) : b;
-    fp2 prod = fp2_mul(x, y);
+    fp2 prod; fp2_dot1(prod, x, y);
     c.B[c.k] = prod;                                          // B[q] = T_q, B[q+3] = S_q
     __syncwarp();
     // which pair feeds this lane: w^0,w^3 <- pair 0 ; w^1,w^4 <- pair 2 ; w^2,w^5 <- pair 1

@@ -392,12 +392,9 @@ BLS_CONST uint32_t EXP_P_MINUS_3_DIV_4[12] = BLS_C_EXP_PM3D4;
 // Barrett estimate of the quotient from the top 63 bits (q or q - 1: T = floor(t / 2^350) < 2^63, mu = floor(2^414 / p), so
 // floor(T mu / 2^64) > t/p - 1/2 - 2^-30), 12 MACs for q p and one conditional subtraction.  Used for the small coefficients of the
 // R1CS matrices (80 % of the non-unit ones in the verify circuit: 2, 3, 4, 12, 2^k ...): 24 MACs instead of 300.
-BLS_HD fp fp_mul_small(const fp& z, uint32_t c) {
+// t (13 limbs, < 2^413) mod p: the Barrett step described above
+BLS_HD fp fp_barrett13(const uint32_t* t) {
     const uint32_t PL[12] = BLS_C_P;
-    uint32_t t[13]; uint64_t carry = 0;
-#pragma unroll
-    for (int i = 0; i < 12; i++) { uint64_t v = (uint64_t)z.l[i] * c + carry; t[i] = (uint32_t)v; carry = v >> 32; }
-    t[12] = (uint32_t)carry;
     uint64_t T = ((uint64_t)t[12] << 34) | ((uint64_t)t[11] << 2) | (uint64_t)(t[10] >> 30);
 #if defined(__CUDA_ARCH__)
     uint32_t q = (uint32_t)__umul64hi(T, BLS_C_MU414);
@@ -411,6 +408,36 @@ BLS_HD fp fp_mul_small(const fp& z, uint32_t c) {
         int64_t d = (int64_t)(uint64_t)t[i] - (int64_t)(uint64_t)(uint32_t)m + br; r.l[i] = (uint32_t)d; br = d >> 32;
     }
     return fp_reduce_once(r);                                 // t - q p < 2p < 2^382: the thirteenth limb cancels
+}
+BLS_HD fp fp_mul_small(const fp& z, uint32_t c) {
+    uint32_t t[13]; uint64_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { uint64_t v = (uint64_t)z.l[i] * c + carry; t[i] = (uint32_t)v; carry = v >> 32; }
+    t[12] = (uint32_t)carry;
+    return fp_barrett13(t);
+}
+// Lazy sums of small-coefficient terms: X = sum c_i z_i (c_i < 2^32, z_i canonical) is accumulated UNREDUCED in 14 limbs -- 12
+// IMAD.WIDE and two carry fix-ups per term instead of a product, a Barrett step and a conditional subtraction each -- and reduced
+// once.  Negative coefficients enter as |c| (p - z).  Capacity: at most 2^19 terms between reductions (X < 2^432).
+struct fp_lacc { uint32_t l[14]; };
+BLS_HD void fp_lacc_zero(fp_lacc& a) {
+#pragma unroll
+    for (int i = 0; i < 14; i++) a.l[i] = 0;
+}
+BLS_HD void fp_lacc_mad(fp_lacc& a, const fp& z, uint32_t c) {
+    uint32_t cy = 0;
+    cmad_n(&a.l[0], cy, z.l[0], z.l[2], z.l[4], z.l[6], z.l[8], z.l[10], c);          // limbs 0..11, carry -> limb 12 (and on into 13)
+    uint64_t s = (uint64_t)a.l[12] + cy; a.l[12] = (uint32_t)s; a.l[13] += (uint32_t)(s >> 32);
+    cmad_n(&a.l[1], a.l[13], z.l[1], z.l[3], z.l[5], z.l[7], z.l[9], z.l[11], c);     // limbs 1..12, carry -> limb 13
+}
+BLS_HD fp fp_lacc_reduce(const fp_lacc& a) {                   // X < 2^432 -> [0, p)
+    const uint32_t K[12] = BLS_C_K400;
+    uint32_t hi = (a.l[12] >> 16) | (a.l[13] << 16);          // X >> 400
+    uint32_t t[13]; uint64_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { uint64_t v = (uint64_t)K[i] * hi + a.l[i] + carry; t[i] = (uint32_t)v; carry = v >> 32; }
+    t[12] = (a.l[12] & 0xffffu) + (uint32_t)carry;            // (X mod 2^400) + hi (2^400 mod p) < 2^400 + 2^413: within fp_barrett13's range
+    return fp_barrett13(t);
 }
 
 BLS_HD fp fp_inv_fermat(const fp& a) { return fp_pow(a, EXP_P_MINUS_2, 12); }          // 0 -> 0

@@ -39,6 +39,7 @@ emit_words("BLS_C_R2", R * R % p, 12)
 emit_words("BLS_C_EXP_PM2", p - 2, 12)
 emit_words("BLS_C_R3", R * R * R % p, 12)           # fix-up factor of the divsteps inversion (fp.cuh: fp_inv)
 out.append("#define BLS_C_MU414 0x%xULL" % ((1 << 414) // p))      # Barrett factor of fp_mul_small
+out.append("#define BLS_C_K400 {" + ", ".join("0x%08xu" % ((pow(2, 400, p) >> (32 * i)) & 0xffffffff) for i in range(12)) + "}")      # 2^400 mod p: folds the top of a lazy 14-limb sum (fp_lacc_reduce)
 out.append("#define BLS_C_P_INV62 0x%016xULL" % pow(p, -1, 1 << 62))
 emit_words("BLS_C_EXP_PM3D4", (p - 3) // 4, 12)
 emit_fp("BLS_C_TWO_INV", pow(2, p - 2, p))

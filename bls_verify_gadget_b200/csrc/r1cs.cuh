@@ -107,8 +107,10 @@ __device__ __forceinline__ fp r1cs_load_z(const u32x4* zt, uint32_t col, int lan
 // One non-zero: class c, column cj with its packed 0/1 view zb, |coefficient| low word cf (small classes).  Every branch is
 // warp-uniform (class per non-zero, zbool per column).  Terms on 0/1 columns with coefficient +-1 or |c| < 2^32 go to the integer
 // side sum (at most R1_SEG terms: |sum| < 2^39); `touched` records whether the field accumulator was used at all.
+// Terms on field-valued columns with coefficient +-1 or |c| < 2^32 go to the LAZY 14-limb sum `la` (fp_lacc_*: 12 IMAD.WIDE per term, one
+// Barrett reduction per range instead of one per term; a negative coefficient enters as |c| (p - z)).
 __device__ __forceinline__ void r1cs_term(const r1cs_sys& s, int m, uint64_t k, uint32_t cj, uint32_t c, uint2 zb, uint32_t cf, const u32x4* zt, int lane,
-                                          fp& acc, int64_t& side, bool& touched) {
+                                          fp& acc, int64_t& side, bool& touched, fp_lacc& la, bool& la_used) {
     if (zb.y) {
         uint32_t bit = (zb.x >> lane) & 1u;
         if (c == R1_PLUS_ONE) side += bit;
@@ -120,25 +122,62 @@ __device__ __forceinline__ void r1cs_term(const r1cs_sys& s, int m, uint64_t k, 
     }
     touched = true;
     fp zv = r1cs_load_z(zt, cj, lane);
-    if (c == R1_PLUS_ONE) acc = fp_add(acc, zv);
-    else if (c == R1_MINUS_ONE) acc = fp_sub(acc, zv);
-    else if (c == R1_SMALL_POS) acc = fp_add(acc, fp_mul_small(zv, cf));
-    else if (c == R1_SMALL_NEG) acc = fp_sub(acc, fp_mul_small(zv, BLS_P0 - cf));
-    else acc = fp_add(acc, fp_mul(s.coeff[m][k], zv));
+    if (c == R1_GENERAL) { acc = fp_add(acc, fp_mul(s.coeff[m][k], zv)); return; }
+    la_used = true;
+    if (c == R1_PLUS_ONE) fp_lacc_mad(la, zv, 1u);
+    else if (c == R1_SMALL_POS) fp_lacc_mad(la, zv, cf);
+    else { fp nz; fp_sub_raw(nz, fp_modulus(), zv); fp_lacc_mad(la, nz, c == R1_MINUS_ONE ? 1u : BLS_P0 - cf); }      // z = 0 enters as |c| p = 0 (mod p)
 }
 // sum over the non-zeros [lo, hi) of one matrix (a segment of a long row): field part returned, integer part in side_out
 __device__ __forceinline__ fp r1cs_range_dot(const r1cs_sys& s, int m, uint64_t lo, uint64_t hi, const u32x4* zt, const uint2* zbool, int lane, int64_t& side_out, bool& touched) {
     const uint32_t* col = s.col[m]; const uint8_t* cls = s.cls[m];
     fp acc = fp_zero(); int64_t side = 0; touched = false;
+    fp_lacc la; fp_lacc_zero(la); bool la_used = false;
     uint32_t cj_n = 0; uint8_t c_n = 0; uint2 zb_n = make_uint2(0u, 0u);
     if (lo < hi) { cj_n = col[lo]; c_n = cls[lo]; zb_n = zbool[cj_n]; }
     for (uint64_t k = lo; k < hi; k++) {
         uint32_t cj = cj_n; uint8_t c = c_n; uint2 zb = zb_n;
         if (k + 1 < hi) { cj_n = col[k + 1]; c_n = cls[k + 1]; zb_n = zbool[cj_n]; }      // the next term's metadata travels while this term's gather does
         uint32_t cf = (c == R1_SMALL_POS || c == R1_SMALL_NEG) ? s.coeffc[m][k].l[0] : 0u;
-        r1cs_term(s, m, k, cj, c, zb, cf, zt, lane, acc, side, touched);
+        r1cs_term(s, m, k, cj, c, zb, cf, zt, lane, acc, side, touched, la, la_used);
     }
+    if (la_used) acc = fp_add(acc, fp_lacc_reduce(la));          // warp-uniform (classes and packed views are)
     side_out = side; return acc;
+}
+// The same sum with the terms' metadata fetched LANE-PARALLEL: lane t loads column, class, packed view and small coefficient of term
+// lo + t (two dependent rounds of independent loads for up to 32 terms), then the terms are evaluated from register broadcasts.  The
+// term-by-term walk above chains column -> packed view (-> gather) per term: fine for the 7-term short rows, but a 32-entry segment of
+// a long row (k_r1cs_segments: long-scoreboard stalls were 36 % of its samples) and the latency-bound witness replay pay that
+// latency once per term.  All 32 lanes must call it together.
+// metadata of up to 32 consecutive non-zeros, one per lane
+struct r1cs_meta { uint32_t col, c, cf, n; uint2 zb; uint64_t base; };
+__device__ __forceinline__ void r1cs_meta_fetch(r1cs_meta& t, const r1cs_sys& s, int m, uint64_t lo, uint64_t hi, int lane) {       // round 1: column, class, small coefficient
+    t.base = lo; t.n = hi - lo < 32 ? (uint32_t)(hi - lo) : 32u; t.col = 0; t.c = R1_PLUS_ONE; t.cf = 0; t.zb = make_uint2(0u, 1u);
+    if ((uint32_t)lane < t.n) {
+        t.col = s.col[m][lo + lane]; t.c = s.cls[m][lo + lane];
+        if (t.c == R1_SMALL_POS || t.c == R1_SMALL_NEG) t.cf = s.coeffc[m][lo + lane].l[0];
+    }
+}
+__device__ __forceinline__ void r1cs_meta_views(r1cs_meta& t, const uint2* zbool, int lane) { if ((uint32_t)lane < t.n) t.zb = zbool[t.col]; }      // round 2: packed 0/1 views
+struct r1cs_accum { fp acc; int64_t side; bool touched; fp_lacc la; bool la_used; };
+__device__ __forceinline__ void r1cs_accum_zero(r1cs_accum& a) { a.acc = fp_zero(); a.side = 0; a.touched = false; fp_lacc_zero(a.la); a.la_used = false; }
+__device__ __forceinline__ void r1cs_meta_eval(const r1cs_meta& t, const r1cs_sys& s, int m, const u32x4* zt, int lane, r1cs_accum& a) {
+    for (uint32_t k = 0; k < t.n; k++) {
+        uint32_t cj = __shfl_sync(0xffffffffu, t.col, k), c = __shfl_sync(0xffffffffu, t.c, k), cf = __shfl_sync(0xffffffffu, t.cf, k);
+        uint2 zb = make_uint2(__shfl_sync(0xffffffffu, t.zb.x, k), __shfl_sync(0xffffffffu, t.zb.y, k));
+        r1cs_term(s, m, t.base + k, cj, c, zb, cf, zt, lane, a.acc, a.side, a.touched, a.la, a.la_used);
+    }
+}
+__device__ __forceinline__ fp r1cs_accum_close(r1cs_accum& a, int64_t& side_out, bool& touched) {
+    if (a.la_used) a.acc = fp_add(a.acc, fp_lacc_reduce(a.la));            // warp-uniform (classes and packed views are)
+    side_out = a.side; touched = a.touched; return a.acc;
+}
+__device__ __forceinline__ fp r1cs_range_dot_wide(const r1cs_sys& s, int m, uint64_t lo, uint64_t hi, const u32x4* zt, const uint2* zbool, int lane, int64_t& side_out, bool& touched) {
+    r1cs_accum a; r1cs_accum_zero(a);                            // at most 2^18 terms between reductions of the lazy sum: no combination is that long
+    for (uint64_t base = lo; base < hi; base += 32) {
+        r1cs_meta t; r1cs_meta_fetch(t, s, m, base, hi, lane); r1cs_meta_views(t, zbool, lane); r1cs_meta_eval(t, s, m, zt, lane, a);
+    }
+    return r1cs_accum_close(a, side_out, touched);
 }
 // field part + integer part as one canonical element
 __device__ __forceinline__ fp r1cs_finalize(const fp& acc, int64_t side, bool touched) {
@@ -263,7 +302,7 @@ __global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_segments(r1cs_sys s, cons
     size_t sg = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
     if (sg >= s.n_seg) return;
     int64_t side; bool touched;
-    fp v = r1cs_range_dot(s, s.seg_mat[sg], s.seg_lo[sg], s.seg_hi[sg], zt, zbool, lane, side, touched);
+    fp v = r1cs_range_dot_wide(s, s.seg_mat[sg], s.seg_lo[sg], s.seg_hi[sg], zt, zbool, lane, side, touched);
     v = r1cs_finalize(v, side, touched);
     soa_store_fp(part, s.n_seg * 32, sg * 32 + lane, 0, v);
 }

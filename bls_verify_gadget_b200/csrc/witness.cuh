@@ -22,8 +22,9 @@ struct wit_prog {
     size_t nvars, nout, nlc, nterms, nlevels;          // nvars: columns of the program (circuit variables, then scratch values); nout: circuit variables
     wit_rule* rules; uint64_t* lc_ptr; uint32_t* col; fp* coeff; fp* coeffc; uint8_t* cls;
     wit_xrule* xrules; uint64_t* level_ptr;          // dependency levels: rules of one level are independent
+    size_t msg_len;                                  // bytes per message of the circuit the program was recorded for (from its input slots)
 };
-#define WIT_INPUTS 262          // 256 message bits, pk.x, pk.y, sig x.c0, x.c1, y.c0, y.c1
+#define WIT_POINT_INPUTS 6      // input slots 0..5: pk.x, pk.y, sig x.c0, x.c1, y.c0, y.c1; slot 6 + 8 i + b = bit b of message byte i (any message length)
 
 __device__ __forceinline__ void wit_store(u32x4* zt, size_t col, int lane, const fp& v) {
     u32x4 a, b, c;
@@ -37,13 +38,9 @@ __device__ __forceinline__ void wit_store(u32x4* zt, size_t col, int lane, const
 __device__ __forceinline__ fp wit_lc_range(const wit_prog& p, uint64_t lo, uint64_t hi, const u32x4* zt, const uint2* zb, int lane) {
     fp acc = fp_zero();
     if (zb) {
-        r1cs_sys view; view.coeff[0] = p.coeff; view.coeffc[0] = p.coeffc;
+        r1cs_sys view; view.coeff[0] = p.coeff; view.coeffc[0] = p.coeffc; view.col[0] = p.col; view.cls[0] = p.cls;
         int64_t side = 0; bool touched = false;
-        for (uint64_t k = lo, e = hi; k < e; k++) {
-            uint32_t cj = p.col[k]; uint8_t c = p.cls[k]; uint2 f = zb[cj];
-            uint32_t cf = (c == R1_SMALL_POS || c == R1_SMALL_NEG) ? p.coeffc[k].l[0] : 0u;
-            r1cs_term(view, 0, k, cj, c, f, cf, zt, lane, acc, side, touched);
-        }
+        acc = r1cs_range_dot_wide(view, 0, lo, hi, zt, zb, lane, side, touched);      // metadata of up to 32 terms fetched in one round: the replay is latency-bound
         return r1cs_finalize(acc, side, touched);
     }
     for (uint64_t k = lo, e = hi; k < e; k++) {
@@ -60,6 +57,25 @@ __device__ __forceinline__ fp wit_lc_range(const wit_prog& p, uint64_t lo, uint6
         }
     }
     return acc;
+}
+// The three combinations of a product rule (a b + d) with their metadata rounds OVERLAPPED: the replay is bound by the chain of dependent
+// loads inside one task (rule -> columns -> packed views -> values), so the column / class / coefficient loads of all three ranges are
+// issued together, then the packed views of all three, and only then are the terms evaluated.  Ranges longer than 32 terms finish
+// through the chunked loop.
+__device__ __forceinline__ void wit_lc3(const wit_prog& p, const wit_xrule& r, const u32x4* zt, const uint2* zb, int lane, fp& a, fp& b, fp& d) {
+    r1cs_sys view; view.coeff[0] = p.coeff; view.coeffc[0] = p.coeffc; view.col[0] = p.col; view.cls[0] = p.cls;
+    r1cs_meta ta, tb, td;
+    r1cs_meta_fetch(ta, view, 0, r.a_lo, r.a_hi, lane); r1cs_meta_fetch(tb, view, 0, r.b_lo, r.b_hi, lane); r1cs_meta_fetch(td, view, 0, r.d_lo, r.d_hi, lane);
+    r1cs_meta_views(ta, zb, lane); r1cs_meta_views(tb, zb, lane); r1cs_meta_views(td, zb, lane);
+    const r1cs_meta* ts[3] = {&ta, &tb, &td}; const uint32_t his[3] = {r.a_hi, r.b_hi, r.d_hi}; fp* outs[3] = {&a, &b, &d};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        r1cs_accum acc; r1cs_accum_zero(acc);
+        r1cs_meta_eval(*ts[k], view, 0, zt, lane, acc);
+        for (uint64_t base = ts[k]->base + 32; base < his[k]; base += 32) { r1cs_meta t; r1cs_meta_fetch(t, view, 0, base, his[k], lane); r1cs_meta_views(t, zb, lane); r1cs_meta_eval(t, view, 0, zt, lane, acc); }
+        int64_t side; bool touched; fp v = r1cs_accum_close(acc, side, touched);
+        *outs[k] = r1cs_finalize(v, side, touched);
+    }
 }
 __device__ __forceinline__ fp wit_lc(const wit_prog& p, uint32_t id, const u32x4* zt, const uint2* zb, int lane) {
     if (!id) return fp_zero();
@@ -79,7 +95,7 @@ __device__ __forceinline__ fp wit_mul_canon(const fp& a, const fp& b) {
     }
     return fp_mul(fp_to_mont(a), b);
 }
-// inputs: fp [WIT_INPUTS][nwit_padded] canonical (slot-major, so a warp reads 32 consecutive elements)
+// inputs: fp [6 + 8 msg_len][nwit_padded] canonical (slot-major, so a warp reads 32 consecutive elements)
 __global__ void __launch_bounds__(32) k_witness_gen(wit_prog p, const fp* inputs, size_t nwit_padded, u32x4* zt_all) {
     size_t group = blockIdx.x; int lane = threadIdx.x;
     u32x4* zt = zt_all + group * p.nvars * 96;                        // 3 chunks x 32 lanes per variable
@@ -127,14 +143,18 @@ __global__ void __launch_bounds__(WIT_TPB, WIT_BPS) k_witness_levels(wit_prog p,
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * (size_t)blockDim.x) >> 5; int lane = threadIdx.x & 31;
     fp one = fp_zero(); one.l[0] = 1;
+    uint64_t lo = p.level_ptr[0], hi = p.level_ptr[1];
+    wit_xrule rn; bool pre = warp < (hi - lo) * groups;              // this warp's first rule of the next level is fetched before the barrier (static data)
+    if (pre) rn = p.xrules[lo + warp / groups];
     for (size_t level = 0; level < p.nlevels; level++) {
-        uint64_t lo = p.level_ptr[level], n = p.level_ptr[level + 1] - lo;
+        uint64_t n = hi - lo, hi_next = level + 2 <= p.nlevels ? p.level_ptr[level + 2] : hi;
         for (size_t t = warp; t < n * groups; t += nwarps) {
-            wit_xrule r = p.xrules[lo + t / groups]; size_t group = t % groups;
+            wit_xrule r = (t == warp && pre) ? rn : p.xrules[lo + t / groups]; size_t group = t % groups;
             u32x4* zt = zt_all + group * p.nvars * 96; const uint2* zb = zbool_all ? zbool_all + group * p.nvars : nullptr;
             fp out;
             switch (r.kind) {
                 case WR_MULADD: {
+                    if (zb) { fp a, b, d; wit_lc3(p, r, zt, zb, lane, a, b, d); out = r.a_hi > r.a_lo ? fp_add(wit_mul_canon(a, b), d) : d; break; }
                     fp d = wit_lc_range(p, r.d_lo, r.d_hi, zt, zb, lane);
                     if (r.a_hi > r.a_lo) { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, zb, lane), b = wit_lc_range(p, r.b_lo, r.b_hi, zt, zb, lane); out = fp_add(wit_mul_canon(a, b), d); }
                     else out = d;
@@ -163,32 +183,102 @@ __global__ void __launch_bounds__(WIT_TPB, WIT_BPS) k_witness_levels(wit_prog p,
                 if (lane == 0) zbool_all[group * p.nvars + r.var] = make_uint2(all ? pack : 0u, all ? 1u : 0u);
             }
         }
+        pre = level + 1 < p.nlevels && warp < (hi_next - hi) * groups;
+        if (pre) rn = p.xrules[hi + warp / groups];
         grid.sync();
+        lo = hi; hi = hi_next;
+    }
+}
+// Cluster form of the level-synchronous replay: one thread-block CLUSTER (WIT_CL CTAs on WIT_CL SMs, 8 x 256 threads = 64 warps) owns
+// one group of 32 assignments, one warp per rule of the current level, and the barrier between levels is the hardware cluster barrier
+// (~0.2 us) instead of a grid-wide barrier over every resident CTA (several us, 14.7 k times per launch).  Groups run independently
+// side by side (18 clusters fill the 148 SMs; further groups queue behind them), so a launch costs (levels x level latency) per WAVE
+// of 18 groups.  The next level's rule record -- static data -- is fetched BEFORE the barrier, so that after it only the loads
+// that depend on the previous level's values remain on the critical path.
+#ifndef WIT_CL
+#define WIT_CL 8
+#endif
+#define WIT_CL_TPB 256
+__device__ __forceinline__ void wit_eval_rule(const wit_prog& p, const wit_xrule& r, const fp* inputs, size_t nwit_padded, size_t group, u32x4* zt, uint2* zbw, int lane) {
+    const uint2* zb = zbw;
+    fp one = fp_zero(); one.l[0] = 1;
+    fp out;
+    switch (r.kind) {
+        case WR_MULADD: {
+            if (zb) { fp a, b, d; wit_lc3(p, r, zt, zb, lane, a, b, d); out = r.a_hi > r.a_lo ? fp_add(wit_mul_canon(a, b), d) : d; break; }
+            fp d = wit_lc_range(p, r.d_lo, r.d_hi, zt, zb, lane);
+            if (r.a_hi > r.a_lo) { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, zb, lane), b = wit_lc_range(p, r.b_lo, r.b_hi, zt, zb, lane); out = fp_add(wit_mul_canon(a, b), d); }
+            else out = d;
+            break;
+        }
+        case WR_INV: out = wit_inv_canon(wit_lc_range(p, r.a_lo, r.a_hi, zt, zb, lane)); break;
+        case WR_NEQ: { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, zb, lane); out = fp_zero(); out.l[0] = fp_is_zero(a) ? 0u : 1u; break; }
+        case WR_NEQMULT: { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, zb, lane); out = fp_is_zero(a) ? one : wit_inv_canon(a); break; }
+        case WR_BIT: { fp a = wit_lc_range(p, r.a_lo, r.a_hi, zt, zb, lane); out = fp_zero(); out.l[0] = (a.l[r.aux >> 5] >> (r.aux & 31)) & 1u; break; }
+        case WR_FP2INV: {
+            fp2 x; x.c0 = fp_to_mont(wit_lc_range(p, r.a_lo, r.a_hi, zt, zb, lane)); x.c1 = fp_to_mont(wit_lc_range(p, r.b_lo, r.b_hi, zt, zb, lane));
+            fp2 iv = fp2_inv(x); out = fp_from_mont(r.aux ? iv.c1 : iv.c0); break;
+        }
+        case WR_FP12INV: {
+            fp12 x, iv; fp* xf = &x.c0.c0.c0;
+            for (int k = 0; k < 12; k++) xf[k] = fp_to_mont(wit_lc(p, r.a_lo + k, zt, zb, lane));
+            fp12_inv(iv, x); out = fp_from_mont((&iv.c0.c0.c0)[r.aux]); break;
+        }
+        default: out = r.aux == 0xffff ? one : inputs[(size_t)r.aux * nwit_padded + group * 32 + lane]; break;       // WR_INPUT; 0xffff: the constant ONE (variable 0)
+    }
+    if (!zbw) { wit_store(zt, r.var, lane, out); return; }
+    bool small = out.l[0] < 2 && !(out.l[1] | out.l[2] | out.l[3] | out.l[4] | out.l[5] | out.l[6] | out.l[7] | out.l[8] | out.l[9] | out.l[10] | out.l[11]);
+    bool all = __all_sync(0xffffffffu, small); uint32_t pack = __ballot_sync(0xffffffffu, out.l[0] & 1u);
+    if (!all) wit_store(zt, r.var, lane, out);                // a 0/1 column lives in its packed word only (every reader tests the flag first)
+    if (lane == 0) zbw[r.var] = make_uint2(all ? pack : 0u, all ? 1u : 0u);
+}
+__global__ void __launch_bounds__(WIT_CL_TPB, 1) k_witness_cluster(wit_prog p, const fp* inputs, size_t nwit_padded, u32x4* zt_all, size_t groups, uint2* zbool_all) {
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+    const unsigned CW = WIT_CL * (WIT_CL_TPB / 32);                                             // warps of the cluster
+    size_t group = blockIdx.x / WIT_CL; unsigned cw = cluster.block_rank() * (WIT_CL_TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
+    u32x4* zt = zt_all + group * p.nvars * 96; uint2* zbw = zbool_all ? zbool_all + group * p.nvars : nullptr;
+    uint64_t lo = p.level_ptr[0], hi = p.level_ptr[1];
+    wit_xrule rn; bool pre = lo + cw < hi;
+    if (pre) rn = p.xrules[lo + cw];
+    for (size_t level = 0; level < p.nlevels; level++) {
+        uint64_t hi_next = level + 2 <= p.nlevels ? p.level_ptr[level + 2] : hi;
+        for (uint64_t t = lo + cw; t < hi; t += CW) {
+            wit_xrule r = (t == lo + cw && pre) ? rn : p.xrules[t];
+            wit_eval_rule(p, r, inputs, nwit_padded, group, zt, zbw, lane);
+        }
+        pre = level + 1 < p.nlevels && hi + cw < hi_next;
+        if (pre) rn = p.xrules[hi + cw];                      // static data: travels while the cluster gathers at the barrier
+        cluster.sync();
+        lo = hi; hi = hi_next;
     }
 }
 // input slots from the decoded points and the message bytes; items whose key or signature does not decode get all-zero inputs
-__global__ void __launch_bounds__(TPB, BLS_MINB) k_witness_inputs(const u32x4* pk_soa, const uint8_t* code_pk, const u32x4* sig_soa, const uint8_t* code_sig, const uint8_t* msg32,
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_witness_inputs(const u32x4* pk_soa, const uint8_t* code_pk, const u32x4* sig_soa, const uint8_t* code_sig, const uint8_t* msg, size_t msg_len,
                                                                   size_t nwit, size_t nwit_padded, fp* inputs, uint8_t* status) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= nwit_padded) return;
     bool live = i < nwit; uint8_t st = ST_OK;
     if (live) { if (code_pk[i] != DEC_OK) st = ST_BAD_PK; else if (code_sig[i] != DEC_OK) st = ST_BAD_SIG; }      // the circuit inverts z of both points: the identity has no assignment
     bool ok = live && st == ST_OK;
     fp zero = fp_zero();
-    for (int k = 0; k < 256; k++) { fp b = zero; if (ok) b.l[0] = (msg32[32 * i + (k >> 3)] >> (k & 7)) & 1u; inputs[(size_t)k * nwit_padded + i] = b; }
+    for (size_t k = 0; k < 8 * msg_len; k++) { fp b = zero; if (ok) b.l[0] = (msg[msg_len * i + (k >> 3)] >> (k & 7)) & 1u; inputs[(size_t)(WIT_POINT_INPUTS + k) * nwit_padded + i] = b; }
     g1_aff pk; g2_aff sg;
     if (ok) { soa_load_g1(pk, pk_soa, nwit, i); soa_load_g2(sg, sig_soa, nwit, i); }
-    inputs[(size_t)256 * nwit_padded + i] = ok ? fp_from_mont(pk.x) : zero; inputs[(size_t)257 * nwit_padded + i] = ok ? fp_from_mont(pk.y) : zero;
-    inputs[(size_t)258 * nwit_padded + i] = ok ? fp_from_mont(sg.x.c0) : zero; inputs[(size_t)259 * nwit_padded + i] = ok ? fp_from_mont(sg.x.c1) : zero;
-    inputs[(size_t)260 * nwit_padded + i] = ok ? fp_from_mont(sg.y.c0) : zero; inputs[(size_t)261 * nwit_padded + i] = ok ? fp_from_mont(sg.y.c1) : zero;
+    inputs[(size_t)0 * nwit_padded + i] = ok ? fp_from_mont(pk.x) : zero; inputs[(size_t)1 * nwit_padded + i] = ok ? fp_from_mont(pk.y) : zero;
+    inputs[(size_t)2 * nwit_padded + i] = ok ? fp_from_mont(sg.x.c0) : zero; inputs[(size_t)3 * nwit_padded + i] = ok ? fp_from_mont(sg.x.c1) : zero;
+    inputs[(size_t)4 * nwit_padded + i] = ok ? fp_from_mont(sg.y.c0) : zero; inputs[(size_t)5 * nwit_padded + i] = ok ? fp_from_mont(sg.y.c1) : zero;
     if (live && status) status[i] = st;
 }
 // transposed group -> z[w][col] (48-byte LE canonical), the layout of blsgpu_r1cs_check
-__global__ void __launch_bounds__(256) k_witness_untranspose(const u32x4* zt_all, size_t ncols, size_t nout, size_t nwit, u32x4* z) {
+__global__ void __launch_bounds__(256) k_witness_untranspose(const u32x4* zt_all, const uint2* zbool_all, size_t ncols, size_t nout, size_t nwit, u32x4* z) {
     size_t col = blockIdx.x * (size_t)8 + (threadIdx.x >> 5); int lane = threadIdx.x & 31; size_t group = blockIdx.y;
     size_t w = group * 32 + lane;
     if (col >= nout || w >= nwit) return;
     const u32x4* zt = zt_all + group * ncols * 96;
     u32x4* dst = z + (w * nout + col) * 3;
+    if (zbool_all) {                                          // a 0/1 column exists only as its packed word
+        uint2 f = zbool_all[group * ncols + col];
+        if (f.y) { u32x4 v; v.x = (f.x >> lane) & 1u; v.y = v.z = v.w = 0; u32x4 zero; zero.x = zero.y = zero.z = zero.w = 0; dst[0] = v; dst[1] = zero; dst[2] = zero; return; }
+    }
     dst[0] = zt[(col * 3) * 32 + lane]; dst[1] = zt[(col * 3 + 1) * 32 + lane]; dst[2] = zt[(col * 3 + 2) * 32 + lane];
 }
 
@@ -208,6 +298,12 @@ int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t*
     wit_prog* p = new (std::nothrow) wit_prog(); if (!p) return fail(ctx, BLSGPU_ERR_ALLOC, "out of host memory");
     memset(p, 0, sizeof *p); p->nvars = nvars; p->nout = nout; p->nlc = nlc; p->nterms = nterms;
     struct guard_t { wit_prog* p; ~guard_t() { if (p) wit_release(p); } } undo{p};          // a failed load leaves nothing behind
+    {   // the message length of the recorded circuit follows from the highest input slot: slots 0..5 are the points, 6 + 8 i + b the message bits
+        const wit_rule* hr = reinterpret_cast<const wit_rule*>(rules16); size_t top = 0;
+        for (size_t k = 0; k < nvars; k++) if (hr[k].kind == WR_INPUT && hr[k].aux != 0xffff && (size_t)hr[k].aux + 1 > top) top = (size_t)hr[k].aux + 1;
+        if (top && (top < WIT_POINT_INPUTS || (top - WIT_POINT_INPUTS) % 8)) return fail(ctx, BLSGPU_ERR_ARG, "witness program: %zu input slots is not 6 + 8 x message bytes", top);
+        p->msg_len = top ? (top - WIT_POINT_INPUTS) / 8 : 0;
+    }
     cudaMemcpyKind kind = ctx->ptr_mode == BLSGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     size_t nt = nterms ? nterms : 1;
     CU(cudaMalloc(&p->rules, 16 * nvars)); CU(cudaMalloc(&p->lc_ptr, 8 * (nlc + 1))); CU(cudaMalloc(&p->col, 4 * nt));
@@ -239,6 +335,8 @@ int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t*
     CU(cudaStreamSynchronize(ctx->stream));
     undo.p = nullptr; ctx->wit[h] = p; *handle = h; return 0;
 }
+// bytes per message of the circuit the loaded program was recorded for (blsgpu_witness_gen / _check take nwit x that many message bytes)
+long blsgpu_witness_msg_len(blsgpu_ctx* ctx, int handle) { return (!ctx || handle < 0 || handle >= 4 || !ctx->wit[handle]) ? -1 : (long)ctx->wit[handle]->msg_len; }
 int blsgpu_witness_free(blsgpu_ctx* ctx, int handle) {
     if (!ctx || handle < 0 || handle >= 4 || !ctx->wit[handle]) return BLSGPU_ERR_ARG;
     dev_guard guard_; cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
@@ -248,25 +346,32 @@ int blsgpu_witness_free(blsgpu_ctx* ctx, int handle) {
 // decode, input slots and the level-synchronous replay for nwit triples: leaves the assignments in the transposed group layout
 // (group stride nvars * 96 u32x4) in the workspace; `extra` bytes of workspace are reserved for the caller's own buffers, which it
 // takes AFTER this returns.  want_zbool: also the packed 0/1 view per (group, variable).
-static int witness_run(blsgpu_ctx* ctx, const wit_prog& p, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, size_t nwit, uint8_t* status, size_t extra,
+static int witness_run(blsgpu_ctx* ctx, const wit_prog& p, const uint8_t* pk48, const uint8_t* msg, const uint8_t* sig96, size_t nwit, uint8_t* status, size_t extra,
                        bool want_zbool, u32x4** zt_out, uint2** zbool_out, uint8_t** dstatus_out) {
-    size_t groups = (nwit + 31) / 32, np = groups * 32;
-    if (int rc = ws_reserve(ctx, al(48 * nwit) + al(96 * nwit) + al(32 * nwit) + al(96 * nwit) + al(192 * nwit) + 3 * al(np) + al(48 * WIT_INPUTS * np) + al(groups * p.nvars * 1536) +
+    size_t groups = (nwit + 31) / 32, np = groups * 32, ninputs = WIT_POINT_INPUTS + 8 * p.msg_len;
+    if (int rc = ws_reserve(ctx, al(48 * nwit) + al(96 * nwit) + al(p.msg_len * nwit + 1) + al(96 * nwit) + al(192 * nwit) + 3 * al(np) + al(48 * ninputs * np) + al(groups * p.nvars * 1536) +
                                  (want_zbool ? al(groups * p.nvars * 8) : 0) + extra + 65536)) return rc;
     const uint8_t *dpk, *dsig, *dmsg;
     if (int rc = stage_in(ctx, dpk, pk48, 48 * nwit)) return rc;
     if (int rc = stage_in(ctx, dsig, sig96, 96 * nwit)) return rc;
-    if (int rc = stage_in(ctx, dmsg, msg32, 32 * nwit)) return rc;
+    if (int rc = stage_in(ctx, dmsg, msg, p.msg_len * nwit ? p.msg_len * nwit : 1)) return rc;
     u32x4* pk_soa = ws_take<u32x4>(ctx, 6 * nwit); u32x4* sig_soa = ws_take<u32x4>(ctx, 12 * nwit);
     uint8_t* code_pk = ws_take<uint8_t>(ctx, np); uint8_t* code_sig = ws_take<uint8_t>(ctx, np);
     uint8_t* dstatus = status ? stage_out(ctx, status, nwit) : nullptr;
-    fp* inputs = ws_take<fp>(ctx, (size_t)WIT_INPUTS * np);
+    fp* inputs = ws_take<fp>(ctx, ninputs * np);
     u32x4* zt_all = ws_take<u32x4>(ctx, groups * p.nvars * 96);
     uint2* zbool_all = want_zbool ? ws_take<uint2>(ctx, groups * p.nvars) : nullptr;
     LAUNCH(k_decode_g1, nblk(nwit), TPB, dpk, nwit, pk_soa, code_pk);
     LAUNCH(k_decode_g2, nblk(nwit), TPB, dsig, nwit, sig_soa, code_sig);
-    LAUNCH(k_witness_inputs, nblk(np), TPB, (const u32x4*)pk_soa, (const uint8_t*)code_pk, (const u32x4*)sig_soa, (const uint8_t*)code_sig, dmsg, nwit, np, inputs, dstatus);
-    if (p.xrules) {                                        // level-synchronous, cooperative launch: every block must be resident
+    LAUNCH(k_witness_inputs, nblk(np), TPB, (const u32x4*)pk_soa, (const uint8_t*)code_pk, (const u32x4*)sig_soa, (const uint8_t*)code_sig, dmsg, p.msg_len, nwit, np, inputs, dstatus);
+    if (p.xrules && ctx->wit_cluster) {                    // level-synchronous per group, hardware cluster barrier between levels
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3((unsigned)(groups * WIT_CL)); cfg.blockDim = dim3(WIT_CL_TPB); cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = WIT_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        wit_prog pc = p; const fp* in_c = inputs;
+        CU(cudaLaunchKernelEx(&cfg, k_witness_cluster, pc, in_c, np, zt_all, groups, zbool_all)); ctx->launches++;
+    } else if (p.xrules) {                                 // level-synchronous over the whole grid, cooperative launch: every block must be resident
         int per_sm = 0, sms = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_witness_levels, WIT_TPB, 0)); if (per_sm > WIT_BPS) per_sm = WIT_BPS; CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
         if (per_sm < 1) return fail(ctx, BLSGPU_ERR_CUDA, "k_witness_levels does not fit on an SM");
@@ -280,20 +385,20 @@ static int witness_run(blsgpu_ctx* ctx, const wit_prog& p, const uint8_t* pk48, 
     return 0;
 }
 extern "C" {
-// assignments of the verify circuit for nwit (pk48, msg32, sig96) triples: z48 = nwit * nout * 48 bytes (the layout of
+// assignments of the verify circuit for nwit (pk48, msg, sig96) triples: z48 = nwit * nout * 48 bytes (the layout of
 // blsgpu_r1cs_check), status[i] = 0, or 2 / 3 when the key / signature does not decode to a non-identity point (its assignment
 // is then all zeros except z[0] = 1 and the constants).  Pointers follow the context's pointer mode.
-int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, size_t nwit, uint8_t* z48, uint8_t* status) {
-    ENTER(); if (handle < 0 || handle >= 4 || !ctx->wit[handle] || !pk48 || !msg32 || !sig96 || !z48) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
+int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const uint8_t* msg, const uint8_t* sig96, size_t nwit, uint8_t* z48, uint8_t* status) {
+    ENTER(); if (handle < 0 || handle >= 4 || !ctx->wit[handle] || !pk48 || !msg || !sig96 || !z48) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
     if (!nwit) return 0;
     wit_prog p = *ctx->wit[handle];
     size_t groups = (nwit + 31) / 32;
     bool host = ctx->ptr_mode == BLSGPU_HOST;
     size_t zbytes = nwit * p.nout * 48;
-    u32x4* zt_all; uint8_t* dstatus;
-    if (int rc = witness_run(ctx, p, pk48, msg32, sig96, nwit, status, host ? al(zbytes) : 0, false, &zt_all, nullptr, &dstatus)) return rc;
+    u32x4* zt_all; uint2* zbool_all = nullptr; uint8_t* dstatus;
+    if (int rc = witness_run(ctx, p, pk48, msg, sig96, nwit, status, host ? al(zbytes) : 0, p.xrules != nullptr, &zt_all, &zbool_all, &dstatus)) return rc;
     uint8_t* dz = host ? ws_take<uint8_t>(ctx, zbytes) : z48;
-    { dim3 grid(nblk(p.nout, 8), (unsigned)groups); k_witness_untranspose<<<grid, 256, 0, ctx->stream>>>((const u32x4*)zt_all, p.nvars, p.nout, nwit, (u32x4*)dz); ctx->launches++; CU(cudaGetLastError()); }
+    { dim3 grid(nblk(p.nout, 8), (unsigned)groups); k_witness_untranspose<<<grid, 256, 0, ctx->stream>>>((const u32x4*)zt_all, (const uint2*)zbool_all, p.nvars, p.nout, nwit, (u32x4*)dz); ctx->launches++; CU(cudaGetLastError()); }
     if (host) CU(cudaMemcpyAsync(z48, dz, zbytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (status) { if (int rc = finish_out(ctx, status, dstatus, nwit)) return rc; }
     return finish_call(ctx);
@@ -301,9 +406,9 @@ int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const u
 // Generation and satisfaction check in one call: the assignments never leave the transposed group layout (no 48-byte row-major
 // copy, no second transpose; 34 MB per assignment stay out of the caller's memory).  sat_bits / all_sat as blsgpu_r1cs_check,
 // status as blsgpu_witness_gen; the R1CS system must be the one the program was recorded with (same column count).
-int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, size_t nwit,
+int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const uint8_t* pk48, const uint8_t* msg, const uint8_t* sig96, size_t nwit,
                          uint64_t* sat_bits, uint8_t* all_sat, uint8_t* status) {
-    ENTER(); if (wit_handle < 0 || wit_handle >= 4 || !ctx->wit[wit_handle] || r1cs_handle < 0 || r1cs_handle >= 16 || !ctx->r1cs[r1cs_handle] || !pk48 || !msg32 || !sig96 || !sat_bits)
+    ENTER(); if (wit_handle < 0 || wit_handle >= 4 || !ctx->wit[wit_handle] || r1cs_handle < 0 || r1cs_handle >= 16 || !ctx->r1cs[r1cs_handle] || !pk48 || !msg || !sig96 || !sat_bits)
         return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
     if (!nwit) return 0;
     wit_prog p = *ctx->wit[wit_handle]; r1cs_sys s = *ctx->r1cs[r1cs_handle];
@@ -312,7 +417,7 @@ int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const
     size_t groups = (nwit + 31) / 32, words = (s.nrows + 63) / 64, part_bytes = (s.n_seg ? s.n_seg : 1) * 32 * 48;
     bool host = ctx->ptr_mode == BLSGPU_HOST;
     u32x4* zt_all; uint2* zbool_all; uint8_t* dstatus;
-    if (int rc = witness_run(ctx, p, pk48, msg32, sig96, nwit, status, al(part_bytes) + (host ? al(8 * words * nwit) + al(nwit) : 0), true, &zt_all, &zbool_all, &dstatus)) return rc;
+    if (int rc = witness_run(ctx, p, pk48, msg, sig96, nwit, status, al(part_bytes) + (host ? al(8 * words * nwit) + al(nwit) : 0), true, &zt_all, &zbool_all, &dstatus)) return rc;
     u32x4* part = ws_take<u32x4>(ctx, part_bytes / 16);
     uint64_t* dbits = host ? ws_take<uint64_t>(ctx, words * nwit) : sat_bits;
     uint8_t* dall = all_sat ? (host ? ws_take<uint8_t>(ctx, nwit) : all_sat) : nullptr;

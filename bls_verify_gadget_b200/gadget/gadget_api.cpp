@@ -65,15 +65,17 @@ int blsgadget_aggregate_verify(const uint8_t* pks48, size_t n, const uint8_t* bi
         return put(std::move(c));
     } catch (...) { return -1; }
 }
-// The witness program of the verify circuit (32-byte messages): a full synthesis with rule recording on a sample input.  The
-// program is input-independent; it is exported with blsgadget_program_export and replayed on the GPU by blsgpu_witness_gen.
-int blsgadget_verify_program(const uint8_t pk48[48], const uint8_t* msg32, const uint8_t sig96[96]) {
+// The witness program of the verify circuit for messages of `len` bytes (the circuit's shape depends on the length through the
+// number of SHA-256 blocks; len <= 8000): a full synthesis with rule recording on a sample input.  The program is otherwise
+// input-independent; it is exported with blsgadget_program_export and replayed on the GPU by blsgpu_witness_gen.
+int blsgadget_verify_program(const uint8_t pk48[48], const uint8_t* msg, size_t len, const uint8_t sig96[96]) {
     try {
         g1_aff pk; g2_aff sig;
         if (g1_decode(pk, pk48) != DEC_OK || g2_decode(sig, sig96) != DEC_OK) return -2;
         auto c = std::make_unique<Circuit>();
         c->cs.record_rules = true;
-        c->result = synthesize_verify(c->cs, pk, msg32, 32, sig) ? 1 : 0;
+        if (len > 8000) return -4;
+        c->result = synthesize_verify(c->cs, pk, msg, len, sig) ? 1 : 0;
         if (c->cs.rules.size() != c->cs.z.size()) return -3;
         return put(std::move(c));
     } catch (...) { return -1; }

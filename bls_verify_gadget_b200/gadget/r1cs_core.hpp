@@ -74,7 +74,7 @@ enum RuleKind : uint8_t {
     RULE_BIT = 4,        // bit `aux` of the canonical integer A z       (addmany results, to_bits_le)
     RULE_FP2INV = 5,     // component `aux` of 1 / (A z + u B z)
     RULE_FP12INV = 6,    // coefficient `aux` (0..11, tower order) of the inverse of the Fp12 element given by LC ids a .. a+11
-    RULE_INPUT = 7       // external input slot `aux`: 0..255 message bits, 256/257 pk.x/y, 258..261 sig x.c0 x.c1 y.c0 y.c1
+    RULE_INPUT = 7       // external input slot `aux`: 0/1 pk.x/y, 2..5 sig x.c0 x.c1 y.c0 y.c1, 6 + 8 i + b = bit b of message byte i
 };
 struct Rule { uint8_t kind; uint8_t pad; uint16_t aux; uint32_t a, b, d; };
 

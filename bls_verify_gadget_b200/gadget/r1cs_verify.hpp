@@ -187,8 +187,8 @@ struct G1Var {
     FpVar x, y, z;
     static G1Var make(const FpVar& x, const FpVar& y, const FpVar& z) { G1Var r; r.x = x; r.y = y; r.z = z; return r; }
     static G1Var zero() { return make(FpVar::zero(), FpVar::one(), FpVar::zero()); }
-    static G1Var witness(ConstraintSystem& cs, const g1_aff& p) {                      // input slots 256 / 257; z = 1
-        FpVar x = FpVar::witness_input(cs, p.x, 256), y = FpVar::witness_input(cs, p.y, 257); return make(x, y, FpVar::witness_const(cs, fp_one()));
+    static G1Var witness(ConstraintSystem& cs, const g1_aff& p) {                      // input slots 0 / 1; z = 1
+        FpVar x = FpVar::witness_input(cs, p.x, 0), y = FpVar::witness_input(cs, p.y, 1); return make(x, y, FpVar::witness_const(cs, fp_one()));
     }
     G1Var add(ConstraintSystem& cs, const G1Var& q) const {
         fp b3 = fp_from_u64(12);
@@ -206,9 +206,9 @@ inline G1Var select_g1(ConstraintSystem& cs, const Boolean& c, const G1Var& t, c
 // BlsSignatureVerifyGadget::verify (constraints.rs:90-128) on an already allocated public key; message bytes and the
 // signature are allocated as witnesses (the modes of the reference's tests, constraints.rs:335-366), parameters constant.
 inline bool verify_gadget(ConstraintSystem& cs, const G1Var& pk, const std::vector<UInt8>& m, const g2_aff& sig, fp12* gt) {
-    G2Var sg;                                                                          // input slots 258..261; z = (1, 0)
-    sg.x.c0 = FpVar::witness_input(cs, sig.x.c0, 258); sg.x.c1 = FpVar::witness_input(cs, sig.x.c1, 259);
-    sg.y.c0 = FpVar::witness_input(cs, sig.y.c0, 260); sg.y.c1 = FpVar::witness_input(cs, sig.y.c1, 261);
+    G2Var sg;                                                                          // input slots 2..5; z = (1, 0)
+    sg.x.c0 = FpVar::witness_input(cs, sig.x.c0, 2); sg.x.c1 = FpVar::witness_input(cs, sig.x.c1, 3);
+    sg.y.c0 = FpVar::witness_input(cs, sig.y.c0, 4); sg.y.c1 = FpVar::witness_input(cs, sig.y.c1, 5);
     sg.z.c0 = FpVar::witness_const(cs, fp_one()); sg.z.c1 = FpVar::witness_const(cs, fp_zero());
     // public_key.enforce_not_equal(zero) and prepare_g1: z has an inverse, affine coordinates by two products
     FpVar zi = pk.z.inverse(cs);
@@ -225,7 +225,7 @@ inline bool verify_gadget(ConstraintSystem& cs, const G1Var& pk, const std::vect
 // (constraints.rs:101-106).  Returns the value of the output Boolean; *gt (nullable) receives the GT element.
 inline bool synthesize_verify(ConstraintSystem& cs, const g1_aff& pk, const uint8_t* msg, size_t len, const g2_aff& sig, fp12* gt = nullptr) {
     G1Var pkv = G1Var::witness(cs, pk);
-    std::vector<UInt8> m(len); for (size_t i = 0; i < len; i++) m[i] = u8_witness_input(cs, msg[i], (uint16_t)(8 * i));     // input slots 0 .. 8 len - 1 (the program assumes len = 32)
+    std::vector<UInt8> m(len); for (size_t i = 0; i < len; i++) m[i] = u8_witness_input(cs, msg[i], (uint16_t)(6 + 8 * i));     // input slots 6 .. 6 + 8 len - 1: any message length (the gadget takes &[UInt8], constraints.rs:90-95)
     return verify_gadget(cs, pkv, m, sig, gt);
 }
 // aggregate_verify / mapped_aggregate (constraints.rs:153-191): keys masked by a witness bitmap (select key or zero), summed

@@ -195,21 +195,28 @@ int blsgpu_r1cs_row_classes(blsgpu_ctx* ctx, int handle, uint64_t counts[4]);
  *      running the gadget code of src/constraints.rs:335-370 under ark-relations) -------------------------------------------------
  * blsgpu_witness_load takes the witness program exported by the host-side builder (libblsgadget.so, blsgadget_program_export):
  * rules16 = ncols records {u8 kind, u8 0, u16 aux, u32 a, u32 b, u32 d}, lc_ptr[nlc + 1], lc_col / lc_coef48 (canonical LE) [nterms].
- * blsgpu_witness_gen replays it for nwit (pk48, msg32, sig96) triples: z48 = nwit * nvars * 48 bytes in the layout of
+ * The program fixes the message length L of its circuit (blsgpu_witness_msg_len; the gadget takes &[UInt8] of any length,
+ * src/constraints.rs:90-95, and the number of SHA-256 blocks depends on it): msg = nwit x L bytes.
+ * blsgpu_witness_gen replays it for nwit (pk48, msg, sig96) triples: z48 = nwit * nvars * 48 bytes in the layout of
  * blsgpu_r1cs_check; status[i] (nullable) = 0, or 2 / 3 when the key / signature does not decode to a non-identity point. */
 int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t* lc_ptr, const uint32_t* lc_col, const uint8_t* lc_coef48,
                         size_t ncols /* rules: circuit variables, then scratch columns */, size_t nvars /* circuit variables */, size_t nlc, size_t nterms,
                         const uint32_t* order /* nullable: variables sorted by dependency level */, const uint64_t* level_ptr /* nlevels + 1 */, size_t nlevels,
                         int* handle);   /* host pointers; with `order` the rules of one level run in parallel (blsgadget_program_levels) */
-int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, size_t nwit,
+int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const uint8_t* msg, const uint8_t* sig96, size_t nwit,
                        uint8_t* z48, uint8_t* status);
 /* Generation and satisfaction check in one call: (pk, msg, sig) bytes in, per-constraint bits (words64 per assignment) and the
  * per-assignment flag out, as blsgpu_r1cs_check would report them for blsgpu_witness_gen's output -- but the assignments stay in
  * the device-side transposed layout (no row-major copy of 34 MB per assignment, no second transpose).  r1cs_handle must be the
  * system of the circuit the program was recorded with; all_sat and status are nullable. */
-int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, size_t nwit,
+int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const uint8_t* pk48, const uint8_t* msg, const uint8_t* sig96, size_t nwit,
                          uint64_t* sat_bits, uint8_t* all_sat, uint8_t* status);
+long blsgpu_witness_msg_len(blsgpu_ctx* ctx, int handle);   /* L of the loaded program, -1 for a bad handle */
 int blsgpu_witness_free(blsgpu_ctx* ctx, int handle);
+/* replay schedule: 0 (default) = one cooperative kernel over all groups with a grid-wide barrier per dependency level; 1 = one thread-block
+ * cluster (8 SMs) per group of 32 assignments with the hardware cluster barrier between levels (measured slower on B200 at 512 and 2,048
+ * assignments: at most 14 clusters of 8 are resident, profiles/r02_tuning.md).  Identical assignments either way. */
+int blsgpu_set_witness_mode(blsgpu_ctx* ctx, int cluster);
 
 /* ---- every GPU of the box behind one handle ---------------------------------------------------------------------
  * blsgpu_create_multi: devices = ndev ordinals (NULL / ndev <= 0: every visible device); one single-GPU context and stream per device and

@@ -72,6 +72,22 @@ def test_emu_mul_small_equals_python(E):
     out = E.run_op(35, x).reshape(len(pairs), 48)
     for (z, c), o in zip(pairs, out): assert int.from_bytes(o.tobytes(), "little") == z * c % P, (z, c)
 
+def test_emu_lazy_small_coefficient_sum_equals_python(E):
+    """fp_lacc_* (unreduced 14-limb sum of 32-bit-coefficient terms, one reduction: the R1CS kernels' accumulator for small coefficients):
+    8 x (c0 z0 + c1 z1 + c2 z2 + c3 (p - z3)) mod p against Python for edge values, maximal coefficients and random inputs"""
+    P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    rng = np.random.default_rng(31)
+    zs = [0, 1, P - 1, P - 2, (P - 1) // 2, (1 << 380), (1 << 381) - 1 - ((1 << 381) - 1 >= P) * ((1 << 381) - P), P // 0xffffffff]
+    cs = [0, 1, 2, 0xffff, 0x80000000, 0xffffffff]
+    cases = [([P - 1] * 4, [0xffffffff] * 3 + [0]), ([P - 1, P - 1, P - 1, 0], [0xffffffff] * 4), ([0] * 4, [0xffffffff] * 4), ([P - 1] * 4, [1] * 4)]
+    cases += [([zs[int(i)] for i in rng.integers(0, len(zs), 4)], [cs[int(i)] for i in rng.integers(0, len(cs), 4)]) for _ in range(2000)]
+    cases += [([int.from_bytes(rng.bytes(48), "little") % P for _ in range(4)], [int(v) for v in rng.integers(0, 1 << 32, 4)]) for _ in range(8000)]
+    x = np.frombuffer(b"".join(b"".join(z.to_bytes(48, "little") for z in z4) + b"".join(c.to_bytes(48, "little") for c in c4) for z4, c4 in cases), np.uint8)
+    out = E.run_op(36, x).reshape(len(cases), 48)
+    for (z4, c4), o in zip(cases, out):
+        want = 8 * (c4[0] * z4[0] + c4[1] * z4[1] + c4[2] * z4[2] + c4[3] * (P - z4[3])) % P
+        assert int.from_bytes(o.tobytes(), "little") == want, (z4, c4)
+
 def test_emu_fixtures(E, eth, pyv):
     k = eth["inline_kats"]
     assert E.hash_to_g2([bytes(32)]).tobytes().hex() == k["hash_to_g2_zero32"]

@@ -63,6 +63,40 @@ def test_fast_aggregate_verify_fixtures(eth):        # tests.rs:297-334
         st = C.fast_aggregate_verify(pks, len(i["pubkeys"]), hx(i["message"]), hx(i["signature"]))[0]
         assert (st == 0) == c["output"], c["name"]
 
+def test_aggregate_verify_pinned_by_the_fast_aggregate_fixtures(eth):
+    """Eth2 AggregateVerify (oracle/bls_oracle.cpp ora_aggregate_verify) has no fixture of its own in the reference
+    (tests/readme.md:4-7 names the category, tests/test_cases/ does not vendor it).  By bilinearity AggregateVerify(pks, [m] * k, sig) ==
+    FastAggregateVerify(pks, m, sig): every fast_aggregate_verify fixture (tests.rs:297-334) must give the same verdict through it; and a
+    single pair is BLS::verify (the 29 verify fixtures)."""
+    import numpy as np
+    for c in eth["fast_aggregate_verify"]:
+        i = c["input"]; keys = [hx(s) for s in i["pubkeys"]]; sgn = hx(i["signature"])
+        if any(len(k) != 48 for k in keys) or len(sgn) != 96: continue
+        st = C.aggregate_verify(b"".join(keys), [hx(i["message"])] * len(keys), np.array([0, len(keys)], np.uint32), sgn)
+        assert (st[0] == 0) == c["output"], c["name"]
+    n = 0
+    for c in eth["verify"]:
+        i = c["input"]; pk, sgn = hx(i["pubkey"]), hx(i["signature"])
+        if len(pk) != 48 or len(sgn) != 96: continue
+        st = C.aggregate_verify(pk, [hx(i["message"])], np.array([0, 1], np.uint32), sgn); n += 1
+        assert (st[0] == 0) == c["output"], c["name"]
+    assert n >= 20
+
+def test_uncompressed_codec_round_trip_and_fixture_verdicts(eth):
+    """the uncompressed ZCash encodings of the oracle: every decodable deserialisation fixture survives compressed -> uncompressed ->
+    compressed byte for byte, undecodable ones are rejected in the first step with the same verdict as tests.rs:337-364"""
+    import numpy as np
+    for kind, key, size, rec in (("deserialization_G1", "pubkey", 48, C.g1_recode), ("deserialization_G2", "signature", 96, C.g2_recode)):
+        seen = 0
+        for c in eth[kind]:
+            s = c["input"][key]
+            if len(s) != 2 * size: continue
+            raw = np.frombuffer(bytes.fromhex(s), np.uint8); unc, st = rec(raw, True)
+            assert (st[0] == 0) == c["output"], c["name"]
+            if st[0] == 0:
+                back, st2 = rec(unc, False); assert st2[0] == 0 and (np.array_equal(back, raw) or (raw[0] & 0x40)), c["name"]; seen += 1      # (a lenient identity encoding normalises)
+        assert seen >= 2
+
 @pytest.mark.parametrize("kind,key,size,fn", [("deserialization_G1", "pubkey", 48, C.deser_g1), ("deserialization_G2", "signature", 96, C.deser_g2)])
 def test_deser_fixtures(eth, kind, key, size, fn):   # tests.rs:337-364
     for c in eth[kind]:
