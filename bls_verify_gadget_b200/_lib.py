@@ -38,7 +38,7 @@ def lib():
 EXPORTS = ["blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_set_stream", "blsgpu_set_pointer_mode", "blsgpu_synchronize",
            "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_set_coop", "blsgpu_verify_batch", "blsgpu_verify_batch_rlc", "blsgpu_verify_batch_rlc_bisect", "blsgpu_fast_aggregate_verify_batch", "blsgpu_aggregate_verify_batch", "blsgpu_g1_uncompress", "blsgpu_g1_compress", "blsgpu_g2_uncompress", "blsgpu_g2_compress", "blsgpu_pool_create", "blsgpu_pool_free", "blsgpu_pool_fast_aggregate_verify", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
            "blsgpu_g2_aggregate", "blsgpu_deserialize_g1", "blsgpu_deserialize_g2", "blsgpu_sk_to_pk_batch", "blsgpu_sign_batch", "blsgpu_pairing_gt",
-           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_r1cs_row_classes", "blsgpu_r1cs_load_file", "blsgpu_r1cs_check_file", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_check", "blsgpu_witness_free", "blsgpu_witness_msg_len", "blsgpu_set_witness_mode",
+           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_r1cs_row_classes", "blsgpu_r1cs_load_file", "blsgpu_r1cs_check_file", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_check", "blsgpu_witness_free", "blsgpu_witness_msg_len", "blsgpu_set_witness_mode", "blsgpu_witness_set_aggregate", "blsgpu_witness_gen_aggregate", "blsgpu_witness_check_aggregate",
            "blsgpu_create_multi", "blsgpu_destroy_multi", "blsgpu_multi_last_error", "blsgpu_multi_ndev", "blsgpu_multi_nccl_version", "blsgpu_multi_ctx", "blsgpu_multi_verify_batch", "blsgpu_multi_peek"]
 
 _sz = ctypes.c_size_t; _vp = ctypes.c_void_p
@@ -236,8 +236,9 @@ class Context:
         r = np.ascontiguousarray(program["rules16"], dtype=np.uint8); lp = np.ascontiguousarray(program["lc_ptr"], dtype=np.uint64)
         lc = np.ascontiguousarray(program["lc_col"], dtype=np.uint32); cf = np.ascontiguousarray(program["lc_coef48"], dtype=np.uint8)
         od = np.ascontiguousarray(program["order"], dtype=np.uint32) if levels else None; lv = np.ascontiguousarray(program["level_ptr"], dtype=np.uint64) if levels else None
-        h = ctypes.c_int(-1)
+        h = ctypes.c_int(-1); nkeys = int(program.get("nkeys", 0))
         self._ck(lib().blsgpu_witness_load(self._h, _p(r), _p(lp), _p(lc), _p(cf), _sz(r.size // 16), _sz(program["nvars"]), _sz(lp.size - 1), _sz(lc.size), _p(od), _p(lv), _sz(lv.size - 1 if levels else 0), ctypes.byref(h)))
+        if nkeys: self.witness_set_aggregate(h.value, nkeys)          # an aggregate_verify program (gadget.aggregate_verify_program)
         return h.value
     def witness_msg_len(self, handle):
         L = int(lib().blsgpu_witness_msg_len(self._h, int(handle)))
@@ -258,6 +259,18 @@ class Context:
         self._ck(lib().blsgpu_witness_check(self._h, int(wit_handle), int(r1cs_handle), _p(pk), _p(m), _p(sg), _sz(n), _p(bits), _p(allsat), _p(st))); return bits, allsat, st
     def witness_check_ptr(self, wit_handle, r1cs_handle, pk, msg, sig, n, bits, allsat=None, status=None):
         self._ck(lib().blsgpu_witness_check(self._h, int(wit_handle), int(r1cs_handle), _p(pk), _p(msg), _p(sig), _sz(n), _p(bits), _p(allsat), _p(status)))
+    def witness_set_aggregate(self, handle, nkeys): self._ck(lib().blsgpu_witness_set_aggregate(self._h, int(handle), _sz(nkeys)))
+    def witness_gen_aggregate(self, handle, pks48, bitmap, msg, sig96, nvars, nkeys):
+        """aggregate_verify circuit: pks48 n x nkeys x 48, bitmap n x nkeys bytes, msg n x L, sig96 n x 96 -> (z [n, nvars * 48], status [n])"""
+        pk = _u8(pks48); bm = np.ascontiguousarray(bitmap, dtype=np.uint8).reshape(-1); m = _u8(msg); sg = _u8(sig96); n = sg.size // 96
+        _need("sig96", sg, 96 * n); _need("pks48", pk, 48 * n * nkeys); _need("bitmap", bm, n * nkeys); _need("msg", m, self.witness_msg_len(handle) * n)
+        z = np.empty(n * nvars * 48, np.uint8); st = np.empty(n, np.uint8)
+        self._ck(lib().blsgpu_witness_gen_aggregate(self._h, int(handle), _p(pk), _p(bm), _p(m), _p(sg), _sz(n), _p(z), _p(st))); return z.reshape(n, nvars * 48), st
+    def witness_check_aggregate(self, wit_handle, r1cs_handle, pks48, bitmap, msg, sig96, nrows, nkeys):
+        pk = _u8(pks48); bm = np.ascontiguousarray(bitmap, dtype=np.uint8).reshape(-1); m = _u8(msg); sg = _u8(sig96); n = sg.size // 96; words = (nrows + 63) // 64
+        _need("sig96", sg, 96 * n); _need("pks48", pk, 48 * n * nkeys); _need("bitmap", bm, n * nkeys); _need("msg", m, self.witness_msg_len(wit_handle) * n)
+        bits = np.zeros((n, words), np.uint64); allsat = np.zeros(n, np.uint8); st = np.empty(n, np.uint8)
+        self._ck(lib().blsgpu_witness_check_aggregate(self._h, int(wit_handle), int(r1cs_handle), _p(pk), _p(bm), _p(m), _p(sg), _sz(n), _p(bits), _p(allsat), _p(st))); return bits, allsat, st
     def witness_free(self, handle): lib().blsgpu_witness_free(self._h, int(handle))
     def set_witness_mode(self, cluster=True): self._ck(lib().blsgpu_set_witness_mode(self._h, 1 if cluster else 0))
 

@@ -110,7 +110,7 @@ __device__ __forceinline__ fp r1cs_load_z(const u32x4* zt, uint32_t col, int lan
 // Terms on field-valued columns with coefficient +-1 or |c| < 2^32 go to the LAZY 14-limb sum `la` (fp_lacc_*: 12 IMAD.WIDE per term, one
 // Barrett reduction per range instead of one per term; a negative coefficient enters as |c| (p - z)).
 __device__ __forceinline__ void r1cs_term(const r1cs_sys& s, int m, uint64_t k, uint32_t cj, uint32_t c, uint2 zb, uint32_t cf, const u32x4* zt, int lane,
-                                          fp& acc, int64_t& side, bool& touched, fp_lacc& la, bool& la_used) {
+                                          fp& acc, int64_t& side, bool& touched, fp_lacc& la, bool& la_used, const fp* zpre = nullptr, wacc* wg = nullptr, int* wn = nullptr) {
     if (zb.y) {
         uint32_t bit = (zb.x >> lane) & 1u;
         if (c == R1_PLUS_ONE) side += bit;
@@ -121,8 +121,15 @@ __device__ __forceinline__ void r1cs_term(const r1cs_sys& s, int m, uint64_t k, 
         return;
     }
     touched = true;
-    fp zv = r1cs_load_z(zt, cj, lane);
-    if (c == R1_GENERAL) { acc = fp_add(acc, fp_mul(s.coeff[m][k], zv)); return; }
+    fp zv = zpre ? *zpre : r1cs_load_z(zt, cj, lane);
+    if (c == R1_GENERAL) {
+        if (!wg) { acc = fp_add(acc, fp_mul(s.coeff[m][k], zv)); return; }
+        // lazy form (witness replay): coefficient (Montgomery, < p) x value (canonical, < p) accumulated unreduced, one Montgomery reduction per
+        // 8 products (sum < 8 p^2 < 9.8 p^2, the bound of wredc) -- 144 IMAD.WIDE per term instead of a 300-MAC product and a modular addition
+        wmac(*wg, s.coeff[m][k], zv);
+        if (++*wn == 8) { acc = fp_add(acc, wredc(*wg)); wacc_zero(*wg); *wn = 0; }
+        return;
+    }
     la_used = true;
     if (c == R1_PLUS_ONE) fp_lacc_mad(la, zv, 1u);
     else if (c == R1_SMALL_POS) fp_lacc_mad(la, zv, cf);
@@ -161,11 +168,22 @@ __device__ __forceinline__ void r1cs_meta_fetch(r1cs_meta& t, const r1cs_sys& s,
 __device__ __forceinline__ void r1cs_meta_views(r1cs_meta& t, const uint2* zbool, int lane) { if ((uint32_t)lane < t.n) t.zb = zbool[t.col]; }      // round 2: packed 0/1 views
 struct r1cs_accum { fp acc; int64_t side; bool touched; fp_lacc la; bool la_used; };
 __device__ __forceinline__ void r1cs_accum_zero(r1cs_accum& a) { a.acc = fp_zero(); a.side = 0; a.touched = false; fp_lacc_zero(a.la); a.la_used = false; }
-__device__ __forceinline__ void r1cs_meta_eval(const r1cs_meta& t, const r1cs_sys& s, int m, const u32x4* zt, int lane, r1cs_accum& a) {
-    for (uint32_t k = 0; k < t.n; k++) {
-        uint32_t cj = __shfl_sync(0xffffffffu, t.col, k), c = __shfl_sync(0xffffffffu, t.c, k), cf = __shfl_sync(0xffffffffu, t.cf, k);
-        uint2 zb = make_uint2(__shfl_sync(0xffffffffu, t.zb.x, k), __shfl_sync(0xffffffffu, t.zb.y, k));
-        r1cs_term(s, m, t.base + k, cj, c, zb, cf, zt, lane, a.acc, a.side, a.touched, a.la, a.la_used);
+// PF terms at a time: the gathers of all PF (for field-valued columns) are issued before the first term is evaluated.  PF = 1 in the
+// satisfaction kernels (they run at 80 registers and are throughput-bound: pairs measured 13 % slower, profiles/r02_tuning.md); PF = 8 in
+// the witness replay, which is bound by the chain of gathers inside one task and has registers to spare.
+template <int PF> __device__ __forceinline__ void r1cs_meta_eval(const r1cs_meta& t, const r1cs_sys& s, int m, const u32x4* zt, int lane, r1cs_accum& a, wacc* wg = nullptr, int* wn = nullptr) {
+    for (uint32_t k0 = 0; k0 < t.n; k0 += PF) {
+        uint32_t cj[PF], c[PF], cf[PF]; uint2 zb[PF]; fp zv[PF];
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            uint32_t k = k0 + j < t.n ? k0 + j : t.n - 1;
+            cj[j] = __shfl_sync(0xffffffffu, t.col, k); c[j] = __shfl_sync(0xffffffffu, t.c, k); cf[j] = __shfl_sync(0xffffffffu, t.cf, k);
+            zb[j] = make_uint2(__shfl_sync(0xffffffffu, t.zb.x, k), __shfl_sync(0xffffffffu, t.zb.y, k));
+            if (PF > 1 && k0 + j < t.n && !zb[j].y) zv[j] = r1cs_load_z(zt, cj[j], lane);
+        }
+#pragma unroll
+        for (int j = 0; j < PF; j++)
+            if (k0 + j < t.n) r1cs_term(s, m, t.base + k0 + j, cj[j], c[j], zb[j], cf[j], zt, lane, a.acc, a.side, a.touched, a.la, a.la_used, PF > 1 ? &zv[j] : nullptr, wg, wn);
     }
 }
 __device__ __forceinline__ fp r1cs_accum_close(r1cs_accum& a, int64_t& side_out, bool& touched) {
@@ -175,7 +193,7 @@ __device__ __forceinline__ fp r1cs_accum_close(r1cs_accum& a, int64_t& side_out,
 __device__ __forceinline__ fp r1cs_range_dot_wide(const r1cs_sys& s, int m, uint64_t lo, uint64_t hi, const u32x4* zt, const uint2* zbool, int lane, int64_t& side_out, bool& touched) {
     r1cs_accum a; r1cs_accum_zero(a);                            // at most 2^18 terms between reductions of the lazy sum: no combination is that long
     for (uint64_t base = lo; base < hi; base += 32) {
-        r1cs_meta t; r1cs_meta_fetch(t, s, m, base, hi, lane); r1cs_meta_views(t, zbool, lane); r1cs_meta_eval(t, s, m, zt, lane, a);
+        r1cs_meta t; r1cs_meta_fetch(t, s, m, base, hi, lane); r1cs_meta_views(t, zbool, lane); r1cs_meta_eval<1>(t, s, m, zt, lane, a);
     }
     return r1cs_accum_close(a, side_out, touched);
 }
@@ -280,13 +298,19 @@ __global__ void __launch_bounds__(256) k_r1cs_lut(r1cs_sys s, const uint2* zbool
     size_t half = row >> 5;                                 // warp-uniform
     if ((size_t)lane < g && half < 2 * words) sat32[(w0 + lane) * 2 * words + half] = mine;
 }
-// one warp per listed row, lane = assignment: the generic evaluation (count_dev != NULL: the fallback list, whose length is on the device)
-__global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_rows_list(r1cs_sys s, const uint32_t* list, const uint32_t* count_dev, size_t count_host, const u32x4* zt, const uint2* zbool,
-                                                                  size_t w0, size_t g, size_t words, uint64_t* sat_bits) {
+// one warp per listed row, lane = assignment: the generic evaluation of the generic short rows and, behind them in the same index
+// space, of the truth-table rows that fell back in this group (their count is on the device)
+#ifndef R1_MINB_ROWS
+#define R1_MINB_ROWS R1_MINB
+#endif
+#ifndef R1_MINB_SEG
+#define R1_MINB_SEG R1_MINB
+#endif
+__global__ void __launch_bounds__(TPB, R1_MINB_ROWS) k_r1cs_rows_list(r1cs_sys s, const u32x4* zt, const uint2* zbool, size_t w0, size_t g, size_t words, uint64_t* sat_bits) {
     size_t warp = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5), nwarps = gridDim.x * (size_t)(TPB / 32); int lane = threadIdx.x & 31;
-    size_t n = count_dev ? (size_t)*count_dev : count_host;
+    size_t n = s.n_gen + (size_t)*s.fb_count;
     for (size_t i = warp; i < n; i += nwarps) {
-        size_t row = list[i];
+        size_t row = i < s.n_gen ? s.gen_rows[i] : s.fb_rows[i - s.n_gen];
         int64_t sa, sb, sc; bool ta, tb, tc;
         fp a = r1cs_range_dot(s, 0, s.rowptr[0][row], s.rowptr[0][row + 1], zt, zbool, lane, sa, ta);
         fp b = r1cs_range_dot(s, 1, s.rowptr[1][row], s.rowptr[1][row + 1], zt, zbool, lane, sb, tb);
@@ -298,7 +322,7 @@ __global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_rows_list(r1cs_sys s, con
     }
 }
 // one warp per segment of a long row: partial dot product of 32 witnesses -> part (limb-SoA over n_seg * 32 slots)
-__global__ void __launch_bounds__(TPB, R1_MINB) k_r1cs_segments(r1cs_sys s, const u32x4* zt, const uint2* zbool, u32x4* part) {
+__global__ void __launch_bounds__(TPB, R1_MINB_SEG) k_r1cs_segments(r1cs_sys s, const u32x4* zt, const uint2* zbool, u32x4* part) {
     size_t sg = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
     if (sg >= s.n_seg) return;
     int64_t side; bool touched;
@@ -502,13 +526,12 @@ int blsgpu_r1cs_row_classes(blsgpu_ctx* ctx, int handle, uint64_t counts[4]) {
 // one group of <= 32 assignments given in the transposed layout (zt, zbool): truth-table rows first (plain stores: this initialises
 // the group's slice of the output), then the rows that fell back, the generic short rows, and the long rows' segments + combination
 #ifndef R1_FB_BLOCKS
-#define R1_FB_BLOCKS 592
+#define R1_FB_BLOCKS 888          // 148 SMs x 6 resident CTAs: one grid-stride pass over both lists
 #endif
 static int r1cs_check_group(blsgpu_ctx* ctx, const r1cs_sys& s, const u32x4* zt, const uint2* zbool, u32x4* part, size_t w0, size_t g, size_t words, uint64_t* dbits) {
     CU(cudaMemsetAsync(s.fb_count, 0, 4, ctx->stream));
     LAUNCH(k_r1cs_lut, nblk(words * 64, 256), 256, s, zbool, w0, g, words, (uint32_t*)dbits);
-    if (s.n_lut) LAUNCH(k_r1cs_rows_list, R1_FB_BLOCKS, TPB, s, (const uint32_t*)s.fb_rows, (const uint32_t*)s.fb_count, (size_t)0, zt, zbool, w0, g, words, dbits);
-    if (s.n_gen) LAUNCH(k_r1cs_rows_list, nblk(s.n_gen, TPB / 32), TPB, s, (const uint32_t*)s.gen_rows, (const uint32_t*)nullptr, s.n_gen, zt, zbool, w0, g, words, dbits);
+    if (s.n_lut || s.n_gen) LAUNCH(k_r1cs_rows_list, R1_FB_BLOCKS, TPB, s, zt, zbool, w0, g, words, dbits);
     if (s.n_long) {
         LAUNCH(k_r1cs_segments, nblk(s.n_seg, TPB / 32), TPB, s, zt, zbool, part);
         LAUNCH(k_r1cs_combine, nblk(s.n_long, TPB / 32), TPB, s, (const u32x4*)part, w0, g, words, dbits);

@@ -13,6 +13,9 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#ifndef WIT_PF
+#define WIT_PF 1          // gathers issued together per batch of terms in the replay (r1cs_meta_eval<PF>): 4 / 8 / 16 measured 1.3x / 1.8x / 4x SLOWER (spills), profiles/r02_tuning.md
+#endif
 enum { WR_MULADD = 0, WR_INV = 1, WR_NEQ = 2, WR_NEQMULT = 3, WR_BIT = 4, WR_FP2INV = 5, WR_FP12INV = 6, WR_INPUT = 7 };
 struct wit_rule { uint8_t kind, pad; uint16_t aux; uint32_t a, b, d; };
 // rule in level order with its term ranges resolved (one dependent load less per combination); for WR_FP12INV a_lo is the
@@ -22,7 +25,7 @@ struct wit_prog {
     size_t nvars, nout, nlc, nterms, nlevels;          // nvars: columns of the program (circuit variables, then scratch values); nout: circuit variables
     wit_rule* rules; uint64_t* lc_ptr; uint32_t* col; fp* coeff; fp* coeffc; uint8_t* cls;
     wit_xrule* xrules; uint64_t* level_ptr;          // dependency levels: rules of one level are independent
-    size_t msg_len;                                  // bytes per message of the circuit the program was recorded for (from its input slots)
+    size_t msg_len, ninputs, nkeys;                  // input slots of the recorded circuit: nkeys = 0: verify (6 + 8 msg_len); nkeys = n: aggregate_verify (3n + 4 + 8 msg_len)
 };
 #define WIT_POINT_INPUTS 6      // input slots 0..5: pk.x, pk.y, sig x.c0, x.c1, y.c0, y.c1; slot 6 + 8 i + b = bit b of message byte i (any message length)
 
@@ -40,7 +43,11 @@ __device__ __forceinline__ fp wit_lc_range(const wit_prog& p, uint64_t lo, uint6
     if (zb) {
         r1cs_sys view; view.coeff[0] = p.coeff; view.coeffc[0] = p.coeffc; view.col[0] = p.col; view.cls[0] = p.cls;
         int64_t side = 0; bool touched = false;
-        acc = r1cs_range_dot_wide(view, 0, lo, hi, zt, zb, lane, side, touched);      // metadata of up to 32 terms fetched in one round: the replay is latency-bound
+        r1cs_accum ac; r1cs_accum_zero(ac);                    // metadata of up to 32 terms fetched in one round: the replay is latency-bound
+        wacc wg; int wn = 0; wacc_zero(wg);                    // general coefficients on field values: lazy 768-bit sum (r1cs_term)
+        for (uint64_t base = lo; base < hi; base += 32) { r1cs_meta t; r1cs_meta_fetch(t, view, 0, base, hi, lane); r1cs_meta_views(t, zb, lane); r1cs_meta_eval<WIT_PF>(t, view, 0, zt, lane, ac, &wg, &wn); }
+        if (wn) ac.acc = fp_add(ac.acc, wredc(wg));
+        acc = r1cs_accum_close(ac, side, touched);
         return r1cs_finalize(acc, side, touched);
     }
     for (uint64_t k = lo, e = hi; k < e; k++) {
@@ -71,8 +78,10 @@ __device__ __forceinline__ void wit_lc3(const wit_prog& p, const wit_xrule& r, c
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         r1cs_accum acc; r1cs_accum_zero(acc);
-        r1cs_meta_eval(*ts[k], view, 0, zt, lane, acc);
-        for (uint64_t base = ts[k]->base + 32; base < his[k]; base += 32) { r1cs_meta t; r1cs_meta_fetch(t, view, 0, base, his[k], lane); r1cs_meta_views(t, zb, lane); r1cs_meta_eval(t, view, 0, zt, lane, acc); }
+        wacc wg; int wn = 0; wacc_zero(wg);
+        r1cs_meta_eval<WIT_PF>(*ts[k], view, 0, zt, lane, acc, &wg, &wn);
+        for (uint64_t base = ts[k]->base + 32; base < his[k]; base += 32) { r1cs_meta t; r1cs_meta_fetch(t, view, 0, base, his[k], lane); r1cs_meta_views(t, zb, lane); r1cs_meta_eval<WIT_PF>(t, view, 0, zt, lane, acc, &wg, &wn); }
+        if (wn) acc.acc = fp_add(acc.acc, wredc(wg));
         int64_t side; bool touched; fp v = r1cs_accum_close(acc, side, touched);
         *outs[k] = r1cs_finalize(v, side, touched);
     }
@@ -139,6 +148,11 @@ __global__ void __launch_bounds__(32) k_witness_gen(wit_prog p, const fp* inputs
 #ifndef WIT_BPS
 #define WIT_BPS 2
 #endif
+#ifdef WIT_TRACE
+// tuning builds only (profiles/tools/wit_trace.py): the global timer at the start of every level, written by warp 0
+__device__ unsigned long long g_wit_trace[32768];
+extern "C" int blsgpu_debug_wit_trace(unsigned long long* out, size_t n) { return cudaMemcpyFromSymbol(out, g_wit_trace, 8 * (n < 32768 ? n : 32768)) == cudaSuccess ? 0 : -1; }
+#endif
 __global__ void __launch_bounds__(WIT_TPB, WIT_BPS) k_witness_levels(wit_prog p, const fp* inputs, size_t nwit_padded, u32x4* zt_all, size_t groups, uint2* zbool_all) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * (size_t)blockDim.x) >> 5; int lane = threadIdx.x & 31;
@@ -148,6 +162,9 @@ __global__ void __launch_bounds__(WIT_TPB, WIT_BPS) k_witness_levels(wit_prog p,
     if (pre) rn = p.xrules[lo + warp / groups];
     for (size_t level = 0; level < p.nlevels; level++) {
         uint64_t n = hi - lo, hi_next = level + 2 <= p.nlevels ? p.level_ptr[level + 2] : hi;
+#ifdef WIT_TRACE
+        if (warp == 0 && lane == 0 && level < 32768) { unsigned long long tm; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tm)); g_wit_trace[level] = tm; }
+#endif
         for (size_t t = warp; t < n * groups; t += nwarps) {
             wit_xrule r = (t == warp && pre) ? rn : p.xrules[lo + t / groups]; size_t group = t % groups;
             u32x4* zt = zt_all + group * p.nvars * 96; const uint2* zb = zbool_all ? zbool_all + group * p.nvars : nullptr;
@@ -268,6 +285,25 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_witness_inputs(const u32x4* p
     inputs[(size_t)4 * nwit_padded + i] = ok ? fp_from_mont(sg.y.c0) : zero; inputs[(size_t)5 * nwit_padded + i] = ok ? fp_from_mont(sg.y.c1) : zero;
     if (live && status) status[i] = st;
 }
+// the same for the aggregate_verify circuit: n keys (decoded into key_soa, item i key k at i * n + k), one bitmap byte per key, message, signature
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_witness_inputs_agg(const u32x4* key_soa, const uint8_t* code_key, size_t n, const uint8_t* bitmap, const u32x4* sig_soa, const uint8_t* code_sig,
+                                                                      const uint8_t* msg, size_t msg_len, size_t nwit, size_t nwit_padded, fp* inputs, uint8_t* status) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= nwit_padded) return;
+    bool live = i < nwit; uint8_t st = ST_OK;
+    if (live) { for (size_t k = 0; k < n; k++) if (code_key[i * n + k] != DEC_OK) { st = ST_BAD_PK; break; } if (st == ST_OK && code_sig[i] != DEC_OK) st = ST_BAD_SIG; }
+    bool ok = live && st == ST_OK;
+    fp zero = fp_zero();
+    for (size_t k = 0; k < n; k++) {
+        g1_aff pk; if (ok) soa_load_g1(pk, key_soa, nwit * n, i * n + k);
+        inputs[(2 * k) * nwit_padded + i] = ok ? fp_from_mont(pk.x) : zero; inputs[(2 * k + 1) * nwit_padded + i] = ok ? fp_from_mont(pk.y) : zero;
+        fp b = zero; if (ok) b.l[0] = bitmap[i * n + k] ? 1u : 0u; inputs[(2 * n + k) * nwit_padded + i] = b;
+    }
+    g2_aff sg; if (ok) soa_load_g2(sg, sig_soa, nwit, i);
+    inputs[(3 * n + 0) * nwit_padded + i] = ok ? fp_from_mont(sg.x.c0) : zero; inputs[(3 * n + 1) * nwit_padded + i] = ok ? fp_from_mont(sg.x.c1) : zero;
+    inputs[(3 * n + 2) * nwit_padded + i] = ok ? fp_from_mont(sg.y.c0) : zero; inputs[(3 * n + 3) * nwit_padded + i] = ok ? fp_from_mont(sg.y.c1) : zero;
+    for (size_t k = 0; k < 8 * msg_len; k++) { fp b = zero; if (ok) b.l[0] = (msg[msg_len * i + (k >> 3)] >> (k & 7)) & 1u; inputs[(3 * n + 4 + k) * nwit_padded + i] = b; }
+    if (live && status) status[i] = st;
+}
 // transposed group -> z[w][col] (48-byte LE canonical), the layout of blsgpu_r1cs_check
 __global__ void __launch_bounds__(256) k_witness_untranspose(const u32x4* zt_all, const uint2* zbool_all, size_t ncols, size_t nout, size_t nwit, u32x4* z) {
     size_t col = blockIdx.x * (size_t)8 + (threadIdx.x >> 5); int lane = threadIdx.x & 31; size_t group = blockIdx.y;
@@ -301,8 +337,8 @@ int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t*
     {   // the message length of the recorded circuit follows from the highest input slot: slots 0..5 are the points, 6 + 8 i + b the message bits
         const wit_rule* hr = reinterpret_cast<const wit_rule*>(rules16); size_t top = 0;
         for (size_t k = 0; k < nvars; k++) if (hr[k].kind == WR_INPUT && hr[k].aux != 0xffff && (size_t)hr[k].aux + 1 > top) top = (size_t)hr[k].aux + 1;
-        if (top && (top < WIT_POINT_INPUTS || (top - WIT_POINT_INPUTS) % 8)) return fail(ctx, BLSGPU_ERR_ARG, "witness program: %zu input slots is not 6 + 8 x message bytes", top);
-        p->msg_len = top ? (top - WIT_POINT_INPUTS) / 8 : 0;
+        p->ninputs = top; p->nkeys = 0;                    // a verify program until blsgpu_witness_set_aggregate says otherwise
+        p->msg_len = (top >= WIT_POINT_INPUTS && (top - WIT_POINT_INPUTS) % 8 == 0) ? (top - WIT_POINT_INPUTS) / 8 : (size_t)-1;
     }
     cudaMemcpyKind kind = ctx->ptr_mode == BLSGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     size_t nt = nterms ? nterms : 1;
@@ -337,6 +373,14 @@ int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t*
 }
 // bytes per message of the circuit the loaded program was recorded for (blsgpu_witness_gen / _check take nwit x that many message bytes)
 long blsgpu_witness_msg_len(blsgpu_ctx* ctx, int handle) { return (!ctx || handle < 0 || handle >= 4 || !ctx->wit[handle]) ? -1 : (long)ctx->wit[handle]->msg_len; }
+// declares a loaded program to be one of the aggregate_verify circuit (src/constraints.rs:153-191) with nkeys public keys: its input slots are
+// [0, 2n) key coordinates, [2n, 3n) bitmap bits, [3n, 3n + 4) the signature, then 8 bits per message byte (blsgadget_aggregate_verify_program)
+int blsgpu_witness_set_aggregate(blsgpu_ctx* ctx, int handle, size_t nkeys) {
+    if (!ctx || handle < 0 || handle >= 4 || !ctx->wit[handle] || !nkeys) return BLSGPU_ERR_ARG;
+    wit_prog* p = ctx->wit[handle];
+    if (p->ninputs < 3 * nkeys + 4 || (p->ninputs - 3 * nkeys - 4) % 8) return fail(ctx, BLSGPU_ERR_ARG, "witness program: %zu input slots is not 3 x %zu keys + 4 + 8 x message bytes", p->ninputs, nkeys);
+    p->nkeys = nkeys; p->msg_len = (p->ninputs - 3 * nkeys - 4) / 8; return 0;
+}
 int blsgpu_witness_free(blsgpu_ctx* ctx, int handle) {
     if (!ctx || handle < 0 || handle >= 4 || !ctx->wit[handle]) return BLSGPU_ERR_ARG;
     dev_guard guard_; cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
@@ -346,24 +390,29 @@ int blsgpu_witness_free(blsgpu_ctx* ctx, int handle) {
 // decode, input slots and the level-synchronous replay for nwit triples: leaves the assignments in the transposed group layout
 // (group stride nvars * 96 u32x4) in the workspace; `extra` bytes of workspace are reserved for the caller's own buffers, which it
 // takes AFTER this returns.  want_zbool: also the packed 0/1 view per (group, variable).
-static int witness_run(blsgpu_ctx* ctx, const wit_prog& p, const uint8_t* pk48, const uint8_t* msg, const uint8_t* sig96, size_t nwit, uint8_t* status, size_t extra,
+// bitmap == NULL: verify program (pk48 = nwit keys); else aggregate program (pk48 = nwit x p.nkeys keys, bitmap = nwit x p.nkeys bytes)
+static int witness_run(blsgpu_ctx* ctx, const wit_prog& p, const uint8_t* pk48, const uint8_t* bitmap, const uint8_t* msg, const uint8_t* sig96, size_t nwit, uint8_t* status, size_t extra,
                        bool want_zbool, u32x4** zt_out, uint2** zbool_out, uint8_t** dstatus_out) {
-    size_t groups = (nwit + 31) / 32, np = groups * 32, ninputs = WIT_POINT_INPUTS + 8 * p.msg_len;
-    if (int rc = ws_reserve(ctx, al(48 * nwit) + al(96 * nwit) + al(p.msg_len * nwit + 1) + al(96 * nwit) + al(192 * nwit) + 3 * al(np) + al(48 * ninputs * np) + al(groups * p.nvars * 1536) +
+    if (p.msg_len == (size_t)-1) return fail(ctx, BLSGPU_ERR_ARG, "witness program: %zu input slots fit no verify circuit (6 + 8 x message bytes); an aggregate program needs blsgpu_witness_set_aggregate", p.ninputs);
+    if ((bitmap != nullptr) != (p.nkeys != 0)) return fail(ctx, BLSGPU_ERR_ARG, p.nkeys ? "this is an aggregate_verify program: use the _aggregate entry points" : "this is a verify program: use blsgpu_witness_gen / _check");
+    size_t groups = (nwit + 31) / 32, np = groups * 32, ninputs = p.ninputs, nk = p.nkeys ? p.nkeys : 1, nkeys_total = nwit * nk;
+    if (int rc = ws_reserve(ctx, al(48 * nkeys_total) + al(nkeys_total) + al(96 * nwit) + al(p.msg_len * nwit + 1) + al(96 * nkeys_total) + al(192 * nwit) + 2 * al(np) + al(nkeys_total + np) + al(48 * ninputs * np) + al(groups * p.nvars * 1536) +
                                  (want_zbool ? al(groups * p.nvars * 8) : 0) + extra + 65536)) return rc;
-    const uint8_t *dpk, *dsig, *dmsg;
-    if (int rc = stage_in(ctx, dpk, pk48, 48 * nwit)) return rc;
+    const uint8_t *dpk, *dsig, *dmsg, *dbm = nullptr;
+    if (int rc = stage_in(ctx, dpk, pk48, 48 * nkeys_total)) return rc;
+    if (bitmap) { if (int rc = stage_in(ctx, dbm, bitmap, nkeys_total)) return rc; }
     if (int rc = stage_in(ctx, dsig, sig96, 96 * nwit)) return rc;
     if (int rc = stage_in(ctx, dmsg, msg, p.msg_len * nwit ? p.msg_len * nwit : 1)) return rc;
-    u32x4* pk_soa = ws_take<u32x4>(ctx, 6 * nwit); u32x4* sig_soa = ws_take<u32x4>(ctx, 12 * nwit);
-    uint8_t* code_pk = ws_take<uint8_t>(ctx, np); uint8_t* code_sig = ws_take<uint8_t>(ctx, np);
+    u32x4* pk_soa = ws_take<u32x4>(ctx, 6 * nkeys_total); u32x4* sig_soa = ws_take<u32x4>(ctx, 12 * nwit);
+    uint8_t* code_pk = ws_take<uint8_t>(ctx, nkeys_total + np); uint8_t* code_sig = ws_take<uint8_t>(ctx, np);
     uint8_t* dstatus = status ? stage_out(ctx, status, nwit) : nullptr;
     fp* inputs = ws_take<fp>(ctx, ninputs * np);
     u32x4* zt_all = ws_take<u32x4>(ctx, groups * p.nvars * 96);
     uint2* zbool_all = want_zbool ? ws_take<uint2>(ctx, groups * p.nvars) : nullptr;
-    LAUNCH(k_decode_g1, nblk(nwit), TPB, dpk, nwit, pk_soa, code_pk);
+    LAUNCH(k_decode_g1, nblk(nkeys_total), TPB, dpk, nkeys_total, pk_soa, code_pk);
     LAUNCH(k_decode_g2, nblk(nwit), TPB, dsig, nwit, sig_soa, code_sig);
-    LAUNCH(k_witness_inputs, nblk(np), TPB, (const u32x4*)pk_soa, (const uint8_t*)code_pk, (const u32x4*)sig_soa, (const uint8_t*)code_sig, dmsg, p.msg_len, nwit, np, inputs, dstatus);
+    if (bitmap) LAUNCH(k_witness_inputs_agg, nblk(np), TPB, (const u32x4*)pk_soa, (const uint8_t*)code_pk, p.nkeys, dbm, (const u32x4*)sig_soa, (const uint8_t*)code_sig, dmsg, p.msg_len, nwit, np, inputs, dstatus);
+    else LAUNCH(k_witness_inputs, nblk(np), TPB, (const u32x4*)pk_soa, (const uint8_t*)code_pk, (const u32x4*)sig_soa, (const uint8_t*)code_sig, dmsg, p.msg_len, nwit, np, inputs, dstatus);
     if (p.xrules && ctx->wit_cluster) {                    // level-synchronous per group, hardware cluster barrier between levels
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
         cfg.gridDim = dim3((unsigned)(groups * WIT_CL)); cfg.blockDim = dim3(WIT_CL_TPB); cfg.stream = ctx->stream;
@@ -388,15 +437,15 @@ extern "C" {
 // assignments of the verify circuit for nwit (pk48, msg, sig96) triples: z48 = nwit * nout * 48 bytes (the layout of
 // blsgpu_r1cs_check), status[i] = 0, or 2 / 3 when the key / signature does not decode to a non-identity point (its assignment
 // is then all zeros except z[0] = 1 and the constants).  Pointers follow the context's pointer mode.
-int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const uint8_t* msg, const uint8_t* sig96, size_t nwit, uint8_t* z48, uint8_t* status) {
-    ENTER(); if (handle < 0 || handle >= 4 || !ctx->wit[handle] || !pk48 || !msg || !sig96 || !z48) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
+static int witness_gen_core(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const uint8_t* bitmap, const uint8_t* msg, const uint8_t* sig96, size_t nwit, uint8_t* z48, uint8_t* status) {
+    if (handle < 0 || handle >= 4 || !ctx->wit[handle] || !pk48 || !msg || !sig96 || !z48) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
     if (!nwit) return 0;
     wit_prog p = *ctx->wit[handle];
     size_t groups = (nwit + 31) / 32;
     bool host = ctx->ptr_mode == BLSGPU_HOST;
     size_t zbytes = nwit * p.nout * 48;
     u32x4* zt_all; uint2* zbool_all = nullptr; uint8_t* dstatus;
-    if (int rc = witness_run(ctx, p, pk48, msg, sig96, nwit, status, host ? al(zbytes) : 0, p.xrules != nullptr, &zt_all, &zbool_all, &dstatus)) return rc;
+    if (int rc = witness_run(ctx, p, pk48, bitmap, msg, sig96, nwit, status, host ? al(zbytes) : 0, p.xrules != nullptr, &zt_all, &zbool_all, &dstatus)) return rc;
     uint8_t* dz = host ? ws_take<uint8_t>(ctx, zbytes) : z48;
     { dim3 grid(nblk(p.nout, 8), (unsigned)groups); k_witness_untranspose<<<grid, 256, 0, ctx->stream>>>((const u32x4*)zt_all, (const uint2*)zbool_all, p.nvars, p.nout, nwit, (u32x4*)dz); ctx->launches++; CU(cudaGetLastError()); }
     if (host) CU(cudaMemcpyAsync(z48, dz, zbytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -406,9 +455,9 @@ int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const u
 // Generation and satisfaction check in one call: the assignments never leave the transposed group layout (no 48-byte row-major
 // copy, no second transpose; 34 MB per assignment stay out of the caller's memory).  sat_bits / all_sat as blsgpu_r1cs_check,
 // status as blsgpu_witness_gen; the R1CS system must be the one the program was recorded with (same column count).
-int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const uint8_t* pk48, const uint8_t* msg, const uint8_t* sig96, size_t nwit,
-                         uint64_t* sat_bits, uint8_t* all_sat, uint8_t* status) {
-    ENTER(); if (wit_handle < 0 || wit_handle >= 4 || !ctx->wit[wit_handle] || r1cs_handle < 0 || r1cs_handle >= 16 || !ctx->r1cs[r1cs_handle] || !pk48 || !msg || !sig96 || !sat_bits)
+static int witness_check_core(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const uint8_t* pk48, const uint8_t* bitmap, const uint8_t* msg, const uint8_t* sig96, size_t nwit,
+                              uint64_t* sat_bits, uint8_t* all_sat, uint8_t* status) {
+    if (wit_handle < 0 || wit_handle >= 4 || !ctx->wit[wit_handle] || r1cs_handle < 0 || r1cs_handle >= 16 || !ctx->r1cs[r1cs_handle] || !pk48 || !msg || !sig96 || !sat_bits)
         return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
     if (!nwit) return 0;
     wit_prog p = *ctx->wit[wit_handle]; r1cs_sys s = *ctx->r1cs[r1cs_handle];
@@ -417,7 +466,7 @@ int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const
     size_t groups = (nwit + 31) / 32, words = (s.nrows + 63) / 64, part_bytes = (s.n_seg ? s.n_seg : 1) * 32 * 48;
     bool host = ctx->ptr_mode == BLSGPU_HOST;
     u32x4* zt_all; uint2* zbool_all; uint8_t* dstatus;
-    if (int rc = witness_run(ctx, p, pk48, msg, sig96, nwit, status, al(part_bytes) + (host ? al(8 * words * nwit) + al(nwit) : 0), true, &zt_all, &zbool_all, &dstatus)) return rc;
+    if (int rc = witness_run(ctx, p, pk48, bitmap, msg, sig96, nwit, status, al(part_bytes) + (host ? al(8 * words * nwit) + al(nwit) : 0), true, &zt_all, &zbool_all, &dstatus)) return rc;
     u32x4* part = ws_take<u32x4>(ctx, part_bytes / 16);
     uint64_t* dbits = host ? ws_take<uint64_t>(ctx, words * nwit) : sat_bits;
     uint8_t* dall = all_sat ? (host ? ws_take<uint8_t>(ctx, nwit) : all_sat) : nullptr;
@@ -433,5 +482,22 @@ int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const
     }
     if (status) { if (int rc = finish_out(ctx, status, dstatus, nwit)) return rc; }
     return finish_call(ctx);
+}
+int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const uint8_t* msg, const uint8_t* sig96, size_t nwit, uint8_t* z48, uint8_t* status) {
+    ENTER(); return witness_gen_core(ctx, handle, pk48, nullptr, msg, sig96, nwit, z48, status);
+}
+int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const uint8_t* pk48, const uint8_t* msg, const uint8_t* sig96, size_t nwit,
+                         uint64_t* sat_bits, uint8_t* all_sat, uint8_t* status) {
+    ENTER(); return witness_check_core(ctx, wit_handle, r1cs_handle, pk48, nullptr, msg, sig96, nwit, sat_bits, all_sat, status);
+}
+// the aggregate_verify circuit (src/constraints.rs:153-191; program from blsgadget_aggregate_verify_program + blsgpu_witness_set_aggregate):
+// pks48 = nwit x nkeys compressed keys, bitmap = nwit x nkeys bytes (0 / non-zero: the participation bits), msg = nwit x L bytes, sig96 = nwit
+// aggregate signatures.  status: 2 when any of an item's keys does not decode to a non-identity point (masked-out keys are witnesses too), 3 for the signature.
+int blsgpu_witness_gen_aggregate(blsgpu_ctx* ctx, int handle, const uint8_t* pks48, const uint8_t* bitmap, const uint8_t* msg, const uint8_t* sig96, size_t nwit, uint8_t* z48, uint8_t* status) {
+    ENTER(); if (!bitmap) return fail(ctx, BLSGPU_ERR_ARG, "null bitmap"); return witness_gen_core(ctx, handle, pks48, bitmap, msg, sig96, nwit, z48, status);
+}
+int blsgpu_witness_check_aggregate(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const uint8_t* pks48, const uint8_t* bitmap, const uint8_t* msg, const uint8_t* sig96, size_t nwit,
+                                   uint64_t* sat_bits, uint8_t* all_sat, uint8_t* status) {
+    ENTER(); if (!bitmap) return fail(ctx, BLSGPU_ERR_ARG, "null bitmap"); return witness_check_core(ctx, wit_handle, r1cs_handle, pks48, bitmap, msg, sig96, nwit, sat_bits, all_sat, status);
 }
 }

@@ -77,13 +77,7 @@ def aggregate_verify_circuit(pks48, bitmap, message, sig96):
     c = Circuit(h, result=bool(res.value) if h >= 0 else None); c.count = cnt.value
     return c
 
-def verify_program(pk48, msg, sig96):
-    """the witness program of the verify circuit for messages of len(msg) bytes (otherwise input-independent; recorded on the given sample triple):
-    dict(rules16 u8[ncols*16] (ncols = nvars + scratch columns), lc_ptr u64[nlc+1], lc_col u32[nterms], lc_coef48 u8[nterms*48], nvars, order u32[nvars] = variables
-    sorted by dependency level, level_ptr u64[nlevels+1]) for Context.witness_load"""
-    pk = _u8(pk48); m = _u8(msg); sg = _u8(sig96)
-    h = lib().blsgadget_verify_program(_p(pk), _p(m) if len(msg) else None, ctypes.c_size_t(len(msg)), _p(sg))
-    if h < 0: raise RuntimeError(f"blsgadget_verify_program failed ({h})")
+def _export_program(h, extra):
     nv = ctypes.c_uint64(); ncol = ctypes.c_uint64(); nl = ctypes.c_uint64(); nt = ctypes.c_uint64(); lib().blsgadget_program_shape(h, ctypes.byref(nv), ctypes.byref(ncol), ctypes.byref(nl), ctypes.byref(nt))
     rules = np.empty(16 * ncol.value, np.uint8); lp = np.empty(nl.value + 1, np.uint64); lc = np.empty(max(nt.value, 1), np.uint32); cf = np.empty(48 * max(nt.value, 1), np.uint8)
     lib().blsgadget_program_export(h, _p(rules), _p(lp), _p(lc), _p(cf))
@@ -92,7 +86,26 @@ def verify_program(pk48, msg, sig96):
     order = np.empty(ncol.value, np.uint32); level_ptr = np.empty(nlev + 1, np.uint64)
     assert lib().blsgadget_program_levels(h, _p(order), _p(level_ptr), ctypes.c_uint64(nlev + 1)) == nlev
     lib().blsgadget_free(h)
-    return {"rules16": rules, "lc_ptr": lp, "lc_col": lc[:nt.value], "lc_coef48": cf[:48 * nt.value], "nvars": nv.value, "ncols": ncol.value, "order": order, "level_ptr": level_ptr, "msg_len": len(msg)}
+    d = {"rules16": rules, "lc_ptr": lp, "lc_col": lc[:nt.value], "lc_coef48": cf[:48 * nt.value], "nvars": nv.value, "ncols": ncol.value, "order": order, "level_ptr": level_ptr}
+    d.update(extra); return d
+
+def aggregate_verify_program(pks48, bitmap, msg, sig96):
+    """the witness program of the aggregate_verify circuit (constraints.rs:153-191) for len(pks48) / 48 keys and messages of len(msg) bytes,
+    recorded on the given sample input; for Context.witness_load(program) and Context.witness_gen_aggregate / witness_check_aggregate"""
+    pk = _u8(pks48); n = len(pk) // 48; bm = np.array([1 if b else 0 for b in bitmap], dtype=np.uint8); assert len(bm) == n
+    m = _u8(msg); sg = _u8(sig96)
+    h = lib().blsgadget_aggregate_verify_program(_p(pk), ctypes.c_size_t(n), _p(bm), _p(m) if len(msg) else None, ctypes.c_size_t(len(msg)), _p(sg))
+    if h < 0: raise RuntimeError(f"blsgadget_aggregate_verify_program failed ({h})")
+    return _export_program(h, {"msg_len": len(msg), "nkeys": n})
+
+def verify_program(pk48, msg, sig96):
+    """the witness program of the verify circuit for messages of len(msg) bytes (otherwise input-independent; recorded on the given sample triple):
+    dict(rules16 u8[ncols*16] (ncols = nvars + scratch columns), lc_ptr u64[nlc+1], lc_col u32[nterms], lc_coef48 u8[nterms*48], nvars, order u32[nvars] = variables
+    sorted by dependency level, level_ptr u64[nlevels+1]) for Context.witness_load"""
+    pk = _u8(pk48); m = _u8(msg); sg = _u8(sig96)
+    h = lib().blsgadget_verify_program(_p(pk), _p(m) if len(msg) else None, ctypes.c_size_t(len(msg)), _p(sg))
+    if h < 0: raise RuntimeError(f"blsgadget_verify_program failed ({h})")
+    return _export_program(h, {"msg_len": len(msg), "nkeys": 0})
 
 def verify_witnesses(triples, threads=None, ncols=None):
     """assignments of the verify circuit for a list of (pk48, msg, sig96) (all with the same message length), synthesised on

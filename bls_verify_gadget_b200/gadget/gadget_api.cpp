@@ -80,6 +80,24 @@ int blsgadget_verify_program(const uint8_t pk48[48], const uint8_t* msg, size_t 
         return put(std::move(c));
     } catch (...) { return -1; }
 }
+// The witness program of the aggregate_verify circuit (constraints.rs:153-191) for n keys and messages of `len` bytes, recorded on a sample
+// input; input slots: [0, 2n) key coordinates, [2n, 3n) bitmap bits, [3n, 3n + 4) signature, then 8 len message bits.
+int blsgadget_aggregate_verify_program(const uint8_t* pks48, size_t n, const uint8_t* bitmap, const uint8_t* msg, size_t len, const uint8_t sig96[96]) {
+    try {
+        std::vector<g1_aff> pks(n); g2_aff sig;
+        for (size_t i = 0; i < n; i++) {
+            if (i && !memcmp(pks48 + 48 * i, pks48 + 48 * (i - 1), 48)) { pks[i] = pks[i - 1]; continue; }
+            if (g1_decode(pks[i], pks48 + 48 * i) != DEC_OK) return -2;
+        }
+        if (g2_decode(sig, sig96) != DEC_OK) return -2;
+        auto c = std::make_unique<Circuit>();
+        c->cs.record_rules = true;
+        uint32_t cnt = 0;
+        c->result = synthesize_aggregate_verify(c->cs, pks, std::vector<uint8_t>(bitmap, bitmap + n), msg, len, sig, &cnt) ? 1 : 0;
+        if (c->cs.rules.size() != c->cs.z.size()) return -3;
+        return put(std::move(c));
+    } catch (...) { return -1; }
+}
 // nvars: circuit variables (the assignment's length); ncols = nvars + scratch columns (the rule count of the program)
 int blsgadget_program_shape(int h, uint64_t* nvars, uint64_t* ncols, uint64_t* nlc, uint64_t* nterms) {
     Circuit* c = get(h); if (!c || c->cs.rules.size() != c->cs.z.size()) return -1;

@@ -187,8 +187,8 @@ struct G1Var {
     FpVar x, y, z;
     static G1Var make(const FpVar& x, const FpVar& y, const FpVar& z) { G1Var r; r.x = x; r.y = y; r.z = z; return r; }
     static G1Var zero() { return make(FpVar::zero(), FpVar::one(), FpVar::zero()); }
-    static G1Var witness(ConstraintSystem& cs, const g1_aff& p) {                      // input slots 0 / 1; z = 1
-        FpVar x = FpVar::witness_input(cs, p.x, 0), y = FpVar::witness_input(cs, p.y, 1); return make(x, y, FpVar::witness_const(cs, fp_one()));
+    static G1Var witness(ConstraintSystem& cs, const g1_aff& p, uint16_t slot0 = 0) {  // input slots slot0 / slot0 + 1 (verify circuit: 0 / 1); z = 1
+        FpVar x = FpVar::witness_input(cs, p.x, slot0), y = FpVar::witness_input(cs, p.y, (uint16_t)(slot0 + 1)); return make(x, y, FpVar::witness_const(cs, fp_one()));
     }
     G1Var add(ConstraintSystem& cs, const G1Var& q) const {
         fp b3 = fp_from_u64(12);
@@ -205,10 +205,10 @@ inline G1Var select_g1(ConstraintSystem& cs, const Boolean& c, const G1Var& t, c
 
 // BlsSignatureVerifyGadget::verify (constraints.rs:90-128) on an already allocated public key; message bytes and the
 // signature are allocated as witnesses (the modes of the reference's tests, constraints.rs:335-366), parameters constant.
-inline bool verify_gadget(ConstraintSystem& cs, const G1Var& pk, const std::vector<UInt8>& m, const g2_aff& sig, fp12* gt) {
-    G2Var sg;                                                                          // input slots 2..5; z = (1, 0)
-    sg.x.c0 = FpVar::witness_input(cs, sig.x.c0, 2); sg.x.c1 = FpVar::witness_input(cs, sig.x.c1, 3);
-    sg.y.c0 = FpVar::witness_input(cs, sig.y.c0, 4); sg.y.c1 = FpVar::witness_input(cs, sig.y.c1, 5);
+inline bool verify_gadget(ConstraintSystem& cs, const G1Var& pk, const std::vector<UInt8>& m, const g2_aff& sig, fp12* gt, uint16_t sig_slot0 = 2) {
+    G2Var sg;                                                                          // input slots sig_slot0 .. +3 (verify circuit: 2..5); z = (1, 0)
+    sg.x.c0 = FpVar::witness_input(cs, sig.x.c0, sig_slot0); sg.x.c1 = FpVar::witness_input(cs, sig.x.c1, (uint16_t)(sig_slot0 + 1));
+    sg.y.c0 = FpVar::witness_input(cs, sig.y.c0, (uint16_t)(sig_slot0 + 2)); sg.y.c1 = FpVar::witness_input(cs, sig.y.c1, (uint16_t)(sig_slot0 + 3));
     sg.z.c0 = FpVar::witness_const(cs, fp_one()); sg.z.c1 = FpVar::witness_const(cs, fp_zero());
     // public_key.enforce_not_equal(zero) and prepare_g1: z has an inverse, affine coordinates by two products
     FpVar zi = pk.z.inverse(cs);
@@ -234,18 +234,21 @@ inline bool synthesize_verify(ConstraintSystem& cs, const g1_aff& pk, const uint
 inline bool synthesize_aggregate_verify(ConstraintSystem& cs, const std::vector<g1_aff>& pks, const std::vector<uint8_t>& bitmap, const uint8_t* msg, size_t len,
                                         const g2_aff& sig, uint32_t* count_out, fp12* gt = nullptr) {
     if (pks.size() != bitmap.size() || pks.empty()) throw std::invalid_argument("public_keys.len() != bitmap.len()");
-    std::vector<G1Var> keys; for (auto& p : pks) keys.push_back(G1Var::witness(cs, p));
-    std::vector<Boolean> bits; for (uint8_t b : bitmap) bits.push_back(Boolean::witness(cs, b != 0));
-    std::vector<UInt8> m(len); for (size_t i = 0; i < len; i++) m[i] = u8_witness(cs, msg[i]);
+    // witness-program input slots of this circuit (n keys, L message bytes): [0, 2n) key coordinates, [2n, 3n) bitmap bits, [3n, 3n + 4) the
+    // signature, [3n + 4, 3n + 4 + 8 L) message bits -- csrc/witness.cuh k_witness_inputs_agg fills them in this order
+    size_t n = pks.size(); if (3 * n + 4 + 8 * len > 65000) throw std::invalid_argument("too many input slots");
+    std::vector<G1Var> keys; for (size_t i = 0; i < n; i++) keys.push_back(G1Var::witness(cs, pks[i], (uint16_t)(2 * i)));
+    std::vector<Boolean> bits; for (size_t i = 0; i < n; i++) { cs.set_rule(RULE_INPUT, (uint16_t)(2 * n + i), nullptr); bits.push_back(Boolean::witness(cs, bitmap[i] != 0)); }
+    std::vector<UInt8> m(len); for (size_t i = 0; i < len; i++) m[i] = u8_witness_input(cs, msg[i], (uint16_t)(3 * n + 4 + 8 * i));
     G1Var zero = G1Var::zero(), ret = zero;
-    UInt32 count; for (int i = 0; i < 32; i++) count.b[i] = Boolean::witness(cs, false);                              // UInt32::new_variable(|| Ok(0), Witness)
+    UInt32 count; for (int i = 0; i < 32; i++) { LC c0 = LC::constant(fp_zero()); cs.set_rule(RULE_MULADD, 0, nullptr, nullptr, &c0); count.b[i] = Boolean::witness(cs, false); }     // UInt32::new_variable(|| Ok(0), Witness)
     for (size_t i = 0; i < keys.size(); i++) {
         ret = ret.add(cs, select_g1(cs, bits[i], keys[i], zero));
         UInt32 inc = UInt32::constant(0); inc.b[0] = bits[i];                                                         // bit.select(&count_one, &count_zero)
         count = u32_addmany(cs, {count, inc});
     }
     if (count_out) *count_out = count.value();
-    return verify_gadget(cs, ret, m, sig, gt);
+    return verify_gadget(cs, ret, m, sig, gt, (uint16_t)(3 * n));
 }
 
 }  // namespace gadget

@@ -212,6 +212,15 @@ int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const u
 int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const uint8_t* pk48, const uint8_t* msg, const uint8_t* sig96, size_t nwit,
                          uint64_t* sat_bits, uint8_t* all_sat, uint8_t* status);
 long blsgpu_witness_msg_len(blsgpu_ctx* ctx, int handle);   /* L of the loaded program, -1 for a bad handle */
+/* The aggregate_verify circuit (BlsSignatureVerifyGadget::aggregate_verify / mapped_aggregate, src/constraints.rs:153-191): load the program
+ * recorded by blsgadget_aggregate_verify_program with blsgpu_witness_load, declare its key count with blsgpu_witness_set_aggregate, then
+ * pks48 = nwit x nkeys compressed keys, bitmap = nwit x nkeys bytes (0 / non-zero = the participation bits), msg = nwit x L bytes,
+ * sig96 = nwit aggregate signatures.  status: 2 when any key of an item does not decode to a non-identity point, 3 for the signature. */
+int blsgpu_witness_set_aggregate(blsgpu_ctx* ctx, int handle, size_t nkeys);
+int blsgpu_witness_gen_aggregate(blsgpu_ctx* ctx, int handle, const uint8_t* pks48, const uint8_t* bitmap, const uint8_t* msg, const uint8_t* sig96, size_t nwit,
+                                 uint8_t* z48, uint8_t* status);
+int blsgpu_witness_check_aggregate(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const uint8_t* pks48, const uint8_t* bitmap, const uint8_t* msg, const uint8_t* sig96, size_t nwit,
+                                   uint64_t* sat_bits, uint8_t* all_sat, uint8_t* status);
 int blsgpu_witness_free(blsgpu_ctx* ctx, int handle);
 /* replay schedule: 0 (default) = one cooperative kernel over all groups with a grid-wide barrier per dependency level; 1 = one thread-block
  * cluster (8 SMs) per group of 32 assignments with the hardware cluster barrier between levels (measured slower on B200 at 512 and 2,048
