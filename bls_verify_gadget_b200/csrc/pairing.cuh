@@ -67,8 +67,9 @@ BLS_NOINLINE void miller_loop2(fp12& f, const g1_aff& p0, const g2_aff& q0, bool
     fp12_conj(f, f);                                        // x < 0
 }
 
-// a^x for a in the cyclotomic subgroup (x negative: conjugate at the end)
-BLS_NOINLINE void fp12_exp_by_x(fp12& r, const fp12& a) {
+// a^x for a in the cyclotomic subgroup (x negative: conjugate at the end): square-and-multiply with Granger-Scott squarings (18 Fp
+// products each).  Kept as the reference form of the compressed version below (tests/devcheck op 39 compares them).
+BLS_NOINLINE void fp12_exp_by_x_gs(fp12& r, const fp12& a) {
     fp12 acc = a;
     const uint64_t x = BLS_X_ABS;
     for (int i = 62; i >= 0; i--) {
@@ -76,6 +77,82 @@ BLS_NOINLINE void fp12_exp_by_x(fp12& r, const fp12& a) {
         if ((x >> i) & 1) fp12_mul(acc, acc, a);
     }
     fp12_conj(r, acc);
+}
+// ---- Karabina's compressed squaring (eprint 2010/542) in the arkworks tower.  With s = v w (s^2 = xi) an element is
+//   (g0 + g1 s) + (g2 + g3 s) w + (g4 + g5 s) w^2,   g0 = c0.c0, g1 = c1.c1, g2 = c1.c0, g3 = c0.c2, g4 = c0.c1, g5 = c1.c2
+// and the Granger-Scott update of (g2, g3, g4, g5) reads only those four coefficients: a squaring of the COMPRESSED form is two Fp4
+// squarings (12 Fp products) instead of three (18).  g1 and g0 come back from the cyclotomic relations
+//   g1 = (g5^2 xi + 3 g4^2 - 2 g3) / (4 g2)      [ g2 = 0:  g1 = 2 g4 g5 / g3,  and g1 = 0 when g3 = 0 too (the element 1) ]
+//   g0 = (2 g1^2 + g2 g5 - 3 g3 g4) xi + 1
+// with ONE inversion for all the elements that are decompressed together.  |x| = 2^63 + 2^62 + 2^60 + 2^57 + 2^48 + 2^16, so
+// a^|x| = prod a^(2^i) over those six i: 63 compressed squarings with six snapshots, one simultaneous decompression, five products --
+// 756 + ~220 Fp products for the squaring part instead of 1,134.  Same group element, hence the same canonical bytes.
+struct fp12c { fp2 g2, g3, g4, g5; };
+BLS_HD void fp12_compress(fp12c& c, const fp12& a) { c.g2 = a.c1.c0; c.g3 = a.c0.c2; c.g4 = a.c0.c1; c.g5 = a.c1.c2; }
+BLS_NOINLINE void fp12c_sqr(fp12c& r, const fp12c& a) {
+    fp12c o;
+    {   // (t2, t3) = (g2 + g3 s)^2:  g4' = 3 t2 - 2 g4,  g5' = 3 t3 + 2 g5
+        fp2 ab = fp2_mul(a.g2, a.g3);
+        fp2 sm = fp2_mul(fp2_add(a.g2, a.g3), fp2_add(a.g2, fp2_mul_xi(a.g3)));
+        fp2 te = fp2_sub(fp2_sub(sm, ab), fp2_mul_xi(ab)), to = fp2_dbl(ab);
+        fp2 z = fp2_sub(te, a.g4); z = fp2_dbl(z); o.g4 = fp2_add(z, te);
+        z = fp2_add(to, a.g5); z = fp2_dbl(z); o.g5 = fp2_add(z, to);
+    }
+    {   // (t4, t5) = (g4 + g5 s)^2:  g3' = 3 t4 - 2 g3,  g2' = 3 xi t5 + 2 g2
+        fp2 ab = fp2_mul(a.g4, a.g5);
+        fp2 sm = fp2_mul(fp2_add(a.g4, a.g5), fp2_add(a.g4, fp2_mul_xi(a.g5)));
+        fp2 te = fp2_sub(fp2_sub(sm, ab), fp2_mul_xi(ab)), to = fp2_mul_xi(fp2_dbl(ab));
+        fp2 z = fp2_sub(te, a.g3); z = fp2_dbl(z); o.g3 = fp2_add(z, te);
+        z = fp2_add(to, a.g2); z = fp2_dbl(z); o.g2 = fp2_add(z, to);
+    }
+    r = o;
+}
+// numerator and denominator of g1 (see above); the rare g2 = 0 branch is taken per thread
+BLS_HD void fp12c_g1_fraction(fp2& num, fp2& den, const fp12c& c) {
+    if (!fp2_is_zero(c.g2)) {
+        fp2 t = fp2_sqr(c.g4);
+        num = fp2_sub(fp2_add(fp2_mul_xi(fp2_sqr(c.g5)), fp2_add(fp2_dbl(t), t)), fp2_dbl(c.g3));
+        den = fp2_dbl(fp2_dbl(c.g2));
+    } else {
+        num = fp2_dbl(fp2_mul(c.g4, c.g5));
+        den = fp2_is_zero(c.g3) ? fp2_one() : c.g3;
+    }
+}
+BLS_HD void fp12_decompress_with(fp12& r, const fp12c& c, const fp2& g1) {
+    fp2 t = fp2_sub(fp2_add(fp2_dbl(fp2_sqr(g1)), fp2_mul(c.g2, c.g5)), fp2_mul(c.g3, c.g4));
+    fp2 u = fp2_mul(c.g3, c.g4); t = fp2_sub(t, fp2_dbl(u));                                  // 2 g1^2 + g2 g5 - 3 g3 g4
+    r.c0.c0 = fp2_add(fp2_mul_xi(t), fp2_one()); r.c1.c1 = g1; r.c1.c0 = c.g2; r.c0.c2 = c.g3; r.c0.c1 = c.g4; r.c1.c2 = c.g5;
+}
+// r = prod of the decompressed c[0..n), n <= 6, one Fp2 inversion (Montgomery's trick over the denominators)
+BLS_NOINLINE void fp12_decompress_product(fp12& r, const fp12c* c, int n) {
+    fp2 num[6], den[6], pre[6];
+    for (int i = 0; i < n; i++) { fp12c_g1_fraction(num[i], den[i], c[i]); pre[i] = i ? fp2_mul(pre[i - 1], den[i]) : den[i]; }
+    fp2 inv = fp2_inv(pre[n - 1]);                            // denominators are never zero
+    fp12 acc, d;
+    for (int i = n - 1; i >= 0; i--) {
+        fp2 di = i ? fp2_mul(inv, pre[i - 1]) : inv;          // 1 / den[i]
+        if (i) inv = fp2_mul(inv, den[i]);
+        fp12_decompress_with(d, c[i], fp2_mul(num[i], di));
+        if (i == n - 1) acc = d; else fp12_mul(acc, acc, d);
+    }
+    r = acc;
+}
+#ifndef BLS_KARABINA
+#define BLS_KARABINA 1
+#endif
+BLS_NOINLINE void fp12_exp_by_x(fp12& r, const fp12& a) {
+#if BLS_KARABINA
+    fp12c c, snap[6]; fp12_compress(c, a);
+    const uint64_t x = BLS_X_ABS; int k = 0;
+    for (int i = 1; i <= 63; i++) {
+        fp12c_sqr(c, c);
+        if ((x >> i) & 1) snap[k++] = c;                      // i = 16, 48, 57, 60, 62, 63
+    }
+    fp12 acc; fp12_decompress_product(acc, snap, 6);
+    fp12_conj(r, acc);
+#else
+    fp12_exp_by_x_gs(r, a);
+#endif
 }
 // f^(3 (p^12 - 1)/r): the exact chain of ark-ec's Bls12::final_exponentiation
 BLS_NOINLINE void final_exponentiation(fp12& r, const fp12& f) {

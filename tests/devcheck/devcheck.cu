@@ -8,7 +8,7 @@ using namespace bls;
 // run-time switch (10 KB frame, ~1 MB of code) was itself miscompiled by nvcc 12.9 (inputs of some cases read back as garbage).
 template <int OP> __global__ void __launch_bounds__(128, 2) k_run_op(const fp* in, fp* out, size_t n, int n_in, int n_out) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
-    fp a[24], r[12];
+    fp a[24], r[24];
     for (int k = 0; k < n_in; k++) a[k] = in[i * n_in + k];
     for (int k = 0; k < n_out; k++) r[k] = fp_zero();
     run_op(OP, a, r);
@@ -22,7 +22,7 @@ extern "C" int dev_run_op(int op, const uint8_t* in, uint8_t* out, size_t n) {
     cudaMemcpy(din, in, bi, cudaMemcpyHostToDevice);
     switch (op) {
 #define L(K) case K: launch<K>(din, dout, n, d); break;
-        L(1) L(2) L(3) L(4) L(5) L(6) L(7) L(8) L(9) L(10) L(11) L(12) L(13) L(14) L(15) L(16) L(17) L(18) L(19) L(20) L(21) L(22) L(23) L(24) L(25) L(26) L(27) L(28) L(29) L(30) L(31) L(32) L(33) L(34) L(35) L(36)
+        L(1) L(2) L(3) L(4) L(5) L(6) L(7) L(8) L(9) L(10) L(11) L(12) L(13) L(14) L(15) L(16) L(17) L(18) L(19) L(20) L(21) L(22) L(23) L(24) L(25) L(26) L(27) L(28) L(29) L(30) L(31) L(32) L(33) L(34) L(35) L(36) L(37) L(38) L(39)
 #undef L
         default: cudaFree(din); cudaFree(dout); return -1;
     }
@@ -34,7 +34,7 @@ extern "C" int dev_run_op(int op, const uint8_t* in, uint8_t* out, size_t n) {
 // ---- throughput ladder (profiles/r01_tuning.md): `reps` dependent applications of one primitive per thread, output fed back
 template <int OP> __global__ void __launch_bounds__(128, 2) k_bench_op(const fp* in, fp* out, size_t n, int n_in, int n_out, int reps) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
-    fp a[24], r[12];
+    fp a[24], r[24];
     for (int k = 0; k < n_in; k++) a[k] = in[i * n_in + k];
     for (int k = 0; k < n_out; k++) r[k] = fp_zero();
     for (int it = 0; it < reps; it++) { run_op(OP, a, r); for (int k = 0; k < n_out && k < n_in; k++) a[k] = r[k]; }

@@ -34,6 +34,9 @@ static inline op_desc op_shape(int op) {
         case 21: return {2, 1};   // fp_mul
         case 22: return {1, 1};   // fp_inv
         case 35: return {2, 1};   // fp_mul_small(z, low word of the second input)
+        case 37: return {12, 24}; // cyclotomic g = easy part of the input: decompress(compress(g)) beside g (Karabina relations)
+        case 38: return {12, 24}; // decompress(compressed squaring of g) beside fp12_cyclo_sqr(g)
+        case 39: return {12, 24}; // fp12_exp_by_x (compressed squarings) beside fp12_exp_by_x_gs
         case 36: return {8, 1};   // lazy 14-limb sum: 8 x (c0 z0 + c1 z1 + c2 z2 + c3 (p - z3)), c_i = low word of inputs 4..7, one reduction (fp_lacc_*)
         case 34: return {1, 2};   // fp_inv (divsteps) beside fp_inv_fermat
         case 23: return {4, 6};   // jac_mul_x_abs<fp2>(aff)
@@ -93,6 +96,12 @@ BLS_HD void run_op(int op, const fp* in, fp* out) {
         case 32: ld2(a, in); ld2(b, in + 2); fp2_dot1(c, a, b); st2(out, c); break;
         case 33: { fp2 x0, y0, x1, y1, x2, y2; ld2(x0, in); ld2(y0, in + 2); ld2(x1, in + 4); ld2(y1, in + 6); ld2(x2, in + 8); ld2(y2, in + 10); fp2_dot3(c, x0, y0, x1, y1, x2, y2); st2(out, c); break; }
         case 35: out[0] = fp_mul_small(in[0], in[1].l[0]); break;
+        case 37: case 38: case 39: {
+            ld12(f, in); fp12 t, e; fp12_conj(t, f); fp12_inv(e, f); fp12_mul(e, t, e); fp12_frob2(t, e); fp12_mul(g, t, e);      // g = f^((p^6-1)(p^2+1)): cyclotomic
+            if (op == 37) { fp12c cc; fp12_compress(cc, g); fp12_decompress_product(h, &cc, 1); st12(out, h); st12(out + 12, g); }
+            else if (op == 38) { fp12c cc; fp12_compress(cc, g); fp12c_sqr(cc, cc); fp12_decompress_product(h, &cc, 1); st12(out, h); fp12_cyclo_sqr(t, g); st12(out + 12, t); }
+            else { fp12_exp_by_x(h, g); st12(out, h); fp12_exp_by_x_gs(t, g); st12(out + 12, t); }
+            break; }
         case 36: { fp_lacc a; fp_lacc_zero(a); fp nz; fp_sub_raw(nz, fp_modulus(), in[3]);
                    for (int k = 0; k < 8; k++) { fp_lacc_mad(a, in[0], in[4].l[0]); fp_lacc_mad(a, in[1], in[5].l[0]); fp_lacc_mad(a, in[2], in[6].l[0]); fp_lacc_mad(a, nz, in[7].l[0]); }
                    out[0] = fp_lacc_reduce(a); break; }

@@ -13,7 +13,7 @@ static inline const uint8_t* msg_at(const uint8_t* msg, const uint32_t* off, siz
 extern "C" {
 int emu_run_op(int op, const uint8_t* in, uint8_t* out, size_t n) {
     op_desc d = op_shape(op); if (!d.n_in) return -1;
-    for (size_t i = 0; i < n; i++) { fp a[24], r[12]; memcpy(a, in + i * d.n_in * 48, d.n_in * 48); for (int k = 0; k < d.n_out; k++) r[k] = fp_zero(); run_op(op, a, r); memcpy(out + i * d.n_out * 48, r, d.n_out * 48); }
+    for (size_t i = 0; i < n; i++) { fp a[24], r[24]; memcpy(a, in + i * d.n_in * 48, d.n_in * 48); for (int k = 0; k < d.n_out; k++) r[k] = fp_zero(); run_op(op, a, r); memcpy(out + i * d.n_out * 48, r, d.n_out * 48); }
     return 0;
 }
 void emu_op_shape(int op, int* n_in, int* n_out) { op_desc d = op_shape(op); *n_in = d.n_in; *n_out = d.n_out; }
