@@ -38,7 +38,7 @@ def lib():
 EXPORTS = ["blsgpu_create", "blsgpu_destroy", "blsgpu_last_error", "blsgpu_set_stream", "blsgpu_set_pointer_mode", "blsgpu_synchronize",
            "blsgpu_launch_count", "blsgpu_set_profiling", "blsgpu_stage_times", "blsgpu_set_chunk", "blsgpu_set_lanes", "blsgpu_set_coop", "blsgpu_verify_batch", "blsgpu_verify_batch_rlc", "blsgpu_verify_batch_rlc_bisect", "blsgpu_fast_aggregate_verify_batch", "blsgpu_aggregate_verify_batch", "blsgpu_g1_uncompress", "blsgpu_g1_compress", "blsgpu_g2_uncompress", "blsgpu_g2_compress", "blsgpu_pool_create", "blsgpu_pool_free", "blsgpu_pool_fast_aggregate_verify", "blsgpu_hash_to_g2_batch", "blsgpu_g1_aggregate",
            "blsgpu_g2_aggregate", "blsgpu_deserialize_g1", "blsgpu_deserialize_g2", "blsgpu_sk_to_pk_batch", "blsgpu_sign_batch", "blsgpu_pairing_gt",
-           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_r1cs_row_classes", "blsgpu_r1cs_load_file", "blsgpu_r1cs_check_file", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_check", "blsgpu_witness_free", "blsgpu_witness_msg_len", "blsgpu_set_witness_mode", "blsgpu_witness_set_aggregate", "blsgpu_witness_gen_aggregate", "blsgpu_witness_check_aggregate",
+           "blsgpu_gt_fold", "blsgpu_fp_mul_raw", "blsgpu_imad_peak", "blsgpu_r1cs_load", "blsgpu_r1cs_check", "blsgpu_r1cs_free", "blsgpu_r1cs_row_classes", "blsgpu_r1cs_load_file", "blsgpu_r1cs_check_file", "blsgpu_witness_load", "blsgpu_witness_gen", "blsgpu_witness_check", "blsgpu_witness_free", "blsgpu_witness_msg_len", "blsgpu_set_witness_mode", "blsgpu_witness_load_aggregate", "blsgpu_witness_shape", "blsgpu_witness_gen_aggregate", "blsgpu_witness_check_aggregate",
            "blsgpu_create_multi", "blsgpu_destroy_multi", "blsgpu_multi_last_error", "blsgpu_multi_ndev", "blsgpu_multi_nccl_version", "blsgpu_multi_ctx", "blsgpu_multi_verify_batch", "blsgpu_multi_peek"]
 
 _sz = ctypes.c_size_t; _vp = ctypes.c_void_p
@@ -237,9 +237,13 @@ class Context:
         lc = np.ascontiguousarray(program["lc_col"], dtype=np.uint32); cf = np.ascontiguousarray(program["lc_coef48"], dtype=np.uint8)
         od = np.ascontiguousarray(program["order"], dtype=np.uint32) if levels else None; lv = np.ascontiguousarray(program["level_ptr"], dtype=np.uint64) if levels else None
         h = ctypes.c_int(-1); nkeys = int(program.get("nkeys", 0))
-        self._ck(lib().blsgpu_witness_load(self._h, _p(r), _p(lp), _p(lc), _p(cf), _sz(r.size // 16), _sz(program["nvars"]), _sz(lp.size - 1), _sz(lc.size), _p(od), _p(lv), _sz(lv.size - 1 if levels else 0), ctypes.byref(h)))
-        if nkeys: self.witness_set_aggregate(h.value, nkeys)          # an aggregate_verify program (gadget.aggregate_verify_program)
+        args = (self._h, _p(r), _p(lp), _p(lc), _p(cf), _sz(r.size // 16), _sz(program["nvars"]), _sz(lp.size - 1), _sz(lc.size), _p(od), _p(lv), _sz(lv.size - 1 if levels else 0))
+        if nkeys: self._ck(lib().blsgpu_witness_load_aggregate(*args, _sz(nkeys), ctypes.byref(h)))      # an aggregate_verify program (gadget.aggregate_verify_program)
+        else: self._ck(lib().blsgpu_witness_load(*args, ctypes.byref(h)))
         return h.value
+    def witness_shape(self, handle):
+        c = (ctypes.c_uint64 * 4)(); self._ck(lib().blsgpu_witness_shape(self._h, int(handle), c))
+        return dict(zip(("light_rules", "light_levels", "field_levels", "integer_slots"), [int(x) for x in c]))
     def witness_msg_len(self, handle):
         L = int(lib().blsgpu_witness_msg_len(self._h, int(handle)))
         if L < 0: raise BlsGpuError("bad witness program handle")
@@ -259,7 +263,6 @@ class Context:
         self._ck(lib().blsgpu_witness_check(self._h, int(wit_handle), int(r1cs_handle), _p(pk), _p(m), _p(sg), _sz(n), _p(bits), _p(allsat), _p(st))); return bits, allsat, st
     def witness_check_ptr(self, wit_handle, r1cs_handle, pk, msg, sig, n, bits, allsat=None, status=None):
         self._ck(lib().blsgpu_witness_check(self._h, int(wit_handle), int(r1cs_handle), _p(pk), _p(msg), _p(sig), _sz(n), _p(bits), _p(allsat), _p(status)))
-    def witness_set_aggregate(self, handle, nkeys): self._ck(lib().blsgpu_witness_set_aggregate(self._h, int(handle), _sz(nkeys)))
     def witness_gen_aggregate(self, handle, pks48, bitmap, msg, sig96, nvars, nkeys):
         """aggregate_verify circuit: pks48 n x nkeys x 48, bitmap n x nkeys bytes, msg n x L, sig96 n x 96 -> (z [n, nvars * 48], status [n])"""
         pk = _u8(pks48); bm = np.ascontiguousarray(bitmap, dtype=np.uint8).reshape(-1); m = _u8(msg); sg = _u8(sig96); n = sg.size // 96

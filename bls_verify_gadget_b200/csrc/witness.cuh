@@ -21,10 +21,21 @@ struct wit_rule { uint8_t kind, pad; uint16_t aux; uint32_t a, b, d; };
 // rule in level order with its term ranges resolved (one dependent load less per combination); for WR_FP12INV a_lo is the
 // id of the first of twelve consecutive combinations
 struct wit_xrule { uint8_t kind, pad; uint16_t aux; uint32_t var; uint32_t a_lo, a_hi, b_lo, b_hi, d_lo, d_hi; };
+// light rule: WL_LUT a[0..4] = columns (WL_NO_COL pads), a[5] = 32-entry truth table; WL_SUM / WL_BIT a[0], a[1] = term range in lt_col / lt_coef,
+// a[2] = integer slot of the result (WL_SUM, integer-valued); WL_INPUT aux = input slot; flags: 1 = WL_SUM with a 0/1 result, 2 = also export the
+// integer as a field element (it is a circuit variable or a field rule reads it)
+enum { WL_LUT = 0, WL_SUM = 1, WL_BIT = 2, WL_INPUT = 3, WL_ONE = 4 };
+#define WL_NO_COL 0xffffffffu
+#define WL_INT 0x80000000u          // lt_col entries with this bit address an integer slot instead of a 0/1 column
+struct wit_lrule { uint8_t kind, flags; uint16_t aux; uint32_t var; uint32_t a[6]; };
 struct wit_prog {
     size_t nvars, nout, nlc, nterms, nlevels;          // nvars: columns of the program (circuit variables, then scratch values); nout: circuit variables
     wit_rule* rules; uint64_t* lc_ptr; uint32_t* col; fp* coeff; fp* coeffc; uint8_t* cls;
     wit_xrule* xrules; uint64_t* level_ptr;          // dependency levels: rules of one level are independent
+    // "light" part (blsgpu_witness_load): rules whose operands and result are 0/1 values or small integers -- the SHA-256 / bit-decomposition
+    // gadgets: 715 k of the verify program's 1.04 M rules on 10.4 k of its dependency levels -- run in k_witness_light, one CTA per group of
+    // 32 assignments with __syncthreads between levels; the remaining (field) rules keep the level-synchronous kernels above, on 4.3 k levels
+    struct wit_lrule* lrules; uint32_t* llevel_ptr; uint32_t* lt_col; long long* lt_coef; size_t n_light, n_llevels, n_islots, n_lterms;
     size_t msg_len, ninputs, nkeys;                  // input slots of the recorded circuit: nkeys = 0: verify (6 + 8 msg_len); nkeys = n: aggregate_verify (3n + 4 + 8 msg_len)
 };
 #define WIT_POINT_INPUTS 6      // input slots 0..5: pk.x, pk.y, sig x.c0, x.c1, y.c0, y.c1; slot 6 + 8 i + b = bit b of message byte i (any message length)
@@ -269,6 +280,53 @@ __global__ void __launch_bounds__(WIT_CL_TPB, 1) k_witness_cluster(wit_prog p, c
         lo = hi; hi = hi_next;
     }
 }
+// ---- the light part: 0/1 and small-integer rules, one CTA per group of 32 assignments.  A truth-table rule is evaluated by ONE THREAD for all
+// 32 assignments (bit-sliced on the packed words, like k_r1cs_lut); sums and bit extractions take a warp (lane = assignment, 64-bit integers).
+// The barrier between levels is __syncthreads: ~0.1 us instead of the grid barrier, and the per-level latency is one dependent load of packed
+// words that this SM wrote itself.  Values: zbool[var] = (packed word, 1); integers in sint[slot][32].
+#define WIT_LIGHT_TPB 1024
+__global__ void __launch_bounds__(WIT_LIGHT_TPB, 1) k_witness_light(wit_prog p, const fp* inputs, size_t nwit_padded, u32x4* zt_all, uint2* zbool_all, long long* sint_all) {
+    size_t group = blockIdx.x; int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint2* zb = zbool_all + group * p.nvars; long long* sint = sint_all + group * p.n_islots * 32; u32x4* zt = zt_all + group * p.nvars * 96;
+    for (size_t L = 0; L < p.n_llevels; L++) {
+        uint32_t lut_lo = p.llevel_ptr[2 * L], w_lo = p.llevel_ptr[2 * L + 1], nxt = p.llevel_ptr[2 * L + 2];
+        for (uint32_t i = lut_lo + tid; i < w_lo; i += WIT_LIGHT_TPB) {
+            wit_lrule r = p.lrules[i];
+            uint32_t x0 = zb[r.a[0]].x, x1 = r.a[1] != WL_NO_COL ? zb[r.a[1]].x : 0u, x2 = r.a[2] != WL_NO_COL ? zb[r.a[2]].x : 0u;
+            uint32_t out;
+            if (r.a[3] != WL_NO_COL) { uint32_t x3 = zb[r.a[3]].x, x4 = r.a[4] != WL_NO_COL ? zb[r.a[4]].x : 0u; out = r1cs_lut5(r.a[5], x0, x1, x2, x3, x4); }
+            else out = r1cs_lut3(r.a[5], x0, x1, x2);
+            zb[r.var] = make_uint2(out, 1u);
+        }
+        for (uint32_t i = w_lo + warp; i < nxt; i += WIT_LIGHT_TPB / 32) {
+            wit_lrule r = p.lrules[i];
+            if (r.kind == WL_ONE) { if (lane == 0) zb[r.var] = make_uint2(0xffffffffu, 1u); continue; }
+            if (r.kind == WL_INPUT) {
+                uint32_t bit = inputs[(size_t)r.aux * nwit_padded + group * 32 + lane].l[0] & 1u;
+                uint32_t pack = __ballot_sync(0xffffffffu, bit); if (lane == 0) zb[r.var] = make_uint2(pack, 1u); continue;
+            }
+            long long sum = 0;
+            for (uint32_t t = r.a[0]; t < r.a[1]; t++) {
+                uint32_t c = p.lt_col[t]; long long k = p.lt_coef[t];
+                long long v = (c & WL_INT) ? sint[(size_t)(c & ~WL_INT) * 32 + lane] : (long long)((zb[c].x >> lane) & 1u);
+                sum += k * v;
+            }
+            if (r.kind == WL_BIT || (r.flags & 1)) {
+                uint32_t bit = r.kind == WL_BIT ? (uint32_t)((unsigned long long)sum >> (r.aux & 63)) & 1u : (uint32_t)sum & 1u;
+                uint32_t pack = __ballot_sync(0xffffffffu, bit); if (lane == 0) zb[r.var] = make_uint2(pack, 1u);
+            } else {
+                sint[(size_t)r.a[2] * 32 + lane] = sum;
+                if (r.flags & 2) {                            // the value as a canonical field element beside the integer
+                    unsigned long long mag = sum < 0 ? (unsigned long long)(-sum) : (unsigned long long)sum;
+                    fp v = fp_zero(); v.l[0] = (uint32_t)mag; v.l[1] = (uint32_t)(mag >> 32);
+                    if (sum < 0) { fp n; fp_sub_raw(n, fp_modulus(), v); v = n; }
+                    wit_store(zt, r.var, lane, v); if (lane == 0) zb[r.var] = make_uint2(0u, 0u);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
 // input slots from the decoded points and the message bytes; items whose key or signature does not decode get all-zero inputs
 __global__ void __launch_bounds__(TPB, BLS_MINB) k_witness_inputs(const u32x4* pk_soa, const uint8_t* code_pk, const u32x4* sig_soa, const uint8_t* code_sig, const uint8_t* msg, size_t msg_len,
                                                                   size_t nwit, size_t nwit_padded, fp* inputs, uint8_t* status) {
@@ -320,66 +378,179 @@ __global__ void __launch_bounds__(256) k_witness_untranspose(const u32x4* zt_all
 
 static void wit_release(wit_prog* p) {
     cudaFree(p->rules); cudaFree(p->lc_ptr); cudaFree(p->col); cudaFree(p->coeff); cudaFree(p->coeffc); cudaFree(p->cls);
-    cudaFree(p->xrules); cudaFree(p->level_ptr);
+    cudaFree(p->xrules); cudaFree(p->level_ptr); cudaFree(p->lrules); cudaFree(p->llevel_ptr); cudaFree(p->lt_col); cudaFree(p->lt_coef);
     delete p;
 }
 
 extern "C" {
-int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t* lc_ptr, const uint32_t* lc_col, const uint8_t* lc_coef48, size_t nvars, size_t nout, size_t nlc, size_t nterms,
-                        const uint32_t* order, const uint64_t* level_ptr, size_t nlevels, int* handle) {
-    ENTER(); if (!rules16 || !lc_ptr || !lc_col || !lc_coef48 || !handle || !nvars || !nout || nout > nvars) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
-    if (ctx->ptr_mode != BLSGPU_HOST) return fail(ctx, BLSGPU_ERR_ARG, "blsgpu_witness_load takes host pointers (the level-ordered rule table is built on the host)");
+// Splits the level-ordered program into its light part (wit_lrule records by light level) and its heavy part (wit_xrule records re-levelled with
+// every light column at level 0).  Walks the rules in the given level order, so operands are classified before their users.
+struct wit_split { std::vector<wit_lrule> lrules; std::vector<uint32_t> llevel_ptr, lt_col; std::vector<long long> lt_coef; size_t n_islots = 0;
+                   std::vector<wit_xrule> xrules; std::vector<uint64_t> hlevel_ptr; };
+static bool wit_small_coef(const uint8_t* c48, long long& out) {            // canonical 48-byte LE -> signed integer when |c| < 2^48
+    static const uint8_t PB[48] = {0xab, 0xaa, 0xff, 0xff, 0xff, 0xff, 0xfe, 0xb9, 0xff, 0xff, 0x53, 0xb1, 0xfe, 0xff, 0xab, 0x1e, 0x24, 0xf6, 0xb0, 0xf6, 0xa0, 0xd2, 0x30, 0x67,
+                                   0xbf, 0x12, 0x85, 0xf3, 0x84, 0x4b, 0x77, 0x64, 0xd7, 0xac, 0x4b, 0x43, 0xb6, 0xa7, 0x1b, 0x4b, 0x9a, 0xe6, 0x7f, 0x39, 0xea, 0x11, 0x01, 0x1a};
+    bool hi = false; for (int i = 6; i < 48; i++) hi |= c48[i] != 0;
+    if (!hi) { long long v = 0; for (int i = 5; i >= 0; i--) v = (v << 8) | c48[i]; out = v; return true; }
+    for (int i = 8; i < 48; i++) if (c48[i] != PB[i]) return false;          // p - c < 2^48 needs the upper bytes of p (a borrow can reach bytes 6, 7 only)
+    unsigned long long lo = 0, pl = 0; for (int i = 7; i >= 0; i--) { lo = (lo << 8) | c48[i]; pl = (pl << 8) | PB[i]; }
+    if (lo > pl) return false;
+    unsigned long long d = pl - lo; if (d >= (1ull << 48)) return false;
+    out = -(long long)d; return true;
+}
+static void wit_split_program(wit_split& S, const wit_rule* hr, const uint64_t* lc_ptr, const uint32_t* lc_col, const uint8_t* lc_coef48, size_t ncols, size_t nout,
+                              const uint32_t* order, size_t nkeys, size_t ninputs) {
+    enum : uint8_t { HEAVY = 0, LB = 1, LI = 2 };
+    std::vector<uint8_t> state(ncols, HEAVY); std::vector<uint32_t> llev(ncols, 0), hlev(ncols, 0), islot(ncols, 0); std::vector<long long> vmin(ncols, 0), vmax(ncols, 0);
+    std::vector<uint8_t> is_small; std::vector<long long> coef;              // decoded lazily per term
+    auto lo_of = [&](uint32_t id) { return id ? lc_ptr[id - 1] : (uint64_t)0; }; auto hi_of = [&](uint32_t id) { return id ? lc_ptr[id] : (uint64_t)0; };
+    size_t nterms = lc_ptr ? 0 : 0; (void)nterms;
+    auto bool_input = [&](uint16_t slot) { return nkeys ? ((slot >= 2 * nkeys && slot < 3 * nkeys) || slot >= 3 * nkeys + 4) : slot >= WIT_POINT_INPUTS; };
+    struct lrec { wit_lrule r; uint32_t level; }; std::vector<lrec> light; std::vector<uint32_t> heavy_vars;
+    const __int128 LIM = (__int128)1 << 62;
+    for (size_t oi = 0; oi < ncols; oi++) {
+        uint32_t v = order[oi]; const wit_rule& r = hr[v];
+        wit_lrule lr; memset(&lr, 0, sizeof lr); lr.var = v; lr.aux = r.aux; for (int k = 0; k < 6; k++) lr.a[k] = WL_NO_COL;
+        bool is_light = false; uint32_t level = 0;
+        if (r.kind == WR_INPUT) {
+            if (r.aux == 0xffff) { lr.kind = WL_ONE; state[v] = LB; is_light = true; }
+            else if ((size_t)r.aux < ninputs && bool_input(r.aux)) { lr.kind = WL_INPUT; state[v] = LB; is_light = true; }
+        } else if (r.kind == WR_MULADD || r.kind == WR_BIT) {
+            // gather the terms; every column must be light and every coefficient a small integer
+            uint32_t ids[3] = {r.a, r.kind == WR_BIT ? 0u : r.b, r.kind == WR_BIT ? 0u : r.d}; bool ok = true; uint32_t mx = 0;
+            struct term { uint32_t col; long long k; int which; }; std::vector<term> ts;
+            for (int q = 0; q < 3 && ok; q++) for (uint64_t t = lo_of(ids[q]); t < hi_of(ids[q]); t++) {
+                uint32_t c = lc_col[t]; long long k;
+                if (state[c] == HEAVY || !wit_small_coef(lc_coef48 + 48 * t, k)) { ok = false; break; }
+                ts.push_back({c, k, q}); if (llev[c] > mx) mx = llev[c];
+            }
+            if (ok) {
+                level = mx + 1;
+                if (r.kind == WR_MULADD && !r.a && r.b) ok = false;                   // (never recorded: a rule without a first factor has no second one)
+                if (!ok) { }
+                else if (r.kind == WR_MULADD && r.a) {                            // product rule: a truth table over <= 5 distinct 0/1 columns
+                    uint32_t cs[5]; int d = 0; bool fits = true;
+                    for (auto& t : ts) { if (state[t.col] != LB) { fits = false; break; } if (t.col == 0) continue;      // column 0 is the constant 1 (the replay writes it), not a table input
+                                         int j = 0; while (j < d && cs[j] != t.col) j++; if (j == d) { if (d == 5) { fits = false; break; } cs[d++] = t.col; } }
+                    if (fits && d == 0) { cs[d++] = 0; }                                              // a product of constants: a one-input table on column 0
+                    if (fits) {
+                        uint32_t table = 0; bool boolean = true;
+                        for (uint32_t idx = 0; idx < 32 && boolean; idx++) {
+                            __int128 s[3] = {0, 0, 0};
+                            for (auto& t : ts) { if (t.col == 0) { s[t.which] += t.k; continue; } int j = 0; while (cs[j] != t.col) j++; if ((idx >> j) & 1) s[t.which] += t.k; }
+                            __int128 val = s[0] * s[1] + s[2];
+                            if (val == 1) table |= 1u << idx; else if (val != 0) boolean = false;
+                        }
+                        if (boolean) { lr.kind = WL_LUT; for (int j = 0; j < d; j++) lr.a[j] = cs[j]; lr.a[5] = table; state[v] = LB; is_light = true; }
+                    }
+                } else {                                                           // a sum (MULADD with d only) or a bit of a sum
+                    __int128 mn = 0, mxv = 0;
+                    for (auto& t : ts) { __int128 a = t.col == 0 ? 1 : state[t.col] == LB ? 0 : vmin[t.col], b = state[t.col] == LB ? 1 : vmax[t.col]; __int128 x = a * t.k, y = b * t.k; mn += x < y ? x : y; mxv += x < y ? y : x; }
+                    bool range_ok = mn > -LIM && mxv < LIM && ts.size() < (1u << 20);
+                    if (range_ok && (r.kind == WR_MULADD || (mn >= 0 && r.aux < 63))) {
+                        lr.kind = r.kind == WR_BIT ? WL_BIT : WL_SUM; lr.a[0] = (uint32_t)S.lt_col.size();
+                        for (auto& t : ts) { S.lt_col.push_back(state[t.col] == LI ? (WL_INT | islot[t.col]) : t.col); S.lt_coef.push_back(t.k); }
+                        lr.a[1] = (uint32_t)S.lt_col.size(); is_light = true;
+                        if (r.kind == WR_BIT || (mn >= 0 && mxv <= 1)) { state[v] = LB; if (r.kind == WR_MULADD) lr.flags |= 1; }
+                        else { state[v] = LI; vmin[v] = (long long)mn; vmax[v] = (long long)mxv; islot[v] = (uint32_t)S.n_islots; lr.a[2] = (uint32_t)S.n_islots++; if (v < nout) lr.flags |= 2; }
+                    }
+                }
+            }
+        }
+        if (is_light) { llev[v] = level; light.push_back({lr, level}); }
+        else heavy_vars.push_back(v);
+    }
+    // heavy rules: levels among themselves (light columns sit at level 0), integers they read are exported as field elements
+    std::vector<uint8_t> export_int(ncols, 0); uint32_t hmax = 0;
+    auto scan = [&](uint32_t id, uint32_t& m) { for (uint64_t t = lo_of(id); t < hi_of(id); t++) { uint32_t c = lc_col[t]; if (state[c] == LI) export_int[c] = 1; if (state[c] == HEAVY && hlev[c] > m) m = hlev[c]; } };
+    for (uint32_t v : heavy_vars) {
+        const wit_rule& r = hr[v]; uint32_t m = 0;
+        if (r.kind == WR_INPUT) { hlev[v] = 0; continue; }
+        if (r.kind == WR_FP12INV) { for (uint32_t k = 0; k < 12; k++) scan(r.a + k, m); } else { scan(r.a, m); scan(r.b, m); scan(r.d, m); }
+        hlev[v] = m + 1; if (hlev[v] > hmax) hmax = hlev[v];
+    }
+    for (auto& l : light) if (l.r.kind == WL_SUM && !(l.r.flags & 1) && export_int[l.r.var]) l.r.flags |= 2;
+    // light records by level, truth-table rules first inside a level
+    uint32_t lmax = 0; for (auto& l : light) if (l.level > lmax) lmax = l.level;
+    size_t nl = light.empty() ? 0 : (size_t)lmax + 1;
+    std::vector<uint32_t> cnt(2 * nl + 1, 0);
+    for (auto& l : light) cnt[2 * l.level + (l.r.kind == WL_LUT ? 0 : 1) + 1]++;
+    for (size_t i = 0; i < 2 * nl; i++) cnt[i + 1] += cnt[i];
+    S.llevel_ptr = cnt; S.lrules.resize(light.size());
+    { std::vector<uint32_t> pos(cnt.begin(), cnt.end() - 1); for (auto& l : light) S.lrules[pos[2 * l.level + (l.r.kind == WL_LUT ? 0 : 1)]++] = l.r; }
+    size_t nh = (size_t)hmax + 1; std::vector<uint64_t> hc(nh + 1, 0);
+    for (uint32_t v : heavy_vars) hc[hlev[v] + 1]++;
+    for (size_t i = 0; i < nh; i++) hc[i + 1] += hc[i];
+    S.hlevel_ptr = hc; S.xrules.resize(heavy_vars.size());
+    { std::vector<uint64_t> pos(hc.begin(), hc.end() - 1);
+      for (uint32_t v : heavy_vars) {
+          const wit_rule& r = hr[v]; wit_xrule& x = S.xrules[pos[hlev[v]]++];
+          x.kind = r.kind; x.pad = 0; x.aux = r.aux; x.var = v;
+          if (r.kind == WR_FP12INV) { x.a_lo = r.a; x.a_hi = r.a + 12; x.b_lo = x.b_hi = x.d_lo = x.d_hi = 0; }
+          else { x.a_lo = (uint32_t)lo_of(r.a); x.a_hi = (uint32_t)hi_of(r.a); x.b_lo = (uint32_t)lo_of(r.b); x.b_hi = (uint32_t)hi_of(r.b); x.d_lo = (uint32_t)lo_of(r.d); x.d_hi = (uint32_t)hi_of(r.d); }
+      } }
+}
+static int witness_load_impl(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t* lc_ptr, const uint32_t* lc_col, const uint8_t* lc_coef48, size_t nvars, size_t nout, size_t nlc, size_t nterms,
+                             const uint32_t* order, const uint64_t* level_ptr, size_t nlevels, size_t nkeys, int* handle) {
+    if (!rules16 || !lc_ptr || !lc_col || !lc_coef48 || !handle || !nvars || !nout || nout > nvars) return fail(ctx, BLSGPU_ERR_ARG, "bad argument");
+    if (ctx->ptr_mode != BLSGPU_HOST) return fail(ctx, BLSGPU_ERR_ARG, "blsgpu_witness_load takes host pointers (the level-ordered rule tables are built on the host)");
     int h = -1; for (int i = 0; i < 4; i++) if (!ctx->wit[i]) { h = i; break; }
     if (h < 0) return fail(ctx, BLSGPU_ERR_ARG, "too many witness programs loaded");
     wit_prog* p = new (std::nothrow) wit_prog(); if (!p) return fail(ctx, BLSGPU_ERR_ALLOC, "out of host memory");
     memset(p, 0, sizeof *p); p->nvars = nvars; p->nout = nout; p->nlc = nlc; p->nterms = nterms;
     struct guard_t { wit_prog* p; ~guard_t() { if (p) wit_release(p); } } undo{p};          // a failed load leaves nothing behind
-    {   // the message length of the recorded circuit follows from the highest input slot: slots 0..5 are the points, 6 + 8 i + b the message bits
-        const wit_rule* hr = reinterpret_cast<const wit_rule*>(rules16); size_t top = 0;
+    const wit_rule* hr = reinterpret_cast<const wit_rule*>(rules16);
+    {   // input slots: verify circuit 0..5 the points, 6 + 8 i + b the message bits; aggregate_verify circuit [0, 2n) keys, [2n, 3n) bitmap bits, [3n, 3n + 4) signature, message bits
+        size_t top = 0;
         for (size_t k = 0; k < nvars; k++) if (hr[k].kind == WR_INPUT && hr[k].aux != 0xffff && (size_t)hr[k].aux + 1 > top) top = (size_t)hr[k].aux + 1;
-        p->ninputs = top; p->nkeys = 0;                    // a verify program until blsgpu_witness_set_aggregate says otherwise
-        p->msg_len = (top >= WIT_POINT_INPUTS && (top - WIT_POINT_INPUTS) % 8 == 0) ? (top - WIT_POINT_INPUTS) / 8 : (size_t)-1;
+        size_t fixed = nkeys ? 3 * nkeys + 4 : WIT_POINT_INPUTS;
+        if (top < fixed || (top - fixed) % 8) return fail(ctx, BLSGPU_ERR_ARG, "witness program: %zu input slots is not %zu + 8 x message bytes%s", top, fixed, nkeys ? "" : " (an aggregate_verify program is loaded with blsgpu_witness_load_aggregate)");
+        p->ninputs = top; p->nkeys = nkeys; p->msg_len = (top - fixed) / 8;
     }
-    cudaMemcpyKind kind = ctx->ptr_mode == BLSGPU_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     size_t nt = nterms ? nterms : 1;
     CU(cudaMalloc(&p->rules, 16 * nvars)); CU(cudaMalloc(&p->lc_ptr, 8 * (nlc + 1))); CU(cudaMalloc(&p->col, 4 * nt));
     CU(cudaMalloc(&p->coeff, 48 * nt)); CU(cudaMalloc(&p->coeffc, 48 * nt)); CU(cudaMalloc(&p->cls, nt));
-    CU(cudaMemcpyAsync(p->rules, rules16, 16 * nvars, kind, ctx->stream)); CU(cudaMemcpyAsync(p->lc_ptr, lc_ptr, 8 * (nlc + 1), kind, ctx->stream));
+    CU(cudaMemcpyAsync(p->rules, rules16, 16 * nvars, cudaMemcpyHostToDevice, ctx->stream)); CU(cudaMemcpyAsync(p->lc_ptr, lc_ptr, 8 * (nlc + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (nterms) {
-        CU(cudaMemcpyAsync(p->col, lc_col, 4 * nterms, kind, ctx->stream));
+        CU(cudaMemcpyAsync(p->col, lc_col, 4 * nterms, cudaMemcpyHostToDevice, ctx->stream));
         dev_tmp raw; CU(cudaMalloc(&raw.p, 48 * nterms));
-        CU(cudaMemcpyAsync(raw.p, lc_coef48, 48 * nterms, kind, ctx->stream));
+        CU(cudaMemcpyAsync(raw.p, lc_coef48, 48 * nterms, cudaMemcpyHostToDevice, ctx->stream));
         LAUNCH(k_r1cs_prepare, nblk(nterms), TPB, (const uint8_t*)raw.p, nterms, p->coeff, p->coeffc, p->cls);
         CU(cudaStreamSynchronize(ctx->stream));
     }
-    if (order && level_ptr && nlevels) {                   // level-ordered rules with resolved term ranges
-        const wit_rule* hr = reinterpret_cast<const wit_rule*>(rules16);
-        std::vector<wit_xrule> xr(nvars);
-        auto lo_of = [&](uint32_t id) { return id ? (uint32_t)lc_ptr[id - 1] : 0u; }; auto hi_of = [&](uint32_t id) { return id ? (uint32_t)lc_ptr[id] : 0u; };
-        for (size_t k = 0; k < nvars; k++) {
-            const wit_rule& r = hr[order[k]]; wit_xrule& x = xr[k];
-            x.kind = r.kind; x.pad = 0; x.aux = r.aux; x.var = order[k];
-            if (r.kind == WR_FP12INV) { x.a_lo = r.a; x.a_hi = r.a + 12; x.b_lo = x.b_hi = x.d_lo = x.d_hi = 0; }
-            else { x.a_lo = lo_of(r.a); x.a_hi = hi_of(r.a); x.b_lo = lo_of(r.b); x.b_hi = hi_of(r.b); x.d_lo = lo_of(r.d); x.d_hi = hi_of(r.d); }
-        }
-        p->nlevels = nlevels;
-        CU(cudaMalloc(&p->xrules, sizeof(wit_xrule) * nvars)); CU(cudaMalloc(&p->level_ptr, 8 * (nlevels + 1)));
-        CU(cudaMemcpyAsync(p->xrules, xr.data(), sizeof(wit_xrule) * nvars, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(p->level_ptr, level_ptr, 8 * (nlevels + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (order && level_ptr && nlevels) {                   // level-synchronous replay: light part + heavy part
+        wit_split S; wit_split_program(S, hr, lc_ptr, lc_col, lc_coef48, nvars, nout, order, nkeys, p->ninputs);
+        p->nlevels = S.hlevel_ptr.size() - 1; p->n_light = S.lrules.size(); p->n_llevels = S.llevel_ptr.size() / 2; p->n_islots = S.n_islots; p->n_lterms = S.lt_col.size();
+        size_t nx = S.xrules.size() ? S.xrules.size() : 1, nlr = S.lrules.size() ? S.lrules.size() : 1, nlt = S.lt_col.size() ? S.lt_col.size() : 1;
+        CU(cudaMalloc(&p->xrules, sizeof(wit_xrule) * nx)); CU(cudaMalloc(&p->level_ptr, 8 * S.hlevel_ptr.size()));
+        CU(cudaMalloc(&p->lrules, sizeof(wit_lrule) * nlr)); CU(cudaMalloc(&p->llevel_ptr, 4 * (S.llevel_ptr.size() ? S.llevel_ptr.size() : 1)));
+        CU(cudaMalloc(&p->lt_col, 4 * nlt)); CU(cudaMalloc(&p->lt_coef, 8 * nlt));
+        if (S.xrules.size()) CU(cudaMemcpyAsync(p->xrules, S.xrules.data(), sizeof(wit_xrule) * S.xrules.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(p->level_ptr, S.hlevel_ptr.data(), 8 * S.hlevel_ptr.size(), cudaMemcpyHostToDevice, ctx->stream));
+        if (S.lrules.size()) CU(cudaMemcpyAsync(p->lrules, S.lrules.data(), sizeof(wit_lrule) * S.lrules.size(), cudaMemcpyHostToDevice, ctx->stream));
+        if (S.llevel_ptr.size()) CU(cudaMemcpyAsync(p->llevel_ptr, S.llevel_ptr.data(), 4 * S.llevel_ptr.size(), cudaMemcpyHostToDevice, ctx->stream));
+        if (S.lt_col.size()) { CU(cudaMemcpyAsync(p->lt_col, S.lt_col.data(), 4 * S.lt_col.size(), cudaMemcpyHostToDevice, ctx->stream)); CU(cudaMemcpyAsync(p->lt_coef, S.lt_coef.data(), 8 * S.lt_coef.size(), cudaMemcpyHostToDevice, ctx->stream)); }
         CU(cudaStreamSynchronize(ctx->stream));
     }
     CU(cudaStreamSynchronize(ctx->stream));
     undo.p = nullptr; ctx->wit[h] = p; *handle = h; return 0;
 }
+int blsgpu_witness_load(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t* lc_ptr, const uint32_t* lc_col, const uint8_t* lc_coef48, size_t nvars, size_t nout, size_t nlc, size_t nterms,
+                        const uint32_t* order, const uint64_t* level_ptr, size_t nlevels, int* handle) {
+    ENTER(); return witness_load_impl(ctx, rules16, lc_ptr, lc_col, lc_coef48, nvars, nout, nlc, nterms, order, level_ptr, nlevels, 0, handle);
+}
+// the same for a program of the aggregate_verify circuit (src/constraints.rs:153-191) with nkeys public keys (blsgadget_aggregate_verify_program): its input
+// slots are [0, 2n) key coordinates, [2n, 3n) bitmap bits, [3n, 3n + 4) the signature, then 8 bits per message byte
+int blsgpu_witness_load_aggregate(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t* lc_ptr, const uint32_t* lc_col, const uint8_t* lc_coef48, size_t nvars, size_t nout, size_t nlc, size_t nterms,
+                                  const uint32_t* order, const uint64_t* level_ptr, size_t nlevels, size_t nkeys, int* handle) {
+    ENTER(); if (!nkeys) return fail(ctx, BLSGPU_ERR_ARG, "nkeys must be positive"); return witness_load_impl(ctx, rules16, lc_ptr, lc_col, lc_coef48, nvars, nout, nlc, nterms, order, level_ptr, nlevels, nkeys, handle);
+}
 // bytes per message of the circuit the loaded program was recorded for (blsgpu_witness_gen / _check take nwit x that many message bytes)
 long blsgpu_witness_msg_len(blsgpu_ctx* ctx, int handle) { return (!ctx || handle < 0 || handle >= 4 || !ctx->wit[handle]) ? -1 : (long)ctx->wit[handle]->msg_len; }
-// declares a loaded program to be one of the aggregate_verify circuit (src/constraints.rs:153-191) with nkeys public keys: its input slots are
-// [0, 2n) key coordinates, [2n, 3n) bitmap bits, [3n, 3n + 4) the signature, then 8 bits per message byte (blsgadget_aggregate_verify_program)
-int blsgpu_witness_set_aggregate(blsgpu_ctx* ctx, int handle, size_t nkeys) {
-    if (!ctx || handle < 0 || handle >= 4 || !ctx->wit[handle] || !nkeys) return BLSGPU_ERR_ARG;
-    wit_prog* p = ctx->wit[handle];
-    if (p->ninputs < 3 * nkeys + 4 || (p->ninputs - 3 * nkeys - 4) % 8) return fail(ctx, BLSGPU_ERR_ARG, "witness program: %zu input slots is not 3 x %zu keys + 4 + 8 x message bytes", p->ninputs, nkeys);
-    p->nkeys = nkeys; p->msg_len = (p->ninputs - 3 * nkeys - 4) / 8; return 0;
+// rule counts of a loaded program: counts[0] light rules, [1] light levels, [2] heavy (field) levels, [3] integer slots
+int blsgpu_witness_shape(blsgpu_ctx* ctx, int handle, uint64_t counts[4]) {
+    if (!ctx || handle < 0 || handle >= 4 || !ctx->wit[handle] || !counts) return BLSGPU_ERR_ARG;
+    const wit_prog* p = ctx->wit[handle]; counts[0] = p->n_light; counts[1] = p->n_llevels; counts[2] = p->nlevels; counts[3] = p->n_islots; return 0;
 }
 int blsgpu_witness_free(blsgpu_ctx* ctx, int handle) {
     if (!ctx || handle < 0 || handle >= 4 || !ctx->wit[handle]) return BLSGPU_ERR_ARG;
@@ -393,11 +564,10 @@ int blsgpu_witness_free(blsgpu_ctx* ctx, int handle) {
 // bitmap == NULL: verify program (pk48 = nwit keys); else aggregate program (pk48 = nwit x p.nkeys keys, bitmap = nwit x p.nkeys bytes)
 static int witness_run(blsgpu_ctx* ctx, const wit_prog& p, const uint8_t* pk48, const uint8_t* bitmap, const uint8_t* msg, const uint8_t* sig96, size_t nwit, uint8_t* status, size_t extra,
                        bool want_zbool, u32x4** zt_out, uint2** zbool_out, uint8_t** dstatus_out) {
-    if (p.msg_len == (size_t)-1) return fail(ctx, BLSGPU_ERR_ARG, "witness program: %zu input slots fit no verify circuit (6 + 8 x message bytes); an aggregate program needs blsgpu_witness_set_aggregate", p.ninputs);
     if ((bitmap != nullptr) != (p.nkeys != 0)) return fail(ctx, BLSGPU_ERR_ARG, p.nkeys ? "this is an aggregate_verify program: use the _aggregate entry points" : "this is a verify program: use blsgpu_witness_gen / _check");
     size_t groups = (nwit + 31) / 32, np = groups * 32, ninputs = p.ninputs, nk = p.nkeys ? p.nkeys : 1, nkeys_total = nwit * nk;
     if (int rc = ws_reserve(ctx, al(48 * nkeys_total) + al(nkeys_total) + al(96 * nwit) + al(p.msg_len * nwit + 1) + al(96 * nkeys_total) + al(192 * nwit) + 2 * al(np) + al(nkeys_total + np) + al(48 * ninputs * np) + al(groups * p.nvars * 1536) +
-                                 (want_zbool ? al(groups * p.nvars * 8) : 0) + extra + 65536)) return rc;
+                                 (want_zbool ? al(groups * p.nvars * 8) : 0) + al(groups * (p.n_islots + 1) * 256) + extra + 65536)) return rc;
     const uint8_t *dpk, *dsig, *dmsg, *dbm = nullptr;
     if (int rc = stage_in(ctx, dpk, pk48, 48 * nkeys_total)) return rc;
     if (bitmap) { if (int rc = stage_in(ctx, dbm, bitmap, nkeys_total)) return rc; }
@@ -409,10 +579,13 @@ static int witness_run(blsgpu_ctx* ctx, const wit_prog& p, const uint8_t* pk48, 
     fp* inputs = ws_take<fp>(ctx, ninputs * np);
     u32x4* zt_all = ws_take<u32x4>(ctx, groups * p.nvars * 96);
     uint2* zbool_all = want_zbool ? ws_take<uint2>(ctx, groups * p.nvars) : nullptr;
+    long long* sint_all = ws_take<long long>(ctx, groups * (p.n_islots + 1) * 32);
     LAUNCH(k_decode_g1, nblk(nkeys_total), TPB, dpk, nkeys_total, pk_soa, code_pk);
     LAUNCH(k_decode_g2, nblk(nwit), TPB, dsig, nwit, sig_soa, code_sig);
     if (bitmap) LAUNCH(k_witness_inputs_agg, nblk(np), TPB, (const u32x4*)pk_soa, (const uint8_t*)code_pk, p.nkeys, dbm, (const u32x4*)sig_soa, (const uint8_t*)code_sig, dmsg, p.msg_len, nwit, np, inputs, dstatus);
     else LAUNCH(k_witness_inputs, nblk(np), TPB, (const u32x4*)pk_soa, (const uint8_t*)code_pk, (const u32x4*)sig_soa, (const uint8_t*)code_sig, dmsg, p.msg_len, nwit, np, inputs, dstatus);
+    if (p.xrules && !want_zbool) return fail(ctx, BLSGPU_ERR_ARG, "the level-synchronous replay works on the packed 0/1 view");
+    if (p.xrules && p.n_light) LAUNCH(k_witness_light, (unsigned)groups, WIT_LIGHT_TPB, p, (const fp*)inputs, np, zt_all, zbool_all, sint_all);      // 0/1 and small-integer rules first
     if (p.xrules && ctx->wit_cluster) {                    // level-synchronous per group, hardware cluster barrier between levels
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
         cfg.gridDim = dim3((unsigned)(groups * WIT_CL)); cfg.blockDim = dim3(WIT_CL_TPB); cfg.stream = ctx->stream;
@@ -490,7 +663,7 @@ int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const
                          uint64_t* sat_bits, uint8_t* all_sat, uint8_t* status) {
     ENTER(); return witness_check_core(ctx, wit_handle, r1cs_handle, pk48, nullptr, msg, sig96, nwit, sat_bits, all_sat, status);
 }
-// the aggregate_verify circuit (src/constraints.rs:153-191; program from blsgadget_aggregate_verify_program + blsgpu_witness_set_aggregate):
+// the aggregate_verify circuit (src/constraints.rs:153-191; program from blsgadget_aggregate_verify_program, loaded with blsgpu_witness_load_aggregate):
 // pks48 = nwit x nkeys compressed keys, bitmap = nwit x nkeys bytes (0 / non-zero: the participation bits), msg = nwit x L bytes, sig96 = nwit
 // aggregate signatures.  status: 2 when any of an item's keys does not decode to a non-identity point (masked-out keys are witnesses too), 3 for the signature.
 int blsgpu_witness_gen_aggregate(blsgpu_ctx* ctx, int handle, const uint8_t* pks48, const uint8_t* bitmap, const uint8_t* msg, const uint8_t* sig96, size_t nwit, uint8_t* z48, uint8_t* status) {

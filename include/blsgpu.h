@@ -212,11 +212,16 @@ int blsgpu_witness_gen(blsgpu_ctx* ctx, int handle, const uint8_t* pk48, const u
 int blsgpu_witness_check(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const uint8_t* pk48, const uint8_t* msg, const uint8_t* sig96, size_t nwit,
                          uint64_t* sat_bits, uint8_t* all_sat, uint8_t* status);
 long blsgpu_witness_msg_len(blsgpu_ctx* ctx, int handle);   /* L of the loaded program, -1 for a bad handle */
+/* how the loaded program was split: counts[0] "light" rules (0/1 and small-integer values: the SHA-256 / bit gadgets, evaluated bit-sliced by one CTA
+ * per group of 32 assignments), [1] their dependency levels, [2] dependency levels of the remaining field rules, [3] integer scratch slots */
+int blsgpu_witness_shape(blsgpu_ctx* ctx, int handle, uint64_t counts[4]);
 /* The aggregate_verify circuit (BlsSignatureVerifyGadget::aggregate_verify / mapped_aggregate, src/constraints.rs:153-191): load the program
- * recorded by blsgadget_aggregate_verify_program with blsgpu_witness_load, declare its key count with blsgpu_witness_set_aggregate, then
+ * recorded by blsgadget_aggregate_verify_program with blsgpu_witness_load_aggregate (which takes its key count), then
  * pks48 = nwit x nkeys compressed keys, bitmap = nwit x nkeys bytes (0 / non-zero = the participation bits), msg = nwit x L bytes,
  * sig96 = nwit aggregate signatures.  status: 2 when any key of an item does not decode to a non-identity point, 3 for the signature. */
-int blsgpu_witness_set_aggregate(blsgpu_ctx* ctx, int handle, size_t nkeys);
+int blsgpu_witness_load_aggregate(blsgpu_ctx* ctx, const uint8_t* rules16, const uint64_t* lc_ptr, const uint32_t* lc_col, const uint8_t* lc_coef48,
+                                  size_t ncols, size_t nvars, size_t nlc, size_t nterms, const uint32_t* order, const uint64_t* level_ptr, size_t nlevels,
+                                  size_t nkeys, int* handle);
 int blsgpu_witness_gen_aggregate(blsgpu_ctx* ctx, int handle, const uint8_t* pks48, const uint8_t* bitmap, const uint8_t* msg, const uint8_t* sig96, size_t nwit,
                                  uint8_t* z48, uint8_t* status);
 int blsgpu_witness_check_aggregate(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, const uint8_t* pks48, const uint8_t* bitmap, const uint8_t* msg, const uint8_t* sig96, size_t nwit,

@@ -5,7 +5,7 @@ dev = torch.device("cuda", 0); ctx = Context(0); stream = torch.cuda.current_str
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 pk, msg, sig, exp = synth.verify_batch_inputs(ctx, n, every=10**9, fast=True)
 t0 = time.time(); prog = G.verify_program(pk[:48].tobytes(), msg[:32].tobytes(), sig[:96].tobytes()); nvars = prog["nvars"]; print("program s", round(time.time() - t0, 1), "nvars", nvars, "levels", prog["level_ptr"].size - 1)
-h = ctx.witness_load(prog)
+h = ctx.witness_load(prog); print('split', ctx.witness_shape(h))
 d_pk, d_msg, d_sig = (torch.from_numpy(x).to(dev) for x in (pk, msg, sig))
 z = torch.empty(n * nvars * 48, dtype=torch.uint8, device=dev); st = torch.empty(n, dtype=torch.uint8, device=dev)
 ctx.set_pointer_mode(True)
