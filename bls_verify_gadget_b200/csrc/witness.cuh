@@ -288,10 +288,14 @@ __global__ void __launch_bounds__(WIT_CL_TPB, 1) k_witness_cluster(wit_prog p, c
 __global__ void __launch_bounds__(WIT_LIGHT_TPB, 1) k_witness_light(wit_prog p, const fp* inputs, size_t nwit_padded, u32x4* zt_all, uint2* zbool_all, long long* sint_all) {
     size_t group = blockIdx.x; int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint2* zb = zbool_all + group * p.nvars; long long* sint = sint_all + group * p.n_islots * 32; u32x4* zt = zt_all + group * p.nvars * 96;
+    // this thread's first truth-table rule and this warp's first sum / bit rule of the NEXT level are fetched before the barrier (static data)
+    uint32_t lut_lo = p.llevel_ptr[0], w_lo = p.llevel_ptr[1], nxt = p.llevel_ptr[2];
+    wit_lrule rt, rw; bool pre_t = lut_lo + tid < w_lo, pre_w = w_lo + warp < nxt;
+    if (pre_t) rt = p.lrules[lut_lo + tid];
+    if (pre_w) rw = p.lrules[w_lo + warp];
     for (size_t L = 0; L < p.n_llevels; L++) {
-        uint32_t lut_lo = p.llevel_ptr[2 * L], w_lo = p.llevel_ptr[2 * L + 1], nxt = p.llevel_ptr[2 * L + 2];
         for (uint32_t i = lut_lo + tid; i < w_lo; i += WIT_LIGHT_TPB) {
-            wit_lrule r = p.lrules[i];
+            wit_lrule r = (pre_t && i == lut_lo + tid) ? rt : p.lrules[i];
             uint32_t x0 = zb[r.a[0]].x, x1 = r.a[1] != WL_NO_COL ? zb[r.a[1]].x : 0u, x2 = r.a[2] != WL_NO_COL ? zb[r.a[2]].x : 0u;
             uint32_t out;
             if (r.a[3] != WL_NO_COL) { uint32_t x3 = zb[r.a[3]].x, x4 = r.a[4] != WL_NO_COL ? zb[r.a[4]].x : 0u; out = r1cs_lut5(r.a[5], x0, x1, x2, x3, x4); }
@@ -299,17 +303,22 @@ __global__ void __launch_bounds__(WIT_LIGHT_TPB, 1) k_witness_light(wit_prog p, 
             zb[r.var] = make_uint2(out, 1u);
         }
         for (uint32_t i = w_lo + warp; i < nxt; i += WIT_LIGHT_TPB / 32) {
-            wit_lrule r = p.lrules[i];
+            wit_lrule r = (pre_w && i == w_lo + warp) ? rw : p.lrules[i];
             if (r.kind == WL_ONE) { if (lane == 0) zb[r.var] = make_uint2(0xffffffffu, 1u); continue; }
             if (r.kind == WL_INPUT) {
                 uint32_t bit = inputs[(size_t)r.aux * nwit_padded + group * 32 + lane].l[0] & 1u;
                 uint32_t pack = __ballot_sync(0xffffffffu, bit); if (lane == 0) zb[r.var] = make_uint2(pack, 1u); continue;
             }
             long long sum = 0;
-            for (uint32_t t = r.a[0]; t < r.a[1]; t++) {
-                uint32_t c = p.lt_col[t]; long long k = p.lt_coef[t];
-                long long v = (c & WL_INT) ? sint[(size_t)(c & ~WL_INT) * 32 + lane] : (long long)((zb[c].x >> lane) & 1u);
-                sum += k * v;
+            for (uint32_t t0 = r.a[0]; t0 < r.a[1]; t0 += 32) {                 // the terms' metadata lane-parallel, then broadcasts
+                uint32_t n = r.a[1] - t0 < 32 ? r.a[1] - t0 : 32u, myc = 0; long long myk = 0;
+                if ((uint32_t)lane < n) { myc = p.lt_col[t0 + lane]; myk = p.lt_coef[t0 + lane]; }
+                uint32_t myw = ((uint32_t)lane < n && !(myc & WL_INT)) ? zb[myc].x : 0u;
+                for (uint32_t t = 0; t < n; t++) {
+                    uint32_t c = __shfl_sync(0xffffffffu, myc, t); long long k = __shfl_sync(0xffffffffu, myk, t); uint32_t wd = __shfl_sync(0xffffffffu, myw, t);
+                    long long v = (c & WL_INT) ? sint[(size_t)(c & ~WL_INT) * 32 + lane] : (long long)((wd >> lane) & 1u);
+                    sum += k * v;
+                }
             }
             if (r.kind == WL_BIT || (r.flags & 1)) {
                 uint32_t bit = r.kind == WL_BIT ? (uint32_t)((unsigned long long)sum >> (r.aux & 63)) & 1u : (uint32_t)sum & 1u;
@@ -323,6 +332,13 @@ __global__ void __launch_bounds__(WIT_LIGHT_TPB, 1) k_witness_light(wit_prog p, 
                     wit_store(zt, r.var, lane, v); if (lane == 0) zb[r.var] = make_uint2(0u, 0u);
                 }
             }
+        }
+        lut_lo = nxt; pre_t = pre_w = false;
+        if (L + 1 < p.n_llevels) {
+            w_lo = p.llevel_ptr[2 * L + 3]; nxt = p.llevel_ptr[2 * L + 4];
+            pre_t = lut_lo + tid < w_lo; pre_w = w_lo + warp < nxt;
+            if (pre_t) rt = p.lrules[lut_lo + tid];
+            if (pre_w) rw = p.lrules[w_lo + warp];
         }
         __syncthreads();
     }
