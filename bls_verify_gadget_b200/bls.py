@@ -74,6 +74,14 @@ class PublicKey:
         return PublicKey(out.tobytes())
     def to_bytes(self): return self.public_key
     def to_hex(self): return self.public_key.hex()
+    def to_uncompressed(self, ctx=None):            # ark-serialize's serialize_uncompressed: 96 bytes x || y
+        out, st = (ctx or default_context()).g1_uncompress(self.public_key); return out.tobytes()
+    @classmethod
+    def try_from_uncompressed(cls, b96, ctx=None):  # deserialize_uncompressed with Validate::Yes
+        if len(b96) < 96: raise SerializationError("short")
+        out, st = (ctx or default_context()).g1_compress(bytes(b96[:96]))
+        if st[0] > 1: raise SerializationError(f"invalid uncompressed G1 encoding (code {st[0]})")
+        return cls(out.tobytes())
     def __eq__(self, o): return isinstance(o, PublicKey) and self.public_key == o.public_key
     def __hash__(self): raise NotImplementedError("unimplemented!() in the reference, src/bls.rs:176-180")
 
@@ -96,6 +104,14 @@ class Signature:
         return Signature(out.tobytes())
     def to_bytes(self): return self.sig
     def to_hex(self): return self.sig.hex()
+    def to_uncompressed(self, ctx=None):            # 192 bytes x.c1 || x.c0 || y.c1 || y.c0
+        out, st = (ctx or default_context()).g2_uncompress(self.sig); return out.tobytes()
+    @classmethod
+    def try_from_uncompressed(cls, b192, ctx=None):
+        if len(b192) < 192: raise SerializationError("short")
+        out, st = (ctx or default_context()).g2_compress(bytes(b192[:192]))
+        if st[0] > 1: raise SerializationError(f"invalid uncompressed G2 encoding (code {st[0]})")
+        return cls(out.tobytes())
     def __eq__(self, o): return isinstance(o, Signature) and self.sig == o.sig
 
 def hash_to_g2(message, ctx=None):
@@ -125,6 +141,18 @@ class BLS:
     def randomize_public_key(*a): raise NotImplementedError("unimplemented!() in the reference, src/bls.rs:460-466")
     @staticmethod
     def randomize_signature(*a): raise NotImplementedError("unimplemented!() in the reference, src/bls.rs:468-474")
+    # ---- the Eth2 calls the reference's harness composes from aggregate + verify (tests/tests.rs:297-334) or does not vendor (tests/readme.md:4-7)
+    @staticmethod
+    def fast_aggregate_verify(parameters, public_keys, message, signature, ctx=None):           # PublicKey::aggregate then verify; None / Err collapse to False (tests.rs:312-316, 328)
+        agg = PublicKey.aggregate(public_keys, ctx)
+        if agg is None: return False
+        try: return BLS.verify(parameters, agg, message, signature, ctx)
+        except BLSError: return False
+    @staticmethod
+    def aggregate_verify(parameters, public_keys, messages, signature, ctx=None):               # distinct messages: one signature over the (pk_i, msg_i) pairs
+        if len(public_keys) != len(messages): raise ValueError("one message per public key")
+        st = (ctx or default_context()).aggregate_verify(b"".join(p.public_key for p in public_keys), [bytes(m) for m in messages], [0, len(public_keys)], signature.sig)[0]
+        return st == 0
     # ---- batch-first forms (no reference counterpart: the reference verifies one triple per call)
     @staticmethod
     def verify_batch(pk48, msgs, sig96, ctx=None, **kw): return (ctx or default_context()).verify(pk48, msgs, sig96, **kw)

@@ -664,6 +664,19 @@ def test_bls_api_like_reference_tests(ctx, eth):
     assert BLS.verify(params, pk, b"hello", sig, ctx=ctx) and not BLS.verify(params, pk, b"hellp", sig, ctx=ctx)
     with pytest.raises(BLSError) as e: BLS.verify(params, PublicKey(), b"hello", sig, ctx=ctx)
     assert e.value.kind == "InvalidPublicKey"
+    # tests.rs:297-334 through the mirror, and the same fixtures as AggregateVerify over k copies of the message
+    for c in eth["fast_aggregate_verify"]:
+        i = c["input"]
+        try: keys = [PublicKey.try_from(s, ctx) for s in i["pubkeys"]]
+        except SerializationError: keys = None
+        try: sg = Signature.try_from(i["signature"], ctx)
+        except SerializationError: sg = Signature()
+        res = keys is not None and BLS.fast_aggregate_verify(params, keys, hx(i["message"]), sg, ctx=ctx)
+        assert res == c["output"], c["name"]
+        if keys: assert BLS.aggregate_verify(params, keys, [hx(i["message"])] * len(keys), sg, ctx=ctx) == c["output"], c["name"]
+    # uncompressed encodings round-trip through the value types
+    assert PublicKey.try_from_uncompressed(pk.to_uncompressed(ctx), ctx) == pk and Signature.try_from_uncompressed(sig.to_uncompressed(ctx), ctx) == sig
+    with pytest.raises(SerializationError): PublicKey.try_from_uncompressed(bytes([0x80]) + pk.to_uncompressed(ctx)[1:], ctx)
 
 # ------------------------------------------------------------------------------------------ per-primitive device check
 def test_device_primitives_match_host_emulation():
