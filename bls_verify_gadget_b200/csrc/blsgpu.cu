@@ -38,6 +38,9 @@ static inline unsigned nblk(size_t n, unsigned tpb = TPB) { return (unsigned)((n
 // fp_mul saturates it; two warps that start together stay in lockstep (both in their IMAD phase, then both in their ALU
 // phase), leaving each pipe idle half of the time.  Delaying every second warp of a sub-partition by about one phase at
 // kernel entry moves the pair to the stable anti-phase schedule.  BLS_SKEW = delay in cycles (0 = off).
+#ifndef BLS_FINAL_RUNS
+#define BLS_FINAL_RUNS 0
+#endif
 #ifndef BLS_F_IN_SMEM
 #define BLS_F_IN_SMEM 0
 #endif
@@ -148,6 +151,72 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_miller(const u32x4* pk_soa, c
 #endif
     stage_miller(f, pk, hm, sig, flags[i]);
     soa_store_fp12(f_soa, n, i, f);
+}
+// ---- split forms of the two long stages (blsgpu_set_split): the same arithmetic in 4 + 5 short launches with the per-item state in global
+// memory between them.  A CTA of k_miller runs ~21 ms and one of k_final_exp ~14 ms; a batch of a few waves (one GPU's shard of an 8-GPU job)
+// loses a tenth of its time to the partly filled last wave of each.  Short launches make the tail short and give the other lane's kernels gaps to fill.
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_miller_part(const u32x4* pk_soa, const u32x4* hm_soa, const u32x4* sig_soa, const uint8_t* flags,
+                                                     const uint8_t* status, size_t n, u32x4* f_soa, u32x4* t_soa, int i_hi, int i_lo) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    if (status[i] != ST_OK) return;
+    g1_aff pk, ng; g2_aff hm, sig; fp12 f; g2_proj r0, r1;
+    soa_load_g1(pk, pk_soa, n, i); soa_load_g2(hm, hm_soa, n, i); soa_load_g2(sig, sig_soa, n, i);
+    ng.x = fp_const(C_G1X); ng.y = fp_const(C_G1Y_NEG);
+    if (i_hi != 62) {
+        soa_load_fp12(f, f_soa, n, i);
+        r0.x = soa_load_fp2(t_soa, n, i, 0); r0.y = soa_load_fp2(t_soa, n, i, 1); r0.z = soa_load_fp2(t_soa, n, i, 2);
+        r1.x = soa_load_fp2(t_soa, n, i, 3); r1.y = soa_load_fp2(t_soa, n, i, 4); r1.z = soa_load_fp2(t_soa, n, i, 5);
+    }
+    uint8_t fl = flags[i];
+    miller_loop2_range(f, r0, r1, ng, sig, !(fl & FL_SIG_INF), pk, hm, !(fl & FL_HM_INF), i_hi, i_lo);
+    soa_store_fp12(f_soa, n, i, f);
+    if (i_lo != 0) {
+        soa_store_fp2(t_soa, n, i, 0, r0.x); soa_store_fp2(t_soa, n, i, 1, r0.y); soa_store_fp2(t_soa, n, i, 2, r0.z);
+        soa_store_fp2(t_soa, n, i, 3, r1.x); soa_store_fp2(t_soa, n, i, 4, r1.y); soa_store_fp2(t_soa, n, i, 5, r1.z);
+    }
+}
+template <int PART> __global__ void __launch_bounds__(TPB, BLS_MINB) k_final_part(u32x4* f_soa, u32x4* y1_soa, u32x4* y2_soa, const uint8_t* status_in, uint8_t* status_out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    if (status_in[i] != ST_OK) { if (PART == 5) status_out[i] = status_in[i]; return; }
+    fp12 r, y1, y2;
+    if (PART == 1 || PART >= 4) soa_load_fp12(r, f_soa, n, i);
+    if (PART >= 2) soa_load_fp12(y1, y1_soa, n, i);
+    if (PART == 5) soa_load_fp12(y2, y2_soa, n, i);
+    final_exponentiation_part<PART>(r, y1, y2);
+    if (PART == 1 || PART >= 4) soa_store_fp12(f_soa, n, i, r);
+    if (PART <= 3) soa_store_fp12(y1_soa, n, i, y1);
+    if (PART == 4) soa_store_fp12(y2_soa, n, i, y2);
+    if (PART == 5) status_out[i] = fp12_is_one(r) ? ST_OK : ST_FALSE;
+}
+// the 63 compressed squarings of one exp_by_x: in = an Fp12 array (cyclotomic elements), out = six snapshots of four Fp2 (24 x 6 uint4 rows per item)
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_final_squarings(const u32x4* in_soa, u32x4* snap_soa, const uint8_t* status, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    if (status[i] != ST_OK) return;
+    fp12c c;                                                  // tower positions of g2, g3, g4, g5: c1.c0 = 3, c0.c2 = 2, c0.c1 = 1, c1.c2 = 5
+    c.g2 = soa_load_fp2(in_soa, n, i, 3); c.g3 = soa_load_fp2(in_soa, n, i, 2); c.g4 = soa_load_fp2(in_soa, n, i, 1); c.g5 = soa_load_fp2(in_soa, n, i, 5);
+    const uint64_t x = BLS_X_ABS; int k = 0;
+    for (int j = 1; j <= 63; j++) {
+        fp12c_sqr(c, c);
+        if ((x >> j) & 1) {
+            soa_store_fp2(snap_soa, n, i, 4 * k, c.g2); soa_store_fp2(snap_soa, n, i, 4 * k + 1, c.g3); soa_store_fp2(snap_soa, n, i, 4 * k + 2, c.g4); soa_store_fp2(snap_soa, n, i, 4 * k + 3, c.g5);
+            k++;
+        }
+    }
+}
+template <int STEP> __global__ void __launch_bounds__(TPB, BLS_MINB) k_final_step(u32x4* f_soa, u32x4* y1_soa, u32x4* y2_soa, const u32x4* snap_soa, const uint8_t* status_in, uint8_t* status_out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    if (status_in[i] != ST_OK) { if (STEP == 5) status_out[i] = status_in[i]; return; }
+    fp12 r, y1, y2; fp12c snap[6];
+    if (STEP != 2 && STEP != 4) soa_load_fp12(r, f_soa, n, i);
+    if (STEP == 2 || STEP == 3 || STEP == 5) soa_load_fp12(y1, y1_soa, n, i);
+    if (STEP >= 1) for (int k = 0; k < 6; k++) {
+        snap[k].g2 = soa_load_fp2(snap_soa, n, i, 4 * k); snap[k].g3 = soa_load_fp2(snap_soa, n, i, 4 * k + 1); snap[k].g4 = soa_load_fp2(snap_soa, n, i, 4 * k + 2); snap[k].g5 = soa_load_fp2(snap_soa, n, i, 4 * k + 3);
+    }
+    final_exponentiation_step<STEP>(r, y1, y2, snap);
+    if (STEP == 0 || STEP == 3 || STEP == 5) soa_store_fp12(f_soa, n, i, r);
+    if (STEP >= 1 && STEP <= 3) soa_store_fp12(y1_soa, n, i, y1);
+    if (STEP == 4) soa_store_fp12(y2_soa, n, i, y2);
+    if (STEP == 5) status_out[i] = fp12_is_one(r) ? ST_OK : ST_FALSE;
 }
 // generic product of pairings for the GT parity hook: npairs in {1,2}
 __global__ void __launch_bounds__(TPB, BLS_MINB) k_miller_pairs(const u32x4* g1_soa, const u32x4* g2_soa, const uint8_t* c1, const uint8_t* c2, size_t npairs, size_t nprod,
@@ -478,6 +547,7 @@ struct blsgpu_ctx {
     int coop;                           // 1 = warp-cooperative hard part of the final exponentiation (coop.cuh)
     int wit_cluster;                    // 1 = witness replay with one thread-block cluster per group of 32 assignments; 0 (default) = grid-wide level barrier
     int lanes; cudaStream_t lane_stream[4]; cudaEvent_t lane_done[4], fork;   // concurrent sub-ranges of a verify pass
+    int split;                          // 1 (default) = Miller loop and final exponentiation as 4 + 5 short launches (k_miller_part / k_final_part), 0 = one launch each
     size_t chunk;                       // items per internal pass of verify_batch (bounds the workspace); multiple of 64
     int prof; cudaEvent_t ev[8];        // stage boundaries of the last verify_batch chunk: g1 | g2 | hash | miller | final | epilogue
 };
@@ -562,7 +632,7 @@ int blsgpu_create(blsgpu_ctx** out, int device) {
     if (prop.major != 10) return BLSGPU_ERR_CUDA;                         // sm_100a cubin only: no other device can run it
     if (cudaSetDevice(device) != cudaSuccess) return BLSGPU_ERR_CUDA;
     blsgpu_ctx* c = new (std::nothrow) blsgpu_ctx(); if (!c) return BLSGPU_ERR_ALLOC;
-    memset(c, 0, sizeof *c); c->device = device; c->ptr_mode = BLSGPU_HOST; c->chunk = VERIFY_CHUNK_DEFAULT; c->lanes = 2; c->wit_cluster = 0;
+    memset(c, 0, sizeof *c); c->device = device; c->ptr_mode = BLSGPU_HOST; c->chunk = VERIFY_CHUNK_DEFAULT; c->lanes = 2; c->wit_cluster = 0; c->split = 1;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return BLSGPU_ERR_CUDA; }
     c->stream = c->own_stream;
     *out = c; return 0;
@@ -588,6 +658,7 @@ int blsgpu_synchronize(blsgpu_ctx* ctx) { if (!ctx) return BLSGPU_ERR_ARG; dev_g
 uint64_t blsgpu_launch_count(blsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int blsgpu_set_coop(blsgpu_ctx* ctx, int on) { if (!ctx) return BLSGPU_ERR_ARG; ctx->coop = on ? 1 : 0; return 0; }
 int blsgpu_set_witness_mode(blsgpu_ctx* ctx, int cluster) { if (!ctx) return BLSGPU_ERR_ARG; ctx->wit_cluster = cluster ? 1 : 0; return 0; }
+int blsgpu_set_split(blsgpu_ctx* ctx, int on) { if (!ctx) return BLSGPU_ERR_ARG; ctx->split = on ? 1 : 0; return 0; }
 int blsgpu_set_lanes(blsgpu_ctx* ctx, int lanes) { if (!ctx || lanes < 1 || lanes > 4) return BLSGPU_ERR_ARG; ctx->lanes = lanes; return 0; }
 int blsgpu_set_chunk(blsgpu_ctx* ctx, size_t items) { if (!ctx || items < 64 || (items & 63)) return BLSGPU_ERR_ARG; ctx->chunk = items; return 0; }
 int blsgpu_set_profiling(blsgpu_ctx* ctx, int on) {
@@ -700,6 +771,35 @@ static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code
     STAGE_MARK(2);
     LAUNCH(k_hash_to_g2, nblk(n), TPB, dmsg, doff, n, code_pk, (const uint8_t*)code_sig, hm_soa, flags, dstatus);
     STAGE_MARK(3);
+    if (ctx->split && !ctx->coop) {
+        // iterations 62..0 in four launches of 16 / 16 / 16 / 15 doublings (the five additions fall at 62, 60, 57, 48, 16)
+        u32x4* t_soa = ws_take<u32x4>(ctx, 36 * n); u32x4* y1_soa = t_soa; u32x4* y2_soa = ws_take<u32x4>(ctx, 36 * n);      // the running points are dead once the loop ends
+        static const int cut[5] = {62, 46, 30, 14, -1};
+        for (int k = 0; k < 4; k++)
+            LAUNCH(k_miller_part, nblk(n), TPB, pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, n, f_soa, t_soa, cut[k], cut[k + 1] + 1);
+        STAGE_MARK(4);
+#if BLS_FINAL_RUNS
+        u32x4* snap_soa = ws_take<u32x4>(ctx, 144 * n);
+        const uint8_t* cst = dstatus;
+        LAUNCH(k_final_step<0>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const u32x4*)snap_soa, cst, dstatus, n);
+        LAUNCH(k_final_squarings, nblk(n), TPB, (const u32x4*)f_soa, snap_soa, cst, n);
+        LAUNCH(k_final_step<1>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const u32x4*)snap_soa, cst, dstatus, n);
+        LAUNCH(k_final_squarings, nblk(n), TPB, (const u32x4*)y1_soa, snap_soa, cst, n);
+        LAUNCH(k_final_step<2>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const u32x4*)snap_soa, cst, dstatus, n);
+        LAUNCH(k_final_squarings, nblk(n), TPB, (const u32x4*)y1_soa, snap_soa, cst, n);
+        LAUNCH(k_final_step<3>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const u32x4*)snap_soa, cst, dstatus, n);
+        LAUNCH(k_final_squarings, nblk(n), TPB, (const u32x4*)y1_soa, snap_soa, cst, n);
+        LAUNCH(k_final_step<4>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const u32x4*)snap_soa, cst, dstatus, n);
+        LAUNCH(k_final_squarings, nblk(n), TPB, (const u32x4*)y2_soa, snap_soa, cst, n);
+        LAUNCH(k_final_step<5>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const u32x4*)snap_soa, cst, dstatus, n);
+#else
+        LAUNCH(k_final_part<1>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const uint8_t*)dstatus, dstatus, n);
+        LAUNCH(k_final_part<2>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const uint8_t*)dstatus, dstatus, n);
+        LAUNCH(k_final_part<3>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const uint8_t*)dstatus, dstatus, n);
+        LAUNCH(k_final_part<4>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const uint8_t*)dstatus, dstatus, n);
+        LAUNCH(k_final_part<5>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const uint8_t*)dstatus, dstatus, n);
+#endif
+    } else {
 #if BLS_F_IN_SMEM
     { static bool attr_set = false; if (!attr_set) { cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, TPB * 592); attr_set = true; }
       k_miller<<<nblk(n), TPB, TPB * 592, ctx->stream>>>(pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, n, f_soa); ctx->launches++; CU(cudaGetLastError()); }
@@ -711,6 +811,7 @@ static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code
         LAUNCH(k_final_easy, nblk(n), TPB, f_soa, (const uint8_t*)dstatus, n);
         LAUNCH(k_final_hard_coop, nblk(n, 20), 128, f_soa, (const uint8_t*)dstatus, dstatus, n);
     } else LAUNCH(k_final_exp, nblk(n), TPB, f_soa, (const uint8_t*)dstatus, dstatus, n);
+    }
     STAGE_MARK(5);
     if (dbitmap) LAUNCH(k_status_bitmap, nblk(((n + 31) / 32) * 32, 256), 256, (const uint8_t*)dstatus, n, dbitmap);
     if (gt_acc) {
@@ -722,7 +823,7 @@ static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code
     return 0;
 }
 static size_t verify_ws_bytes(size_t n, size_t mb) {
-    return al(48 * n) + al(96 * n) + al(mb + 1) + al(4 * (n + 1)) + al(n) * 6 + al(96 * n) + 2 * al(192 * n) + al(576 * n) + al(8 * ((n + 63) / 64)) +
+    return (2 + 4 * BLS_FINAL_RUNS) * al(576 * n) /* state of the split stage kernels */ + al(48 * n) + al(96 * n) + al(mb + 1) + al(4 * (n + 1)) + al(n) * 6 + al(96 * n) + 2 * al(192 * n) + al(576 * n) + al(8 * ((n + 63) / 64)) +
            al(576 * ((n + 7) / 8)) + al(576 * ((n + 63) / 64)) + 3 * al(576) + 65536;
 }
 // One contiguous sub-range [base, base+m) of a verify batch, enqueued entirely on ctx->stream (the caller may have pointed

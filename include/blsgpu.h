@@ -76,6 +76,11 @@ int blsgpu_set_chunk(blsgpu_ctx* ctx, size_t items);
  * join the context's stream, so that the tail wave of a stage kernel overlaps the other sub-range's work; 1 = strictly serial kernels
  * (use it with blsgpu_set_profiling: stage events of concurrent lanes would overlap) */
 int blsgpu_set_lanes(blsgpu_ctx* ctx, int lanes);
+/* 1 (default): the Miller loop and the final exponentiation run as 4 + 5 short launches with the per-item state (1.2 KB) kept in the
+ * workspace between them; 0: one launch each (k_miller, k_final_exp).  Same results.  The short launches are faster at every batch size
+ * measured (smaller kernels: +3 % at 2^20 items) and much faster for batches of a few waves (+8 % at 2^17: a CTA of the one-launch kernels
+ * runs 14-21 ms, and the partly filled last wave of each costs a tenth of the pass). */
+int blsgpu_set_split(blsgpu_ctx* ctx, int on);
 /* final exponentiation: 0 = one thread per item throughout; 1 = hard part with six lanes per item (warp-cooperative Fp12, coop.cuh).
  * Both produce identical GT bytes. */
 int blsgpu_set_coop(blsgpu_ctx* ctx, int on);
