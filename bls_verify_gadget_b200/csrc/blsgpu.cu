@@ -34,13 +34,37 @@ using namespace bls;
 #endif
 static inline unsigned nblk(size_t n, unsigned tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
 
+// resident CTAs per SM of single kernels (register cap 65536 / (TPB * MINB)); BLS_MINB is the default for all stage kernels.  Measured at 2^20
+// (profiles/r02_tuning.md): the two decoders gain 4 % / 2 % at 4 CTAs (128 registers), the compressed-squaring run 1 % at 3; k_hash_to_g2 loses 6 % at 3,
+// its split forms k_hash_field / k_hash_map gain 1 % of the stage at 4 / 3.
+#ifndef BLS_MINB_DG1
+#define BLS_MINB_DG1 4
+#endif
+#ifndef BLS_MINB_DG2
+#define BLS_MINB_DG2 4
+#endif
+#ifndef BLS_MINB_HASH
+#define BLS_MINB_HASH BLS_MINB
+#endif
+#ifndef BLS_MINB_SQR
+#define BLS_MINB_SQR 3
+#endif
+#ifndef BLS_MINB_HFIELD
+#define BLS_MINB_HFIELD 4
+#endif
+#ifndef BLS_MINB_HMAP
+#define BLS_MINB_HMAP 3
+#endif
+#ifndef BLS_MINB_LINES
+#define BLS_MINB_LINES BLS_MINB
+#endif
+#define MILLER_LINE_ITERS 8        // iterations per k_miller_lines / k_miller_accum pair
+#define MILLER_LINE_STEPS 11       // most doubling + addition steps in 8 iterations (62..55 holds the additions of bits 62, 60, 57)
+
 // Phase skew: the IMAD.WIDE pipe issues one warp instruction per 4 cycles per SM sub-partition and a single warp inside
 // fp_mul saturates it; two warps that start together stay in lockstep (both in their IMAD phase, then both in their ALU
 // phase), leaving each pipe idle half of the time.  Delaying every second warp of a sub-partition by about one phase at
 // kernel entry moves the pair to the stable anti-phase schedule.  BLS_SKEW = delay in cycles (0 = off).
-#ifndef BLS_FINAL_RUNS
-#define BLS_FINAL_RUNS 0
-#endif
 #ifndef BLS_F_IN_SMEM
 #define BLS_F_IN_SMEM 0
 #endif
@@ -103,14 +127,14 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* sink, int iters, in
     }
 }
 
-__global__ void __launch_bounds__(TPB, BLS_MINB) k_decode_g1(const uint8_t* in48, size_t n, u32x4* soa, uint8_t* code) {
+__global__ void __launch_bounds__(TPB, BLS_MINB_DG1) k_decode_g1(const uint8_t* in48, size_t n, u32x4* soa, uint8_t* code) {
     phase_skew();
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     g1_aff p; int rc = g1_decode(p, in48 + 48 * i);
     if (soa) soa_store_g1(soa, n, i, p);
     code[i] = (uint8_t)rc;
 }
-__global__ void __launch_bounds__(TPB, BLS_MINB) k_decode_g2(const uint8_t* in96, size_t n, u32x4* soa, uint8_t* code) {
+__global__ void __launch_bounds__(TPB, BLS_MINB_DG2) k_decode_g2(const uint8_t* in96, size_t n, u32x4* soa, uint8_t* code) {
     phase_skew();
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     g2_aff p; int rc = g2_decode(p, in96 + 96 * i);
@@ -118,7 +142,7 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_decode_g2(const uint8_t* in96
     code[i] = (uint8_t)rc;
 }
 // status/flags from the two decode codes (bls.rs:434-447), then H(m) for the items still alive
-__global__ void __launch_bounds__(TPB, BLS_MINB) k_hash_to_g2(const uint8_t* msg, const uint32_t* off, size_t n, const uint8_t* code_pk, const uint8_t* code_sig,
+__global__ void __launch_bounds__(TPB, BLS_MINB_HASH) k_hash_to_g2(const uint8_t* msg, const uint32_t* off, size_t n, const uint8_t* code_pk, const uint8_t* code_sig,
                                                     u32x4* hm_soa, uint8_t* flags, uint8_t* status) {
     phase_skew();
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
@@ -136,6 +160,43 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_hash_to_g2(const uint8_t* msg
     }
     flags[i] = fl; if (status) status[i] = st;
 }
+// ---- hash-to-G2 of the verify path in three launches: SHA-256 / hash_to_field (small state), the two SSWU + isogeny maps with
+// one field element per thread (2n threads), then the addition, cofactor clearing and the affine conversion.  Same status / flags rule as above.
+__global__ void __launch_bounds__(TPB, BLS_MINB_HFIELD) k_hash_field(const uint8_t* msg, const uint32_t* off, size_t n, const uint8_t* code_pk, const uint8_t* code_sig,
+                                                               u32x4* u_soa, uint8_t* flags, uint8_t* status) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    uint8_t st = ST_OK, fl = 0;
+    if (code_pk) {
+        if (code_pk[i] != DEC_OK) st = ST_BAD_PK;
+        else if (code_sig[i] != DEC_OK && code_sig[i] != DEC_INF) st = ST_BAD_SIG;
+        else if (code_sig[i] == DEC_INF) fl = FL_SIG_INF;
+    }
+    if (st == ST_OK) {
+        const uint8_t* m; uint32_t len;
+        if (off) { m = msg + off[i]; len = off[i + 1] - off[i]; } else { m = msg + 32 * i; len = 32; }
+        fp2 u0, u1; hash_to_field(u0, u1, m, len);
+        soa_store_fp2(u_soa, n, i, 0, u0); soa_store_fp2(u_soa, n, i, 1, u1);
+    }
+    flags[i] = fl; if (status) status[i] = st;
+}
+__global__ void __launch_bounds__(TPB, BLS_MINB_HMAP) k_hash_map(const u32x4* u_soa, const uint8_t* status, size_t n, u32x4* q_soa) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (t >= 2 * n) return;
+    int j = t >= n; size_t i = t - (j ? n : 0);
+    if (status[i] != ST_OK) return;
+    fp2 u = soa_load_fp2(u_soa, n, i, j), xn, xd, y; g2_jac q;
+    sswu_map(xn, xd, y, u); iso3_map(q, xn, xd, y);
+    soa_store_fp2(q_soa, n, i, 3 * j, q.X); soa_store_fp2(q_soa, n, i, 3 * j + 1, q.Y); soa_store_fp2(q_soa, n, i, 3 * j + 2, q.Z);
+}
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_hash_clear(const u32x4* q_soa, const uint8_t* status, size_t n, u32x4* hm_soa, uint8_t* flags) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    if (status[i] != ST_OK) return;
+    g2_jac q0, q1, h; g2_aff hm;
+    q0.X = soa_load_fp2(q_soa, n, i, 0); q0.Y = soa_load_fp2(q_soa, n, i, 1); q0.Z = soa_load_fp2(q_soa, n, i, 2);
+    q1.X = soa_load_fp2(q_soa, n, i, 3); q1.Y = soa_load_fp2(q_soa, n, i, 4); q1.Z = soa_load_fp2(q_soa, n, i, 5);
+    jac_add(q0, q0, q1); g2_clear_cofactor(h, q0);
+    if (!jac_to_aff(hm, h)) flags[i] |= FL_HM_INF;
+    soa_store_g2(hm_soa, n, i, hm);
+}
 __global__ void __launch_bounds__(TPB, BLS_MINB) k_miller(const u32x4* pk_soa, const u32x4* hm_soa, const u32x4* sig_soa, const uint8_t* flags,
                                                 const uint8_t* status, size_t n, u32x4* f_soa) {
     phase_skew();
@@ -152,44 +213,56 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_miller(const u32x4* pk_soa, c
     stage_miller(f, pk, hm, sig, flags[i]);
     soa_store_fp12(f_soa, n, i, f);
 }
-// ---- split forms of the two long stages (blsgpu_set_split): the same arithmetic in 4 + 5 short launches with the per-item state in global
-// memory between them.  A CTA of k_miller runs ~21 ms and one of k_final_exp ~14 ms; a batch of a few waves (one GPU's shard of an 8-GPU job)
-// loses a tenth of its time to the partly filled last wave of each.  Short launches make the tail short and give the other lane's kernels gaps to fill.
-__global__ void __launch_bounds__(TPB, BLS_MINB) k_miller_part(const u32x4* pk_soa, const u32x4* hm_soa, const u32x4* sig_soa, const uint8_t* flags,
-                                                     const uint8_t* status, size_t n, u32x4* f_soa, u32x4* t_soa, int i_hi, int i_lo) {
+// ---- split forms of the long stages (blsgpu_set_split, default on): the same arithmetic as a sequence of short, specialised launches with the
+// per-item state in global memory between them.  Two effects, both measured (profiles/r02_tuning.md): (1) a kernel that holds only the point
+// arithmetic, or only the accumulator update, or only the compressed squarings has a smaller working set and less code than the one-launch
+// stage kernel and runs faster (Miller 585 -> 505 ms, final exponentiation 389 -> 352 ms at 2^20); (2) a CTA of k_miller runs ~21 ms and one of
+// k_final_exp ~14 ms, so a batch of a few waves (one GPU's shard of an 8-GPU job) loses a tenth of its time to the partly filled last wave of
+// each: short launches make the tail short and give the other lane's kernels gaps to fill (+8 % at 2^17 items).
+// Miller loop: the point arithmetic and the accumulation are separate kernels.  k_miller_lines runs the
+// doubling / addition steps of ONE pair per thread (2n threads: small state, small code) for a range of iterations and leaves the line
+// coefficients, already scaled by the G1 coordinates, in global memory; k_miller_accum squares f and multiplies the lines in (fp12_sqr and
+// mul_by_014 only).  Line buffer: step s, pair j, coefficient k at rows ((2 s + j) * 3 + k) * 6 .. of an n-column limb-SoA matrix.
+__global__ void __launch_bounds__(TPB, BLS_MINB_LINES) k_miller_lines(const u32x4* pk_soa, const u32x4* hm_soa, const u32x4* sig_soa, const uint8_t* flags, const uint8_t* status,
+                                                                size_t n, u32x4* t_soa, u32x4* lines, int i_hi, int i_lo) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (t >= 2 * n) return;
+    int j = t >= n; size_t i = t - (j ? n : 0);
+    if (status[i] != ST_OK) return;
+    if (flags[i] & (j ? FL_HM_INF : FL_SIG_INF)) return;
+    g1_aff p; g2_aff q; g2_proj r;
+    if (j) { soa_load_g1(p, pk_soa, n, i); soa_load_g2(q, hm_soa, n, i); } else { p.x = fp_const(C_G1X); p.y = fp_const(C_G1Y_NEG); soa_load_g2(q, sig_soa, n, i); }
+    if (i_hi == 62) { r.x = q.x; r.y = q.y; r.z = fp2_one(); }
+    else { r.x = soa_load_fp2(t_soa, n, i, 3 * j); r.y = soa_load_fp2(t_soa, n, i, 3 * j + 1); r.z = soa_load_fp2(t_soa, n, i, 3 * j + 2); }
+    const uint64_t x = BLS_X_ABS; int s = 0; fp2 c0, c1, c2;
+    for (int it = i_hi; it >= i_lo; it--) {
+        miller_dbl(r, c0, c1, c2);
+        { u32x4* L = lines + (size_t)(2 * s + j) * 18 * n; soa_store_fp2(L, n, i, 0, c0); soa_store_fp2(L, n, i, 1, fp2_mul_fp(c1, p.x)); soa_store_fp2(L, n, i, 2, fp2_mul_fp(c2, p.y)); s++; }
+        if ((x >> it) & 1) {
+            miller_add(r, q, c0, c1, c2);
+            u32x4* L = lines + (size_t)(2 * s + j) * 18 * n; soa_store_fp2(L, n, i, 0, c0); soa_store_fp2(L, n, i, 1, fp2_mul_fp(c1, p.x)); soa_store_fp2(L, n, i, 2, fp2_mul_fp(c2, p.y)); s++;
+        }
+    }
+    if (i_lo != 0) { soa_store_fp2(t_soa, n, i, 3 * j, r.x); soa_store_fp2(t_soa, n, i, 3 * j + 1, r.y); soa_store_fp2(t_soa, n, i, 3 * j + 2, r.z); }
+}
+__global__ void __launch_bounds__(TPB, BLS_MINB) k_miller_accum(const uint8_t* flags, const uint8_t* status, size_t n, u32x4* f_soa, const u32x4* lines, int i_hi, int i_lo) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     if (status[i] != ST_OK) return;
-    g1_aff pk, ng; g2_aff hm, sig; fp12 f; g2_proj r0, r1;
-    soa_load_g1(pk, pk_soa, n, i); soa_load_g2(hm, hm_soa, n, i); soa_load_g2(sig, sig_soa, n, i);
-    ng.x = fp_const(C_G1X); ng.y = fp_const(C_G1Y_NEG);
-    if (i_hi != 62) {
-        soa_load_fp12(f, f_soa, n, i);
-        r0.x = soa_load_fp2(t_soa, n, i, 0); r0.y = soa_load_fp2(t_soa, n, i, 1); r0.z = soa_load_fp2(t_soa, n, i, 2);
-        r1.x = soa_load_fp2(t_soa, n, i, 3); r1.y = soa_load_fp2(t_soa, n, i, 4); r1.z = soa_load_fp2(t_soa, n, i, 5);
+    uint8_t fl = flags[i]; bool use0 = !(fl & FL_SIG_INF), use1 = !(fl & FL_HM_INF);
+    fp12 f; if (i_hi == 62) fp12_one(f); else soa_load_fp12(f, f_soa, n, i);
+    const uint64_t x = BLS_X_ABS; int s = 0;
+    for (int it = i_hi; it >= i_lo; it--) {
+        if (it != 62) fp12_sqr(f, f);
+        int steps = 1 + (int)((x >> it) & 1);
+        for (int a = 0; a < steps; a++, s++) {
+            if (use0) { const u32x4* L = lines + (size_t)(2 * s) * 18 * n; fp12_mul_by_014(f, soa_load_fp2(L, n, i, 0), soa_load_fp2(L, n, i, 1), soa_load_fp2(L, n, i, 2)); }
+            if (use1) { const u32x4* L = lines + (size_t)(2 * s + 1) * 18 * n; fp12_mul_by_014(f, soa_load_fp2(L, n, i, 0), soa_load_fp2(L, n, i, 1), soa_load_fp2(L, n, i, 2)); }
+        }
     }
-    uint8_t fl = flags[i];
-    miller_loop2_range(f, r0, r1, ng, sig, !(fl & FL_SIG_INF), pk, hm, !(fl & FL_HM_INF), i_hi, i_lo);
+    if (i_lo == 0) fp12_conj(f, f);
     soa_store_fp12(f_soa, n, i, f);
-    if (i_lo != 0) {
-        soa_store_fp2(t_soa, n, i, 0, r0.x); soa_store_fp2(t_soa, n, i, 1, r0.y); soa_store_fp2(t_soa, n, i, 2, r0.z);
-        soa_store_fp2(t_soa, n, i, 3, r1.x); soa_store_fp2(t_soa, n, i, 4, r1.y); soa_store_fp2(t_soa, n, i, 5, r1.z);
-    }
-}
-template <int PART> __global__ void __launch_bounds__(TPB, BLS_MINB) k_final_part(u32x4* f_soa, u32x4* y1_soa, u32x4* y2_soa, const uint8_t* status_in, uint8_t* status_out, size_t n) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
-    if (status_in[i] != ST_OK) { if (PART == 5) status_out[i] = status_in[i]; return; }
-    fp12 r, y1, y2;
-    if (PART == 1 || PART >= 4) soa_load_fp12(r, f_soa, n, i);
-    if (PART >= 2) soa_load_fp12(y1, y1_soa, n, i);
-    if (PART == 5) soa_load_fp12(y2, y2_soa, n, i);
-    final_exponentiation_part<PART>(r, y1, y2);
-    if (PART == 1 || PART >= 4) soa_store_fp12(f_soa, n, i, r);
-    if (PART <= 3) soa_store_fp12(y1_soa, n, i, y1);
-    if (PART == 4) soa_store_fp12(y2_soa, n, i, y2);
-    if (PART == 5) status_out[i] = fp12_is_one(r) ? ST_OK : ST_FALSE;
 }
 // the 63 compressed squarings of one exp_by_x: in = an Fp12 array (cyclotomic elements), out = six snapshots of four Fp2 (24 x 6 uint4 rows per item)
-__global__ void __launch_bounds__(TPB, BLS_MINB) k_final_squarings(const u32x4* in_soa, u32x4* snap_soa, const uint8_t* status, size_t n) {
+__global__ void __launch_bounds__(TPB, BLS_MINB_SQR) k_final_squarings(const u32x4* in_soa, u32x4* snap_soa, const uint8_t* status, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     if (status[i] != ST_OK) return;
     fp12c c;                                                  // tower positions of g2, g3, g4, g5: c1.c0 = 3, c0.c2 = 2, c0.c1 = 1, c1.c2 = 5
@@ -206,13 +279,15 @@ __global__ void __launch_bounds__(TPB, BLS_MINB) k_final_squarings(const u32x4* 
 template <int STEP> __global__ void __launch_bounds__(TPB, BLS_MINB) k_final_step(u32x4* f_soa, u32x4* y1_soa, u32x4* y2_soa, const u32x4* snap_soa, const uint8_t* status_in, uint8_t* status_out, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     if (status_in[i] != ST_OK) { if (STEP == 5) status_out[i] = status_in[i]; return; }
-    fp12 r, y1, y2; fp12c snap[6];
-    if (STEP != 2 && STEP != 4) soa_load_fp12(r, f_soa, n, i);
-    if (STEP == 2 || STEP == 3 || STEP == 5) soa_load_fp12(y1, y1_soa, n, i);
-    if (STEP >= 1) for (int k = 0; k < 6; k++) {
-        snap[k].g2 = soa_load_fp2(snap_soa, n, i, 4 * k); snap[k].g3 = soa_load_fp2(snap_soa, n, i, 4 * k + 1); snap[k].g4 = soa_load_fp2(snap_soa, n, i, 4 * k + 2); snap[k].g5 = soa_load_fp2(snap_soa, n, i, 4 * k + 3);
+    fp12 r, y1, y2, e;
+    if (STEP >= 1) {                                            // the exp_by_x result first: nothing else is live while the six snapshots are decompressed
+        fp12_decompress_product_from(e, [&](int k) { fp12c c; c.g2 = soa_load_fp2(snap_soa, n, i, 4 * k); c.g3 = soa_load_fp2(snap_soa, n, i, 4 * k + 1);
+                                                     c.g4 = soa_load_fp2(snap_soa, n, i, 4 * k + 2); c.g5 = soa_load_fp2(snap_soa, n, i, 4 * k + 3); return c; }, 6);
+        fp12_conj(e, e);
     }
-    final_exponentiation_step<STEP>(r, y1, y2, snap);
+    if (STEP == 0 || STEP == 1 || STEP == 3 || STEP == 5) soa_load_fp12(r, f_soa, n, i);
+    if (STEP == 2 || STEP == 3 || STEP == 5) soa_load_fp12(y1, y1_soa, n, i);
+    final_exponentiation_step<STEP>(r, y1, y2, e);
     if (STEP == 0 || STEP == 3 || STEP == 5) soa_store_fp12(f_soa, n, i, r);
     if (STEP >= 1 && STEP <= 3) soa_store_fp12(y1_soa, n, i, y1);
     if (STEP == 4) soa_store_fp12(y2_soa, n, i, y2);
@@ -547,7 +622,7 @@ struct blsgpu_ctx {
     int coop;                           // 1 = warp-cooperative hard part of the final exponentiation (coop.cuh)
     int wit_cluster;                    // 1 = witness replay with one thread-block cluster per group of 32 assignments; 0 (default) = grid-wide level barrier
     int lanes; cudaStream_t lane_stream[4]; cudaEvent_t lane_done[4], fork;   // concurrent sub-ranges of a verify pass
-    int split;                          // 1 (default) = Miller loop and final exponentiation as 4 + 5 short launches (k_miller_part / k_final_part), 0 = one launch each
+    int split;                          // 1 (default) = hash-to-G2, Miller loop and final exponentiation as sequences of short specialised launches, 0 = one launch each
     size_t chunk;                       // items per internal pass of verify_batch (bounds the workspace); multiple of 64
     int prof; cudaEvent_t ev[8];        // stage boundaries of the last verify_batch chunk: g1 | g2 | hash | miller | final | epilogue
 };
@@ -769,17 +844,24 @@ static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code
     STAGE_MARK(1);
     LAUNCH(k_decode_g2, nblk(n), TPB, dsig, n, sig_soa, code_sig);
     STAGE_MARK(2);
-    LAUNCH(k_hash_to_g2, nblk(n), TPB, dmsg, doff, n, code_pk, (const uint8_t*)code_sig, hm_soa, flags, dstatus);
+    if (ctx->split) {
+        u32x4* q_soa = f_soa;                                  // the accumulator array is not live yet: 36 rows hold the two mapped points, the first 12 rows of hm_soa hold u0, u1
+        LAUNCH(k_hash_field, nblk(n), TPB, dmsg, doff, n, code_pk, (const uint8_t*)code_sig, hm_soa, flags, dstatus);
+        LAUNCH(k_hash_map, nblk(2 * n), TPB, (const u32x4*)hm_soa, (const uint8_t*)dstatus, n, q_soa);
+        LAUNCH(k_hash_clear, nblk(n), TPB, (const u32x4*)q_soa, (const uint8_t*)dstatus, n, hm_soa, flags);
+    } else LAUNCH(k_hash_to_g2, nblk(n), TPB, dmsg, doff, n, code_pk, (const uint8_t*)code_sig, hm_soa, flags, dstatus);
     STAGE_MARK(3);
     if (ctx->split && !ctx->coop) {
-        // iterations 62..0 in four launches of 16 / 16 / 16 / 15 doublings (the five additions fall at 62, 60, 57, 48, 16)
+        // iterations 62..0 eight at a time: lines of both pairs, then the accumulator update
         u32x4* t_soa = ws_take<u32x4>(ctx, 36 * n); u32x4* y1_soa = t_soa; u32x4* y2_soa = ws_take<u32x4>(ctx, 36 * n);      // the running points are dead once the loop ends
-        static const int cut[5] = {62, 46, 30, 14, -1};
-        for (int k = 0; k < 4; k++)
-            LAUNCH(k_miller_part, nblk(n), TPB, pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, n, f_soa, t_soa, cut[k], cut[k + 1] + 1);
+        u32x4* lines = ws_take<u32x4>(ctx, (size_t)MILLER_LINE_STEPS * 2 * 18 * n);
+        for (int hi = 62; hi >= 0; hi -= MILLER_LINE_ITERS) {
+            int lo = hi - MILLER_LINE_ITERS + 1 < 0 ? 0 : hi - MILLER_LINE_ITERS + 1;
+            LAUNCH(k_miller_lines, nblk(2 * n), TPB, pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, n, t_soa, lines, hi, lo);
+            LAUNCH(k_miller_accum, nblk(n), TPB, (const uint8_t*)flags, (const uint8_t*)dstatus, n, f_soa, (const u32x4*)lines, hi, lo);
+        }
         STAGE_MARK(4);
-#if BLS_FINAL_RUNS
-        u32x4* snap_soa = ws_take<u32x4>(ctx, 144 * n);
+        u32x4* snap_soa = lines;                               // 144 rows of the 396-row line buffer, which is dead once the loop ends
         const uint8_t* cst = dstatus;
         LAUNCH(k_final_step<0>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const u32x4*)snap_soa, cst, dstatus, n);
         LAUNCH(k_final_squarings, nblk(n), TPB, (const u32x4*)f_soa, snap_soa, cst, n);
@@ -792,13 +874,6 @@ static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code
         LAUNCH(k_final_step<4>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const u32x4*)snap_soa, cst, dstatus, n);
         LAUNCH(k_final_squarings, nblk(n), TPB, (const u32x4*)y2_soa, snap_soa, cst, n);
         LAUNCH(k_final_step<5>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const u32x4*)snap_soa, cst, dstatus, n);
-#else
-        LAUNCH(k_final_part<1>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const uint8_t*)dstatus, dstatus, n);
-        LAUNCH(k_final_part<2>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const uint8_t*)dstatus, dstatus, n);
-        LAUNCH(k_final_part<3>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const uint8_t*)dstatus, dstatus, n);
-        LAUNCH(k_final_part<4>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const uint8_t*)dstatus, dstatus, n);
-        LAUNCH(k_final_part<5>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const uint8_t*)dstatus, dstatus, n);
-#endif
     } else {
 #if BLS_F_IN_SMEM
     { static bool attr_set = false; if (!attr_set) { cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, TPB * 592); attr_set = true; }
@@ -823,7 +898,7 @@ static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code
     return 0;
 }
 static size_t verify_ws_bytes(size_t n, size_t mb) {
-    return (2 + 4 * BLS_FINAL_RUNS) * al(576 * n) /* state of the split stage kernels */ + al(48 * n) + al(96 * n) + al(mb + 1) + al(4 * (n + 1)) + al(n) * 6 + al(96 * n) + 2 * al(192 * n) + al(576 * n) + al(8 * ((n + 63) / 64)) +
+    return 2 * al(576 * n) + al((size_t)MILLER_LINE_STEPS * 2 * 288 * n) /* state of the split stage kernels: running points / y1, y2, line buffer / snapshots */ + al(48 * n) + al(96 * n) + al(mb + 1) + al(4 * (n + 1)) + al(n) * 6 + al(96 * n) + 2 * al(192 * n) + al(576 * n) + al(8 * ((n + 63) / 64)) +
            al(576 * ((n + 7) / 8)) + al(576 * ((n + 63) / 64)) + 3 * al(576) + 65536;
 }
 // One contiguous sub-range [base, base+m) of a verify batch, enqueued entirely on ctx->stream (the caller may have pointed
@@ -864,7 +939,7 @@ int blsgpu_verify_batch(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg
                         uint8_t* status, uint64_t* ok_bitmap, uint8_t* gt_acc_le576) {
     ENTER(); if (!pk48 || !msg || !sig96 || !status) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
     int rc = 0;
-    // Passes of <= ctx->chunk items bound the workspace (~1.2 GB at 2^20).  Inside a pass the items are split into `lanes`
+    // Passes of <= ctx->chunk items bound the workspace (8.7 KB per item: ~9 GB at 2^20, of which 6.3 KB is the line buffer of the split Miller loop).  Inside a pass the items are split into `lanes`
     // contiguous sub-ranges enqueued on separate streams: the stage kernels of different sub-ranges are independent, so the
     // tail wave of one kernel overlaps the next sub-range's kernels (and, in host mode, its H2D copies) instead of idling SMs.
     // All range boundaries are multiples of 64 so bitmap words never straddle ranges.

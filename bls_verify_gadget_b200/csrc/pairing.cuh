@@ -67,29 +67,6 @@ BLS_NOINLINE void miller_loop2(fp12& f, const g1_aff& p0, const g2_aff& q0, bool
     fp12_conj(f, f);                                        // x < 0
 }
 
-// The same loop as a resumable range: iterations i_hi .. i_lo (62 .. 0 overall) on a state (f, r0, r1) the caller keeps between calls.
-// i_hi == 62 initialises the state, i_lo == 0 applies the final conjugation.  Used by the split stage kernels (short launches for small batches).
-BLS_NOINLINE void miller_loop2_range(fp12& f, g2_proj& r0, g2_proj& r1, const g1_aff& p0, const g2_aff& q0, bool use0, const g1_aff& p1, const g2_aff& q1, bool use1,
-                                     int i_hi, int i_lo) {
-    if (i_hi == 62) {
-        r0.x = q0.x; r0.y = q0.y; r0.z = fp2_one();
-        r1.x = q1.x; r1.y = q1.y; r1.z = fp2_one();
-        fp12_one(f);
-    }
-    fp2 c0, c1, c2;
-    const uint64_t x = BLS_X_ABS;
-    for (int i = i_hi; i >= i_lo; i--) {
-        if (i != 62) fp12_sqr(f, f);
-        if (use0) { miller_dbl(r0, c0, c1, c2); miller_ell(f, c0, c1, c2, p0); }
-        if (use1) { miller_dbl(r1, c0, c1, c2); miller_ell(f, c0, c1, c2, p1); }
-        if ((x >> i) & 1) {
-            if (use0) { miller_add(r0, q0, c0, c1, c2); miller_ell(f, c0, c1, c2, p0); }
-            if (use1) { miller_add(r1, q1, c0, c1, c2); miller_ell(f, c0, c1, c2, p1); }
-        }
-    }
-    if (i_lo == 0) fp12_conj(f, f);
-}
-
 // a^x for a in the cyclotomic subgroup (x negative: conjugate at the end): square-and-multiply with Granger-Scott squarings (18 Fp
 // products each).  Kept as the reference form of the compressed version below (tests/devcheck op 39 compares them).
 BLS_NOINLINE void fp12_exp_by_x_gs(fp12& r, const fp12& a) {
@@ -160,6 +137,22 @@ BLS_NOINLINE void fp12_decompress_product(fp12& r, const fp12c* c, int n) {
     }
     r = acc;
 }
+// the same with the snapshots fetched through `load(i)` when they are needed (twice each) instead of sitting in a local array: the split
+// final-exponentiation kernels read them from global memory, which keeps 2.3 KB per thread out of the L1-backed stack
+template <class LOAD> BLS_HD void fp12_decompress_product_from(fp12& r, LOAD load, int n) {
+    fp2 num[6], den[6], pre[6];
+    for (int i = 0; i < n; i++) { fp12c c = load(i); fp12c_g1_fraction(num[i], den[i], c); pre[i] = i ? fp2_mul(pre[i - 1], den[i]) : den[i]; }
+    fp2 inv = fp2_inv(pre[n - 1]);
+    fp12 acc, d;
+    for (int i = n - 1; i >= 0; i--) {
+        fp2 di = i ? fp2_mul(inv, pre[i - 1]) : inv;
+        if (i) inv = fp2_mul(inv, den[i]);
+        fp12c c = load(i);
+        fp12_decompress_with(d, c, fp2_mul(num[i], di));
+        if (i == n - 1) acc = d; else fp12_mul(acc, acc, d);
+    }
+    r = acc;
+}
 #ifndef BLS_KARABINA
 #define BLS_KARABINA 1
 #endif
@@ -202,77 +195,33 @@ BLS_NOINLINE void final_exponentiation(fp12& r, const fp12& f) {
     fp12_mul(r, r, y1);
 }
 
-// The same chain cut after each exp_by_x, for the split stage kernels: part 1..5 on the state (r, y1, y2) kept in global memory between
-// launches.  y0 = r^2 of the monolithic form is recomputed where it is used (one cyclotomic squaring) instead of being carried.
-template <int PART> BLS_HD void final_exponentiation_part(fp12& r, fp12& y1, fp12& y2) {
-    if (PART == 1) {
-        fp12 t, y0;
-        fp12_conj(t, r); fp12_inv(y0, r); fp12_mul(r, t, y0);
-        fp12_frob2(t, r); fp12_mul(r, t, r);
-        fp12_exp_by_x(y1, r);
-        fp12_conj(y2, r);
-        fp12_mul(y1, y1, y2);
-    } else if (PART == 2) {
-        fp12_exp_by_x(y2, y1);
-        fp12_conj(y1, y1);
-        fp12_mul(y1, y1, y2);
-    } else if (PART == 3) {
-        fp12_exp_by_x(y2, y1);
-        fp12_frob(y1, y1);
-        fp12_mul(y1, y1, y2);
-    } else if (PART == 4) {
-        fp12 y0; fp12_cyclo_sqr(y0, r); fp12_mul(r, r, y0);
-        fp12_exp_by_x(y2, y1);                                       // y2 holds the monolithic form's second y0
-    } else {
-        fp12 y0 = y2;
-        fp12_exp_by_x(y2, y0);
-        fp12_frob2(y0, y1);
-        fp12_conj(y1, y1);
-        fp12_mul(y1, y1, y2);
-        fp12_mul(y1, y1, y0);
-        fp12_mul(r, r, y1);
-    }
-}
-
-// Finer cut (BLS_FINAL_RUNS): every exp_by_x is a launch of the 63 compressed squarings alone (a 4-coefficient state and one small loop body)
-// that leaves its six snapshots in global memory, followed by a launch that decompresses them and does the products up to the next exp_by_x.
-BLS_HD void fp12_exp_by_x_squarings(fp12c* snap, const fp12& a) {
-    fp12c c; fp12_compress(c, a);
-    const uint64_t x = BLS_X_ABS; int k = 0;
-    for (int i = 1; i <= 63; i++) {
-        fp12c_sqr(c, c);
-        if ((x >> i) & 1) snap[k++] = c;
-    }
-}
-BLS_HD void fp12_exp_by_x_finish(fp12& r, const fp12c* snap) { fp12 acc; fp12_decompress_product(acc, snap, 6); fp12_conj(r, acc); }
-// STEP 0: easy part (r -> r).  STEP k = 1..5: e = the k-th exp_by_x result (from its snapshots), then the products that follow it in the chain.
-// The next exp_by_x runs on: r after step 0, y1 after steps 1..3, y2 after step 4.
-template <int STEP> BLS_HD void final_exponentiation_step(fp12& r, fp12& y1, fp12& y2, const fp12c* snap) {
+// The same chain for the split stage kernels (k_final_squarings / k_final_step in blsgpu.cu): every exp_by_x is a launch of the 63 compressed
+// squarings alone (a 4-coefficient state and one small loop body) that leaves its six snapshots in global memory, followed by a launch that
+// decompresses them and does the products up to the next exp_by_x.  y0 = r^2 of the one-launch form is recomputed where it is used.
+// STEP 0: easy part (r -> r).  STEP k = 1..5: e = the k-th exp_by_x result (decompressed product of its snapshots, conjugated), then the
+// products that follow it in the chain.  The next exp_by_x runs on: r after step 0, y1 after steps 1..3, y2 after step 4.
+template <int STEP> BLS_HD void final_exponentiation_step(fp12& r, fp12& y1, fp12& y2, const fp12& e) {
     if (STEP == 0) {
         fp12 t, y0;
         fp12_conj(t, r); fp12_inv(y0, r); fp12_mul(r, t, y0);
         fp12_frob2(t, r); fp12_mul(r, t, r);
     } else if (STEP == 1) {
-        fp12_exp_by_x_finish(y1, snap);
         fp12_conj(y2, r);
-        fp12_mul(y1, y1, y2);
+        fp12_mul(y1, e, y2);
     } else if (STEP == 2) {
-        fp12_exp_by_x_finish(y2, snap);
         fp12_conj(y1, y1);
-        fp12_mul(y1, y1, y2);
+        fp12_mul(y1, y1, e);
     } else if (STEP == 3) {
-        fp12_exp_by_x_finish(y2, snap);
         fp12_frob(y1, y1);
-        fp12_mul(y1, y1, y2);
+        fp12_mul(y1, y1, e);
         fp12 y0; fp12_cyclo_sqr(y0, r); fp12_mul(r, r, y0);
     } else if (STEP == 4) {
-        fp12_exp_by_x_finish(y2, snap);
+        y2 = e;
     } else {
         fp12 y0;
-        fp12_exp_by_x_finish(y2, snap);
         fp12_frob2(y0, y1);
         fp12_conj(y1, y1);
-        fp12_mul(y1, y1, y2);
+        fp12_mul(y1, y1, e);
         fp12_mul(y1, y1, y0);
         fp12_mul(r, r, y1);
     }

@@ -70,16 +70,20 @@ uint64_t blsgpu_launch_count(blsgpu_ctx* ctx);
  * blsgpu_stage_times synchronises and returns the device time in ms of the last call's (last chunk's) stages:
  * [0] decode+check G1, [1] decode+check G2, [2] hash-to-G2, [3] Miller loop, [4] final exponentiation, [5] epilogue */
 int blsgpu_set_profiling(blsgpu_ctx* ctx, int on);
-/* blsgpu_verify_batch works in internal passes of at most `items` triples (default 2^20, ~1.2 GB of workspace); a multiple of 64 */
+/* blsgpu_verify_batch works in internal passes of at most `items` triples (default 2^20, ~9 GB of workspace with the split stage kernels,
+ * ~1.2 GB without); a multiple of 64 */
 int blsgpu_set_chunk(blsgpu_ctx* ctx, size_t items);
 /* inside a pass the items are split into `lanes` (1..4, default 2) sub-ranges enqueued on separate internal streams that fork from and
  * join the context's stream, so that the tail wave of a stage kernel overlaps the other sub-range's work; 1 = strictly serial kernels
  * (use it with blsgpu_set_profiling: stage events of concurrent lanes would overlap) */
 int blsgpu_set_lanes(blsgpu_ctx* ctx, int lanes);
-/* 1 (default): the Miller loop and the final exponentiation run as 4 + 5 short launches with the per-item state (1.2 KB) kept in the
- * workspace between them; 0: one launch each (k_miller, k_final_exp).  Same results.  The short launches are faster at every batch size
- * measured (smaller kernels: +3 % at 2^20 items) and much faster for batches of a few waves (+8 % at 2^17: a CTA of the one-launch kernels
- * runs 14-21 ms, and the partly filled last wave of each costs a tenth of the pass). */
+/* 1 (default): inside blsgpu_verify_batch and the aggregate entry points hash-to-G2, the Miller loop and the final exponentiation run as
+ * sequences of short specialised launches with the per-item state kept in the workspace between them -- hash_to_field | SSWU + isogeny per
+ * field element | cofactor clearing; 8 x (line coefficients of both pairs | accumulator update); easy part, then 5 x (63 compressed
+ * squarings | decompression + products).  0: one launch per stage (k_hash_to_g2, k_miller, k_final_exp).  Same results.  The short launches
+ * are faster at every batch size measured (+12 % at 2^20 items: smaller working sets and less code per kernel) and much faster for batches
+ * of a few waves (a CTA of the one-launch kernels runs 14-21 ms; the partly filled last wave of each costs a tenth of a 2^17-item pass).
+ * Workspace: 8.7 KB per item of a pass instead of 1.2 KB (blsgpu_set_chunk bounds the pass). */
 int blsgpu_set_split(blsgpu_ctx* ctx, int on);
 /* final exponentiation: 0 = one thread per item throughout; 1 = hard part with six lanes per item (warp-cooperative Fp12, coop.cuh).
  * Both produce identical GT bytes. */

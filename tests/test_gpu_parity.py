@@ -757,6 +757,32 @@ def test_cooperative_final_exponentiation_matches(ctx, C):
     assert list(st0) == list(st1) == list(ost) == list(exp) and gt0.tobytes() == gt1.tobytes() == ogt.tobytes()
 
 
+def test_split_stage_kernels_match_one_launch_form(ctx, C):
+    """blsgpu_set_split: the default sequence of short launches (hash_to_field | SSWU + isogeny | cofactor clearing; 8 x (line coefficients |
+    accumulator update); easy part + 5 x (compressed squarings | decompression + products)) against the one-launch stage kernels and the
+    oracle: statuses, ok-bitmap and GT bytes, on a batch with every corruption kind, the identity signature (its pair is skipped), ragged
+    messages, and through the committee path that shares the verify core."""
+    from bls_verify_gadget_b200 import synth
+    n = 1500                                                              # not a multiple of the CTA size; 2n threads in the per-pair kernels
+    pk, msg, sig, exp = synth.verify_batch_inputs(ctx, n, every=5, fast=False)
+    sig = sig.copy(); sig[96 * 7:96 * 8] = 0; sig[96 * 7] = 0xc0          # item 7: identity signature -> decodes, verifies false
+    msgs = [msg[32 * i:32 * i + 32].tobytes()[: 1 + (i * 7) % 32] for i in range(n)]      # ragged lengths 1..32
+    sk = synth.secret_keys(n); pk2, st = ctx.sk_to_pk(sk); sig2, st = ctx.sign(sk, msgs)
+    sig2 = sig2.copy(); sig2[96 * 7:96 * 8] = sig[96 * 7:96 * 8]; sig2[96 * 11 + 5] ^= 0x40
+    out = {}
+    for mode in (1, 0):
+        ctx.set_split(mode)
+        try:
+            out[mode] = (ctx.verify(pk, msg, sig, want_bitmap=True, want_gt=True, fixed32=True), ctx.verify(pk2, msgs, sig2, want_bitmap=True, want_gt=True))
+        finally: ctx.set_split(1)
+    for a, b in zip(out[1], out[0]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2].tobytes() == b[2].tobytes()
+    exp = np.array(exp); exp[7] = 1
+    assert list(out[1][0][0]) == list(exp)
+    ost, ogt = C.verify(pk2, msgs, sig2, want_gt=True, threads=8)
+    assert list(out[1][1][0]) == list(ost) and out[1][1][2].tobytes() == ogt.tobytes() and ost[7] == 1 and ost[11] != 0 and int(np.count_nonzero(ost)) == 2
+
+
 def test_multi_gpu_abi_matches_single_gpu(ctx):
     """blsgpu_create_multi / blsgpu_multi_verify_batch (every visible device, NCCL all-gather + fold inside the library): status bytes,
     ok-bitmap and GT accumulator must equal the single-GPU call's for a batch with every corruption kind, on every device's copy;
