@@ -58,8 +58,16 @@ static inline unsigned nblk(size_t n, unsigned tpb = TPB) { return (unsigned)((n
 #ifndef BLS_MINB_LINES
 #define BLS_MINB_LINES BLS_MINB
 #endif
+#ifndef BLS_MINB_HCLEAR
+#define BLS_MINB_HCLEAR BLS_MINB
+#endif
+#ifndef BLS_MINB_ACCUM
+#define BLS_MINB_ACCUM BLS_MINB
+#endif
+#ifndef MILLER_LINE_ITERS
 #define MILLER_LINE_ITERS 8        // iterations per k_miller_lines / k_miller_accum pair
 #define MILLER_LINE_STEPS 11       // most doubling + addition steps in 8 iterations (62..55 holds the additions of bits 62, 60, 57)
+#endif
 
 // Phase skew: the IMAD.WIDE pipe issues one warp instruction per 4 cycles per SM sub-partition and a single warp inside
 // fp_mul saturates it; two warps that start together stay in lockstep (both in their IMAD phase, then both in their ALU
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(TPB, BLS_MINB_HMAP) k_hash_map(const u32x4* u_
     sswu_map(xn, xd, y, u); iso3_map(q, xn, xd, y);
     soa_store_fp2(q_soa, n, i, 3 * j, q.X); soa_store_fp2(q_soa, n, i, 3 * j + 1, q.Y); soa_store_fp2(q_soa, n, i, 3 * j + 2, q.Z);
 }
-__global__ void __launch_bounds__(TPB, BLS_MINB) k_hash_clear(const u32x4* q_soa, const uint8_t* status, size_t n, u32x4* hm_soa, uint8_t* flags) {
+__global__ void __launch_bounds__(TPB, BLS_MINB_HCLEAR) k_hash_clear(const u32x4* q_soa, const uint8_t* status, size_t n, u32x4* hm_soa, uint8_t* flags) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     if (status[i] != ST_OK) return;
     g2_jac q0, q1, h; g2_aff hm;
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(TPB, BLS_MINB_LINES) k_miller_lines(const u32x
     }
     if (i_lo != 0) { soa_store_fp2(t_soa, n, i, 3 * j, r.x); soa_store_fp2(t_soa, n, i, 3 * j + 1, r.y); soa_store_fp2(t_soa, n, i, 3 * j + 2, r.z); }
 }
-__global__ void __launch_bounds__(TPB, BLS_MINB) k_miller_accum(const uint8_t* flags, const uint8_t* status, size_t n, u32x4* f_soa, const u32x4* lines, int i_hi, int i_lo) {
+__global__ void __launch_bounds__(TPB, BLS_MINB_ACCUM) k_miller_accum(const uint8_t* flags, const uint8_t* status, size_t n, u32x4* f_soa, const u32x4* lines, int i_hi, int i_lo) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
     if (status[i] != ST_OK) return;
     uint8_t fl = flags[i]; bool use0 = !(fl & FL_SIG_INF), use1 = !(fl & FL_HM_INF);

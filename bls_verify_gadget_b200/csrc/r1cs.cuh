@@ -15,13 +15,16 @@
 //    side sum, a larger coefficient as a masked addition of its canonical value (warp-uniform branches), and test a row that
 //    touched nothing else as a * b == c on integers;
 //  * a few hundred rows carry 300-760 general coefficients (linear combinations that grow through runs of cyclotomic
-//    squarings): rows longer than R1_LONG are cut into R1_SEG-entry segments, one warp each, and combined afterwards --
-//    otherwise one warp serialises ~10^7 instructions while the rest of the GPU idles (measured: 34 ms per group -> see
-//    profiles/r01_summary.md).
+//    squarings).  Round 1 cut rows longer than R1_LONG into R1_SEG-entry segments, one warp each, and combined them afterwards
+//    (with the round-1 term code a 760-term row serialised ~10^7 instructions on one warp: 34 ms per group).  With the term paths of
+//    round 2 a term costs ~70 warp instructions, and the long rows run one warp per ROW again, longest first (k_r1cs_long_rows):
+//    no partial sums through global memory, one closing reduction per combination instead of one per segment -- 651 -> 506 us per
+//    group for the 21,537 long rows of the verify circuit.  The segment kernels stay behind R1_LONG_ROWS = 0.
 // Coefficients +1 / -1 (the bulk of boolean/uint gadget rows) skip the multiply; coefficients of magnitude below 2^32 (2, 3, 4, 12,
 // 2^k ...: 80 % of the remaining ones in the verify circuit) take fp_mul_small (24 MACs); z stays canonical:
 // coeff(Montgomery) x z(canonical) -> canonical, no conversion of z needed.
 #pragma once
+#include <algorithm>
 #include <vector>
 
 struct r1cs_sys {
@@ -29,6 +32,7 @@ struct r1cs_sys {
     uint64_t* rowptr[3]; uint32_t* col[3]; fp* coeff[3]; fp* coeffc[3]; uint8_t* cls[3];
     uint8_t* is_long; size_t n_long, n_seg;
     uint32_t* long_row;            // [n_long] row index
+    uint32_t* long_sorted;         // [n_long] the same rows, longest first (k_r1cs_long_rows takes them in this order: longest-processing-time-first over the warps)
     uint32_t* seg_ptr;             // [n_long * 3 + 1] first segment of (long row, matrix)
     uint64_t* seg_lo; uint64_t* seg_hi; uint8_t* seg_mat;     // [n_seg] non-zero range and matrix of a segment
     // rows specialised at load time (see "row classes" below)
@@ -233,7 +237,7 @@ __device__ __forceinline__ bool r1cs_product_ok(const fp& a, const fp& b, const 
 //    k_r1cs_lut then evaluates it BIT-SLICED with lane = row on the packed 32-assignment words: no field arithmetic, no CSR walk,
 //    ~40 logic instructions per row and 32 assignments.  A row that meets a column which is not 0/1 in this group is appended to a
 //    fallback list and evaluated generically, so the result is exact for every input.
-//  * long rows (more than R1_LONG non-zeros): segments + combine, as before.
+//  * long rows (more than R1_LONG non-zeros): one warp per row, longest first (k_r1cs_long_rows).
 //  * the rest ("generic" short rows, mostly the field rows of the pairing part): one warp per row, lane = assignment.
 #define R1_NOT_LUT 0xffffffffu
 #define R1_NO_COL 0xffffffffu
@@ -336,6 +340,26 @@ __global__ void __launch_bounds__(TPB, R1_MINB_ROWS) k_r1cs_rows_list(r1cs_sys s
         if ((size_t)lane < g && ok) atomicOr((unsigned long long*)&sat_bits[(w0 + lane) * words + (row >> 6)], 1ull << (row & 63));
     }
 }
+// one warp per long row, longest rows first: the three combinations through the lane-parallel metadata path, product test, bit.  Replaces the
+// segment + combine pair (R1_LONG_ROWS): no partial sums through global memory (301 MB per launch), one closing reduction per combination
+// instead of one per 32-term segment (5.4 segments per long row on the verify circuit).
+#ifndef R1_LONG_ROWS
+#define R1_LONG_ROWS 1
+#endif
+#ifndef R1_MINB_LONG
+#define R1_MINB_LONG R1_MINB_SEG
+#endif
+__global__ void __launch_bounds__(TPB, R1_MINB_LONG) k_r1cs_long_rows(r1cs_sys s, const u32x4* zt, const uint2* zbool, size_t w0, size_t g, size_t words, uint64_t* sat_bits) {
+    size_t li = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
+    if (li >= s.n_long) return;
+    size_t row = s.long_sorted[li];
+    int64_t sa, sb, sc; bool ta, tb, tc;
+    fp a = r1cs_range_dot_wide(s, 0, s.rowptr[0][row], s.rowptr[0][row + 1], zt, zbool, lane, sa, ta); a = r1cs_finalize(a, sa, ta);
+    fp b = r1cs_range_dot_wide(s, 1, s.rowptr[1][row], s.rowptr[1][row + 1], zt, zbool, lane, sb, tb); b = r1cs_finalize(b, sb, tb);
+    fp c = r1cs_range_dot_wide(s, 2, s.rowptr[2][row], s.rowptr[2][row + 1], zt, zbool, lane, sc, tc); c = r1cs_finalize(c, sc, tc);
+    bool ok = r1cs_product_ok(a, b, c);
+    if ((size_t)lane < g && ok) atomicOr((unsigned long long*)&sat_bits[(w0 + lane) * words + (row >> 6)], 1ull << (row & 63));
+}
 // one warp per segment of a long row: partial dot product of 32 witnesses -> part (limb-SoA over n_seg * 32 slots)
 __global__ void __launch_bounds__(TPB, R1_MINB_SEG) k_r1cs_segments(r1cs_sys s, const u32x4* zt, const uint2* zbool, u32x4* part) {
     size_t sg = blockIdx.x * (size_t)(TPB / 32) + (threadIdx.x >> 5); int lane = threadIdx.x & 31;
@@ -380,7 +404,7 @@ template <class T> static int r1cs_upload(blsgpu_ctx* ctx, T** dst, const std::v
 }
 static void r1cs_release(r1cs_sys* s) {
     for (int m = 0; m < 3; m++) { cudaFree(s->rowptr[m]); cudaFree(s->col[m]); cudaFree(s->coeff[m]); cudaFree(s->coeffc[m]); cudaFree(s->cls[m]); }
-    cudaFree(s->is_long); cudaFree(s->long_row); cudaFree(s->seg_ptr); cudaFree(s->seg_lo); cudaFree(s->seg_hi); cudaFree(s->seg_mat);
+    cudaFree(s->is_long); cudaFree(s->long_row); cudaFree(s->long_sorted); cudaFree(s->seg_ptr); cudaFree(s->seg_lo); cudaFree(s->seg_hi); cudaFree(s->seg_mat);
     cudaFree(s->lut_a); cudaFree(s->lut_b); cudaFree(s->gen_rows); cudaFree(s->fb_rows); cudaFree(s->fb_count);
     delete s;
 }
@@ -442,6 +466,10 @@ static int r1cs_build(blsgpu_ctx* ctx, r1cs_sys* s, const uint64_t* const rowptr
     s->n_long = long_row.size(); s->n_seg = seg_lo.size(); s->n_gen = gen_rows.size(); s->n_lut = lut_rows.size();
     if (int rc = r1cs_upload(ctx, &s->is_long, is_long)) return rc;
     if (int rc = r1cs_upload(ctx, &s->long_row, long_row)) return rc;
+    {   std::vector<uint32_t> ls = long_row;
+        auto len_of = [&](uint32_t r) { size_t l = 0; for (int m = 0; m < 3; m++) l += hrp[m][r + 1] - hrp[m][r]; return l; };
+        std::stable_sort(ls.begin(), ls.end(), [&](uint32_t x, uint32_t y) { return len_of(x) > len_of(y); });
+        if (int rc = r1cs_upload(ctx, &s->long_sorted, ls)) return rc; }
     if (int rc = r1cs_upload(ctx, &s->seg_ptr, seg_ptr)) return rc;
     if (int rc = r1cs_upload(ctx, &s->seg_lo, seg_lo)) return rc;
     if (int rc = r1cs_upload(ctx, &s->seg_hi, seg_hi)) return rc;
@@ -547,10 +575,15 @@ static int r1cs_check_group(blsgpu_ctx* ctx, const r1cs_sys& s, const u32x4* zt,
     CU(cudaMemsetAsync(s.fb_count, 0, 4, ctx->stream));
     LAUNCH(k_r1cs_lut, nblk(words * 64, 256), 256, s, zbool, w0, g, words, (uint32_t*)dbits);
     if (s.n_lut || s.n_gen) LAUNCH(k_r1cs_rows_list, R1_FB_BLOCKS, TPB, s, zt, zbool, w0, g, words, dbits);
+#if R1_LONG_ROWS
+    if (s.n_long) LAUNCH(k_r1cs_long_rows, nblk(s.n_long, TPB / 32), TPB, s, zt, zbool, w0, g, words, dbits);
+    (void)part;
+#else
     if (s.n_long) {
         LAUNCH(k_r1cs_segments, nblk(s.n_seg, TPB / 32), TPB, s, zt, zbool, part);
         LAUNCH(k_r1cs_combine, nblk(s.n_long, TPB / 32), TPB, s, (const u32x4*)part, w0, g, words, dbits);
     }
+#endif
     return 0;
 }
 extern "C" {
@@ -561,7 +594,7 @@ int blsgpu_r1cs_check(blsgpu_ctx* ctx, int handle, const uint8_t* z48, size_t nw
     size_t words = (s.nrows + 63) / 64;
     bool host = ctx->ptr_mode == BLSGPU_HOST;
     // host mode stages one group of 32 witnesses at a time (32 * ncols * 48 bytes) so the workspace stays bounded
-    size_t zgroup = (size_t)R1_GROUP * s.ncols * 48, part_bytes = (s.n_seg ? s.n_seg : 1) * 32 * 48;
+    size_t zgroup = (size_t)R1_GROUP * s.ncols * 48, part_bytes = R1_LONG_ROWS ? 64 : (s.n_seg ? s.n_seg : 1) * 32 * 48;      // partial sums exist in the segment form only
     if (int rc = ws_reserve(ctx, (host ? al(zgroup) : 0) + al(zgroup) + al(8 * s.ncols) + al(part_bytes) + (host ? al(8 * words * nwit) + al(nwit) : 0) + 8192)) return rc;
     u32x4* zstage = host ? ws_take<u32x4>(ctx, zgroup / 16) : nullptr;
     u32x4* zt = ws_take<u32x4>(ctx, zgroup / 16);

@@ -652,7 +652,7 @@ static int witness_check_core(blsgpu_ctx* ctx, int wit_handle, int r1cs_handle, 
     wit_prog p = *ctx->wit[wit_handle]; r1cs_sys s = *ctx->r1cs[r1cs_handle];
     if (p.nout != s.ncols) return fail(ctx, BLSGPU_ERR_ARG, "witness program and R1CS system have different column counts");
     if (!p.xrules) return fail(ctx, BLSGPU_ERR_ARG, "blsgpu_witness_check needs a program loaded with its level order");
-    size_t groups = (nwit + 31) / 32, words = (s.nrows + 63) / 64, part_bytes = (s.n_seg ? s.n_seg : 1) * 32 * 48;
+    size_t groups = (nwit + 31) / 32, words = (s.nrows + 63) / 64, part_bytes = R1_LONG_ROWS ? 64 : (s.n_seg ? s.n_seg : 1) * 32 * 48;
     bool host = ctx->ptr_mode == BLSGPU_HOST;
     u32x4* zt_all; uint2* zbool_all; uint8_t* dstatus;
     if (int rc = witness_run(ctx, p, pk48, bitmap, msg, sig96, nwit, status, al(part_bytes) + (host ? al(8 * words * nwit) + al(nwit) : 0), true, &zt_all, &zbool_all, &dstatus)) return rc;
