@@ -102,8 +102,8 @@ def run(ctx, dev, stream, world, rank, steps=3, warmup=3, per_gpu=512, cpu=True)
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
                              "algorithmic_bytes_per_unit": alg_bytes, "units_per_launch": 32, "unit_name": "assignment (a launch = one kernel over a group of 32)",
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6549.4 GB/s (the value MEASURED_PEAKS.json held when this was written)",
-                             "note": "whole step (transpose + truth-table rows + generic rows + long-row segments + combine) against SURVEY 8(d) bytes: 48 B x ncols read once + nrows / 8 written per assignment; "
-                                     "per-kernel times: profiles/r02_launches_r1cs.csv"}}
+                             "note": "whole step (transpose + truth-table rows + generic rows + long rows) against SURVEY 8(d) bytes: 48 B x ncols read once + nrows / 8 written per assignment; "
+                                     "per-kernel times: profiles/launches_r1cs_r02.csv"}}
         if cpu:
             from oracle import cwrap as C
             thr = C.hw_threads(); ns = 2; zs = dz[:ns * ncols * 48].cpu().numpy()

@@ -43,8 +43,8 @@ struct r1cs_sys {
 enum { R1_GENERAL = 0, R1_PLUS_ONE = 1, R1_MINUS_ONE = 2, R1_SMALL_POS = 3, R1_SMALL_NEG = 4 };      // SMALL: |c| < 2^32 (fp_mul_small), c = +|c| or p - |c|
 #define R1_GROUP 32
 #ifndef R1_LONG
-#define R1_LONG 16
-#endif
+#define R1_LONG 8          // rows that are not truth-table rows and have more non-zeros than this take the lane-parallel metadata path (k_r1cs_long_rows);
+#endif                     // measured on the verify circuit: 16 -> 3.67 ms per 128 assignments, 8 / 4 / 2 -> 3.54 / 3.55 / 3.54
 #ifndef R1_SEG
 #define R1_SEG 32
 #endif
@@ -442,14 +442,7 @@ static int r1cs_build(blsgpu_ctx* ctx, r1cs_sys* s, const uint64_t* const rowptr
     for (size_t r = 0; r < nrows; r++) {
         lut_a[r] = make_uint4(R1_NOT_LUT, R1_NO_COL, R1_NO_COL, 0u); lut_b[r] = make_uint2(R1_NO_COL, R1_NO_COL);
         size_t len = 0; for (int m = 0; m < 3; m++) len += hrp[m][r + 1] - hrp[m][r];
-        if (len > R1_LONG) {
-            is_long[r] = 1; long_row.push_back((uint32_t)r);
-            for (int m = 0; m < 3; m++) {
-                seg_ptr.push_back((uint32_t)seg_lo.size());
-                for (uint64_t k = hrp[m][r]; k < hrp[m][r + 1]; k += R1_SEG) { seg_lo.push_back(k); seg_hi.push_back(k + R1_SEG < hrp[m][r + 1] ? k + R1_SEG : hrp[m][r + 1]); seg_mat.push_back((uint8_t)m); }
-            }
-            continue;
-        }
+        // truth-table shape first (at most R1_LUT_NNZ non-zeros over at most five columns), then long / generic by length
         uint32_t c[5]; int d = 0; bool fits = len <= R1_LUT_NNZ && ncols < 0x7fffffffu;
         for (int m = 0; m < 3 && fits; m++)
             for (uint64_t k = hrp[m][r]; k < hrp[m][r + 1] && fits; k++) {
@@ -460,6 +453,12 @@ static int r1cs_build(blsgpu_ctx* ctx, r1cs_sys* s, const uint64_t* const rowptr
             lut_a[r] = make_uint4(c[0] | (d > 3 ? 0x80000000u : 0u), d > 1 ? c[1] : R1_NO_COL, d > 2 ? c[2] : R1_NO_COL, 0u);
             lut_b[r] = make_uint2(d > 3 ? c[3] : R1_NO_COL, d > 4 ? c[4] : R1_NO_COL);
             lut_rows.push_back((uint32_t)r);
+        } else if (len > R1_LONG) {
+            is_long[r] = 1; long_row.push_back((uint32_t)r);
+            for (int m = 0; m < 3; m++) {
+                seg_ptr.push_back((uint32_t)seg_lo.size());
+                for (uint64_t k = hrp[m][r]; k < hrp[m][r + 1]; k += R1_SEG) { seg_lo.push_back(k); seg_hi.push_back(k + R1_SEG < hrp[m][r + 1] ? k + R1_SEG : hrp[m][r + 1]); seg_mat.push_back((uint8_t)m); }
+            }
         } else gen_rows.push_back((uint32_t)r);
     }
     seg_ptr.push_back((uint32_t)seg_lo.size());

@@ -1,0 +1,6 @@
+set -x
+BLSGPU_SO=build_var/fuse.so python -m pytest tests -m gpu -x -q -k "r1cs or witness" 2>&1 | tail -3
+for v in base fuse fuse_l32 fuse_l8; do
+  echo "== $v"; export BLSGPU_SO=build_var/$v.so
+  python bench_configs.py --cfg 5r --steps 2 --scale 0.5 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d.get('value'), d.get('ms'))"
+done

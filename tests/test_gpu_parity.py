@@ -343,7 +343,10 @@ def test_r1cs_row_classes(ctx, C):
     rows.append(([(ONE, 3)], [(ONE, 5)], [(ONE, 15)]))                                                                # constant row (satisfied), one column
     rows.append(([(ONE, 3)], [(ONE, 5)], [(ONE, 16)]))                                                                # constant row (never satisfied)
     fa, fb = newcol(), newcol(); fc = newcol(); rows.append(([(fa, 1)], [(fb, 1)], [(fc, 1)]))                        # a field product on three columns: truth-table shape, always falls back
-    wide = [newcol() for _ in range(7)]; wc = newcol(); rows.append(([(c, 1 + k) for k, c in enumerate(wide)], [(ONE, 1)], [(wc, 1)]))      # 9 distinct columns: generic short row
+    wide = [newcol() for _ in range(6)]; wc = newcol(); rows.append(([(c, 1 + k) for k, c in enumerate(wide)], [(ONE, 1)], [(wc, 1)]))      # 8 distinct columns, 8 non-zeros: generic short row
+    lcols = [newcol() for _ in range(40)]; lc = newcol()                                                              # 42 non-zeros: a long row (bit-packing shape with a few odd coefficients)
+    lcoef = [(1 << (k + 20)) if k % 7 else (P - 3 - k if k % 2 else (0x1234567 << 200) + k) for k in range(40)]
+    rows.append(([(c, lcoef[k]) for k, c in enumerate(lcols)], [(ONE, 1)], [(lc, 1)]))
     ncols = nextc[0]; nrows = len(rows)
     z = np.zeros((nwit, ncols), dtype=object); z[:, 0] = 1; z[:, 1:1 + nb] = rng.integers(0, 2, size=(nwit, nb))
     fn = {"and": lambda a, b: a & b, "xor": lambda a, b: a ^ b, "or": lambda a, b: a | b, "sel": lambda s, a, b: a if s else b}
@@ -352,6 +355,8 @@ def test_r1cs_row_classes(ctx, C):
         z[w, fa] = int.from_bytes(rng.bytes(48), "little") % P; z[w, fb] = int.from_bytes(rng.bytes(48), "little") % P; z[w, fc] = z[w, fa] * z[w, fb] % P
         for c in wide: z[w, c] = int(rng.integers(0, 2)) if w < 32 else int.from_bytes(rng.bytes(48), "little") % P
         z[w, wc] = sum((1 + k) * z[w, c] for k, c in enumerate(wide)) % P
+        for k, c in enumerate(lcols): z[w, c] = int(rng.integers(0, 2)) if (w < 32 or k % 3) else int.from_bytes(rng.bytes(48), "little") % P
+        z[w, lc] = (sum(lcoef[k] * z[w, c] for k, c in enumerate(lcols)) + (1 if w in (7, 50) else 0)) % P             # two assignments break the long row
     flips = [(2, outs[0][0]), (31, outs[5][0]), (33, outs[9][0]), (64, outs[39][0]), (69, outs[17][0])]              # wrong gate outputs (still 0/1)
     for w, c in flips: z[w, c] ^= 1
     z[40, cols["b"][2]] = 2; z[66, outs[3][0]] = P - 1; z[5, fc] = (z[5, fc] + 1) % P                                 # non-0/1 values: second and third group only
@@ -365,7 +370,7 @@ def test_r1cs_row_classes(ctx, C):
     zb = np.frombuffer(b"".join(int(v).to_bytes(48, "little") for v in z.reshape(-1)), np.uint8)
     h = ctx.r1cs_load([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], nrows, ncols)
     cls = ctx.r1cs_row_classes(h)
-    assert cls == {"truth_table": nrows - 1, "generic": 1, "long": 0, "segments": 0}
+    assert cls == {"truth_table": nrows - 2, "generic": 1, "long": 1, "segments": 4}
     bits, allsat = ctx.r1cs_check(h, zb, nwit, nrows); ctx.r1cs_free(h)
     obits, oall = C.r1cs_check([m[0] for m in mats], [m[1] for m in mats], [m[2] for m in mats], nrows, ncols, zb, nwit, threads=4)
     assert np.array_equal(bits, obits) and list(allsat) == list(oall)
