@@ -19,6 +19,10 @@ extern "C" {
     pub fn blsgpu_last_error(ctx: *mut blsgpu_ctx) -> *const c_char;
     pub fn blsgpu_set_stream(ctx: *mut blsgpu_ctx, cuda_stream: *mut c_void, use_own: c_int) -> c_int;
     pub fn blsgpu_set_pointer_mode(ctx: *mut blsgpu_ctx, mode: c_int) -> c_int;
+    // memory / tuning switches; results do not depend on them
+    pub fn blsgpu_set_chunk(ctx: *mut blsgpu_ctx, items: usize) -> c_int;
+    pub fn blsgpu_set_lanes(ctx: *mut blsgpu_ctx, lanes: c_int) -> c_int;
+    pub fn blsgpu_set_split(ctx: *mut blsgpu_ctx, on: c_int) -> c_int;
     pub fn blsgpu_synchronize(ctx: *mut blsgpu_ctx) -> c_int;
     // <BLS<P> as SignatureScheme>::verify, src/bls.rs:427-458 (incl. the TryFrom decoding of tests/tests.rs:244-254)
     pub fn blsgpu_verify_batch(ctx: *mut blsgpu_ctx, pk48: *const u8, msg: *const u8, msg_off: *const u32, sig96: *const u8, n: usize,
