@@ -844,6 +844,27 @@ int blsgpu_hash_to_g2_batch(blsgpu_ctx* ctx, const uint8_t* msg, const uint32_t*
     return finish_call(ctx);
 }
 
+// hash-to-G2 stage of the verify paths: status / flags from the decode codes, H(m) into hm_soa.  scratch36 = 36 n rows that are not live yet
+// (the Miller accumulator array): the split form keeps the two mapped points there, and u0, u1 in the 12 rows of hm_soa.
+static int hash_stage(blsgpu_ctx* ctx, const uint8_t* dmsg, const uint32_t* doff, size_t n, const uint8_t* code_pk, const uint8_t* code_sig, u32x4* hm_soa, u32x4* scratch36,
+                      uint8_t* flags, uint8_t* dstatus) {
+    if (ctx->split) {
+        LAUNCH(k_hash_field, nblk(n), TPB, dmsg, doff, n, code_pk, code_sig, hm_soa, flags, dstatus);
+        LAUNCH(k_hash_map, nblk(2 * n), TPB, (const u32x4*)hm_soa, (const uint8_t*)dstatus, n, scratch36);
+        LAUNCH(k_hash_clear, nblk(n), TPB, (const u32x4*)scratch36, (const uint8_t*)dstatus, n, hm_soa, flags);
+    } else LAUNCH(k_hash_to_g2, nblk(n), TPB, dmsg, doff, n, code_pk, code_sig, hm_soa, flags, dstatus);
+    return 0;
+}
+// Miller loop in its split form: iterations 62..0 eight at a time, lines of both pairs (a pair switched off in flags costs nothing), then the accumulator update
+static int miller_stage_split(blsgpu_ctx* ctx, const u32x4* pk_soa, const u32x4* hm_soa, const u32x4* sig_soa, const uint8_t* flags, const uint8_t* dstatus, size_t n,
+                              u32x4* f_soa, u32x4* t_soa /* 36 n rows */, u32x4* lines /* MILLER_LINE_STEPS * 36 n rows */) {
+    for (int hi = 62; hi >= 0; hi -= MILLER_LINE_ITERS) {
+        int lo = hi - MILLER_LINE_ITERS + 1 < 0 ? 0 : hi - MILLER_LINE_ITERS + 1;
+        LAUNCH(k_miller_lines, nblk(2 * n), TPB, pk_soa, hm_soa, sig_soa, flags, dstatus, n, t_soa, lines, hi, lo);
+        LAUNCH(k_miller_accum, nblk(n), TPB, flags, dstatus, n, f_soa, (const u32x4*)lines, hi, lo);
+    }
+    return 0;
+}
 // core of verify once pk (limb-SoA + code) is known: decode sig, hash, Miller, final exp, epilogue
 static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code_pk, const uint8_t* dmsg, const uint32_t* doff, const uint8_t* dsig, size_t n,
                        uint8_t* dstatus, uint32_t* dbitmap, u32x4* gt_acc /* limb-SoA n=1, multiplied into; nullable */) {
@@ -852,22 +873,13 @@ static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code
     STAGE_MARK(1);
     LAUNCH(k_decode_g2, nblk(n), TPB, dsig, n, sig_soa, code_sig);
     STAGE_MARK(2);
-    if (ctx->split) {
-        u32x4* q_soa = f_soa;                                  // the accumulator array is not live yet: 36 rows hold the two mapped points, the first 12 rows of hm_soa hold u0, u1
-        LAUNCH(k_hash_field, nblk(n), TPB, dmsg, doff, n, code_pk, (const uint8_t*)code_sig, hm_soa, flags, dstatus);
-        LAUNCH(k_hash_map, nblk(2 * n), TPB, (const u32x4*)hm_soa, (const uint8_t*)dstatus, n, q_soa);
-        LAUNCH(k_hash_clear, nblk(n), TPB, (const u32x4*)q_soa, (const uint8_t*)dstatus, n, hm_soa, flags);
-    } else LAUNCH(k_hash_to_g2, nblk(n), TPB, dmsg, doff, n, code_pk, (const uint8_t*)code_sig, hm_soa, flags, dstatus);
+    if (int rc = hash_stage(ctx, dmsg, doff, n, code_pk, code_sig, hm_soa, f_soa, flags, dstatus)) return rc;
     STAGE_MARK(3);
     if (ctx->split && !ctx->coop) {
         // iterations 62..0 eight at a time: lines of both pairs, then the accumulator update
         u32x4* t_soa = ws_take<u32x4>(ctx, 36 * n); u32x4* y1_soa = t_soa; u32x4* y2_soa = ws_take<u32x4>(ctx, 36 * n);      // the running points are dead once the loop ends
         u32x4* lines = ws_take<u32x4>(ctx, (size_t)MILLER_LINE_STEPS * 2 * 18 * n);
-        for (int hi = 62; hi >= 0; hi -= MILLER_LINE_ITERS) {
-            int lo = hi - MILLER_LINE_ITERS + 1 < 0 ? 0 : hi - MILLER_LINE_ITERS + 1;
-            LAUNCH(k_miller_lines, nblk(2 * n), TPB, pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, n, t_soa, lines, hi, lo);
-            LAUNCH(k_miller_accum, nblk(n), TPB, (const uint8_t*)flags, (const uint8_t*)dstatus, n, f_soa, (const u32x4*)lines, hi, lo);
-        }
+        if (int rc = miller_stage_split(ctx, pk_soa, hm_soa, sig_soa, flags, dstatus, n, f_soa, t_soa, lines)) return rc;
         STAGE_MARK(4);
         u32x4* snap_soa = lines;                               // 144 rows of the 396-row line buffer, which is dead once the loop ends
         const uint8_t* cst = dstatus;
@@ -1045,7 +1057,7 @@ int blsgpu_verify_batch_rlc(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t*
         u32x4* ta = ws_take<u32x4>(ctx, 36 * ((m + 7) / 8)); u32x4* tb = ws_take<u32x4>(ctx, 36 * ((m + 63) / 64)); u32x4* one = ws_take<u32x4>(ctx, 36);
         LAUNCH(k_decode_g1, nblk(m), TPB, dpk, m, pk_soa, code_pk);
         LAUNCH(k_decode_g2, nblk(m), TPB, dsig, m, sig_soa, code_sig);
-        LAUNCH(k_hash_to_g2, nblk(m), TPB, dmsg, doff, m, (const uint8_t*)code_pk, (const uint8_t*)code_sig, hm_soa, flags, dstatus);
+        if ((rc = hash_stage(ctx, dmsg, doff, m, code_pk, code_sig, hm_soa, f_soa, flags, dstatus))) break;
         LAUNCH(k_any_bad, nblk(((m + 31) / 32) * 32, 256), 256, (const uint8_t*)dstatus, m, bad);
         LAUNCH(k_rlc_scale, nblk(m), TPB, pk_soa, (const u32x4*)sig_soa, flags, (const uint8_t*)dstatus, m, base, (const uint8_t*)dseed, rs);
         {   // sum of the scaled signatures (radix-8 tree, like the GT product)
@@ -1058,7 +1070,10 @@ int blsgpu_verify_batch_rlc(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t*
             }
             LAUNCH(k_g2_jac_add_into, 1, 32, s_acc, (const u32x4*)jone);
         }
-        LAUNCH(k_miller, nblk(m), TPB, (const u32x4*)pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, m, f_soa);
+        if (ctx->split) {                                        // verify_ws_bytes counts the running-point array and the line buffer
+            u32x4* t_soa = ws_take<u32x4>(ctx, 36 * m); u32x4* lines = ws_take<u32x4>(ctx, (size_t)MILLER_LINE_STEPS * 2 * 18 * m);
+            if ((rc = miller_stage_split(ctx, pk_soa, hm_soa, sig_soa, flags, dstatus, m, f_soa, t_soa, lines))) break;
+        } else LAUNCH(k_miller, nblk(m), TPB, (const u32x4*)pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, m, f_soa);
         if ((rc = gt_product(ctx, f_soa, dstatus, m, ta, tb, one))) break;
         LAUNCH(k_gt_mul_into, 1, 32, f_acc, (const u32x4*)one);
         if (status && (rc = finish_out(ctx, status + base, dstatus, m))) break;
@@ -1113,7 +1128,7 @@ int blsgpu_verify_batch_rlc_bisect(blsgpu_ctx* ctx, const uint8_t* pk48, const u
         u32x4* ta = ws_take<u32x4>(ctx, 36 * P * T0); u32x4* tb = ws_take<u32x4>(ctx, 36 * P * T0); uint8_t* dok = ws_take<uint8_t>(ctx, P);
         LAUNCH(k_decode_g1, nblk(m), TPB, dpk, m, pk_soa, code_pk);
         LAUNCH(k_decode_g2, nblk(m), TPB, dsig, m, sig_soa, code_sig);
-        LAUNCH(k_hash_to_g2, nblk(m), TPB, dmsg, doff, m, (const uint8_t*)code_pk, (const uint8_t*)code_sig, hm_soa, flags, dstatus);
+        if ((rc = hash_stage(ctx, dmsg, doff, m, code_pk, code_sig, hm_soa, f_soa, flags, dstatus))) return rc;
         LAUNCH(k_rlc_scale, nblk(m), TPB, pk_soa, (const u32x4*)sig_soa, flags, (const uint8_t*)dstatus, m, base, (const uint8_t*)dseed, rs);
         const u32x4* s_piece; const u32x4* f_piece;
         {   // per-piece sums of the scaled signatures: radix-8 trees, all pieces in one launch per level
@@ -1126,7 +1141,10 @@ int blsgpu_verify_batch_rlc_bisect(blsgpu_ctx* ctx, const uint8_t* pk48, const u
             }
             s_piece = cur;
         }
-        LAUNCH(k_miller, nblk(m), TPB, (const u32x4*)pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, m, f_soa);
+        if (ctx->split) {
+            u32x4* t_soa = ws_take<u32x4>(ctx, 36 * m); u32x4* lines = ws_take<u32x4>(ctx, (size_t)MILLER_LINE_STEPS * 2 * 18 * m);
+            if ((rc = miller_stage_split(ctx, pk_soa, hm_soa, sig_soa, flags, dstatus, m, f_soa, t_soa, lines))) return rc;
+        } else LAUNCH(k_miller, nblk(m), TPB, (const u32x4*)pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, m, f_soa);
         {
             const u32x4* cur = f_soa; const uint8_t* st = dstatus; size_t cnt_n = m, len = L; u32x4* bufs[2] = {ta, tb}; int which = 0;
             while (true) {
