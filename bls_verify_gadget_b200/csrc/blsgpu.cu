@@ -190,14 +190,14 @@ __global__ void __launch_bounds__(TPB, BLS_MINB_HFIELD) k_hash_field(const uint8
 __global__ void __launch_bounds__(TPB, BLS_MINB_HMAP) k_hash_map(const u32x4* u_soa, const uint8_t* status, size_t n, u32x4* q_soa) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (t >= 2 * n) return;
     int j = t >= n; size_t i = t - (j ? n : 0);
-    if (status[i] != ST_OK) return;
+    if (status && status[i] != ST_OK) return;
     fp2 u = soa_load_fp2(u_soa, n, i, j), xn, xd, y; g2_jac q;
     sswu_map(xn, xd, y, u); iso3_map(q, xn, xd, y);
     soa_store_fp2(q_soa, n, i, 3 * j, q.X); soa_store_fp2(q_soa, n, i, 3 * j + 1, q.Y); soa_store_fp2(q_soa, n, i, 3 * j + 2, q.Z);
 }
 __global__ void __launch_bounds__(TPB, BLS_MINB_HCLEAR) k_hash_clear(const u32x4* q_soa, const uint8_t* status, size_t n, u32x4* hm_soa, uint8_t* flags) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
-    if (status[i] != ST_OK) return;
+    if (status && status[i] != ST_OK) return;
     g2_jac q0, q1, h; g2_aff hm;
     q0.X = soa_load_fp2(q_soa, n, i, 0); q0.Y = soa_load_fp2(q_soa, n, i, 1); q0.Z = soa_load_fp2(q_soa, n, i, 2);
     q1.X = soa_load_fp2(q_soa, n, i, 3); q1.Y = soa_load_fp2(q_soa, n, i, 4); q1.Z = soa_load_fp2(q_soa, n, i, 5);
@@ -829,16 +829,19 @@ int blsgpu_deserialize_g2(blsgpu_ctx* ctx, const uint8_t* in96, size_t n, uint8_
     return finish_call(ctx);
 }
 
+static int hash_stage(blsgpu_ctx* ctx, const uint8_t* dmsg, const uint32_t* doff, size_t n, const uint8_t* code_pk, const uint8_t* code_sig, u32x4* hm_soa, u32x4* scratch36,
+                      uint8_t* flags, uint8_t* dstatus);
 int blsgpu_hash_to_g2_batch(blsgpu_ctx* ctx, const uint8_t* msg, const uint32_t* msg_off, size_t n, uint8_t* out96) {
     ENTER(); if (!msg || !out96) return fail(ctx, BLSGPU_ERR_ARG, "null pointer");
     if (!n) return 0;
     int rc; size_t mb = msg_bytes_total(ctx, msg_off, n, rc); if (rc) return fail(ctx, rc, "reading msg_off failed");
-    if ((rc = ws_reserve(ctx, al(mb + 1) + al(4 * (n + 1)) + al(192 * n) + al(96 * n) + al(n) + 8192))) return rc;
+    if ((rc = ws_reserve(ctx, al(mb + 1) + al(4 * (n + 1)) + al(192 * n) + al(96 * n) + al(n) + (ctx->split ? al(576 * n) : 0) + 8192))) return rc;
     const uint8_t* dmsg; const uint32_t* doff;
     if ((rc = stage_in(ctx, dmsg, msg, mb ? mb : 1))) return rc; if ((rc = stage_in(ctx, doff, msg_off, n + 1))) return rc;
     u32x4* hm = ws_take<u32x4>(ctx, 12 * n); uint8_t* flags = ws_take<uint8_t>(ctx, n);
     uint8_t* dout = stage_out(ctx, out96, 96 * n);
-    LAUNCH(k_hash_to_g2, nblk(n), TPB, dmsg, doff, n, (const uint8_t*)nullptr, (const uint8_t*)nullptr, hm, flags, (uint8_t*)nullptr);
+    u32x4* scratch = ctx->split ? ws_take<u32x4>(ctx, 36 * n) : nullptr;
+    if ((rc = hash_stage(ctx, dmsg, doff, n, nullptr, nullptr, hm, scratch, flags, nullptr))) return rc;
     LAUNCH(k_encode_g2, nblk(n), TPB, hm, flags, (uint8_t)FL_HM_INF, n, dout);
     if ((rc = finish_out(ctx, out96, dout, 96 * n))) return rc;
     return finish_call(ctx);
