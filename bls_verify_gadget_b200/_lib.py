@@ -78,7 +78,7 @@ class Context:
     def set_pointer_mode(self, device): self._ck(lib().blsgpu_set_pointer_mode(self._h, 1 if device else 0))
     def synchronize(self): self._ck(lib().blsgpu_synchronize(self._h))
     def launch_count(self): return int(lib().blsgpu_launch_count(self._h))
-    def set_coop(self, on): self._ck(lib().blsgpu_set_coop(self._h, 1 if on else 0))
+    def set_coop(self, mode): self._ck(lib().blsgpu_set_coop(self._h, int(mode)))      # 0 never, 1 always, 2 (library default) small passes only
     def set_lanes(self, lanes): self._ck(lib().blsgpu_set_lanes(self._h, int(lanes)))
     def set_split(self, mode): self._ck(lib().blsgpu_set_split(self._h, int(mode)))
     def set_chunk(self, items): self._ck(lib().blsgpu_set_chunk(self._h, _sz(items)))

@@ -29,6 +29,9 @@ using namespace bls;
 #endif
 #define TPB BLS_TPB
 #define VERIFY_CHUNK_DEFAULT ((size_t)1 << 20)
+#ifndef VERIFY_COOP_BELOW
+#define VERIFY_COOP_BELOW 4096     // blsgpu_set_coop(ctx, 2): passes of at most this many items take the six-lane final exponentiation
+#endif
 #ifndef BLS_MINB
 #define BLS_MINB 2      // resident 128-thread CTAs per SM the heavy kernels are compiled for (register cap = 65536 / (128 * BLS_MINB))
 #endif
@@ -627,7 +630,7 @@ struct blsgpu_ctx {
     struct r1cs_sys* r1cs[16]; struct wit_prog* wit[4];
     uint8_t* rlc_acc;                   // accumulators of blsgpu_verify_batch_rlc that live across passes (allocated on first use)
     struct { u32x4* soa; uint8_t* code; size_t n; } pool[16];   // resident decoded validator pools
-    int coop;                           // 1 = warp-cooperative hard part of the final exponentiation (coop.cuh)
+    int coop;                           // hard part of the final exponentiation with six lanes per item (coop.cuh): 0 = never, 1 = always, 2 (default) = for passes of at most VERIFY_COOP_BELOW items
     int wit_cluster;                    // 1 = witness replay with one thread-block cluster per group of 32 assignments; 0 (default) = grid-wide level barrier
     int lanes; cudaStream_t lane_stream[4]; cudaEvent_t lane_done[4], fork;   // concurrent sub-ranges of a verify pass
     int split;                          // 1 (default) = hash-to-G2, Miller loop and final exponentiation as sequences of short specialised launches, 0 = one launch each
@@ -715,7 +718,7 @@ int blsgpu_create(blsgpu_ctx** out, int device) {
     if (prop.major != 10) return BLSGPU_ERR_CUDA;                         // sm_100a cubin only: no other device can run it
     if (cudaSetDevice(device) != cudaSuccess) return BLSGPU_ERR_CUDA;
     blsgpu_ctx* c = new (std::nothrow) blsgpu_ctx(); if (!c) return BLSGPU_ERR_ALLOC;
-    memset(c, 0, sizeof *c); c->device = device; c->ptr_mode = BLSGPU_HOST; c->chunk = VERIFY_CHUNK_DEFAULT; c->lanes = 2; c->wit_cluster = 0; c->split = 1;
+    memset(c, 0, sizeof *c); c->device = device; c->ptr_mode = BLSGPU_HOST; c->chunk = VERIFY_CHUNK_DEFAULT; c->lanes = 2; c->wit_cluster = 0; c->split = 1; c->coop = 2;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return BLSGPU_ERR_CUDA; }
     c->stream = c->own_stream;
     *out = c; return 0;
@@ -739,7 +742,7 @@ int blsgpu_set_stream(blsgpu_ctx* ctx, void* s, int use_own) { if (!ctx) return 
 int blsgpu_set_pointer_mode(blsgpu_ctx* ctx, int mode) { if (!ctx || (mode != BLSGPU_HOST && mode != BLSGPU_DEVICE)) return BLSGPU_ERR_ARG; ctx->ptr_mode = mode; return 0; }
 int blsgpu_synchronize(blsgpu_ctx* ctx) { if (!ctx) return BLSGPU_ERR_ARG; dev_guard guard_; CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); return 0; }
 uint64_t blsgpu_launch_count(blsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
-int blsgpu_set_coop(blsgpu_ctx* ctx, int on) { if (!ctx) return BLSGPU_ERR_ARG; ctx->coop = on ? 1 : 0; return 0; }
+int blsgpu_set_coop(blsgpu_ctx* ctx, int on) { if (!ctx || on < 0 || on > 2) return BLSGPU_ERR_ARG; ctx->coop = on; return 0; }
 int blsgpu_set_witness_mode(blsgpu_ctx* ctx, int cluster) { if (!ctx) return BLSGPU_ERR_ARG; ctx->wit_cluster = cluster ? 1 : 0; return 0; }
 int blsgpu_set_split(blsgpu_ctx* ctx, int on) { if (!ctx) return BLSGPU_ERR_ARG; ctx->split = on ? 1 : 0; return 0; }
 int blsgpu_set_lanes(blsgpu_ctx* ctx, int lanes) { if (!ctx || lanes < 1 || lanes > 4) return BLSGPU_ERR_ARG; ctx->lanes = lanes; return 0; }
@@ -878,13 +881,29 @@ static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code
     STAGE_MARK(2);
     if (int rc = hash_stage(ctx, dmsg, doff, n, code_pk, code_sig, hm_soa, f_soa, flags, dstatus)) return rc;
     STAGE_MARK(3);
-    if (ctx->split && !ctx->coop) {
+    // Small passes are latency-bound (one item per thread: a lone warp walks the whole Miller loop and final exponentiation): below
+    // VERIFY_COOP_BELOW items the hard part of the final exponentiation runs with six lanes per item (coop.cuh), which shortens its chain.
+    bool coop = ctx->coop == 1 || (ctx->coop == 2 && n <= VERIFY_COOP_BELOW);
+    u32x4 *y1_soa = nullptr, *y2_soa = nullptr, *snap_soa = nullptr;
+    if (ctx->split) {
         // iterations 62..0 eight at a time: lines of both pairs, then the accumulator update
-        u32x4* t_soa = ws_take<u32x4>(ctx, 36 * n); u32x4* y1_soa = t_soa; u32x4* y2_soa = ws_take<u32x4>(ctx, 36 * n);      // the running points are dead once the loop ends
+        u32x4* t_soa = ws_take<u32x4>(ctx, 36 * n); y1_soa = t_soa; y2_soa = ws_take<u32x4>(ctx, 36 * n);      // the running points are dead once the loop ends
         u32x4* lines = ws_take<u32x4>(ctx, (size_t)MILLER_LINE_STEPS * 2 * 18 * n);
         if (int rc = miller_stage_split(ctx, pk_soa, hm_soa, sig_soa, flags, dstatus, n, f_soa, t_soa, lines)) return rc;
-        STAGE_MARK(4);
-        u32x4* snap_soa = lines;                               // 144 rows of the 396-row line buffer, which is dead once the loop ends
+        snap_soa = lines;                                      // 144 rows of the 396-row line buffer, which is dead once the loop ends
+    } else {
+#if BLS_F_IN_SMEM
+    { static bool attr_set = false; if (!attr_set) { cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, TPB * 592); attr_set = true; }
+      k_miller<<<nblk(n), TPB, TPB * 592, ctx->stream>>>(pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, n, f_soa); ctx->launches++; CU(cudaGetLastError()); }
+#else
+    LAUNCH(k_miller, nblk(n), TPB, pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, n, f_soa);
+#endif
+    }
+    STAGE_MARK(4);
+    if (coop) {
+        LAUNCH(k_final_easy, nblk(n), TPB, f_soa, (const uint8_t*)dstatus, n);
+        LAUNCH(k_final_hard_coop, nblk(n, 20), 128, f_soa, (const uint8_t*)dstatus, dstatus, n);
+    } else if (ctx->split) {
         const uint8_t* cst = dstatus;
         LAUNCH(k_final_step<0>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const u32x4*)snap_soa, cst, dstatus, n);
         LAUNCH(k_final_squarings, nblk(n), TPB, (const u32x4*)f_soa, snap_soa, cst, n);
@@ -897,19 +916,7 @@ static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code
         LAUNCH(k_final_step<4>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const u32x4*)snap_soa, cst, dstatus, n);
         LAUNCH(k_final_squarings, nblk(n), TPB, (const u32x4*)y2_soa, snap_soa, cst, n);
         LAUNCH(k_final_step<5>, nblk(n), TPB, f_soa, y1_soa, y2_soa, (const u32x4*)snap_soa, cst, dstatus, n);
-    } else {
-#if BLS_F_IN_SMEM
-    { static bool attr_set = false; if (!attr_set) { cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, TPB * 592); attr_set = true; }
-      k_miller<<<nblk(n), TPB, TPB * 592, ctx->stream>>>(pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, n, f_soa); ctx->launches++; CU(cudaGetLastError()); }
-#else
-    LAUNCH(k_miller, nblk(n), TPB, pk_soa, (const u32x4*)hm_soa, (const u32x4*)sig_soa, (const uint8_t*)flags, (const uint8_t*)dstatus, n, f_soa);
-#endif
-    STAGE_MARK(4);
-    if (ctx->coop) {
-        LAUNCH(k_final_easy, nblk(n), TPB, f_soa, (const uint8_t*)dstatus, n);
-        LAUNCH(k_final_hard_coop, nblk(n, 20), 128, f_soa, (const uint8_t*)dstatus, dstatus, n);
     } else LAUNCH(k_final_exp, nblk(n), TPB, f_soa, (const uint8_t*)dstatus, dstatus, n);
-    }
     STAGE_MARK(5);
     if (dbitmap) LAUNCH(k_status_bitmap, nblk(((n + 31) / 32) * 32, 256), 256, (const uint8_t*)dstatus, n, dbitmap);
     if (gt_acc) {

@@ -195,8 +195,12 @@ def test_gt_bytes(ctx, C, pyv):                                           # SURV
 def test_verify_fixtures(ctx, eth):                                       # tests.rs:240-268
     pk = b"".join(hx(c["input"]["pubkey"]) for c in eth["verify"]); sig = b"".join(hx(c["input"]["signature"]) for c in eth["verify"])
     msgs = [hx(c["input"]["message"]) for c in eth["verify"]]
-    st = ctx.verify(pk, msgs, sig)                                        # one batch
+    st = ctx.verify(pk, msgs, sig)                                        # one batch (a small pass: six-lane final exponentiation by default)
     for c, s in zip(eth["verify"], st): assert (s == 0) == c["output"], c["name"]
+    ctx.set_coop(0)                                                       # the same through the thread-per-item final-exponentiation kernels of the large passes
+    try: st0 = ctx.verify(pk, msgs, sig)
+    finally: ctx.set_coop(2)
+    assert np.array_equal(st0, st)
     for c in eth["verify"]:                                               # and one by one (n = 1 calls must work)
         i = c["input"]; assert (ctx.verify(hx(i["pubkey"]), [hx(i["message"])], hx(i["signature"]))[0] == 0) == c["output"]
 
@@ -213,6 +217,10 @@ def test_verify_differential_with_corruptions(ctx, C):
     assert bits == [int(s == 0) for s in st]
     # fixed-32 fast path and ragged path agree
     assert np.array_equal(ctx.verify(pk, msg, sig, fixed32=True), st)
+    ctx.set_coop(0)                                                       # thread-per-item final exponentiation (what passes above 4,096 items run)
+    try: st0, gt0 = ctx.verify(pk, msgs, sig, want_gt=True)
+    finally: ctx.set_coop(2)
+    assert np.array_equal(st0, st) and gt0.tobytes() == gt.tobytes()
 
 def test_verify_ragged_messages_and_identity_signature(ctx, C):
     from bls_verify_gadget_b200 import synth
@@ -754,10 +762,10 @@ def test_cooperative_final_exponentiation_matches(ctx, C):
     n = 333                                                               # not a multiple of 5 (items per warp) nor 20 (items per CTA)
     pk, msg, sig, exp = synth.verify_batch_inputs(ctx, n, every=6, fast=False)
     msgs = [msg[32 * i:32 * i + 32].tobytes() for i in range(n)]
-    st0, gt0 = ctx.verify(pk, msgs, sig, want_gt=True)
+    ctx.set_coop(0); st0, gt0 = ctx.verify(pk, msgs, sig, want_gt=True)                     # n = 333 would take the six-lane form by default
     ctx.set_coop(True)
     try: st1, gt1 = ctx.verify(pk, msgs, sig, want_gt=True)
-    finally: ctx.set_coop(False)
+    finally: ctx.set_coop(2)
     ost, ogt = C.verify(pk, msgs, sig, want_gt=True, threads=8)
     assert list(st0) == list(st1) == list(ost) == list(exp) and gt0.tobytes() == gt1.tobytes() == ogt.tobytes()
 
@@ -775,13 +783,15 @@ def test_split_stage_kernels_match_one_launch_form(ctx, C):
     sk = synth.secret_keys(n); pk2, st = ctx.sk_to_pk(sk); sig2, st = ctx.sign(sk, msgs)
     sig2 = sig2.copy(); sig2[96 * 7:96 * 8] = sig[96 * 7:96 * 8]; sig2[96 * 11 + 5] ^= 0x40
     out = {}
-    for mode in (1, 0):
-        ctx.set_split(mode)
+    for mode, coop in ((1, 0), (0, 0), (1, 2)):              # (1, 0): the short launches incl. k_final_squarings / k_final_step; (0, 0): one launch per stage; (1, 2): the defaults (six-lane final exponentiation at this size)
+        ctx.set_split(mode); ctx.set_coop(coop)
         try:
-            out[mode] = (ctx.verify(pk, msg, sig, want_bitmap=True, want_gt=True, fixed32=True), ctx.verify(pk2, msgs, sig2, want_bitmap=True, want_gt=True))
-        finally: ctx.set_split(1)
-    for a, b in zip(out[1], out[0]):
-        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2].tobytes() == b[2].tobytes()
+            out[(mode, coop)] = (ctx.verify(pk, msg, sig, want_bitmap=True, want_gt=True, fixed32=True), ctx.verify(pk2, msgs, sig2, want_bitmap=True, want_gt=True))
+        finally: ctx.set_split(1); ctx.set_coop(2)
+    for other in ((0, 0), (1, 2)):
+        for a, b in zip(out[(1, 0)], out[other]):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2].tobytes() == b[2].tobytes()
+    out = {1: out[(1, 0)]}
     exp = np.array(exp); exp[7] = 1
     assert list(out[1][0][0]) == list(exp)
     ost, ogt = C.verify(pk2, msgs, sig2, want_gt=True, threads=8)
