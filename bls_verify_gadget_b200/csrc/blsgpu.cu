@@ -355,6 +355,34 @@ __global__ void __launch_bounds__(128, 2) k_final_hard_coop(u32x4* f_soa, const 
     if (active) soa_store_fp2(f_soa, n, item, COOP_TOWER_POS[c.k], r);
     if (in_range && c.k == 0) status_out[item] = active ? ((((ball >> (6 * g)) & 63u) == 63u) ? (uint8_t)ST_OK : (uint8_t)ST_FALSE) : st;
 }
+// The accumulator update of the split Miller loop with six lanes per item (small passes, blsgpu_set_coop): lane k holds the w^k coefficient of f,
+// a line l0 + l1 v + l2 v w sits in lanes 0, 2, 3 (w^0, w^2, w^3) of an otherwise zero operand, a pair that is switched off multiplies by one.
+// Three to five generic six-lane products per iteration instead of one squaring and two sparse products in one thread: more work, a third of the chain.
+__global__ void __launch_bounds__(128, 2) k_miller_accum_coop(const uint8_t* flags, const uint8_t* status, size_t n, u32x4* f_soa, const u32x4* lines, int i_hi, int i_lo) {
+    __shared__ coop_smem sm[4];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane / 6;
+    coop_lane c = coop_init(&sm[warp]);
+    size_t item = (blockIdx.x * (size_t)4 + warp) * 5 + g;
+    bool active = g < 5 && item < n && status[item] == ST_OK;
+    uint8_t fl = active ? flags[item] : (uint8_t)(FL_SIG_INF | FL_HM_INF);
+    bool use[2] = {!(fl & FL_SIG_INF), !(fl & FL_HM_INF)};
+    fp2 unit = c.k == 0 ? fp2_one() : fp2_zero();
+    fp2 f = (active && i_hi != 62) ? soa_load_fp2(f_soa, n, item, COOP_TOWER_POS[c.k]) : unit;
+    int slot = c.k == 0 ? 0 : c.k == 2 ? 1 : c.k == 3 ? 2 : -1;           // which line coefficient this lane carries
+    const uint64_t x = BLS_X_ABS; int s = 0;
+    for (int it = i_hi; it >= i_lo; it--) {
+        if (it != 62) f = coop_mul(c, f, f);
+        int steps = 1 + (int)((x >> it) & 1);
+        for (int a = 0; a < steps; a++, s++)
+            for (int j = 0; j < 2; j++) {
+                const u32x4* L = lines + (size_t)(2 * s + j) * 18 * n;
+                fp2 b = !use[j] ? unit : slot >= 0 ? soa_load_fp2(L, n, item, slot) : fp2_zero();
+                f = coop_mul(c, f, b);
+            }
+    }
+    if (i_lo == 0) f = coop_conj(c, f);
+    if (active) soa_store_fp2(f_soa, n, item, COOP_TOWER_POS[c.k], f);
+}
 // out[t] = prod_{i = t, t+T, ...} in[i] over items with status <= ST_FALSE (status == NULL: all items)
 __global__ void __launch_bounds__(TPB, BLS_MINB) k_gt_reduce(const u32x4* in_soa, const uint8_t* status, size_t n, u32x4* out_soa, size_t T) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (t >= T) return;
@@ -863,11 +891,12 @@ static int hash_stage(blsgpu_ctx* ctx, const uint8_t* dmsg, const uint32_t* doff
 }
 // Miller loop in its split form: iterations 62..0 eight at a time, lines of both pairs (a pair switched off in flags costs nothing), then the accumulator update
 static int miller_stage_split(blsgpu_ctx* ctx, const u32x4* pk_soa, const u32x4* hm_soa, const u32x4* sig_soa, const uint8_t* flags, const uint8_t* dstatus, size_t n,
-                              u32x4* f_soa, u32x4* t_soa /* 36 n rows */, u32x4* lines /* MILLER_LINE_STEPS * 36 n rows */) {
+                              u32x4* f_soa, u32x4* t_soa /* 36 n rows */, u32x4* lines /* MILLER_LINE_STEPS * 36 n rows */, bool coop = false) {
     for (int hi = 62; hi >= 0; hi -= MILLER_LINE_ITERS) {
         int lo = hi - MILLER_LINE_ITERS + 1 < 0 ? 0 : hi - MILLER_LINE_ITERS + 1;
         LAUNCH(k_miller_lines, nblk(2 * n), TPB, pk_soa, hm_soa, sig_soa, flags, dstatus, n, t_soa, lines, hi, lo);
-        LAUNCH(k_miller_accum, nblk(n), TPB, flags, dstatus, n, f_soa, (const u32x4*)lines, hi, lo);
+        if (coop) LAUNCH(k_miller_accum_coop, nblk(n, 20), 128, flags, dstatus, n, f_soa, (const u32x4*)lines, hi, lo);
+        else LAUNCH(k_miller_accum, nblk(n), TPB, flags, dstatus, n, f_soa, (const u32x4*)lines, hi, lo);
     }
     return 0;
 }
@@ -889,7 +918,7 @@ static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code
         // iterations 62..0 eight at a time: lines of both pairs, then the accumulator update
         u32x4* t_soa = ws_take<u32x4>(ctx, 36 * n); y1_soa = t_soa; y2_soa = ws_take<u32x4>(ctx, 36 * n);      // the running points are dead once the loop ends
         u32x4* lines = ws_take<u32x4>(ctx, (size_t)MILLER_LINE_STEPS * 2 * 18 * n);
-        if (int rc = miller_stage_split(ctx, pk_soa, hm_soa, sig_soa, flags, dstatus, n, f_soa, t_soa, lines)) return rc;
+        if (int rc = miller_stage_split(ctx, pk_soa, hm_soa, sig_soa, flags, dstatus, n, f_soa, t_soa, lines, coop)) return rc;
         snap_soa = lines;                                      // 144 rows of the 396-row line buffer, which is dead once the loop ends
     } else {
 #if BLS_F_IN_SMEM

@@ -85,10 +85,11 @@ int blsgpu_set_lanes(blsgpu_ctx* ctx, int lanes);
  * of a few waves (a CTA of the one-launch kernels runs 14-21 ms; the partly filled last wave of each costs a tenth of a 2^17-item pass).
  * Workspace: 8.7 KB per item of a pass instead of 1.2 KB (blsgpu_set_chunk bounds the pass). */
 int blsgpu_set_split(blsgpu_ctx* ctx, int on);
-/* hard part of the final exponentiation with six lanes per item (warp-cooperative Fp12, coop.cuh) instead of one thread per item:
- * 0 = never, 1 = always, 2 (default) = for passes of at most 4,096 items.  A small pass is latency-bound -- every item is one thread's serial
- * chain -- and the six-lane form shortens the chain: a single verify takes 22 ms instead of 28.5 ms, 1,024 take 23 ms instead of 30 ms; from
- * ~30,000 items on the thread-per-item form is faster (profiles/latency_r02.json).  All forms produce identical GT bytes. */
+/* six lanes per item (warp-cooperative Fp12, coop.cuh) in the accumulator update of the Miller loop and the hard part of the final
+ * exponentiation, instead of one thread per item: 0 = never, 1 = always, 2 (default) = for passes of at most 4,096 items.  A small pass is
+ * latency-bound -- every item is one thread's serial chain -- and the six-lane kernels shorten the chain at the price of more work: a single
+ * verify takes 16.6 ms instead of 28.6 ms, 1,024 take 17 ms instead of 30 ms; from one wave of resident threads (~38,000 items) on the
+ * thread-per-item kernels are faster (profiles/latency_r02.json).  All forms produce identical statuses and GT bytes. */
 int blsgpu_set_coop(blsgpu_ctx* ctx, int on);
 int blsgpu_stage_times(blsgpu_ctx* ctx, float ms6[6]);
 

@@ -13,6 +13,6 @@ for n in (1, 32, 1024, 8192, 37888, 65536, 131072):
             t0 = time.perf_counter(); st = ctx.verify(pk[:48 * n], msg[:32 * n], sig[:96 * n], fixed32=True); dt = time.perf_counter() - t0
             assert list(st) == list(exp[:n])
             if rep: best = min(best, dt)
-        out.append({"n": n, "split_stage_kernels": bool(split), "six_lane_final_exp": bool(coop), "ms_per_call": round(1e3 * best, 2), "verifies_per_sec": round(n / best)})
+        out.append({"n": n, "split_stage_kernels": bool(split), "six_lane_small_pass_kernels": bool(coop), "ms_per_call": round(1e3 * best, 2), "verifies_per_sec": round(n / best)})
         print(out[-1], flush=True)
 json.dump(out, open("gpurun_out/latency_r02.json", "w"), indent=1)
