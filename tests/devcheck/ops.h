@@ -37,6 +37,8 @@ static inline op_desc op_shape(int op) {
         case 37: return {12, 24}; // cyclotomic g = easy part of the input: decompress(compress(g)) beside g (Karabina relations)
         case 38: return {12, 24}; // decompress(compressed squaring of g) beside fp12_cyclo_sqr(g)
         case 39: return {12, 24}; // fp12_exp_by_x (compressed squarings) beside fp12_exp_by_x_gs
+        case 40: return {12, 24}; // final exponentiation as the split stage kernels run it (easy part, 5 x (63 compressed squarings | decompression from the snapshots + products)) beside final_exponentiation
+        case 41: return {12, 24}; // Miller loop of two pairs as the split stage runs it (8 iterations at a time: scaled line coefficients of each pair, then the accumulator update) beside miller_loop2; inputs (p0.x, p0.y, q0, p1.x, p1.y, q1) need not be curve points
         case 36: return {8, 1};   // lazy 14-limb sum: 8 x (c0 z0 + c1 z1 + c2 z2 + c3 (p - z3)), c_i = low word of inputs 4..7, one reduction (fp_lacc_*)
         case 34: return {1, 2};   // fp_inv (divsteps) beside fp_inv_fermat
         case 23: return {4, 6};   // jac_mul_x_abs<fp2>(aff)
@@ -101,6 +103,42 @@ BLS_HD void run_op(int op, const fp* in, fp* out) {
             if (op == 37) { fp12c cc; fp12_compress(cc, g); fp12_decompress_product(h, &cc, 1); st12(out, h); st12(out + 12, g); }
             else if (op == 38) { fp12c cc; fp12_compress(cc, g); fp12c_sqr(cc, cc); fp12_decompress_product(h, &cc, 1); st12(out, h); fp12_cyclo_sqr(t, g); st12(out + 12, t); }
             else { fp12_exp_by_x(h, g); st12(out, h); fp12_exp_by_x_gs(t, g); st12(out + 12, t); }
+            break; }
+        case 40: {
+            ld12(f, in); fp12 r = f, y1, y2, e; fp12c snap[6];
+            auto run = [&](const fp12& a) { fp12c cc; fp12_compress(cc, a); int k = 0; for (int i = 1; i <= 63; i++) { fp12c_sqr(cc, cc); if ((BLS_X_ABS >> i) & 1) snap[k++] = cc; } };   // k_final_squarings
+            auto fin = [&](fp12& x) { fp12_decompress_product_from(x, [&](int k) { return snap[k]; }, 6); fp12_conj(x, x); };                                                        // head of k_final_step<1..5>
+            final_exponentiation_step<0>(r, y1, y2, e);
+            run(r); fin(e); final_exponentiation_step<1>(r, y1, y2, e);
+            run(y1); fin(e); final_exponentiation_step<2>(r, y1, y2, e);
+            run(y1); fin(e); final_exponentiation_step<3>(r, y1, y2, e);
+            run(y1); fin(e); final_exponentiation_step<4>(r, y1, y2, e);
+            run(y2); fin(e); final_exponentiation_step<5>(r, y1, y2, e);
+            st12(out, r); final_exponentiation(h, f); st12(out + 12, h);
+            break; }
+        case 41: {
+            g1_aff p[2]; g2_aff q[2]; p[0].x = in[0]; p[0].y = in[1]; ld2(q[0].x, in + 2); ld2(q[0].y, in + 4); p[1].x = in[6]; p[1].y = in[7]; ld2(q[1].x, in + 8); ld2(q[1].y, in + 10);
+            g2_proj r[2]; fp2 line[11][2][3]; fp2 c0, c1, c2; const uint64_t xx = BLS_X_ABS;
+            for (int j = 0; j < 2; j++) { r[j].x = q[j].x; r[j].y = q[j].y; r[j].z = fp2_one(); }
+            fp12_one(f);
+            for (int hi = 62; hi >= 0; hi -= 8) {
+                int lo = hi - 7 < 0 ? 0 : hi - 7;
+                for (int j = 0; j < 2; j++) {                                                     // k_miller_lines: one pair per thread
+                    int s = 0;
+                    for (int it = hi; it >= lo; it--) {
+                        miller_dbl(r[j], c0, c1, c2); line[s][j][0] = c0; line[s][j][1] = fp2_mul_fp(c1, p[j].x); line[s][j][2] = fp2_mul_fp(c2, p[j].y); s++;
+                        if ((xx >> it) & 1) { miller_add(r[j], q[j], c0, c1, c2); line[s][j][0] = c0; line[s][j][1] = fp2_mul_fp(c1, p[j].x); line[s][j][2] = fp2_mul_fp(c2, p[j].y); s++; }
+                    }
+                }
+                int s = 0;                                                                        // k_miller_accum
+                for (int it = hi; it >= lo; it--) {
+                    if (it != 62) fp12_sqr(f, f);
+                    int steps = 1 + (int)((xx >> it) & 1);
+                    for (int a2 = 0; a2 < steps; a2++, s++) for (int j = 0; j < 2; j++) fp12_mul_by_014(f, line[s][j][0], line[s][j][1], line[s][j][2]);
+                }
+            }
+            fp12_conj(f, f); st12(out, f);
+            miller_loop2(g, p[0], q[0], true, p[1], q[1], true); st12(out + 12, g);
             break; }
         case 36: { fp_lacc a; fp_lacc_zero(a); fp nz; fp_sub_raw(nz, fp_modulus(), in[3]);
                    for (int k = 0; k < 8; k++) { fp_lacc_mad(a, in[0], in[4].l[0]); fp_lacc_mad(a, in[1], in[5].l[0]); fp_lacc_mad(a, in[2], in[6].l[0]); fp_lacc_mad(a, nz, in[7].l[0]); }

@@ -35,7 +35,7 @@ def edge_fp(rng, n):
         out[i] = np.frombuffer(v.to_bytes(48, "little"), np.uint8)
     return out
 EDGE_OPS = (1, 2, 3, 4, 8, 9, 10, 11, 12, 21, 22, 26, 27, 29, 30, 31, 32, 33, 34, 35, 36)      # pure field arithmetic: any canonical input is valid
-def check(ops=range(1, 40), n=256, seed=1, edge=False):
+def check(ops=range(1, 42), n=256, seed=1, edge=False):
     D = dev_lib(); rng = np.random.default_rng(seed); bad = []
     for op in ops:
         n_in, n_out = emu.op_shape(op)

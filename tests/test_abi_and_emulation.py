@@ -98,9 +98,20 @@ def test_emu_karabina_compressed_squaring_matches_granger_scott(E):
     vals.append([pow(2, 384, P)] + [0] * 11)                       # f = 1 (Montgomery image): g = 1, compressed form (0, 0, 0, 0)
     vals.append([5 * pow(2, 384, P) % P] + [0] * 11)               # f in Fp: g = 1 as well
     x = np.frombuffer(b"".join(v.to_bytes(48, "little") for f in vals for v in f), np.uint8)
-    for op in (37, 38, 39):
+    for op in (37, 38, 39, 40):              # 40: the final exponentiation cut as the split stage kernels run it == final_exponentiation()
         out = E.run_op(op, x).reshape(len(vals), 2, 12 * 48)
         assert np.array_equal(out[:, 0], out[:, 1]), op
+
+def test_emu_split_miller_loop_matches_one_thread_form(E):
+    """The Miller loop as the split stage kernels run it -- eight iterations at a time: the scaled line coefficients of each pair
+    (k_miller_lines), then squarings and sparse products into the accumulator (k_miller_accum) -- equals miller_loop2 (lines produced and
+    consumed in the same iteration) for arbitrary field inputs; the GPU suite compares the kernels themselves through the GT bytes."""
+    P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    rng = np.random.default_rng(78)
+    vals = [[int.from_bytes(rng.bytes(48), "little") % P for _ in range(12)] for _ in range(6)]
+    x = np.frombuffer(b"".join(v.to_bytes(48, "little") for f in vals for v in f), np.uint8)
+    out = E.run_op(41, x).reshape(len(vals), 2, 12 * 48)
+    assert np.array_equal(out[:, 0], out[:, 1]) and out.any()
 
 def test_emu_fixtures(E, eth, pyv):
     k = eth["inline_kats"]
