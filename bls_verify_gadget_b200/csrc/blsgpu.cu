@@ -190,6 +190,15 @@ __global__ void __launch_bounds__(TPB, BLS_MINB_HFIELD) k_hash_field(const uint8
     }
     flags[i] = fl; if (status) status[i] = st;
 }
+// small passes hash every message while the two decoders run on other streams (verify_core, `forked`): the status / flags rule afterwards
+__global__ void k_status_merge(const uint8_t* code_pk, const uint8_t* code_sig, size_t n, uint8_t* flags, uint8_t* status) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+    uint8_t st = ST_OK, fl = 0;
+    if (code_pk[i] != DEC_OK) st = ST_BAD_PK;
+    else if (code_sig[i] != DEC_OK && code_sig[i] != DEC_INF) st = ST_BAD_SIG;
+    else if (code_sig[i] == DEC_INF) fl = FL_SIG_INF;
+    flags[i] = (uint8_t)((flags[i] & FL_HM_INF) | fl); status[i] = st;
+}
 __global__ void __launch_bounds__(TPB, BLS_MINB_HMAP) k_hash_map(const u32x4* u_soa, const uint8_t* status, size_t n, u32x4* q_soa) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (t >= 2 * n) return;
     int j = t >= n; size_t i = t - (j ? n : 0);
@@ -902,13 +911,28 @@ static int miller_stage_split(blsgpu_ctx* ctx, const u32x4* pk_soa, const u32x4*
 }
 // core of verify once pk (limb-SoA + code) is known: decode sig, hash, Miller, final exp, epilogue
 static int verify_core(blsgpu_ctx* ctx, const u32x4* pk_soa, const uint8_t* code_pk, const uint8_t* dmsg, const uint32_t* doff, const uint8_t* dsig, size_t n,
-                       uint8_t* dstatus, uint32_t* dbitmap, u32x4* gt_acc /* limb-SoA n=1, multiplied into; nullable */) {
+                       uint8_t* dstatus, uint32_t* dbitmap, u32x4* gt_acc /* limb-SoA n=1, multiplied into; nullable */, bool forked = false) {
     u32x4* sig_soa = ws_take<u32x4>(ctx, 12 * n); u32x4* hm_soa = ws_take<u32x4>(ctx, 12 * n); u32x4* f_soa = ws_take<u32x4>(ctx, 36 * n);
     uint8_t* code_sig = ws_take<uint8_t>(ctx, n); uint8_t* flags = ws_take<uint8_t>(ctx, n);
+    if (forked) {
+        // Small pass (the caller recorded ctx->fork before it enqueued the key decoder on ctx->stream): the signature decoder and the hash run on
+        // the two lane streams beside it -- three independent serial chains instead of one after the other -- and the status rule follows the join.
+        cudaStream_t main_stream = ctx->stream; int rc = 0;
+        ctx->stream = ctx->lane_stream[0]; cudaStreamWaitEvent(ctx->stream, ctx->fork, 0);
+        k_decode_g2<<<nblk(n), TPB, 0, ctx->stream>>>(dsig, n, sig_soa, code_sig); ctx->launches++; cudaEventRecord(ctx->lane_done[0], ctx->stream);
+        ctx->stream = ctx->lane_stream[1]; cudaStreamWaitEvent(ctx->stream, ctx->fork, 0);
+        rc = hash_stage(ctx, dmsg, doff, n, nullptr, nullptr, hm_soa, f_soa, flags, nullptr); cudaEventRecord(ctx->lane_done[1], ctx->stream);
+        ctx->stream = main_stream;
+        CU(cudaStreamWaitEvent(main_stream, ctx->lane_done[0], 0)); CU(cudaStreamWaitEvent(main_stream, ctx->lane_done[1], 0));
+        if (rc) return rc;
+        CU(cudaGetLastError());
+        LAUNCH(k_status_merge, nblk(n, 256), 256, code_pk, (const uint8_t*)code_sig, n, flags, dstatus);
+    } else {
     STAGE_MARK(1);
     LAUNCH(k_decode_g2, nblk(n), TPB, dsig, n, sig_soa, code_sig);
     STAGE_MARK(2);
     if (int rc = hash_stage(ctx, dmsg, doff, n, code_pk, code_sig, hm_soa, f_soa, flags, dstatus)) return rc;
+    }
     STAGE_MARK(3);
     // Small passes are latency-bound (one item per thread: a lone warp walks the whole Miller loop and final exponentiation): below
     // VERIFY_COOP_BELOW items the hard part of the final exponentiation runs with six lanes per item (coop.cuh), which shortens its chain.
@@ -960,6 +984,7 @@ static size_t verify_ws_bytes(size_t n, size_t mb) {
     return 2 * al(576 * n) + al((size_t)MILLER_LINE_STEPS * 2 * 288 * n) /* state of the split stage kernels: running points / y1, y2, line buffer / snapshots */ + al(48 * n) + al(96 * n) + al(mb + 1) + al(4 * (n + 1)) + al(n) * 6 + al(96 * n) + 2 * al(192 * n) + al(576 * n) + al(8 * ((n + 63) / 64)) +
            al(576 * ((n + 7) / 8)) + al(576 * ((n + 63) / 64)) + 3 * al(576) + 65536;
 }
+static int ensure_lanes(blsgpu_ctx* ctx);
 // One contiguous sub-range [base, base+m) of a verify batch, enqueued entirely on ctx->stream (the caller may have pointed
 // it at a lane stream): staging, the five stage kernels, epilogue, outputs, and the range's GT partial (limb-SoA, n = 1).
 static int verify_range(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg, const uint32_t* msg_off, const uint8_t* sig96, size_t base, size_t m,
@@ -980,8 +1005,12 @@ static int verify_range(blsgpu_ctx* ctx, const uint8_t* pk48, const uint8_t* msg
     if (gt_acc) LAUNCH(k_gt_set_one, 1, 32, gt_acc);
     if (dbitmap) CU(cudaMemsetAsync(dbitmap, 0, 8 * ((m + 63) / 64), ctx->stream));
     STAGE_MARK(0);
+    // a small pass on the context's own stream (not a lane of a larger pass, not a profiled pass): decoders and hash side by side
+    bool forked = ctx->coop == 2 && m <= VERIFY_COOP_BELOW && !ctx->prof && ctx->split && ctx->stream != ctx->lane_stream[0] && ctx->stream != ctx->lane_stream[1];
+    if (forked) { if ((rc = ensure_lanes(ctx))) return rc; forked = ctx->stream != ctx->lane_stream[0] && ctx->stream != ctx->lane_stream[1]; }
+    if (forked) CU(cudaEventRecord(ctx->fork, ctx->stream));
     LAUNCH(k_decode_g1, nblk(m), TPB, dpk, m, pk_soa, code_pk);
-    if ((rc = verify_core(ctx, pk_soa, code_pk, dmsg, doff, dsig, m, dstatus, dbitmap, gt_acc))) return rc;
+    if ((rc = verify_core(ctx, pk_soa, code_pk, dmsg, doff, dsig, m, dstatus, dbitmap, gt_acc, forked))) return rc;
     if ((rc = finish_out(ctx, status + base, dstatus, m))) return rc;
     if (ok_bitmap && (rc = finish_out(ctx, ok_bitmap + base / 64, (uint64_t*)dbitmap, (m + 63) / 64))) return rc;
     return 0;

@@ -87,9 +87,10 @@ int blsgpu_set_lanes(blsgpu_ctx* ctx, int lanes);
 int blsgpu_set_split(blsgpu_ctx* ctx, int on);
 /* six lanes per item (warp-cooperative Fp12, coop.cuh) in the accumulator update of the Miller loop and the hard part of the final
  * exponentiation, instead of one thread per item: 0 = never, 1 = always, 2 (default) = for passes of at most 4,096 items.  A small pass is
- * latency-bound -- every item is one thread's serial chain -- and the six-lane kernels shorten the chain at the price of more work: a single
- * verify takes 16.6 ms instead of 28.6 ms, 1,024 take 17 ms instead of 30 ms; from one wave of resident threads (~38,000 items) on the
- * thread-per-item kernels are faster (profiles/latency_r02.json).  All forms produce identical statuses and GT bytes. */
+ * latency-bound -- every item is one thread's serial chain -- and the six-lane kernels shorten the chain at the price of more work; in mode 2
+ * such a pass also runs its two decoders and its hash side by side on internal streams.  A single verify takes 12.4 ms instead of 28.6 ms, 1,024
+ * take 12.7 ms instead of 30 ms; from one wave of resident threads (~38,000 items) on the thread-per-item kernels are faster
+ * (profiles/latency_r02.json, latency_default_r02.json).  All forms produce identical statuses and GT bytes. */
 int blsgpu_set_coop(blsgpu_ctx* ctx, int on);
 int blsgpu_stage_times(blsgpu_ctx* ctx, float ms6[6]);
 
