@@ -3,9 +3,10 @@
 //
 // Kernel inventory (one item per thread, 128-thread CTAs, grid = ceil(n/128) >> 148 SMs):
 //   k_decode_g1 / k_decode_g2   K1  compressed bytes -> affine Montgomery limb-SoA + decode code
-//   k_hash_to_g2                K2  message -> H(m) affine limb-SoA
-//   k_miller                    K4  (pk, H(m), sig) -> Fp12 Miller value limb-SoA
-//   k_final_exp                 K5  Fp12 -> GT, is_one -> status
+//   k_hash_to_g2                K2  message -> H(m) affine limb-SoA            | split form (default): k_hash_field -> k_hash_map (2n threads) -> k_hash_clear
+//   k_miller                    K4  (pk, H(m), sig) -> Fp12 Miller value limb-SoA | split form: 8 x (k_miller_lines (2n threads) -> k_miller_accum)
+//   k_final_exp                 K5  Fp12 -> GT, is_one -> status                   | split form: k_final_step<0>, 5 x (k_final_squarings -> k_final_step<k>)
+//   k_miller_accum_coop, k_final_hard_coop   six lanes per item: passes of at most VERIFY_COOP_BELOW items (latency), blsgpu_set_coop
 //   k_gt_reduce                 K5' strided product of GT values (per-batch accumulator)
 //   k_status_bitmap                 status -> packed ok bitmap
 //   k_segsum_g1 / k_segsum_g2   K3  warp-per-segment aggregation, tree reduction in shared memory
